@@ -1,0 +1,167 @@
+"""Shared parity cases: one plain-dict description from which the oracle, the real
+reference (oracle/ref_loader.build_reference_solver) and the b200 backend
+(tests/util.build_b200_solver) are all constructed.
+
+Everything is deterministic (fields start at zero; geometry / material masks come
+from closed-form rules), so no RNG state has to travel with the fixtures.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _block_geometry(shape, lo, hi):
+    g = np.ones(shape, dtype=bool)
+    g[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = False
+    return g
+
+
+def _sphere_mask(shape, centre, radius):
+    i, j, k = np.ogrid[:shape[0], :shape[1], :shape[2]]
+    return ((i - centre[0]) ** 2 + (j - centre[1]) ** 2 + (k - centre[2]) ** 2) < radius ** 2
+
+
+def _stretched(n, base, ratio):
+    """Cell-centre coordinates with geometric growth away from the centre (own construction)."""
+    half = n // 2
+    sizes_r = base * ratio ** np.arange(n - half, dtype=np.float64)
+    sizes_l = base * ratio ** np.arange(half, dtype=np.float64)
+    sizes = np.concatenate([sizes_l[::-1], sizes_r])
+    edges = np.concatenate([[0.0], np.cumsum(sizes)])
+    return 0.5 * (edges[:-1] + edges[1:])
+
+
+# benign dispersive material of SURVEY.md F9 (bounded for >= 1000 steps)
+BENIGN_POLES = [
+    {"type": "debye", "target": "density", "delta_chi": 0.1, "tau": 1e-4},
+    {"type": "debye", "target": "modulus", "delta_chi": 0.1, "tau": 1e-5},
+    {"type": "lorentz", "target": "modulus", "delta_chi": 0.05, "omega_0": 2 * np.pi * 2000.0, "gamma": 2 * np.pi * 200.0},
+]
+SECOND_POLES = [
+    {"type": "lorentz", "target": "density", "delta_chi": 0.02, "omega_0": 2 * np.pi * 5000.0, "gamma": 2 * np.pi * 500.0},
+    {"type": "debye", "target": "density", "delta_chi": 0.05, "tau": 5e-5},
+    {"type": "debye", "target": "modulus", "delta_chi": 0.08, "tau": 2e-5},
+]
+
+
+def make_cases() -> dict:
+    C = {}
+
+    # --- uniform, sponge on all axes, point source, probes + omni mics
+    C["uniform_pml"] = dict(
+        shape=(24, 20, 28), resolution=1e-3, steps=240,
+        pml=[dict(depth=5)],
+        sources=[dict(kind="point", position=(6, 10, 14), frequency=20e3)],
+        probes=[("a", (18, 10, 14)), ("b", (12, 4, 20)), ("at_source", (6, 10, 14))],
+        mics=[("m0", (0.0123, 0.0101, 0.0137)), ("m1", (0.0031, 0.0152, 0.0209))],
+    )
+
+    # --- odd extents (nz not a multiple of 4), no sponge: rigid box, positions in metres
+    C["odd_rigid_box"] = dict(
+        shape=(17, 23, 13), resolution=2e-3, steps=200,
+        sources=[dict(kind="point", position=(0.010, 0.020, 0.012), frequency=8e3, amplitude=2.5)],
+        probes=[("far", (0.030, 0.040, 0.020)), ("idx", (3, 3, 3))],
+    )
+
+    # --- the bit-exactness configuration of SURVEY.md F6: solid block + sponge
+    C["block_pml"] = dict(
+        shape=(48, 40, 56), resolution=1e-3, steps=300,
+        geometry=_block_geometry((48, 40, 56), (20, 14, 22), (30, 26, 36)),
+        pml=[dict(depth=8)],
+        sources=[dict(kind="point", position=(10, 20, 28), frequency=20e3)],
+        probes=[("shadow", (40, 20, 28)), ("side", (24, 6, 28))],
+    )
+
+    # --- sponge on a subset of axes, two boundary objects, plane source, explicit max_sigma
+    C["partial_pml_plane"] = dict(
+        shape=(30, 22, 26), resolution=1e-3, steps=200,
+        geometry=_block_geometry((30, 22, 26), (14, 0, 10), (18, 8, 16)),
+        pml=[dict(depth=6, axes=("x", "z")), dict(depth=4, axes=("y",), order=2, max_sigma=4.0e5)],
+        sources=[dict(kind="plane", axis=0, index=8, frequency=15e3, amplitude=0.5),
+                 dict(kind="point", position=(22, 11, 13), frequency=12e3)],
+        probes=[("p0", (25, 11, 13)), ("on_plane", (8, 5, 5))],
+    )
+
+    # --- nonuniform grid + geometry + sponge
+    xs, ys, zs = _stretched(26, 1e-3, 1.04), _stretched(22, 1e-3, 1.0), _stretched(30, 1e-3, 1.03)
+    C["nonuniform_block_pml"] = dict(
+        nonuniform=dict(x_coords=xs, y_coords=ys, z_coords=zs), steps=240,
+        geometry=_block_geometry((26, 22, 30), (11, 8, 12), (15, 14, 18)),
+        pml=[dict(depth=5)],
+        sources=[dict(kind="point", position=(6, 11, 15), frequency=18e3)],
+        probes=[("q", (20, 11, 15)), ("r", (13, 4, 25))],
+        mics=[("nm", (0.0102, 0.0098, 0.0131))],
+    )
+
+    # --- ADE: material sphere (2 Debye + 1 Lorentz), sponge, uniform
+    sh = (32, 32, 32)
+    mid = np.zeros(sh, dtype=np.uint8)
+    mid[_sphere_mask(sh, (20, 16, 16), 6.5)] = 1
+    C["ade_sphere"] = dict(
+        shape=sh, resolution=1e-3, steps=300,
+        pml=[dict(depth=6)],
+        sources=[dict(kind="point", position=(8, 16, 16), frequency=20e3)],
+        probes=[("behind", (28, 16, 16)), ("inside", (20, 16, 16)), ("front", (12, 16, 16))],
+        materials=[dict(id=1, rho_inf=1.2, K_inf=1.2 * 343.0 ** 2, poles=BENIGN_POLES)],
+        material_id=mid,
+    )
+
+    # --- ADE: two materials (one with density Lorentz), touching each other and a solid, on a nonuniform grid
+    xs2, ys2, zs2 = _stretched(28, 1e-3, 1.02), _stretched(24, 1e-3, 1.03), _stretched(26, 1e-3, 1.0)
+    sh2 = (28, 24, 26)
+    mid2 = np.zeros(sh2, dtype=np.uint8)
+    mid2[16:24, 4:20, 5:21] = 3
+    mid2[12:16, 6:18, 8:18] = 7
+    g2 = _block_geometry(sh2, (18, 10, 10), (21, 14, 16))        # solid inside material 3
+    C["ade_two_materials_nonuniform"] = dict(
+        nonuniform=dict(x_coords=xs2, y_coords=ys2, z_coords=zs2), steps=260,
+        geometry=g2,
+        pml=[dict(depth=4)],
+        sources=[dict(kind="point", position=(6, 12, 13), frequency=16e3)],
+        probes=[("m3", (17, 12, 13)), ("m7", (13, 12, 13)), ("air", (8, 6, 6))],
+        materials=[dict(id=3, rho_inf=1.5, K_inf=1.5 * 320.0 ** 2, poles=BENIGN_POLES),
+                   dict(id=7, rho_inf=1.1, K_inf=1.1 * 350.0 ** 2, poles=SECOND_POLES)],
+        material_id=mid2,
+    )
+    return C
+
+
+def c1_case(steps: int = 1000) -> dict:
+    """BASELINE config 1 as worded: 100^3, 1 mm, PML 10, 1 kHz Gaussian pulse, 1 probe."""
+    return dict(shape=(100, 100, 100), resolution=1e-3, steps=steps, pml=[dict(depth=10)],
+                sources=[dict(kind="point", position=(25, 50, 50), frequency=1000.0)],
+                probes=[("probe", (75, 50, 50))])
+
+
+def c2_case(n: int = 200, steps: int = 1000, with_geometry: bool = False) -> dict:
+    """BASELINE config 2: N^3 uniform + PML(10), source at (N/4, N/2, N/2)."""
+    c = dict(shape=(n, n, n), resolution=1e-3, steps=steps, pml=[dict(depth=10)],
+             sources=[dict(kind="point", position=(n // 4, n // 2, n // 2), frequency=1000.0)],
+             probes=[("probe", (3 * n // 4, n // 2, n // 2))])
+    if with_geometry:
+        a, b = int(0.45 * n), int(0.55 * n)
+        c["geometry"] = _block_geometry((n, n, n), (a, a, a), (b, b, b))
+    return c
+
+
+def c3_case(n: int = 512, steps: int = 1000, slab: bool = False) -> dict:
+    """BASELINE config 3: N^3 + PML + ADE material sphere (radius N/10) + 64 probes."""
+    sh = (n, n, n)
+    mid = np.zeros(sh, dtype=np.uint8)
+    if slab:
+        mid[3 * n // 4:, :, :] = 1
+    else:
+        c = n // 2
+        r = n / 10.0
+        # cell-centre SDF < 0, evaluated plane by plane to bound temporaries
+        j, k = np.ogrid[:n, :n]
+        for i in range(max(0, int(c - r) - 1), min(n, int(c + r) + 2)):
+            mid[i][((i - c) ** 2 + (j - c) ** 2 + (k - c) ** 2) < r * r] = 1
+    s = n / 512.0
+    probes = [(f"p{a}{b}", (int(384 * s), int((32 + 64 * a) * s), int((32 + 64 * b) * s)))
+              for a in range(8) for b in range(8)]
+    return dict(shape=sh, resolution=1e-3, steps=steps, pml=[dict(depth=10)],
+                sources=[dict(kind="point", position=(int(77 * s), n // 2, n // 2), frequency=40e3)],
+                probes=probes,
+                materials=[dict(id=1, rho_inf=1.2, K_inf=1.2 * 343.0 ** 2, poles=BENIGN_POLES)],
+                material_id=mid)
