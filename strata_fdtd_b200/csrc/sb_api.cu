@@ -1,0 +1,705 @@
+// sb_api.cu -- C ABI (include/strata_b200.h) over the sm_100a kernels in sb_kernels.cuh.
+// Host side only: table upload, list building, launch sequencing, CUDA-graph caching.
+#include "../../include/strata_b200.h"
+#include "sb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace sb;
+
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CHECK_H(h) do { if (!(h)) return fail("null handle"); CU(cudaSetDevice((h)->device)); } while (0)
+
+template <typename T> struct DBuf {
+    T *p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        release();
+        if (count == 0) count = 1;
+        CU(cudaMalloc(&p, count * sizeof(T)));
+        n = count; return 0;
+    }
+    int upload(const T *host, size_t count, cudaStream_t s) {
+        if (alloc(count)) return 1;
+        if (count) { CU(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s)); CU(cudaStreamSynchronize(s)); }
+        return 0;
+    }
+    int upload(const std::vector<T> &v, cudaStream_t s) { return upload(v.data(), v.size(), s); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Sponge { DBuf<float> x, y, z; };
+
+struct sb_solver {
+    sb_grid_desc d{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long plane = 0, elems = 0;
+    float *set[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    int cur = 0;
+    // tables
+    DBuf<float> cvx, cvy, cvz, icx, icy, icz;
+    bool nonuniform = false, have_coeffs = false;
+    float cp = 0.f;
+    DBuf<uint8_t> mask; bool have_mask = false;
+    std::vector<Sponge *> sponges;
+    // sources / records
+    int n_sources = 0, n_src_cells = 0;
+    DBuf<long long> src_off; DBuf<int> src_start, src_id, src_field; DBuf<double> src_weight;
+    int n_probes = 0, n_mics = 0;
+    DBuf<long long> probe_off, mic_off; DBuf<float> mic_w;
+    DBuf<double> d_src_vals; DBuf<float> d_record; DBuf<int> d_step_ctr;
+    // ADE
+    bool have_ade = false;
+    AdeTable ade{};
+    DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat; DBuf<float> ade_J, ade_Jp;
+    // options
+    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 2, opt_wj = 8, opt_wk = 1, opt_chunk_i = 0, opt_graph = 0;
+    // graph cache: key = (n_steps, starting set)
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    // stats
+    long long steps_done = 0, kernels_launched = 0;
+    int last_variant = 0;
+    DBuf<double> d_energy;
+};
+
+static void drop_graphs(sb_solver *h)
+{
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+}
+
+extern "C" const char *sb_last_error(void) { return g_err.c_str(); }
+extern "C" int sb_abi_version(void) { return SB_ABI_VERSION; }
+
+extern "C" int sb_choose_pitch(int32_t nz, int32_t *pitch_out)
+{
+    if (nz <= 0 || !pitch_out) return fail("bad nz");
+    *pitch_out = (nz + 31) / 32 * 32;          // rows start on 128-byte lines
+    return 0;
+}
+
+extern "C" int64_t sb_field_elems(const sb_grid_desc *d)
+{
+    int32_t pitch = d->pitch;
+    if (pitch == 0) sb_choose_pitch(d->nz, &pitch);
+    return (int64_t)(d->nx + 2) * d->ny * pitch;
+}
+
+extern "C" int sb_create(const sb_grid_desc *desc, int device, void *stream, sb_solver **out)
+{
+    if (!desc || !out) return fail("null argument");
+    if (desc->nx < 1 || desc->ny < 1 || desc->nz < 1) return fail("grid extents must be >= 1");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail("no CUDA device available (%s); the b200 backend has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail("device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    sb_solver *h = new sb_solver();
+    h->d = *desc;
+    if (h->d.pitch == 0) sb_choose_pitch(h->d.nz, &h->d.pitch);
+    if (h->d.pitch < h->d.nz || h->d.pitch % 4) { delete h; return fail("pitch must be >= nz and a multiple of 4"); }
+    if ((long long)h->d.ny * h->d.pitch * (long long)(h->d.nx + 2) >= (1LL << 40)) { delete h; return fail("slab too large"); }
+    h->device = device;
+    h->stream = (cudaStream_t)stream;
+    h->plane = (long long)h->d.ny * h->d.pitch;
+    h->elems = sb_field_elems(&h->d);
+    if (h->d_step_ctr.alloc(1)) { delete h; return 1; }
+    if (h->d_energy.alloc(2)) { delete h; return 1; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int sb_destroy(sb_solver *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    drop_graphs(h);
+    for (auto *s : h->sponges) { s->x.release(); s->y.release(); s->z.release(); delete s; }
+    for (DBuf<float> *b : {&h->cvx, &h->cvy, &h->cvz, &h->icx, &h->icy, &h->icz, &h->mic_w, &h->d_record, &h->ade_J, &h->ade_Jp}) b->release();
+    h->mask.release(); h->src_off.release(); h->src_start.release(); h->src_id.release(); h->src_field.release();
+    h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
+    h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release();
+    h->d_energy.release();
+    delete h;
+    return 0;
+}
+
+extern "C" int sb_bind_fields(sb_solver *h, float *const set0[4], float *const set1[4])
+{
+    CHECK_H(h);
+    for (int f = 0; f < 4; f++) {
+        if (!set0[f] || !set1[f]) return fail("null field buffer");
+        if (((uintptr_t)set0[f] | (uintptr_t)set1[f]) & 15) return fail("field buffers must be 16-byte aligned");
+        h->set[0][f] = set0[f]; h->set[1][f] = set1[f];
+    }
+    h->cur = 0;
+    drop_graphs(h);
+    return 0;
+}
+
+extern "C" int sb_current_set(sb_solver *h, int *set_out) { if (!h || !set_out) return fail("null argument"); *set_out = h->cur; return 0; }
+
+static inline float *plane0(sb_solver *h, int set, int f) { return h->set[set][f] + h->plane; }
+
+extern "C" int sb_upload_field(sb_solver *h, int field, const float *host)
+{
+    CHECK_H(h);
+    if (field < 0 || field > 3 || !host) return fail("bad field / null host pointer");
+    if (!h->set[0][0]) return fail("fields not bound");
+    const sb_grid_desc &d = h->d;
+    CU(cudaMemcpy2DAsync(plane0(h, h->cur, field), (size_t)d.pitch * 4, host, (size_t)d.nz * 4, (size_t)d.nz * 4,
+                         (size_t)d.nx * d.ny, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int sb_download_field(sb_solver *h, int field, float *host)
+{
+    CHECK_H(h);
+    if (field < 0 || field > 3 || !host) return fail("bad field / null host pointer");
+    if (!h->set[0][0]) return fail("fields not bound");
+    const sb_grid_desc &d = h->d;
+    CU(cudaMemcpy2DAsync(host, (size_t)d.nz * 4, plane0(h, h->cur, field), (size_t)d.pitch * 4, (size_t)d.nz * 4,
+                         (size_t)d.nx * d.ny, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// table of n entries padded to `padded` with `fill`, optionally with one leading ghost entry
+static int upload_table(DBuf<float> &buf, const float *src, int n, int padded, float fill, cudaStream_t s)
+{
+    std::vector<float> t((size_t)padded, fill);
+    if (src) std::copy(src, src + n, t.begin());
+    return buf.upload(t, s);
+}
+
+extern "C" int sb_set_coefficients(sb_solver *h, const float *cv_x, const float *cv_y, const float *cv_z,
+                                   const float *ic_x, const float *ic_y, const float *ic_z, float cp)
+{
+    CHECK_H(h);
+    if (!cv_x || !cv_y || !cv_z) return fail("null coefficient table");
+    const bool nu = ic_x || ic_y || ic_z;
+    if (nu && !(ic_x && ic_y && ic_z)) return fail("inv_cell tables must be all NULL or all given");
+    const sb_grid_desc &d = h->d;
+    const int gx = d.nx + d.has_lower;            // x tables arrive with the live lower ghost first
+    {   // x tables are stored with one leading slot so that index -1 is addressable
+        std::vector<float> t((size_t)d.nx + 2, 0.0f);
+        std::copy(cv_x, cv_x + gx, t.begin() + (d.has_lower ? 0 : 1));
+        if (h->cvx.upload(t, h->stream)) return 1;
+        if (nu) {
+            std::vector<float> u((size_t)d.nx + 2, 1.0f);
+            std::copy(ic_x, ic_x + gx, u.begin() + (d.has_lower ? 0 : 1));
+            if (h->icx.upload(u, h->stream)) return 1;
+        }
+    }
+    if (upload_table(h->cvy, cv_y, d.ny, d.ny + 4, 0.0f, h->stream)) return 1;
+    if (upload_table(h->cvz, cv_z, d.nz, d.pitch + 4, 0.0f, h->stream)) return 1;
+    if (nu) {
+        if (upload_table(h->icy, ic_y, d.ny, d.ny + 4, 1.0f, h->stream)) return 1;
+        if (upload_table(h->icz, ic_z, d.nz, d.pitch + 4, 1.0f, h->stream)) return 1;
+    }
+    h->nonuniform = nu; h->cp = cp; h->have_coeffs = true;
+    drop_graphs(h);
+    return 0;
+}
+
+extern "C" int sb_set_geometry(sb_solver *h, const uint8_t *geom_host, int rigid)
+{
+    CHECK_H(h);
+    drop_graphs(h);
+    if (!geom_host) { h->have_mask = false; return 0; }
+    const sb_grid_desc &d = h->d;
+    const size_t gplanes = (size_t)d.nx + d.has_lower + d.has_upper;
+    const size_t gbytes = gplanes * d.ny * d.nz;
+    // all-air + nothing to zero -> no mask traffic at all
+    bool all_air = true;
+    for (size_t q = 0; q < gbytes; q++) if (!geom_host[q]) { all_air = false; break; }
+    if (all_air) { h->have_mask = false; return 0; }
+    DBuf<uint8_t> g;
+    if (g.upload(geom_host, gbytes, h->stream)) return 1;
+    if (h->mask.alloc((size_t)h->elems)) { g.release(); return 1; }
+    CU(cudaMemsetAsync(h->mask.p, 0, (size_t)h->elems, h->stream));
+    dim3 blk(128), grd((d.nz + 127) / 128, d.ny, d.nx + 2);
+    k_build_mask<<<grd, blk, 0, h->stream>>>(g.p, h->mask.p + h->plane, d.nx, d.ny, d.nz, d.pitch, h->plane,
+                                             d.has_lower, d.has_upper, rigid ? 1 : 0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    g.release();
+    h->have_mask = true;
+    h->kernels_launched++;
+    return 0;
+}
+
+extern "C" int sb_sponge_decay(const float *sigma, int n, float dt, float *out)
+{
+    if (!sigma || !out || n < 0) return fail("bad argument");
+    for (int m = 0; m < n; m++) out[m] = std::exp(-sigma[m] * dt);     // float overload = glibc expf
+    return 0;
+}
+
+extern "C" int sb_clear_sponges(sb_solver *h)
+{
+    CHECK_H(h);
+    for (auto *s : h->sponges) { s->x.release(); s->y.release(); s->z.release(); delete s; }
+    h->sponges.clear();
+    drop_graphs(h);
+    return 0;
+}
+
+extern "C" int sb_add_sponge(sb_solver *h, const float *dx, const float *dy, const float *dz)
+{
+    CHECK_H(h);
+    if ((int)h->sponges.size() >= MAX_SPONGES) return fail("at most %d sponge layers", MAX_SPONGES);
+    const sb_grid_desc &d = h->d;
+    Sponge *s = new Sponge();
+    std::vector<float> t((size_t)d.nx + 2, 1.0f);         // absent axis = multiply by 1.0f (exact identity)
+    if (dx) std::copy(dx, dx + d.nx + d.has_lower, t.begin() + (d.has_lower ? 0 : 1));
+    if (s->x.upload(t, h->stream) || upload_table(s->y, dy, d.ny, d.ny + 4, 1.0f, h->stream) ||
+        upload_table(s->z, dz, d.nz, d.pitch + 4, 1.0f, h->stream)) { delete s; return 1; }
+    h->sponges.push_back(s);
+    drop_graphs(h);
+    return 0;
+}
+
+static inline long long dense_to_off(const sb_solver *h, long long dense)
+{
+    const sb_grid_desc &d = h->d;
+    const long long k = dense % d.nz, j = (dense / d.nz) % d.ny, i = dense / ((long long)d.nz * d.ny);
+    return i * h->plane + j * d.pitch + k;
+}
+
+extern "C" int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const int64_t *cell_idx,
+                              const int32_t *start, const int32_t *src_id, const int32_t *field,
+                              const double *weight)
+{
+    CHECK_H(h);
+    drop_graphs(h);
+    h->n_sources = n_sources; h->n_src_cells = n_cells;
+    if (n_cells == 0) return 0;
+    if (!cell_idx || !start || !src_id || !field || !weight) return fail("null source table");
+    const long long ncell = (long long)h->d.nx * h->d.ny * h->d.nz;
+    std::vector<long long> off((size_t)n_cells);
+    for (int u = 0; u < n_cells; u++) {
+        if (cell_idx[u] < 0 || cell_idx[u] >= ncell) return fail("source cell %d out of range", u);
+        off[u] = dense_to_off(h, cell_idx[u]);
+    }
+    const int n_ent = start[n_cells];
+    for (int e = 0; e < n_ent; e++)
+        if (src_id[e] < 0 || src_id[e] >= n_sources || field[e] < 0 || field[e] > 3) return fail("bad source entry %d", e);
+    if (h->src_off.upload(off, h->stream) || h->src_start.upload(start, (size_t)n_cells + 1, h->stream) ||
+        h->src_id.upload(src_id, (size_t)n_ent, h->stream) || h->src_field.upload(field, (size_t)n_ent, h->stream) ||
+        h->src_weight.upload(weight, (size_t)n_ent, h->stream)) return 1;
+    return 0;
+}
+
+extern "C" int sb_set_probes(sb_solver *h, int n_probes, const int64_t *flat_idx)
+{
+    CHECK_H(h);
+    drop_graphs(h);
+    const long long ncell = (long long)h->d.nx * h->d.ny * h->d.nz;
+    std::vector<long long> off((size_t)n_probes);
+    for (int t = 0; t < n_probes; t++) {
+        if (flat_idx[t] < 0 || flat_idx[t] >= ncell) return fail("probe %d out of range", t);
+        off[t] = dense_to_off(h, flat_idx[t]);
+    }
+    h->n_probes = n_probes;
+    return n_probes ? h->probe_off.upload(off, h->stream) : 0;
+}
+
+extern "C" int sb_set_mics(sb_solver *h, int n_mics, const int64_t *idx8, const float *w8)
+{
+    CHECK_H(h);
+    drop_graphs(h);
+    const long long ncell = (long long)h->d.nx * h->d.ny * h->d.nz;
+    std::vector<long long> off((size_t)n_mics * 8);
+    for (int t = 0; t < n_mics * 8; t++) {
+        if (idx8[t] < 0 || idx8[t] >= ncell) return fail("microphone corner %d out of range", t);
+        off[t] = dense_to_off(h, idx8[t]);
+    }
+    h->n_mics = n_mics;
+    if (!n_mics) return 0;
+    return h->mic_off.upload(off, h->stream) || h->mic_w.upload(w8, (size_t)n_mics * 8, h->stream);
+}
+
+// microphones.cpp:16-80 restated (fp32 arithmetic, corner order of microphones.hpp:30-32)
+extern "C" int sb_mic_tables(const float *gp, int n_mics, int ny, int nz, int64_t *idx8, float *w8)
+{
+    if (!gp || !idx8 || !w8) return fail("null argument");
+    for (int m = 0; m < n_mics; m++) {
+        const float g[3] = {gp[3 * m], gp[3 * m + 1], gp[3 * m + 2]};
+        int base[3]; float lo[3], hi[3];
+        for (int a = 0; a < 3; a++) { base[a] = (int)g[a]; hi[a] = g[a] - (float)base[a]; lo[a] = 1.0f - hi[a]; }
+        for (int c = 0; c < 8; c++) {
+            const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
+            idx8[8 * m + c] = ((int64_t)(base[0] + bx) * ny + (base[1] + by)) * nz + (base[2] + bz);
+            w8[8 * m + c] = ((bx ? hi[0] : lo[0]) * (by ? hi[1] : lo[1])) * (bz ? hi[2] : lo[2]);
+        }
+    }
+    return 0;
+}
+
+extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const uint8_t *mat,
+                          const float *rho_inf, const float *K_inf, int n_ids, float dt, float inv_dx)
+{
+    CHECK_H(h);
+    drop_graphs(h);
+    h->have_ade = false;
+    if (n_poles == 0 || !mat) return 0;
+    if (n_poles > MAX_POLES) return fail("at most %d ADE poles", MAX_POLES);
+    if (h->d.has_lower || h->d.has_upper) return fail("ADE materials are not supported on decomposed slabs yet");
+    const sb_grid_desc &d = h->d;
+    bool used[256] = {false};
+    AdeTable &A = h->ade;
+    A = AdeTable{};
+    for (int q = 0; q < n_poles; q++) {
+        const sb_pole &s = poles[q];
+        if (s.material_id < 1 || s.material_id > 255 || s.material_id >= n_ids) return fail("pole %d: bad material id", q);
+        used[s.material_id] = true;
+        PoleDev &Q = A.poles[q];
+        Q.mat_id = s.material_id; Q.is_lorentz = s.is_lorentz; Q.target = s.target;
+        Q.c0 = s.c0; Q.c1 = s.c1; Q.c2 = s.c2;
+        Q.vcoef = -dt / rho_inf[s.material_id] * inv_dx;          // ade.cpp:242 (fp32, left to right)
+        Q.pcoef = -K_inf[s.material_id] * dt;                     // ade.cpp:417
+    }
+    // compact list of cells whose material carries poles, in dense order; neighbour slots via rolling plane maps
+    const size_t pl = (size_t)d.ny * d.nz;
+    std::vector<long long> off; std::vector<int> ijk; std::vector<uint8_t> cm;
+    std::vector<long long> plane_start((size_t)d.nx + 1, 0);
+    for (int i = 0; i < d.nx; i++) {
+        const uint8_t *m = mat + (size_t)i * pl;
+        long long cnt = 0;
+        for (size_t q = 0; q < pl; q++) cnt += used[m[q]];
+        plane_start[i + 1] = plane_start[i] + cnt;
+    }
+    const long long n = plane_start[d.nx];
+    if (n == 0) return 0;
+    if (n >= (1LL << 31)) return fail("too many material cells");
+    off.resize((size_t)n); ijk.resize((size_t)n * 3); cm.resize((size_t)n);
+    std::vector<int> nbr((size_t)n * 6, -1);
+    std::vector<int> slot_prev(pl, -1), slot_cur(pl, -1), slot_next(pl, -1);
+    auto fill_slots = [&](int i, std::vector<int> &slots) {
+        if (i < 0 || i >= d.nx) { std::fill(slots.begin(), slots.end(), -1); return; }
+        const uint8_t *m = mat + (size_t)i * pl;
+        int s = (int)plane_start[i];
+        for (size_t q = 0; q < pl; q++) slots[q] = used[m[q]] ? s++ : -1;
+    };
+    fill_slots(0, slot_cur); fill_slots(1, slot_next);
+    for (int i = 0; i < d.nx; i++) {
+        const uint8_t *m = mat + (size_t)i * pl;
+        const uint8_t *mp = i > 0 ? m - pl : nullptr, *mn = i + 1 < d.nx ? m + pl : nullptr;
+        for (int j = 0; j < d.ny; j++)
+            for (int k = 0; k < d.nz; k++) {
+                const size_t q = (size_t)j * d.nz + k;
+                const int s = slot_cur[q];
+                if (s < 0) continue;
+                const uint8_t id = m[q];
+                off[s] = (long long)i * h->plane + (long long)j * d.pitch + k;
+                ijk[3 * (size_t)s] = i; ijk[3 * (size_t)s + 1] = j; ijk[3 * (size_t)s + 2] = k; cm[s] = id;
+                if (mn && mn[q] == id) nbr[0 * n + s] = slot_next[q];
+                if (j + 1 < d.ny && m[q + d.nz] == id) nbr[1 * n + s] = slot_cur[q + d.nz];
+                if (k + 1 < d.nz && m[q + 1] == id) nbr[2 * n + s] = slot_cur[q + 1];
+                if (mp && mp[q] == id) nbr[3 * n + s] = slot_prev[q];
+                if (j > 0 && m[q - d.nz] == id) nbr[4 * n + s] = slot_cur[q - d.nz];
+                if (k > 0 && m[q - 1] == id) nbr[5 * n + s] = slot_cur[q - 1];
+            }
+        slot_prev.swap(slot_cur); slot_cur.swap(slot_next); fill_slots(i + 2, slot_next);
+    }
+    if (h->ade_off.upload(off, h->stream) || h->ade_ijk.upload(ijk, h->stream) || h->ade_mat.upload(cm, h->stream) ||
+        h->ade_nbr.upload(nbr, h->stream)) return 1;
+    if (h->ade_J.alloc((size_t)n * n_poles) || h->ade_Jp.alloc((size_t)n * n_poles)) return 1;
+    CU(cudaMemsetAsync(h->ade_J.p, 0, (size_t)n * n_poles * 4, h->stream));
+    CU(cudaMemsetAsync(h->ade_Jp.p, 0, (size_t)n * n_poles * 4, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    A.n_cells = (int)n; A.n_poles = n_poles;
+    A.cell_off = h->ade_off.p; A.cell_ijk = h->ade_ijk.p; A.cell_mat = h->ade_mat.p; A.nbr = h->ade_nbr.p;
+    A.J = h->ade_J.p; A.Jp = h->ade_Jp.p; A.inv_dx = inv_dx;
+    h->have_ade = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stepping
+static void fill_params(sb_solver *h, StepParams &P)
+{
+    const int in = h->cur, out = 1 - h->cur;
+    const sb_grid_desc &d = h->d;
+    P.p_in = plane0(h, in, 0); P.vx_in = plane0(h, in, 1); P.vy_in = plane0(h, in, 2); P.vz_in = plane0(h, in, 3);
+    P.p_out = plane0(h, out, 0); P.vx_out = plane0(h, out, 1); P.vy_out = plane0(h, out, 2); P.vz_out = plane0(h, out, 3);
+    P.mask = h->have_mask ? h->mask.p + h->plane : nullptr;
+    P.cvx = h->cvx.p + 1; P.cvy = h->cvy.p; P.cvz = h->cvz.p;
+    P.icx = h->nonuniform ? h->icx.p + 1 : nullptr; P.icy = h->nonuniform ? h->icy.p : nullptr; P.icz = h->nonuniform ? h->icz.p : nullptr;
+    P.n_sponge = (int)h->sponges.size();
+    for (int s = 0; s < MAX_SPONGES; s++) {
+        const bool on = s < P.n_sponge;
+        P.decx[s] = on ? h->sponges[s]->x.p + 1 : nullptr;
+        P.decy[s] = on ? h->sponges[s]->y.p : nullptr;
+        P.decz[s] = on ? h->sponges[s]->z.p : nullptr;
+    }
+    P.cp = h->cp;
+    P.nx = d.nx; P.ny = d.ny; P.nz = d.nz; P.pitch = d.pitch; P.plane = h->plane;
+    P.has_lower = d.has_lower; P.has_upper = d.has_upper;
+    P.i_begin = 0; P.i_end = d.nx; P.chunk_i = d.nx;
+}
+
+template <int RJ>
+static void launch_march(sb_solver *h, const StepParams &P, dim3 grd, dim3 blk)
+{
+    if (P.mask) k1_step_march<RJ, true><<<grd, blk, 0, h->stream>>>(P);
+    else        k1_step_march<RJ, false><<<grd, blk, 0, h->stream>>>(P);
+}
+
+static int launch_step_kernel(sb_solver *h, StepParams &P)
+{
+    const sb_grid_desc &d = h->d;
+    int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
+    if (variant == SB_KERNEL_TMA) variant = SB_KERNEL_MARCH;
+    h->last_variant = variant;
+    if (variant == SB_KERNEL_NAIVE) {
+        P.i_begin = d.has_lower ? -1 : 0; P.i_end = d.nx;
+        dim3 blk(128), grd((d.nz + 127) / 128, d.ny, P.i_end - P.i_begin);
+        if (P.mask) k0_step_naive<true><<<grd, blk, 0, h->stream>>>(P);
+        else        k0_step_naive<false><<<grd, blk, 0, h->stream>>>(P);
+    } else {
+        const int rj = h->opt_rj, wj = h->opt_wj, wk = h->opt_wk;
+        if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
+        const int gx = (d.nz + 128 * wk - 1) / (128 * wk), gy = (d.ny + rj * wj - 1) / (rj * wj);
+        int chunk = h->opt_chunk_i;
+        if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
+            const long long want = 148LL * 8;
+            long long nchunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
+            nchunks = std::max(1LL, std::min<long long>(nchunks, (d.nx + 7) / 8));
+            chunk = (int)((d.nx + nchunks - 1) / nchunks);
+            chunk = std::max(chunk, std::min(d.nx, 8));
+            chunk = std::min(chunk, 64);
+        }
+        P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
+        dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
+        if (grd.z > 65535) return fail("too many i-chunks");
+        switch (rj) {
+            case 1: launch_march<1>(h, P, grd, blk); break;
+            case 2: launch_march<2>(h, P, grd, blk); break;
+            case 4: launch_march<4>(h, P, grd, blk); break;
+            default: return fail("rows_per_thread must be 1, 2 or 4");
+        }
+    }
+    h->kernels_launched++;
+    return 0;
+}
+
+static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
+{
+    StepParams P;
+    fill_params(h, P);
+    if (h->have_ade) {
+        const int nb = (h->ade.n_cells + 255) / 256;
+        k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
+        h->kernels_launched++;
+    }
+    if (launch_step_kernel(h, P)) return 1;
+    if (h->have_ade) {
+        const int nb = (h->ade.n_cells + 255) / 256;
+        StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx;
+        k2b_fixup<<<nb, 256, 0, h->stream>>>(Q, h->ade);
+        h->kernels_launched++;
+    }
+    const int n_rec = h->n_probes + h->n_mics;
+    SourceTable T{h->n_sources, h->n_src_cells, h->src_off.p, h->src_start.p, h->src_id.p, h->src_field.p, h->src_weight.p};
+    if (h->n_src_cells <= 4096 && n_rec <= 4096) {
+        k3_small<<<1, 1024, 0, h->stream>>>(T, P.p_out, P.vx_out, P.vy_out, P.vz_out, src_dev, h->n_probes,
+                                            h->probe_off.p, h->n_mics, h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p);
+        h->kernels_launched++;
+    } else {
+        if (h->n_src_cells) {
+            k3_inject<<<(h->n_src_cells + 255) / 256, 256, 0, h->stream>>>(T, P.p_out, P.vx_out, P.vy_out, P.vz_out,
+                                                                            src_dev, h->d_step_ctr.p);
+            h->kernels_launched++;
+        }
+        if (n_rec) {
+            k3_record<<<(n_rec + 255) / 256, 256, 0, h->stream>>>(P.p_out, h->n_probes, h->probe_off.p, h->n_mics,
+                                                                  h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p);
+            h->kernels_launched++;
+        }
+        k3_advance<<<1, 1, 0, h->stream>>>(h->d_step_ctr.p);
+        h->kernels_launched++;
+    }
+    h->cur = 1 - h->cur;
+    h->steps_done++;
+    return 0;
+}
+
+extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev, float *rec_dev)
+{
+    CHECK_H(h);
+    if (n_steps < 0) return fail("negative step count");
+    if (!h->set[0][0]) return fail("fields not bound");
+    if (!h->have_coeffs) return fail("coefficients not set");
+    if (h->n_src_cells && !src_dev) return fail("source values required");
+    if ((h->n_probes + h->n_mics) && !rec_dev) return fail("record buffer required");
+    CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
+    if (h->opt_graph && n_steps > 1) {
+        // graphs are keyed on (n_steps, starting set); pointers src_dev/rec_dev must be the internal staging buffers
+        const bool internal = (src_dev == h->d_src_vals.p || !src_dev) && (rec_dev == h->d_record.p || !rec_dev);
+        if (internal) {
+            auto key = std::make_pair(n_steps, h->cur);
+            auto it = h->graphs.find(key);
+            if (it == h->graphs.end()) {
+                cudaGraph_t g;
+                const long long k0 = h->kernels_launched; const int cur0 = h->cur; const long long s0 = h->steps_done;
+                CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (int s = 0; s < n_steps && !rc; s++) rc = enqueue_one_step(h, src_dev, rec_dev);
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+                h->cur = cur0; h->steps_done = s0;
+                const long long per_launch = h->kernels_launched - k0; h->kernels_launched = k0;
+                if (rc) return 1;
+                if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+                cudaGraphExec_t ge;
+                CU(cudaGraphInstantiate(&ge, g, 0));
+                cudaGraphDestroy(g);
+                it = h->graphs.emplace(key, ge).first;
+                (void)per_launch;
+            }
+            CU(cudaGraphLaunch(it->second, h->stream));
+            // bookkeeping equivalent to n_steps enqueues
+            const int per_step = (h->have_ade ? 2 : 0) + 1 + ((h->n_src_cells <= 4096 && (h->n_probes + h->n_mics) <= 4096) ? 1 :
+                                 ((h->n_src_cells ? 1 : 0) + ((h->n_probes + h->n_mics) ? 1 : 0) + 1));
+            h->kernels_launched += (long long)per_step * n_steps;
+            h->steps_done += n_steps;
+            if (n_steps & 1) h->cur = 1 - h->cur;
+            return 0;
+        }
+    }
+    for (int s = 0; s < n_steps; s++)
+        if (enqueue_one_step(h, src_dev, rec_dev)) return 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sb_step_n(sb_solver *h, int n_steps, const double *src_host, float *rec_host)
+{
+    CHECK_H(h);
+    if (n_steps <= 0) return n_steps == 0 ? 0 : fail("negative step count");
+    const int n_rec = h->n_probes + h->n_mics;
+    if (h->n_sources && h->n_src_cells && !src_host) return fail("source values required");
+    if (h->d_src_vals.alloc((size_t)std::max(1, n_steps * std::max(1, h->n_sources)))) return 1;
+    if (h->d_record.alloc((size_t)std::max(1, n_steps * std::max(1, n_rec)))) return 1;
+    if (h->n_sources && src_host)
+        CU(cudaMemcpyAsync(h->d_src_vals.p, src_host, (size_t)n_steps * h->n_sources * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
+    if (sb_step_n_async(h, n_steps, h->d_src_vals.p, h->d_record.p)) return 1;
+    if (n_rec && rec_host)
+        CU(cudaMemcpyAsync(rec_host, h->d_record.p, (size_t)n_steps * n_rec * sizeof(float),
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sb_halo_planes(sb_solver *h, float **send_lo, float **send_hi, float **recv_lo, float **recv_hi,
+                              int64_t *plane_elems)
+{
+    CHECK_H(h);
+    if (!h->set[0][0]) return fail("fields not bound");
+    float *p = h->set[h->cur][0];
+    if (recv_lo) *recv_lo = p;
+    if (send_lo) *send_lo = p + h->plane;
+    if (send_hi) *send_hi = p + (long long)h->d.nx * h->plane;
+    if (recv_hi) *recv_hi = p + (long long)(h->d.nx + 1) * h->plane;
+    if (plane_elems) *plane_elems = h->plane;
+    return 0;
+}
+
+extern "C" int sb_energy(sb_solver *h, double rho, double c, double dV, double *out)
+{
+    CHECK_H(h);
+    if (!out) return fail("null argument");
+    const sb_grid_desc &d = h->d;
+    CU(cudaMemsetAsync(h->d_energy.p, 0, 2 * sizeof(double), h->stream));
+    k_energy<<<148 * 4, 256, 0, h->stream>>>(plane0(h, h->cur, 0), plane0(h, h->cur, 1), plane0(h, h->cur, 2),
+                                             plane0(h, h->cur, 3), h->have_mask ? h->mask.p + h->plane : nullptr,
+                                             d.nx, d.ny, d.nz, d.pitch, h->plane, h->d_energy.p);
+    h->kernels_launched++;
+    double s[2];
+    CU(cudaMemcpyAsync(s, h->d_energy.p, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = 0.5 * s[0] / (rho * c * c) * dV + 0.5 * rho * s[1] * dV;
+    return 0;
+}
+
+extern "C" int sb_reset(sb_solver *h)
+{
+    CHECK_H(h);
+    for (int s = 0; s < 2; s++)
+        for (int f = 0; f < 4; f++)
+            if (h->set[s][f]) CU(cudaMemsetAsync(h->set[s][f], 0, (size_t)h->elems * 4, h->stream));
+    if (h->have_ade) {
+        CU(cudaMemsetAsync(h->ade_J.p, 0, h->ade_J.n * 4, h->stream));
+        CU(cudaMemsetAsync(h->ade_Jp.p, 0, h->ade_Jp.n * 4, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->cur = 0; h->steps_done = 0;
+    return 0;
+}
+
+extern "C" int sb_set_option(sb_solver *h, int option, int value)
+{
+    if (!h) return fail("null handle");
+    switch (option) {
+        case SB_OPT_KERNEL: if (value < 0 || value > 3) return fail("bad kernel variant"); h->opt_kernel = value; break;
+        case SB_OPT_ROWS_PER_THREAD: if (value != 1 && value != 2 && value != 4) return fail("rows_per_thread must be 1, 2 or 4"); h->opt_rj = value; break;
+        case SB_OPT_WARPS_J: if (value < 1 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
+        case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
+        case SB_OPT_CHUNK_I: if (value < 0) return fail("chunk_i must be >= 0"); h->opt_chunk_i = value; break;
+        case SB_OPT_USE_GRAPH: h->opt_graph = value ? 1 : 0; break;
+        default: return fail("unknown option %d", option);
+    }
+    drop_graphs(h);
+    return 0;
+}
+
+extern "C" int sb_query(sb_solver *h, sb_stats *out)
+{
+    if (!h || !out) return fail("null argument");
+    out->cells = (int64_t)h->d.nx * h->d.ny * h->d.nz;
+    out->steps_done = h->steps_done;
+    out->kernels_launched = h->kernels_launched;
+    double b = 32.0;
+    if (h->have_mask) b += 1.0;
+    if (h->have_ade) {
+        double per_cell = 0.0;
+        for (int q = 0; q < h->ade.n_poles; q++) per_cell += h->ade.poles[q].is_lorentz ? 16.0 : 8.0;
+        b += per_cell * (double)h->ade.n_cells / (double)out->cells;
+    }
+    out->algorithmic_bytes_per_cell = b;
+    out->kernel_variant = h->last_variant;
+    out->pitch = h->d.pitch;
+    return 0;
+}
+
+extern "C" int sb_synchronize(sb_solver *h)
+{
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}

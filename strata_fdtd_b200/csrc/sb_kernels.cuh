@@ -1,0 +1,564 @@
+// sb_kernels.cuh -- sm_100a kernels for the strata-fdtd time-stepping hot path.
+//
+// Arithmetic contract: every fp32 operation is separately rounded, in the order the
+// reference's C++ backend performs it (this file is compiled with --fmad=false and
+// without --use_fast_math), so results are bit-identical to
+// /root/reference/src/strata_fdtd/_kernels/src/{fdtd_step,boundaries,pml,ade,microphones}.cpp.
+//
+// Layout: fields are [i][j][k] with k contiguous, row pitch `pitch` floats (multiple of 4),
+// plane stride `plane` = ny*pitch, and the pointers handed to the kernels address local
+// plane 0, so plane -1 (lower ghost) and plane nx (upper ghost) are valid addresses.
+//
+// One time step reads the "in" set {p,vx,vy,vz} and writes the "out" set (ping-pong), which
+// makes every cell independent: 4 reads + 4 writes of fp32 = 32 B per cell update.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int MAX_SPONGES = 4;
+constexpr uint8_t M_AIR = 1, M_XOPEN = 2, M_YOPEN = 4, M_ZOPEN = 8;
+
+struct StepParams {
+    const float *p_in, *vx_in, *vy_in, *vz_in;
+    float *p_out, *vx_out, *vy_out, *vz_out;
+    const uint8_t *mask;                 // nullptr = all air, nothing rigid
+    const float *cvx, *cvy, *cvz;        // per-face velocity coefficients (cvx valid from index -1)
+    const float *icx, *icy, *icz;        // per-cell inverse spacing, or nullptr (uniform grid)
+    const float *decx[MAX_SPONGES], *decy[MAX_SPONGES], *decz[MAX_SPONGES];   // decx valid from -1
+    int n_sponge;
+    float cp;
+    int nx, ny, nz, pitch;
+    long long plane;
+    int has_lower, has_upper;
+    int i_begin, i_end, chunk_i;
+};
+
+// ------------------------------------------------------------------------------------------
+// K0: one thread per cell, every face velocity recomputed from the "in" set.  Reference
+// implementation of the fused step on the device; also the cross-check for the marching kernel.
+//   velocity  fdtd_step.cpp:34-80 / 235-307      rigid     boundaries.cpp:66-89
+//   pressure  fdtd_step.cpp:109-211 / 309-439    sponge    pml.cpp:47-149
+// ------------------------------------------------------------------------------------------
+template <bool GEOM>
+__device__ __forceinline__ float face_v(const StepParams &P, const float *v_in, const float *cv_tab,
+                                        long long c, long long c_next, int m_idx, bool update,
+                                        uint8_t open_bit)
+{
+    float v = v_in[c];
+    if (update) {
+        v = v + cv_tab[m_idx] * (P.p_in[c_next] - P.p_in[c]);
+        if (GEOM && !(P.mask[c] & open_bit)) v = 0.0f;
+    }
+    return v;
+}
+
+template <bool GEOM>
+__global__ void __launch_bounds__(256) k0_step_naive(StepParams P)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int i = P.i_begin + (int)blockIdx.z;       // i_begin may be -1 (ghost vx maintenance)
+    if (k >= P.nz || i >= P.i_end) return;
+    const long long c = (long long)i * P.plane + (long long)j * P.pitch + k;
+    const bool upd_x = (i < P.nx - 1) || P.has_upper;
+    const float vxn = face_v<GEOM>(P, P.vx_in, P.cvx, c, c + P.plane, i, upd_x, M_XOPEN);
+    if (i < 0) {                                      // ghost plane: only vx is maintained here
+        float v = vxn;
+        for (int s = 0; s < P.n_sponge; s++) v = v * P.decx[s][i];
+        P.vx_out[c] = v;
+        return;
+    }
+    const float vyn = face_v<GEOM>(P, P.vy_in, P.cvy, c, c + P.pitch, j, j < P.ny - 1, M_YOPEN);
+    const float vzn = face_v<GEOM>(P, P.vz_in, P.cvz, c, c + 1, k, k < P.nz - 1, M_ZOPEN);
+    float ddx = vxn, ddy = vyn, ddz = vzn;
+    if (i > 0 || P.has_lower)
+        ddx = vxn - face_v<GEOM>(P, P.vx_in, P.cvx, c - P.plane, c, i - 1, true, M_XOPEN);
+    if (j > 0)
+        ddy = vyn - face_v<GEOM>(P, P.vy_in, P.cvy, c - P.pitch, c, j - 1, true, M_YOPEN);
+    if (k > 0)
+        ddz = vzn - face_v<GEOM>(P, P.vz_in, P.cvz, c - 1, c, k - 1, true, M_ZOPEN);
+    if (P.icx) { ddx = P.icx[i] * ddx; ddy = P.icy[j] * ddy; ddz = P.icz[k] * ddz; }
+    float pn = P.p_in[c] + P.cp * ((ddx + ddy) + ddz);
+    if (GEOM && !(P.mask[c] & M_AIR)) pn = 0.0f;
+    float ox = vxn, oy = vyn, oz = vzn;
+    for (int s = 0; s < P.n_sponge; s++) {
+        const float dx = P.decx[s][i], dy = P.decy[s][j], dz = P.decz[s][k];
+        ox = ox * dx; oy = oy * dy; oz = oz * dz;
+        pn = ((pn * dx) * dy) * dz;
+    }
+    P.p_out[c] = pn; P.vx_out[c] = ox; P.vy_out[c] = oy; P.vz_out[c] = oz;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: 2.5-D marching kernel.  A warp owns a strip of 128 cells along k (float4 per lane) by RJ
+// rows along j and marches along i over one chunk, keeping the p planes i / i+1 and the
+// undamped vx of plane i-1 in registers.  Neighbours along k come from warp shuffles, the two
+// strip-edge values from scalar loads that hit lines the neighbouring strip streams anyway.
+// No shared memory, no block barrier: warps are independent; the block only groups strips
+// that are adjacent in j so that their halo rows hit in L1.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 mul4s(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 sel4(bool cx, bool cy, bool cz, bool cw, float4 a, float4 b)
+{ return make_float4(cx ? a.x : b.x, cy ? a.y : b.y, cz ? a.z : b.z, cw ? a.w : b.w); }
+
+template <int RJ, bool GEOM>
+__global__ void __launch_bounds__(256) k1_step_march(StepParams P)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp_k = threadIdx.x >> 5;                       // blockDim.x = 32 * WK
+    const int strip_k0 = (blockIdx.x * (blockDim.x >> 5) + warp_k) * 128;
+    const int k0 = strip_k0 + lane * 4;
+    const int j0 = (blockIdx.y * blockDim.y + threadIdx.y) * RJ;
+    const int ib = P.i_begin + (int)blockIdx.z * P.chunk_i;
+    const int ie = min(ib + P.chunk_i, P.i_end);
+    if (strip_k0 >= P.nz || j0 >= P.ny || ib >= ie) return;     // warp-uniform exit
+    const bool lane_ok = k0 < P.nz;
+    const int nz = P.nz, ny = P.ny;
+    // per-element validity and "z face is updated" flags
+    const bool e0 = k0 < nz, e1 = k0 + 1 < nz, e2 = k0 + 2 < nz, e3 = k0 + 3 < nz;
+    const bool u0 = k0 < nz - 1, u1 = k0 + 1 < nz - 1, u2 = k0 + 2 < nz - 1, u3 = k0 + 3 < nz - 1;
+    const bool edge_hi = (lane == 31) && (k0 + 4 < nz);        // needs p[k0+4] from the next strip
+    const bool edge_lo = (lane == 0) && (k0 > 0);              // needs the z face k0-1 of the previous strip
+    const float4 z4 = f4(0.0f);
+
+    // k tables (hoisted)
+    const float4 cvz4 = lane_ok ? ld4(P.cvz + k0) : z4;
+    const float4 icz4 = (P.icz && lane_ok) ? ld4(P.icz + k0) : f4(1.0f);
+    const float4 dz0 = (P.n_sponge > 0 && lane_ok) ? ld4(P.decz[0] + k0) : f4(1.0f);
+    const float cvz_lo = edge_lo ? P.cvz[k0 - 1] : 0.0f;
+    // j tables (hoisted); row index r = -1 .. RJ-1 stored at [r+1]
+    float cvy[RJ + 1], icy[RJ], dy0[RJ];
+    bool row_ok[RJ + 2];                                       // rows -1 .. RJ
+#pragma unroll
+    for (int r = -1; r <= RJ; r++) row_ok[r + 1] = (j0 + r >= 0) && (j0 + r < ny);
+#pragma unroll
+    for (int r = -1; r < RJ; r++) cvy[r + 1] = (row_ok[r + 1] && j0 + r < ny - 1) ? P.cvy[j0 + r] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < RJ; r++) {
+        icy[r] = (P.icy && row_ok[r + 1]) ? P.icy[j0 + r] : 1.0f;
+        dy0[r] = (P.n_sponge > 0 && row_ok[r + 1]) ? P.decy[0][j0 + r] : 1.0f;
+    }
+    const long long col = (long long)j0 * P.pitch + k0;         // offset of (row 0, k0) inside a plane
+
+    // ---- prologue: p rows of plane ib, undamped vx of plane ib-1 --------------------------
+    float4 pc[RJ + 2];
+    float4 vxp[RJ];
+    {
+        const long long base = (long long)ib * P.plane + col;
+#pragma unroll
+        for (int r = 0; r < RJ; r++)
+            pc[r + 1] = (row_ok[r + 1] && lane_ok) ? ld4(P.p_in + base + (long long)r * P.pitch) : z4;
+        const bool have_prev = (ib > 0) || P.has_lower;
+        const float cx = have_prev ? P.cvx[ib - 1] : 0.0f;
+#pragma unroll
+        for (int r = 0; r < RJ; r++) {
+            float4 v = z4;
+            if (have_prev && row_ok[r + 1] && lane_ok) {
+                const long long cm = base - P.plane + (long long)r * P.pitch;
+                v = add4(ld4(P.vx_in + cm), mul4s(sub4(pc[r + 1], ld4(P.p_in + cm)), cx));
+                if (GEOM) {
+                    const uchar4 m = *reinterpret_cast<const uchar4 *>(P.mask + cm);
+                    v = sel4(m.x & M_XOPEN, m.y & M_XOPEN, m.z & M_XOPEN, m.w & M_XOPEN, v, z4);
+                }
+                if (ib == 0) {                                   // maintain the lower ghost plane of vx
+                    float4 o = v;
+                    for (int s = 0; s < P.n_sponge; s++) o = mul4s(o, P.decx[s][-1]);
+                    st4(P.vx_out + cm, sel4(e0, e1, e2, e3, o, z4));
+                }
+            }
+            vxp[r] = v;
+        }
+    }
+
+    // ---- march ----------------------------------------------------------------------------
+    for (int i = ib; i < ie; i++) {
+        const long long base = (long long)i * P.plane + col;
+        const bool upd_x = (i < P.nx - 1) || P.has_upper;
+        const float cx = upd_x ? P.cvx[i] : 0.0f;
+        const float icx = P.icx ? P.icx[i] : 1.0f;
+        const float dx0 = (P.n_sponge > 0) ? P.decx[0][i] : 1.0f;
+
+        // loads (all issued before use)
+        float4 pn[RJ], vx[RJ], vy[RJ + 1], vz[RJ];
+        uchar4 mk[RJ + 1];
+        float p_hi[RJ], p_lo[RJ], vz_lo[RJ];
+        uint8_t m_lo[RJ];
+#pragma unroll
+        for (int r = 0; r < RJ; r++) {
+            const bool ok = row_ok[r + 1] && lane_ok;
+            const long long c = base + (long long)r * P.pitch;
+            pn[r] = (ok && upd_x) ? ld4(P.p_in + c + P.plane) : z4;
+            vx[r] = ok ? ld4(P.vx_in + c) : z4;
+            vz[r] = ok ? ld4(P.vz_in + c) : z4;
+            p_hi[r] = (edge_hi && row_ok[r + 1]) ? P.p_in[c + 4] : 0.0f;
+            p_lo[r] = (edge_lo && row_ok[r + 1]) ? P.p_in[c - 1] : 0.0f;
+            vz_lo[r] = (edge_lo && row_ok[r + 1]) ? P.vz_in[c - 1] : 0.0f;
+            if (GEOM) m_lo[r] = (edge_lo && row_ok[r + 1]) ? P.mask[c - 1] : (uint8_t)0;
+        }
+#pragma unroll
+        for (int r = -1; r < RJ; r++) {
+            const bool ok = row_ok[r + 1] && lane_ok;
+            const long long c = base + (long long)r * P.pitch;
+            vy[r + 1] = ok ? ld4(P.vy_in + c) : z4;
+            if (GEOM) mk[r + 1] = ok ? *reinterpret_cast<const uchar4 *>(P.mask + c) : make_uchar4(0, 0, 0, 0);
+        }
+        pc[0] = (row_ok[0] && lane_ok) ? ld4(P.p_in + base - P.pitch) : z4;
+        pc[RJ + 1] = (row_ok[RJ + 1] && lane_ok) ? ld4(P.p_in + base + (long long)RJ * P.pitch) : z4;
+
+        // undamped, rigid-masked y faces for rows -1 .. RJ-1
+        float4 vyn[RJ + 1];
+#pragma unroll
+        for (int r = -1; r < RJ; r++) {
+            float4 v = vy[r + 1];
+            if (row_ok[r + 1] && (j0 + r < ny - 1)) {
+                v = add4(v, mul4s(sub4(pc[r + 2], pc[r + 1]), cvy[r + 1]));
+                if (GEOM) {
+                    const uchar4 m = mk[r + 1];
+                    v = sel4(m.x & M_YOPEN, m.y & M_YOPEN, m.z & M_YOPEN, m.w & M_YOPEN, v, z4);
+                }
+            }
+            vyn[r + 1] = v;                                      // row -1 outside the grid stays 0
+        }
+
+#pragma unroll
+        for (int r = 0; r < RJ; r++) {
+            const float4 p = pc[r + 1];
+            // x face
+            float4 vxn = vx[r];
+            if (upd_x) {
+                vxn = add4(vxn, mul4s(sub4(pn[r], p), cx));
+                if (GEOM) {
+                    const uchar4 m = mk[r + 1];
+                    vxn = sel4(m.x & M_XOPEN, m.y & M_XOPEN, m.z & M_XOPEN, m.w & M_XOPEN, vxn, z4);
+                }
+            }
+            // z faces: p[k+1] from the next lane (or the next strip)
+            float p_next = __shfl_down_sync(FULL, p.x, 1);
+            if (lane == 31) p_next = p_hi[r];
+            const float4 pk1 = make_float4(p.y, p.z, p.w, p_next);
+            float4 vzn = vz[r];
+            {
+                const float4 upd = add4(vzn, mul4(sub4(pk1, p), cvz4));
+                vzn = sel4(u0, u1, u2, u3, upd, vzn);
+                if (GEOM) {
+                    const uchar4 m = mk[r + 1];
+                    vzn = sel4(!u0 || (m.x & M_ZOPEN), !u1 || (m.y & M_ZOPEN), !u2 || (m.z & M_ZOPEN),
+                               !u3 || (m.w & M_ZOPEN), vzn, z4);
+                }
+            }
+            // z face k0-1: previous lane's .w, or recomputed from the previous strip's values
+            float vz_prev = __shfl_up_sync(FULL, vzn.w, 1);
+            if (lane == 0) {
+                vz_prev = 0.0f;
+                if (edge_lo) {
+                    vz_prev = vz_lo[r] + cvz_lo * (p.x - p_lo[r]);
+                    if (GEOM && !(m_lo[r] & M_ZOPEN)) vz_prev = 0.0f;
+                }
+            }
+            const float4 vzm = make_float4(vz_prev, vzn.x, vzn.y, vzn.z);
+            // divergence and pressure
+            float4 ddx = sub4(vxn, vxp[r]);
+            float4 ddy = sub4(vyn[r + 1], vyn[r]);
+            float4 ddz = sub4(vzn, vzm);
+            if (P.icx) { ddx = mul4s(ddx, icx); ddy = mul4s(ddy, icy[r]); ddz = mul4(ddz, icz4); }
+            float4 pnew = add4(p, mul4s(add4(add4(ddx, ddy), ddz), P.cp));
+            if (GEOM) {
+                const uchar4 m = mk[r + 1];
+                pnew = sel4(m.x & M_AIR, m.y & M_AIR, m.z & M_AIR, m.w & M_AIR, pnew, z4);
+            }
+            // sponge
+            float4 ox = vxn, oy = vyn[r + 1], oz = vzn;
+            if (P.n_sponge > 0) {
+                ox = mul4s(ox, dx0); oy = mul4s(oy, dy0[r]); oz = mul4(oz, dz0);
+                pnew = mul4(mul4s(mul4s(pnew, dx0), dy0[r]), dz0);
+                for (int s = 1; s < P.n_sponge; s++) {
+                    const float dxs = P.decx[s][i];
+                    const float dys = row_ok[r + 1] ? P.decy[s][j0 + r] : 1.0f;
+                    const float4 dzs = lane_ok ? ld4(P.decz[s] + k0) : f4(1.0f);
+                    ox = mul4s(ox, dxs); oy = mul4s(oy, dys); oz = mul4(oz, dzs);
+                    pnew = mul4(mul4s(mul4s(pnew, dxs), dys), dzs);
+                }
+            }
+            if (row_ok[r + 1] && lane_ok) {
+                const long long c = base + (long long)r * P.pitch;
+                st4(P.p_out + c, sel4(e0, e1, e2, e3, pnew, z4));
+                st4(P.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
+                st4(P.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
+                st4(P.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
+            }
+            vxp[r] = vxn;
+            pc[r + 1] = pn[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Face-mask derivation (replaces precompute_boundary_cells, boundaries.cpp:13-64).
+// geom: dense uint8 with the slab's live ghost planes, plane index gi = i + has_lower.
+// ------------------------------------------------------------------------------------------
+__global__ void k_build_mask(const uint8_t *geom, uint8_t *mask, int nx, int ny, int nz, int pitch,
+                             long long plane, int has_lower, int has_upper, int rigid)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int i = (int)blockIdx.z - 1;                            // -1 .. nx
+    if (k >= nz) return;
+    const long long c = (long long)i * plane + (long long)j * pitch + k;
+    if ((i < 0 && !has_lower) || (i >= nx && !has_upper)) { mask[c] = 0; return; }
+    auto G = [&](int ii, int jj, int kk) -> bool {
+        return geom[((long long)(ii + has_lower) * ny + jj) * nz + kk] != 0;
+    };
+    const bool air = G(i, j, k);
+    uint8_t m = air ? M_AIR : 0;
+    const bool have_xn = (i + 1 < nx) || (i + 1 == nx && has_upper);
+    if (!rigid || (air && (!have_xn || G(i + 1, j, k)))) m |= M_XOPEN;
+    if (!rigid || (air && (j + 1 >= ny || G(i, j + 1, k)))) m |= M_YOPEN;
+    if (!rigid || (air && (k + 1 >= nz || G(i, j, k + 1)))) m |= M_ZOPEN;
+    mask[c] = m;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: source injection and probe / microphone recording (core/solver.py:2386-2439,
+// microphones.cpp:82-116).  `step_ctr` is a device counter so the kernels can live in a
+// replayed CUDA graph; the recording kernel advances it.
+// ------------------------------------------------------------------------------------------
+struct SourceTable {
+    int n_sources, n_cells;
+    const long long *cell_off;          // padded-layout offset of each cell
+    const int *start, *src_id, *field;
+    const double *weight;
+};
+
+__global__ void k3_inject(SourceTable T, float *p, float *vx, float *vy, float *vz,
+                          const double *src_vals, const int *step_ctr)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= T.n_cells) return;
+    const double *w = src_vals + (long long)(*step_ctr) * T.n_sources;
+    const long long off = T.cell_off[u];
+    for (int e = T.start[u]; e < T.start[u + 1]; e++) {
+        float *f = T.field[e] == 0 ? p : (T.field[e] == 1 ? vx : (T.field[e] == 2 ? vy : vz));
+        // float64 add, float32 store (solver.py:2421); w*weight is one fp64 multiply (solver.py:2404)
+        f[off] = (float)((double)f[off] + __dmul_rn(w[T.src_id[e]], T.weight[e]));
+    }
+}
+
+__global__ void k3_record(const float *p, int n_probes, const long long *probe_off,
+                          int n_mics, const long long *mic_off8, const float *mic_w8,
+                          float *record_out, int *step_ctr)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_rec = n_probes + n_mics;
+    const int step = *step_ctr;
+    if (t < n_probes) {
+        record_out[(long long)step * n_rec + t] = p[probe_off[t]];
+    } else if (t < n_rec) {
+        const int m = t - n_probes;
+        float sum = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * p[mic_off8[8 * m + c]];
+        record_out[(long long)step * n_rec + t] = sum;
+    }
+}
+
+__global__ void k3_advance(int *step_ctr) { *step_ctr += 1; }
+
+// Small-problem variant: one block does inject -> record -> advance (saves two launches).
+__global__ void __launch_bounds__(1024) k3_small(SourceTable T, float *p, float *vx, float *vy, float *vz,
+                                                 const double *src_vals, int n_probes, const long long *probe_off,
+                                                 int n_mics, const long long *mic_off8, const float *mic_w8,
+                                                 float *record_out, int *step_ctr)
+{
+    const int step = *step_ctr;
+    for (int u = threadIdx.x; u < T.n_cells; u += blockDim.x) {
+        const double *w = src_vals + (long long)step * T.n_sources;
+        const long long off = T.cell_off[u];
+        for (int e = T.start[u]; e < T.start[u + 1]; e++) {
+            float *f = T.field[e] == 0 ? p : (T.field[e] == 1 ? vx : (T.field[e] == 2 ? vy : vz));
+            f[off] = (float)((double)f[off] + __dmul_rn(w[T.src_id[e]], T.weight[e]));
+        }
+    }
+    __syncthreads();
+    const int n_rec = n_probes + n_mics;
+    for (int t = threadIdx.x; t < n_rec; t += blockDim.x) {
+        if (t < n_probes) {
+            record_out[(long long)step * n_rec + t] = p[probe_off[t]];
+        } else {
+            const int m = t - n_probes;
+            float sum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * p[mic_off8[8 * m + c]];
+            record_out[(long long)step * n_rec + t] = sum;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_ctr = step + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: ADE recursions over the compact list of material cells (ade.cpp:25-692), in the order of
+// core/solver.py:2135-2193.  K1 has already written the material-free update of every cell to
+// the "out" set; because the "in" set is untouched, K2b can recompute the few cells and faces
+// that the auxiliary fields change and overwrite K1's values there:
+//   faces whose two cells carry the same material with density poles  (ade.cpp:228-401)
+//   pressure of every material cell                                   (ade.cpp:403-473)
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_POLES = 16;
+struct PoleDev {
+    int mat_id, is_lorentz, target;      // target 0 = density, 1 = modulus
+    float c0, c1, c2;                    // Debye: alpha, beta.  Lorentz: a, b, d
+    float vcoef;                         // -dt / rho_inf * inv_dx          (ade.cpp:242)
+    float pcoef;                         // -K_inf * dt                     (ade.cpp:417)
+};
+struct AdeTable {
+    int n_cells, n_poles;
+    const long long *cell_off;           // padded offset of each material cell
+    const int *cell_ijk;                 // 3 ints per cell
+    const uint8_t *cell_mat;
+    const int *nbr;                      // [6][n_cells]: +x,+y,+z,-x,-y,-z slot of a SAME-material neighbour or -1
+    float *J, *Jp;                       // [n_poles][n_cells]
+    float inv_dx;                        // uniform-grid divergence scale (solver.py:3158)
+    PoleDev poles[MAX_POLES];
+};
+
+__device__ __forceinline__ void ade_pole_update(const PoleDev &q, float *J, float *Jp, long long s, float src)
+{
+    if (!q.is_lorentz) {
+        J[s] = q.c0 * J[s] + q.c1 * src;                                   // ade.cpp:57-59
+    } else {
+        const float jo = J[s], jpo = Jp[s];
+        const float jn = q.c0 * jo + q.c1 * jpo + q.c2 * src;               // ade.cpp:158-160
+        Jp[s] = jo; J[s] = jn;
+    }
+}
+
+// K2a: density poles, source = p of the previous step (solver.py:2138-2139)
+__global__ void k2a_density(AdeTable A, const float *p_in)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n_cells) return;
+    const int mat = A.cell_mat[s];
+    const float src = p_in[A.cell_off[s]];
+    for (int q = 0; q < A.n_poles; q++) {
+        const PoleDev &Q = A.poles[q];
+        if (Q.target == 0 && Q.mat_id == mat)
+            ade_pole_update(Q, A.J + (long long)q * A.n_cells, A.Jp + (long long)q * A.n_cells, s, src);
+    }
+}
+
+// undamped face velocity between lower cell a and upper cell b (= a + stride) with ADE correction
+__device__ __forceinline__ float ade_face(const StepParams &P, const AdeTable &A, const float *v_in,
+                                          float cv, long long a, long long b, int slot_a, int slot_b,
+                                          int mat, uint8_t open_bit)
+{
+    float v = v_in[a] + cv * (P.p_in[b] - P.p_in[a]);
+    if (slot_a >= 0 && slot_b >= 0) {
+        for (int q = 0; q < A.n_poles; q++) {
+            const PoleDev &Q = A.poles[q];
+            if (Q.target == 0 && Q.mat_id == mat) {
+                const float *J = A.J + (long long)q * A.n_cells;
+                v = v + Q.vcoef * (J[slot_b] - J[slot_a]);                  // ade.cpp:262-264
+            }
+        }
+    }
+    if (P.mask && !(P.mask[a] & open_bit)) v = 0.0f;
+    return v;
+}
+
+__global__ void k2b_fixup(StepParams P, AdeTable A)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n_cells) return;
+    const long long c = A.cell_off[s];
+    const int i = A.cell_ijk[3 * s], j = A.cell_ijk[3 * s + 1], k = A.cell_ijk[3 * s + 2];
+    const int mat = A.cell_mat[s];
+    const int n = A.n_cells;
+    const int sxp = A.nbr[s], syp = A.nbr[n + s], szp = A.nbr[2 * n + s];
+    const int sxm = A.nbr[3 * n + s], sym = A.nbr[4 * n + s], szm = A.nbr[5 * n + s];
+
+    const bool upd_x = (i < P.nx - 1) || P.has_upper, upd_y = j < P.ny - 1, upd_z = k < P.nz - 1;
+    const float vxn = upd_x ? ade_face(P, A, P.vx_in, P.cvx[i], c, c + P.plane, s, sxp, mat, M_XOPEN) : P.vx_in[c];
+    const float vyn = upd_y ? ade_face(P, A, P.vy_in, P.cvy[j], c, c + P.pitch, s, syp, mat, M_YOPEN) : P.vy_in[c];
+    const float vzn = upd_z ? ade_face(P, A, P.vz_in, P.cvz[k], c, c + 1, s, szp, mat, M_ZOPEN) : P.vz_in[c];
+    float ddx = vxn, ddy = vyn, ddz = vzn;
+    if (i > 0 || P.has_lower)
+        ddx = vxn - ade_face(P, A, P.vx_in, P.cvx[i - 1], c - P.plane, c, sxm, s, mat, M_XOPEN);
+    if (j > 0)
+        ddy = vyn - ade_face(P, A, P.vy_in, P.cvy[j - 1], c - P.pitch, c, sym, s, mat, M_YOPEN);
+    if (k > 0)
+        ddz = vzn - ade_face(P, A, P.vz_in, P.cvz[k - 1], c - 1, c, szm, s, mat, M_ZOPEN);
+
+    // divergence for the modulus poles: d = dx*ix; d += dy*iy; d += dz*iz   (ade.cpp:479-692)
+    const float ix = P.icx ? P.icx[i] : A.inv_dx, iy = P.icy ? P.icy[j] : A.inv_dx, iz = P.icz ? P.icz[k] : A.inv_dx;
+    float div = ddx * ix;
+    div = div + ddy * iy;
+    div = div + ddz * iz;
+    for (int q = 0; q < A.n_poles; q++) {
+        const PoleDev &Q = A.poles[q];
+        if (Q.target == 1 && Q.mat_id == mat)
+            ade_pole_update(Q, A.J + (long long)q * n, A.Jp + (long long)q * n, s, div);
+    }
+    // pressure (fdtd_step.cpp:109-211 / 345-355), then modulus correction (ade.cpp:403-473)
+    float ex = ddx, ey = ddy, ez = ddz;
+    if (P.icx) { ex = P.icx[i] * ddx; ey = P.icy[j] * ddy; ez = P.icz[k] * ddz; }
+    float pn = P.p_in[c] + P.cp * ((ex + ey) + ez);
+    const bool air = !P.mask || (P.mask[c] & M_AIR);
+    if (!air) pn = 0.0f;
+    for (int q = 0; q < A.n_poles; q++) {
+        const PoleDev &Q = A.poles[q];
+        if (Q.target == 1 && Q.mat_id == mat) pn = pn + Q.pcoef * A.J[(long long)q * n + s];
+    }
+    if (!air) pn = 0.0f;                                                    // solver.py:2193
+    float ox = vxn, oy = vyn, oz = vzn;
+    for (int sp = 0; sp < P.n_sponge; sp++) {
+        const float dx = P.decx[sp][i], dy = P.decy[sp][j], dz = P.decz[sp][k];
+        ox = ox * dx; oy = oy * dy; oz = oz * dz;
+        pn = ((pn * dx) * dy) * dz;
+    }
+    P.p_out[c] = pn;
+    if (sxp >= 0 && upd_x) P.vx_out[c] = ox;       // only faces the ADE correction touched
+    if (syp >= 0 && upd_y) P.vy_out[c] = oy;
+    if (szp >= 0 && upd_z) P.vz_out[c] = oz;
+}
+
+// ------------------------------------------------------------------------------------------
+// Energy (core/solver.py:2689-2706): sums of p^2 and v^2 over air cells, fp64 accumulation.
+// ------------------------------------------------------------------------------------------
+__global__ void k_energy(const float *p, const float *vx, const float *vy, const float *vz,
+                         const uint8_t *mask, int nx, int ny, int nz, int pitch, long long plane,
+                         double *out2)
+{
+    double sp = 0.0, sv = 0.0;
+    const long long rows = (long long)nx * ny;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long c0 = (row / ny) * plane + (row % ny) * pitch;
+        for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+            const long long c = c0 + k;
+            if (mask && !(mask[c] & M_AIR)) continue;
+            const float pp = p[c] * p[c];
+            const float vv = (vx[c] * vx[c] + vy[c] * vy[c]) + vz[c] * vz[c];
+            sp += (double)pp; sv += (double)vv;
+        }
+    }
+    __shared__ double s_p[32], s_v[32];
+    for (int o = 16; o > 0; o >>= 1) { sp += __shfl_down_sync(0xffffffffu, sp, o); sv += __shfl_down_sync(0xffffffffu, sv, o); }
+    if ((threadIdx.x & 31) == 0) { s_p[threadIdx.x >> 5] = sp; s_v[threadIdx.x >> 5] = sv; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = blockDim.x >> 5;
+        sp = threadIdx.x < nw ? s_p[threadIdx.x] : 0.0; sv = threadIdx.x < nw ? s_v[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) { sp += __shfl_down_sync(0xffffffffu, sp, o); sv += __shfl_down_sync(0xffffffffu, sv, o); }
+        if (threadIdx.x == 0) { atomicAdd(out2, sp); atomicAdd(out2 + 1, sv); }
+    }
+}
+
+}  // namespace sb

@@ -1,0 +1,681 @@
+"""``FDTDSolver`` with ``backend="b200"``: the reference's solver surface, driven on one B200.
+
+Mirrors the public interface of /root/reference/src/strata_fdtd/core/solver.py:1442-3442
+(constructor :1507-1518, set_geometry :1682, add_source :1782, add_probe :1843,
+add_microphone :1887, add_boundary :1983, step :2003, run :2520, get_probe_data :2608,
+compute_energy :2689, reset :2781, materials :2836-2942) so that scripts written for the
+reference run unchanged.  What differs is where the work happens: the whole step --
+velocity, rigid faces, pressure, sponge, ADE, source injection, probe/microphone recording --
+runs on the device in chunks of steps through the C ABI of include/strata_b200.h; the host
+only evaluates source waveforms (float64, as the reference does) and collects traces.
+
+PyTorch is used for nothing but device buffers and the stream handle.  There is no CPU
+fallback: without the CUDA library or a CUDA device, construction of the device state raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time as _time_mod
+import warnings
+from collections.abc import Callable
+
+import numpy as np
+
+from . import _lib
+from .boundaries import sponge_tables
+from .grid import NonuniformGrid, UniformGrid
+from .sources import Microphone, Probe
+
+_FIELDS = ("p", "vx", "vy", "vz")
+
+
+class _DeviceState:
+    """Owns the torch buffers and the sb_solver handle of one slab."""
+
+    def __init__(self, shape, device_index: int | None, slab=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.B200BackendError("backend='b200' needs a CUDA device; none is visible (no CPU fallback)")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.index = torch.cuda.current_device() if device_index is None else int(device_index)
+        self.device = torch.device("cuda", self.index)
+        nx, ny, nz = shape
+        has_lower, has_upper, global_nx, i_offset = slab or (0, 0, nx, 0)
+        self.desc = _lib.GridDesc(nx=nx, ny=ny, nz=nz, pitch=0, global_nx=global_nx, i_offset=i_offset,
+                                  has_lower=has_lower, has_upper=has_upper)
+        pitch = C.c_int32(0)
+        _lib.check(self.lib.sb_choose_pitch(nz, C.byref(pitch)))
+        self.desc.pitch = pitch.value
+        self.pitch = pitch.value
+        with torch.cuda.device(self.index):
+            self.stream = torch.cuda.current_stream()
+            # two ping-pong sets of {p, vx, vy, vz}; planes -1 and nx are the slab ghosts
+            self.sets = [[torch.zeros((nx + 2, ny, self.pitch), dtype=torch.float32, device=self.device)
+                          for _ in range(4)] for _ in range(2)]
+            handle = C.c_void_p()
+            _lib.check(self.lib.sb_create(C.byref(self.desc), self.index, C.c_void_p(self.stream.cuda_stream),
+                                          C.byref(handle)))
+        self.handle = handle
+        arr = lambda ts: (C.c_void_p * 4)(*[t.data_ptr() for t in ts])
+        _lib.check(self.lib.sb_bind_fields(self.handle, arr(self.sets[0]), arr(self.sets[1])))
+
+    def current_set(self) -> int:
+        s = C.c_int(0)
+        _lib.check(self.lib.sb_current_set(self.handle, C.byref(s)))
+        return s.value
+
+    def field_view(self, name: str):
+        """torch view [nx, ny, nz] of the current device field (no copy)."""
+        t = self.sets[self.current_set()][_FIELDS.index(name)]
+        return t[1:-1, :, : self.desc.nz]
+
+    def close(self):
+        if self.handle:
+            self.lib.sb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FDTDSolver:
+    """3-D acoustic pressure-velocity FDTD on a staggered grid, executed on a B200."""
+
+    def __init__(self, shape=None, resolution=None, grid=None, c: float = 343.0, rho: float = 1.2,
+                 courant: float = 0.95, backend: str = "b200", warn_energy_drift: bool = False,
+                 energy_drift_threshold: float = 0.01, device: int | None = None, chunk_steps: int = 256):
+        if backend not in ("b200", "auto"):
+            raise ValueError(f"strata_fdtd_b200 provides backend='b200' only (got {backend!r}); "
+                             "use the reference package for 'native' / 'python'")
+        if grid is not None:
+            self._grid = grid
+            self.shape = tuple(grid.shape)
+        elif shape is not None and resolution is not None:
+            self._grid = UniformGrid(shape=shape, resolution=resolution)
+            self.shape = tuple(int(n) for n in shape)
+        else:
+            raise ValueError("Must provide either 'grid' or both 'shape' and 'resolution'")
+        self.dx = self._grid.min_spacing
+        self.c, self.rho = c, rho
+        self.backend = "b200"
+        # dt and coefficients in float64, as core/solver.py:1576-1592
+        self.dt = courant * (self._grid.min_spacing / (self.c * np.sqrt(3)))
+        if self._grid.is_uniform:
+            self._coeff_p = -self.rho * self.c**2 * self.dt / self.dx
+            self._coeff_v = -self.dt / (self.rho * self.dx)
+        else:
+            self._coeff_p_base = -self.rho * self.c**2 * self.dt
+            self._coeff_v_base = -self.dt / self.rho
+            self._spacing_arrays = self._grid.get_spacing_arrays_for_stencil()
+
+        self._host = {f: np.zeros(self.shape, dtype=np.float32) for f in _FIELDS}
+        self._host_stale: set[str] = set()     # device holds newer data
+        self._host_dirty: set[str] = set()     # host may hold newer data (array was handed out)
+        self._geometry = np.ones(self.shape, dtype=bool)
+        self._rigid = False                    # face zeroing only after set_geometry (solver.py:1779-1780)
+
+        self._sources: list = []
+        self._probes: dict[str, Probe] = {}
+        self._microphones: dict[str, Microphone] = {}
+        self._boundaries: list = []
+        self._step_count = 0
+        self._time = 0.0
+        self._snapshots: list = []
+        self._velocity_snapshots: list = []
+        self._snapshot_interval: int | None = None
+        self._snapshot_velocity = False
+        self._warn_energy_drift = warn_energy_drift
+        self._energy_drift_threshold = energy_drift_threshold
+        self._energy_history: list = []
+        self._track_energy = False
+        self._energy_sample_interval = 1
+        self._materials: dict = {}
+        self._material_id = np.zeros(self.shape, dtype=np.uint8)
+
+        self._device_index = device
+        self._chunk_steps = int(chunk_steps)
+        self._dev: _DeviceState | None = None
+        self._dirty = {"coeffs", "geometry", "sponges", "sources", "records", "ade"}
+        self._options: dict[int, int] = {}
+        self.last_run_stats: dict = {}
+
+    # ------------------------------------------------------------------ properties
+    time = property(lambda self: self._time)
+    step_count = property(lambda self: self._step_count)
+    using_native = property(lambda self: False)
+    using_gpu = property(lambda self: True)
+    using_b200 = property(lambda self: True)
+    grid = property(lambda self: self._grid)
+    microphones = property(lambda self: self._microphones)
+    has_materials = property(lambda self: len(self._materials) > 0)
+    material_count = property(lambda self: len(self._materials))
+
+    def _field_get(self, name):
+        if name in self._host_stale:
+            self._download(name)
+        self._host_dirty.add(name)             # caller may write through the returned array
+        return self._host[name]
+
+    def _field_set(self, name, value):
+        self._host[name][...] = value
+        self._host_stale.discard(name)
+        self._host_dirty.add(name)
+
+    p = property(lambda s: s._field_get("p"), lambda s, v: s._field_set("p", v))
+    vx = property(lambda s: s._field_get("vx"), lambda s, v: s._field_set("vx", v))
+    vy = property(lambda s: s._field_get("vy"), lambda s, v: s._field_set("vy", v))
+    vz = property(lambda s: s._field_get("vz"), lambda s, v: s._field_set("vz", v))
+
+    def get_field(self, name: str) -> np.ndarray:
+        """Read-only copy of a field; unlike ``solver.p`` it does not force a re-upload."""
+        if name in self._host_stale:
+            self._download(name)
+        return self._host[name].copy()
+
+    @property
+    def geometry(self):
+        self._dirty |= {"geometry", "sources"}  # may be edited in place by the caller
+        return self._geometry
+
+    @geometry.setter
+    def geometry(self, value):
+        value = np.asarray(value)
+        if value.shape != self.shape:
+            raise ValueError(f"Geometry shape {value.shape} doesn't match solver shape {self.shape}")
+        self._geometry = value.astype(bool)
+        self._dirty |= {"geometry", "sources"}
+
+    # ------------------------------------------------------------------ set-up API
+    def set_geometry(self, geometry) -> None:
+        """bool array (True = air), an SDF primitive, or a MaterializedGeometry (solver.py:1682-1780)."""
+        if hasattr(geometry, "voxelize_with_materials"):
+            mask, ids = geometry.voxelize_with_materials(self.grid)
+            if mask.shape != self.shape:
+                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.shape}")
+            self._geometry = np.ascontiguousarray(mask, dtype=bool)
+            for mat_id, material in geometry.get_material_table().items():
+                if mat_id == 0:
+                    continue
+                if mat_id not in self._materials:
+                    self.register_material(material, material_id=mat_id)
+                region = ids == mat_id
+                if np.any(region):
+                    self.set_material_region(region, material_id=mat_id)
+        elif hasattr(geometry, "voxelize"):
+            mask = geometry.voxelize(self.grid)
+            if mask.shape != self.shape:
+                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.shape}")
+            self._geometry = np.ascontiguousarray(mask, dtype=bool)
+            self._material_id.fill(0)
+            self._dirty.add("ade")
+        else:
+            mask = np.asarray(geometry)
+            if mask.shape != self.shape:
+                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.shape}")
+            self._geometry = np.ascontiguousarray(mask.astype(bool))
+        self._rigid = True
+        self._dirty |= {"geometry", "sources"}
+
+    def _to_index(self, pos, what: str):
+        """metres -> int(round(pos/dx)) when any entry is a float below max(shape) (solver.py:1818-1839)."""
+        if isinstance(pos, tuple) and len(pos) == 3 and any(isinstance(q, float) and q < max(self.shape) for q in pos):
+            idx = tuple(int(round(q / self.dx)) for q in pos)
+            for a, (i, n) in enumerate(zip(idx, self.shape)):
+                if not 0 <= i < n:
+                    raise ValueError(f"{what} {'xyz'[a]} position {pos[a]:.4f}m (index {i}) is outside grid (0-{n-1})")
+            return idx
+        return pos
+
+    def add_source(self, source) -> None:
+        kind = getattr(source, "source_type", "point")
+        if kind == "membrane":
+            ext = self._grid.physical_extent()
+            for a, (q, hi) in enumerate(zip(source.center, ext)):
+                if not 0 <= q <= hi:
+                    raise ValueError(f"Membrane center {'xyz'[a]}={q:.4f}m is outside grid (0-{hi:.4f}m)")
+        elif kind == "point":
+            source.position = self._to_index(source.position, "Source")
+        self._sources.append(source)
+        self._dirty.add("sources")
+
+    def add_probe(self, name: str, position) -> None:
+        if name in self._probes:
+            raise ValueError(f"Probe '{name}' already exists")
+        self._probes[name] = Probe(name=name, position=self._to_index(position, "Probe"))
+        self._dirty.add("records")
+
+    def add_microphone(self, position, name=None, pattern="omni", direction=None, up=None):
+        if hasattr(position, "_initialize"):
+            mic = position
+            if mic.is_directional():
+                raise NotImplementedError("directional microphones are not on the b200 device path yet")
+        else:
+            mic = Microphone(position=position, name=name, pattern=pattern, direction=direction, up=up)
+        mic.name = mic.name or f"mic_{len(self._microphones)}"
+        if mic.name in self._microphones:
+            raise ValueError(f"Microphone '{mic.name}' already exists")
+        mic._initialize(self)
+        self._microphones[mic.name] = mic
+        self._dirty.add("records")
+        return mic
+
+    def add_boundary(self, boundary) -> None:
+        boundary.initialize(self)
+        if sponge_tables(boundary, self) is None and type(boundary).__name__ != "RigidBoundary":
+            raise NotImplementedError(f"{type(boundary).__name__} is not on the b200 device path yet "
+                                      "(PML / RigidBoundary are)")
+        self._boundaries.append(boundary)
+        self._dirty.add("sponges")
+
+    def enable_snapshots(self, interval: int, capture_velocity: bool = False) -> None:
+        self._snapshot_interval = interval
+        self._snapshot_velocity = capture_velocity
+
+    # ------------------------------------------------------------------ materials (solver.py:2836-2942)
+    def register_material(self, material, material_id: int | None = None) -> int:
+        if material_id is None:
+            material_id = next((q for q in range(1, 256) if q not in self._materials), None)
+            if material_id is None:
+                raise ValueError("Maximum of 255 materials reached")
+        if not 1 <= material_id <= 255:
+            raise ValueError("material_id must be in range 1-255 (0 is reserved for air)")
+        if material_id in self._materials:
+            raise ValueError(f"Material ID {material_id} is already registered")
+        self._materials[material_id] = material
+        self._dirty.add("ade")
+        return material_id
+
+    def set_material_region(self, mask, material_id: int) -> None:
+        if mask.shape != self.shape:
+            raise ValueError(f"Mask shape {mask.shape} doesn't match solver shape {self.shape}")
+        if material_id != 0 and material_id not in self._materials:
+            raise ValueError(f"Material ID {material_id} not registered. Use register_material() first.")
+        self._material_id[mask] = material_id
+        self._dirty.add("ade")
+
+    def set_material_box(self, material_id: int, x_range, y_range, z_range) -> None:
+        mask = np.zeros(self.shape, dtype=bool)
+        mask[x_range[0]:x_range[1], y_range[0]:y_range[1], z_range[0]:z_range[1]] = True
+        self.set_material_region(mask, material_id)
+
+    def get_material_at(self, position):
+        mat_id = self._material_id[position]
+        return None if mat_id == 0 else self._materials.get(mat_id)
+
+    # ------------------------------------------------------------------ device plumbing
+    def set_kernel_option(self, option: int, value: int) -> None:
+        """Tuning knobs of the step kernel (``_lib.OPT_*``); results never depend on them."""
+        self._options[option] = int(value)
+        if self._dev is not None:
+            _lib.check(self._dev.lib.sb_set_option(self._dev.handle, option, int(value)))
+
+    def _ensure_device(self) -> _DeviceState:
+        if self._dev is None:
+            self._dev = _DeviceState(self.shape, self._device_index)
+            for opt, val in self._options.items():
+                _lib.check(self._dev.lib.sb_set_option(self._dev.handle, opt, val))
+            self._host_dirty = set(_FIELDS)
+        return self._dev
+
+    def _download(self, name: str) -> None:
+        dev = self._ensure_device()
+        _lib.check(dev.lib.sb_download_field(dev.handle, _FIELDS.index(name), _lib.ptr(self._host[name])))
+        self._host_stale.discard(name)
+
+    def _coefficient_tables(self):
+        """fp32 per-face velocity coefficients and per-cell inverse spacings (see strata_b200.h)."""
+        nx, ny, nz = self.shape
+        if self._grid.is_uniform:
+            cv = np.float32(self._coeff_v)
+            return [np.full(n, cv, dtype=np.float32) for n in (nx, ny, nz)], [None] * 3, np.float32(self._coeff_p)
+        sa = self._spacing_arrays
+        cvb = np.float32(self._coeff_v_base)
+        faces = []
+        for a, n in zip("xyz", (nx, ny, nz)):
+            t = np.zeros(n, dtype=np.float32)
+            t[: n - 1] = cvb * sa[f"inv_d{a}_face"]          # one rounded fp32 multiply (fdtd_step.cpp:263)
+            faces.append(t)
+        cells = [np.ascontiguousarray(sa[f"inv_d{a}_cell"], dtype=np.float32) for a in "xyz"]
+        return faces, cells, np.float32(self._coeff_p_base)
+
+    def _build_source_table(self):
+        """CSR over cells: (cell, [source id, field, weight]...) in source order (solver.py:2386-2433)."""
+        nx, ny, nz = self.shape
+        cells, sids, flds, wts = [], [], [], []
+        g = self._geometry
+        for sid, src in enumerate(self._sources):
+            kind = getattr(src, "source_type", "point")
+            if kind == "point":
+                i, j, k = src.position
+                if g[i, j, k]:
+                    cells.append(np.array([(i * ny + j) * nz + k], dtype=np.int64))
+                    wts.append(np.ones(1)); flds.append(np.zeros(1, dtype=np.int32))
+                    sids.append(np.full(1, sid, dtype=np.int32))
+            elif kind == "plane":
+                sel = [slice(None)] * 3
+                sel[src.position["axis"]] = src.position["index"]
+                m = np.zeros(self.shape, dtype=bool)
+                m[tuple(sel)] = g[tuple(sel)]
+                idx = np.flatnonzero(m)
+                cells.append(idx); wts.append(np.ones(idx.size)); flds.append(np.zeros(idx.size, dtype=np.int32))
+                sids.append(np.full(idx.size, sid, dtype=np.int32))
+            elif kind == "membrane":
+                if getattr(src, "_cached_weights", None) is None:
+                    src._check_grid_alignment(self._grid)
+                    src._cached_weights = src.get_injection_weights(self._grid)
+                    src._cached_mask = src._cached_weights > 0
+                m = src._cached_mask & g
+                idx = np.flatnonzero(m)
+                fld = 0 if src.injection_type == "pressure" else 1 + "xyz".index(src.normal_axis)
+                cells.append(idx); wts.append(np.asarray(src._cached_weights, dtype=np.float64)[m])
+                flds.append(np.full(idx.size, fld, dtype=np.int32)); sids.append(np.full(idx.size, sid, dtype=np.int32))
+            else:
+                raise ValueError(f"unknown source_type {kind!r}")
+        if not cells:
+            z = np.zeros(0, dtype=np.int64)
+            return z, np.zeros(1, dtype=np.int32), z.astype(np.int32), z.astype(np.int32), z.astype(np.float64)
+        cells, sids, flds, wts = (np.concatenate(q) for q in (cells, sids, flds, wts))
+        order = np.argsort(cells, kind="stable")             # keeps source order inside a cell
+        cells, sids, flds, wts = cells[order], sids[order], flds[order], wts[order]
+        uniq, first = np.unique(cells, return_index=True)
+        start = np.append(first, cells.size).astype(np.int32)
+        return (uniq.astype(np.int64), start, np.ascontiguousarray(sids, dtype=np.int32),
+                np.ascontiguousarray(flds, dtype=np.int32), np.ascontiguousarray(wts, dtype=np.float64))
+
+    def _pole_table(self):
+        """Debye poles of all materials first, then Lorentz, each in registration order (solver.py:3024-3054)."""
+        deb, lor = [], []
+        n_ids = max(self._materials) + 1
+        rho_inf = np.zeros(n_ids, dtype=np.float32)
+        k_inf = np.zeros(n_ids, dtype=np.float32)
+        for mat_id, mat in self._materials.items():
+            rho_inf[mat_id] = float(mat.rho_inf)
+            k_inf[mat_id] = float(mat.K_inf)
+            for pole in mat.poles:
+                co = pole.fdtd_coefficients(self.dt)
+                tgt = 0 if pole.target == "density" else 1
+                if pole.is_debye:
+                    deb.append(_lib.Pole(mat_id, 0, tgt, 0, float(co[0]), float(co[1]), 0.0, 0.0))
+                else:
+                    lor.append(_lib.Pole(mat_id, 1, tgt, 0, float(co[0]), float(co[1]), float(co[2]), 0.0))
+        poles = deb + lor
+        return (_lib.Pole * max(1, len(poles)))(*poles), len(poles), rho_inf, k_inf
+
+    def _sync_to_device(self) -> _DeviceState:
+        dev = self._ensure_device()
+        lib, h = dev.lib, dev.handle
+        nx, ny, nz = self.shape
+        if "coeffs" in self._dirty:
+            faces, cells, cp = self._coefficient_tables()
+            _lib.check(lib.sb_set_coefficients(h, *(_lib.ptr(t) for t in faces), *(_lib.ptr(t) for t in cells),
+                                               float(cp)))
+        if "geometry" in self._dirty:
+            g = np.ascontiguousarray(self._geometry, dtype=np.uint8)
+            _lib.check(lib.sb_set_geometry(h, _lib.ptr(g), int(self._rigid)))
+        if "sponges" in self._dirty:
+            _lib.check(lib.sb_clear_sponges(h))
+            for b in self._boundaries:                       # application order = list order (solver.py:2044-2047)
+                tabs = sponge_tables(b, self)
+                if tabs is not None:
+                    _lib.check(lib.sb_add_sponge(h, *(_lib.ptr(t) for t in tabs)))
+        if "sources" in self._dirty:
+            cells, start, sids, flds, wts = self._build_source_table()
+            _lib.check(lib.sb_set_sources(h, len(self._sources), len(cells), _lib.ptr(cells), _lib.ptr(start),
+                                          _lib.ptr(sids), _lib.ptr(flds), _lib.ptr(wts)))
+        if "records" in self._dirty:
+            flat = np.array([(i * ny + j) * nz + k for (i, j, k) in (pr.position for pr in self._probes.values())],
+                            dtype=np.int64)
+            _lib.check(lib.sb_set_probes(h, len(flat), _lib.ptr(flat) if len(flat) else None))
+            mics = list(self._microphones.values())
+            if mics:
+                gp = np.array([q for m in mics for q in m._grid_position], dtype=np.float32)   # fp32 store, solver.py:2502-2509
+                idx8 = np.zeros(8 * len(mics), dtype=np.int64)
+                w8 = np.zeros(8 * len(mics), dtype=np.float32)
+                _lib.check(lib.sb_mic_tables(_lib.ptr(gp), len(mics), ny, nz, _lib.ptr(idx8), _lib.ptr(w8)))
+                self._mic_tables = (idx8, w8)
+                _lib.check(lib.sb_set_mics(h, len(mics), _lib.ptr(idx8), _lib.ptr(w8)))
+            else:
+                _lib.check(lib.sb_set_mics(h, 0, None, None))
+        if "ade" in self._dirty:
+            if self._materials and any(len(m.poles) for m in self._materials.values()):
+                poles, n_poles, rho_inf, k_inf = self._pole_table()
+                mid = np.ascontiguousarray(self._material_id, dtype=np.uint8)
+                _lib.check(lib.sb_set_ade(h, poles, n_poles, _lib.ptr(mid), _lib.ptr(rho_inf), _lib.ptr(k_inf),
+                                          len(rho_inf), float(self.dt), float(1.0 / self.dx)))
+            else:
+                _lib.check(lib.sb_set_ade(h, None, 0, None, None, None, 0, 0.0, 0.0))
+        self._dirty.clear()
+        for name in list(self._host_dirty):
+            if name not in self._host_stale:
+                _lib.check(lib.sb_upload_field(h, _FIELDS.index(name), _lib.ptr(self._host[name])))
+        self._host_dirty.clear()
+        return dev
+
+    # ------------------------------------------------------------------ time stepping
+    def _waveform_table(self, times: np.ndarray) -> np.ndarray:
+        """W[n, s] = sample of source s at step n, float64, evaluated exactly like solver.py:2391/2416.
+
+        The vectorised evaluation is spot-checked against the reference's one-element-array form;
+        any difference (a SIMD/scalar libm split) falls back to per-step evaluation."""
+        n = len(times)
+        W = np.zeros((n, max(1, len(self._sources))), dtype=np.float64)
+        for s, src in enumerate(self._sources):
+            fn = src.waveform.waveform if getattr(src, "source_type", "") == "membrane" else src.waveform
+            col = np.asarray(fn(times.copy(), self.dt), dtype=np.float64)
+            probe_at = sorted({0, n - 1, n // 2, n // 3, (2 * n) // 3})
+            same = col.shape == (n,) and all(
+                np.float64(fn(np.array([times[q]]), self.dt)[0]).tobytes() == col[q].tobytes() for q in probe_at)
+            if not same:
+                col = np.array([fn(np.array([t]), self.dt)[0] for t in times], dtype=np.float64)
+            W[:, s] = col
+        return W
+
+    def _advance(self, n_steps: int, callback=None, writer=None, snapshot_interval=None) -> None:
+        dev = self._sync_to_device()
+        lib, h = dev.lib, dev.handle
+        n_rec = len(self._probes) + len(self._microphones)
+        probes = list(self._probes.values())
+        mics = list(self._microphones.values())
+        done = 0
+        while done < n_steps:
+            m = min(self._chunk_steps, n_steps - done)
+            # a chunk ends right after any step whose fields the host has to see
+            for q in range(m):
+                idx = self._step_count + q
+                need = (self._snapshot_interval and idx % self._snapshot_interval == 0) or \
+                       (self._track_energy and (idx + 1) % self._energy_sample_interval == 0) or \
+                       (writer is not None and snapshot_interval is not None and (done + q) % snapshot_interval == 0)
+                if need:
+                    m = q + 1
+                    break
+            times = np.empty(m, dtype=np.float64)
+            t = self._time
+            for q in range(m):
+                times[q] = t
+                t = t + self.dt                               # same float64 accumulation as solver.py:2072
+            W = self._waveform_table(times) if self._sources else None
+            rec = np.empty((m, max(1, n_rec)), dtype=np.float32)
+            _lib.check(lib.sb_step_n(h, m, _lib.ptr(W), _lib.ptr(rec) if n_rec else None))
+            self._host_stale = set(_FIELDS)
+            for q, pr in enumerate(probes):
+                pr.data.extend(rec[:, q].tolist())
+            for q, mic in enumerate(mics):
+                mic._data.extend(rec[:, len(probes) + q].tolist())
+                mic._times.extend(times.tolist())
+            last_idx = self._step_count + m - 1
+            self._step_count += m
+            self._time = t
+            if self._snapshot_interval and last_idx % self._snapshot_interval == 0:
+                self._snapshots.append((float(times[-1]), self.get_field("p")))
+                if self._snapshot_velocity:
+                    self._velocity_snapshots.append((float(times[-1]), *self._centred_velocities()))
+            if self._track_energy and self._step_count % self._energy_sample_interval == 0:
+                self._energy_history.append((self._step_count, self._time, self.compute_energy()))
+            if writer is not None:
+                if probes:
+                    writer.append_probe_block([pr.name for pr in probes], rec[:, :len(probes)])
+                if snapshot_interval is not None and (done + m - 1) % snapshot_interval == 0:
+                    writer.write_snapshot(self.get_field("p"))
+            if callback is not None:
+                for q in range(m):
+                    callback(last_idx - (m - 1 - q))
+            done += m
+
+    def step(self) -> None:
+        """Advance one time step (solver.py:2003-2077)."""
+        self._advance(1)
+
+    def run(self, duration: float | None = None, progress: bool = False, track_energy: bool = False,
+            energy_sample_interval: int = 1, output_file: str | None = None, script_content: str | None = None,
+            callback: Callable[[int], None] | None = None, snapshot_interval: int | None = None,
+            steps: int | None = None, output: str | None = None) -> None:
+        """Run for ``duration`` seconds (or ``steps`` steps) -- solver.py:2520-2606."""
+        if steps is None:
+            if duration is None:
+                raise ValueError("run() needs duration= or steps=")
+            steps = int(np.ceil(duration / self.dt))
+        output_file = output_file or output
+        t0 = _time_mod.time()
+        self._track_energy = track_energy
+        self._energy_sample_interval = energy_sample_interval
+        if track_energy and not self._energy_history:
+            self._energy_history.append((self._step_count, self._time, self.compute_energy()))
+        writer = None
+        if output_file:
+            from .io import ResultWriter
+            writer = ResultWriter(output_file, self, script_content)
+        bar = None
+        cb = callback
+        if progress:
+            try:
+                from tqdm import tqdm
+                bar = tqdm(total=steps, desc="FDTD simulation (b200)")
+                cb = (lambda s: (bar.update(1), callback(s) if callback else None))
+            except ImportError:
+                bar = None
+        launches0 = self.kernel_launches()
+        try:
+            self._advance(steps, callback=cb, writer=writer, snapshot_interval=snapshot_interval)
+            if self._warn_energy_drift and len(self._energy_history) >= 2:
+                rep = self.energy_report()
+                if abs(rep["energy_change_percent"]) > self._energy_drift_threshold * 100:
+                    warnings.warn(f"Energy drift detected: {rep['energy_change_percent']:.2f}% change "
+                                  f"(threshold: {self._energy_drift_threshold * 100:.1f}%). "
+                                  f"Status: {rep['conservation_status']}", UserWarning, stacklevel=2)
+        finally:
+            runtime = _time_mod.time() - t0
+            if bar is not None:
+                bar.close()
+            cells = int(np.prod(self.shape, dtype=np.int64))
+            self.last_run_stats = {"steps": steps, "runtime_s": runtime,
+                                   "cell_updates_per_s": cells * steps / runtime if runtime > 0 else float("inf"),
+                                   "kernel_launches": self.kernel_launches() - launches0}
+            if writer is not None:
+                writer.finalize(runtime=runtime, backend="b200", num_threads=0)
+
+    # ------------------------------------------------------------------ results / diagnostics
+    def get_probe_data(self, name: str | None = None) -> dict:
+        if name is not None:
+            if name not in self._probes:
+                raise KeyError(f"Probe '{name}' not found")
+            return {name: self._probes[name].get_data()}
+        return {n: pr.get_data() for n, pr in self._probes.items()}
+
+    def get_snapshots(self):
+        return self._snapshots
+
+    def get_velocity_snapshots(self):
+        return self._velocity_snapshots
+
+    def _centred_velocities(self):
+        out = []
+        for axis, name in enumerate(("vx", "vy", "vz")):
+            v = self.get_field(name)
+            c = np.zeros_like(v)
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3; first = [slice(None)] * 3
+            lo[axis] = slice(0, -1); hi[axis] = slice(1, None); first[axis] = 0
+            c[tuple(hi)] = 0.5 * (v[tuple(lo)] + v[tuple(hi)])
+            c[tuple(first)] = 0.5 * v[tuple(first)]
+            out.append(c)
+        return out
+
+    def compute_energy(self) -> float:
+        """(1/2) sum(p^2/(rho c^2) + rho |v|^2) dV over air cells (solver.py:2689-2706), reduced on the device."""
+        dev = self._sync_to_device()
+        out = C.c_double(0.0)
+        _lib.check(dev.lib.sb_energy(dev.handle, float(self.rho), float(self.c), float(self.dx**3), C.byref(out)))
+        return out.value
+
+    def get_energy_history(self):
+        return self._energy_history.copy()
+
+    def energy_report(self) -> dict:
+        if not self._energy_history:
+            raise ValueError("No energy history recorded. Call run() with track_energy=True first.")
+        e = np.array([q[2] for q in self._energy_history])
+        first, last = e[0], e[-1]
+        if first == 0:
+            change = 0.0 if last == 0 else float("inf")
+        else:
+            change = (last - first) / first * 100
+        status = "stable" if abs(change) <= 1.0 else ("growing" if change > 0 else "decaying")
+        return {"initial_energy": float(first), "final_energy": float(last), "max_energy": float(e.max()),
+                "min_energy": float(e.min()), "energy_change_percent": change, "conservation_status": status,
+                "n_samples": len(e)}
+
+    def get_sample_rate(self) -> float:
+        return 1.0 / self.dt
+
+    def get_frequency_response(self, probe_name: str, n_fft: int | None = None):
+        data = self._probes[probe_name].get_data()
+        if n_fft is None:
+            n_fft = int(2 ** np.ceil(np.log2(len(data))))
+        return np.fft.rfftfreq(n_fft, self.dt), np.abs(np.fft.rfft(data, n=n_fft))
+
+    def reset(self) -> None:
+        """Back to t = 0 with zero fields (solver.py:2781-2800)."""
+        for f in _FIELDS:
+            self._host[f].fill(0)
+        self._host_stale.clear()
+        self._host_dirty.clear()
+        if self._dev is not None:
+            _lib.check(self._dev.lib.sb_reset(self._dev.handle))
+        self._step_count = 0
+        self._time = 0.0
+        self._snapshots.clear()
+        self._velocity_snapshots.clear()
+        self._energy_history.clear()
+        self._track_energy = False
+        for pr in self._probes.values():
+            pr.clear()
+        for mic in self._microphones.values():
+            mic.clear()
+        for b in self._boundaries:
+            b.reset()
+
+    def kernel_launches(self) -> int:
+        if self._dev is None:
+            return 0
+        st = _lib.Stats()
+        _lib.check(self._dev.lib.sb_query(self._dev.handle, C.byref(st)))
+        return int(st.kernels_launched)
+
+    def device_stats(self) -> dict:
+        dev = self._ensure_device()
+        st = _lib.Stats()
+        _lib.check(dev.lib.sb_query(dev.handle, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def device_field(self, name: str):
+        """Zero-copy torch view [nx, ny, nz] of a field on the device (valid until the next step)."""
+        dev = self._sync_to_device()
+        return dev.field_view(name)
+
+    def close(self) -> None:
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None

@@ -1,0 +1,186 @@
+"""CPU tests of the host side: the C ABI library loads and exports every declared symbol, and the
+host mirrors (grids, sponge profiles, position rounding, pole coefficients, source tables) reproduce
+the reference's numbers exactly (fixtures; live reference where available)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import strata_fdtd_b200 as sb
+from cases import make_cases
+from oracle import oracle as O
+from oracle import ref_loader as R
+from strata_fdtd_b200 import _lib
+from util import build_b200_solver
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLDEN = ROOT / "tests" / "golden"
+CASES = make_cases()
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = (ROOT / "include" / "strata_b200.h").read_text()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sb_solver"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/strata_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.sb_abi_version() == 1
+    # no-GPU calls only
+    pitch = ctypes.c_int32(0)
+    assert lib.sb_choose_pitch(100, ctypes.byref(pitch)) == 0 and pitch.value == 128
+    d = _lib.GridDesc(nx=10, ny=7, nz=100, pitch=0, global_nx=10, i_offset=0, has_lower=0, has_upper=0)
+    assert lib.sb_field_elems(ctypes.byref(d)) == 12 * 7 * 128
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    s = sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3)
+    with pytest.raises(sb.B200BackendError, match="no CPU fallback"):
+        s.step()
+    lib = _lib.load()
+    d = _lib.GridDesc(nx=8, ny=8, nz=8, pitch=0, global_nx=8, i_offset=0, has_lower=0, has_upper=0)
+    h = ctypes.c_void_p()
+    assert lib.sb_create(ctypes.byref(d), 0, None, ctypes.byref(h)) != 0
+    assert b"no CPU fallback" in lib.sb_last_error()
+
+
+def test_decay_table_is_libm_expf():
+    sig = np.linspace(0, 4e5, 57, dtype=np.float32)
+    dt = 1.599075089592258e-06
+    got = sb.boundaries.decay_table(sig, dt)
+    want = np.empty_like(sig)
+    O.lib().orc_decay_table(sig.ctypes.data_as(O._f32p), 57, ctypes.c_float(dt), want.ctypes.data_as(O._f32p))
+    assert np.array_equal(got, want)
+    assert got[0] == 1.0
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_host_numbers_match_golden(name):
+    case = CASES[name]
+    g = np.load(GOLDEN / f"{name}.npz")
+    s = build_b200_solver(case)
+    assert float(s.dt) == float(g["dt"])
+    faces, cells, cp = s._coefficient_tables()
+    assert np.float32(cp) == g["cp"]
+    if s.grid.is_uniform:
+        assert all(np.all(t == g["cv"]) for t in faces)
+    else:
+        for a, t, c in zip("xyz", faces, cells):
+            assert np.array_equal(c, g[f"sp_inv_d{a}_cell"])
+            assert np.array_equal(t[:-1], np.float32(g["cv"]) * g[f"sp_inv_d{a}_face"])
+    for bi, b in enumerate(s._boundaries):
+        assert float(b._max_sigma) == float(g[f"pml{bi}_max_sigma"])
+        for a, sig, dec in zip("xyz", (b._sigma_x, b._sigma_y, b._sigma_z), b._decay):
+            if sig is not None:
+                assert np.array_equal(sig, g[f"pml{bi}_sigma_{a}"])
+                assert np.array_equal(dec, g[f"pml{bi}_decay_{a}"])
+    ny, nz = s.shape[1], s.shape[2]
+    for pname, pr in s._probes.items():
+        i, j, k = pr.position
+        assert (i * ny + j) * nz + k == int(g["probe_idx_" + pname])
+    for si, src in enumerate(s._sources):
+        if src.source_type == "point":
+            i, j, k = src.position
+            assert (i * ny + j) * nz + k == int(g[f"source_idx_{si}"])
+    if s.microphones:
+        lib = _lib.load()
+        mics = list(s.microphones.values())
+        gp = np.array([q for m in mics for q in m._grid_position], dtype=np.float32)
+        idx8 = np.zeros(8 * len(mics), dtype=np.int64); w8 = np.zeros(8 * len(mics), dtype=np.float32)
+        assert lib.sb_mic_tables(_lib.ptr(gp), len(mics), ny, nz, _lib.ptr(idx8), _lib.ptr(w8)) == 0
+        assert np.array_equal(idx8, g["mic_flat_indices"]) and np.array_equal(w8, g["mic_weights"])
+
+
+def test_source_table_csr_orders_and_masks():
+    case = CASES["partial_pml_plane"]
+    s = build_b200_solver(case)
+    cells, start, sids, flds, wts = s._build_source_table()
+    g = case["geometry"]
+    n_plane = int(g[8].sum())
+    assert len(cells) == n_plane + 1 and start[-1] == len(sids)
+    assert np.all(np.diff(cells) > 0) and np.all(wts == 1.0) and np.all(flds == 0)
+    # a source inside a solid is dropped, as the reference's per-step geometry test does (solver.py:2420)
+    s2 = build_b200_solver(dict(case, sources=[dict(kind="point", position=(15, 2, 12), frequency=1e3)]))
+    assert len(s2._build_source_table()[0]) == 0
+
+
+def test_waveform_table_equals_per_step_evaluation():
+    s = build_b200_solver(CASES["uniform_pml"])
+    t, times = 0.0, []
+    for _ in range(300):
+        times.append(t); t = t + s.dt
+    W = s._waveform_table(np.array(times))
+    src = s._sources[0]
+    ref = np.array([src.waveform(np.array([q]), s.dt)[0] for q in times])
+    assert W[:, 0].tobytes() == ref.tobytes()
+    assert W[:, 0].tobytes() == np.array([O.gaussian_pulse(q, 20e3, None, 1.0) for q in times]).tobytes()
+
+
+def test_position_rounding_and_errors():
+    s = sb.FDTDSolver(shape=(17, 23, 13), resolution=2e-3)
+    s.add_probe("m", (0.030, 0.040, 0.020))
+    assert s._probes["m"].position == (15, 20, 10)
+    s.add_probe("i", (3, 3, 3))
+    assert s._probes["i"].position == (3, 3, 3)
+    with pytest.raises(ValueError):
+        s.add_probe("m", (1, 1, 1))
+    with pytest.raises(ValueError):
+        s.add_probe("far", (0.5, 0.01, 0.01))
+    with pytest.raises(ValueError):
+        s.add_microphone(position=(0.5, 0.01, 0.01), name="out")
+    with pytest.raises(ValueError):
+        s.set_geometry(np.ones((3, 3, 3), bool))
+    with pytest.raises(NotImplementedError):
+        s.add_microphone(position=(0.01, 0.01, 0.01), name="c", pattern="cardioid")
+
+
+def test_pole_coefficients_match_oracle_restatement():
+    dt = 1.599075089592258e-06
+    for p in CASES["ade_two_materials_nonuniform"]["materials"][1]["poles"]:
+        if p["type"] == "debye":
+            pole = sb.Pole(sb.PoleType.DEBYE, p["delta_chi"], p["target"], tau=p["tau"])
+        else:
+            pole = sb.Pole(sb.PoleType.LORENTZ, p["delta_chi"], p["target"], omega_0=p["omega_0"], gamma=p["gamma"])
+        assert pole.fdtd_coefficients(dt) == O.pole_coefficients(p, dt)
+
+
+@pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
+def test_grids_match_reference_live():
+    ref = R.load_reference_package()
+    for kw in (dict(shape=(41, 30, 52), base_resolution=1e-3, stretch_x=1.03, stretch_z=1.05),
+               dict(shape=(40, 31, 20), base_resolution=2e-3, stretch_y=1.02, center_fine=False)):
+        a, b = sb.NonuniformGrid.from_stretch(**kw), ref.NonuniformGrid.from_stretch(**kw)
+        for attr in ("x_coords", "y_coords", "z_coords", "dx", "dy", "dz"):
+            assert np.array_equal(getattr(a, attr), getattr(b, attr)), attr
+        assert a.min_spacing == b.min_spacing and a.shape == b.shape
+        sa, sb_ = a.get_spacing_arrays_for_stencil(), b.get_spacing_arrays_for_stencil()
+        assert all(np.array_equal(sa[k], sb_[k]) for k in sb_)
+    regs = [(0, 0.05, 2e-3), (0.05, 0.15, 1e-3), (0.15, 0.2, 2e-3)]
+    a = sb.NonuniformGrid.from_regions(regs, [(0, 0.1, 1e-3)], [(0, 0.1, 1e-3)])
+    b = ref.NonuniformGrid.from_regions(regs, [(0, 0.1, 1e-3)], [(0, 0.1, 1e-3)])
+    assert np.array_equal(a.x_coords, b.x_coords) and a.shape == b.shape
+    # the reference's own PML accepts our solver object (duck typing) and yields the same profiles
+    s = sb.FDTDSolver(grid=sb.NonuniformGrid.from_stretch((40, 24, 30), 1e-3, stretch_x=1.04))
+    ours, theirs = sb.PML(depth=6), ref.PML(depth=6)
+    ours.initialize(s); theirs.initialize(s)
+    for a_ in "xyz":
+        assert np.array_equal(getattr(ours, "_sigma_" + a_), getattr(theirs, "_sigma_" + a_))
+
+
+@pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
+def test_shim_registers_backend_with_reference():
+    ref = R.load_reference_package()
+    sb.install_into_reference(ref)
+    s = ref.FDTDSolver(shape=(12, 12, 12), resolution=1e-3, backend="b200")
+    assert type(s).__module__.startswith("strata_fdtd_b200") and s.backend == "b200"
+    assert s.grid.num_cells == 12 ** 3
+    r = ref.FDTDSolver(shape=(12, 12, 12), resolution=1e-3, backend="native")
+    assert r.using_native and r.grid.num_cells == 12 ** 3
+    r.step()

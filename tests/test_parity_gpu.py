@@ -1,0 +1,138 @@
+"""Parity of the CUDA path (through FDTDSolver -> C ABI) with the CPU oracle and with the
+committed fixtures generated from the unmodified reference.  Bit-exact: every comparison is
+np.array_equal on fp32 fields and traces (the stated tolerance of 1e-5 relative is slack)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from cases import c1_case, c2_case, make_cases
+from oracle import oracle as O
+from strata_fdtd_b200 import _lib
+from util import assert_same_as_oracle, build_b200_solver, sha
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+CASES = make_cases()
+VARIANTS = {
+    "naive": {_lib.OPT_KERNEL: _lib.KERNEL_NAIVE},
+    "march_r1": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1},
+    "march_r2": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2},
+    "march_r4_chunk5": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 4, _lib.OPT_CHUNK_I: 5,
+                        _lib.OPT_WARPS_J: 2},
+    "march_r2_graph": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_USE_GRAPH: 1},
+}
+
+
+def _with_options(s, opts):
+    for k, v in opts.items():
+        s.set_kernel_option(k, v)
+    return s
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_oracle_and_golden(name, variant):
+    case = CASES[name]
+    g = np.load(GOLDEN / f"{name}.npz")
+    s = _with_options(build_b200_solver(case, chunk_steps=37), VARIANTS[variant])
+    assert float(s.dt) == float(g["dt"])
+    s.run(steps=case["steps"])
+    # fixtures from the reference itself
+    for f in ("p", "vx", "vy", "vz"):
+        assert sha(s.get_field(f)) == str(g["sha_" + f]), f"{name}/{variant}: final {f} != reference"
+    for pname in s._probes:
+        assert np.array_equal(s.get_probe_data(pname)[pname], g["probe_" + pname])
+    for mname, mic in s.microphones.items():
+        assert np.array_equal(mic.get_waveform(), g["mic_" + mname])
+    # and the oracle run live on the same inputs
+    o = O.OracleSolver(case)
+    o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"{name}/{variant}")
+    assert s.kernel_launches() > 0
+    s.close()
+
+
+def test_sponge_tables_and_indices_match_golden():
+    case = CASES["partial_pml_plane"]
+    g = np.load(GOLDEN / "partial_pml_plane.npz")
+    s = build_b200_solver(case)
+    for bi, b in enumerate(s._boundaries):
+        assert float(b._max_sigma) == float(g[f"pml{bi}_max_sigma"])
+        for a, sig, dec in zip("xyz", (b._sigma_x, b._sigma_y, b._sigma_z), b._decay):
+            if sig is None:
+                assert f"pml{bi}_sigma_{a}" not in g
+            else:
+                assert np.array_equal(sig, g[f"pml{bi}_sigma_{a}"])
+                assert np.array_equal(dec, g[f"pml{bi}_decay_{a}"])
+
+
+def test_step_by_step_with_host_pokes():
+    """solver.p is a live view: writes between steps are honoured (reference tests/test_fdtd.py:228)."""
+    case = dict(shape=(20, 18, 22), resolution=1e-3, steps=0, pml=[dict(depth=4)])
+    s = build_b200_solver(case)
+    o = O.OracleSolver(case)
+    s.p[10, 9, 11] = 1.0
+    o.p[10, 9, 11] = 1.0
+    for n in range(25):
+        s.step(); o.step()
+        if n == 7:
+            s.vx[3, 4, 5] = 0.25; o.vx[3, 4, 5] = 0.25
+            s.p[2, 2, 2] += 0.5;  o.p[2, 2, 2] += 0.5
+    assert_same_as_oracle(s, o, "pokes")
+    # last-face velocities are never updated but are damped
+    s.vx[19, 5, 5] = 1.0; o.vx[19, 5, 5] = 1.0
+    s.step(); o.step()
+    assert_same_as_oracle(s, o, "last face")
+
+
+def test_c1_full_config_against_reference_fixture():
+    """BASELINE config 1: 100^3, PML 10, 1 kHz, 1 probe, 1000 steps -- vs the reference's own output."""
+    g = np.load(GOLDEN / "c1_100cubed_1000.npz")
+    s = build_b200_solver(c1_case(1000))
+    s.run(steps=1000)
+    assert np.array_equal(s.get_probe_data("probe")["probe"], g["probe_probe"])
+    for f in ("p", "vx", "vy", "vz"):
+        assert sha(s.get_field(f)) == str(g["sha_" + f])
+
+
+def test_c2_200cubed_vs_oracle_with_geometry():
+    case = c2_case(200, steps=120, with_geometry=True)
+    s = build_b200_solver(case)
+    o = O.OracleSolver(case)
+    s.run(steps=120); o.run_steps(120)
+    assert_same_as_oracle(s, o, "c2")
+
+
+def test_large_grid_march_equals_naive():
+    """Size-independent property at a size the oracle cannot reach quickly: the marching kernel and the
+    one-thread-per-cell kernel are two independent implementations and must agree bit-for-bit."""
+    case = c2_case(320, steps=60, with_geometry=True)
+    a = _with_options(build_b200_solver(case), VARIANTS["march_r2"])
+    b = _with_options(build_b200_solver(case), VARIANTS["naive"])
+    a.run(steps=60); b.run(steps=60)
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(a.get_field(f), b.get_field(f)), f
+    assert np.array_equal(a.get_probe_data("probe")["probe"], b.get_probe_data("probe")["probe"])
+    assert np.abs(a.get_field("p")).max() > 0
+
+
+def test_energy_and_reset():
+    case = dict(shape=(24, 24, 24), resolution=1e-3, steps=0)
+    s = build_b200_solver(case)
+    s.p[12, 12, 12] = 1.0
+    e0 = s.compute_energy()
+    p = np.zeros((24, 24, 24), np.float32); p[12, 12, 12] = 1.0
+    want = 0.5 * float((p.astype(np.float64) ** 2).sum()) / (1.2 * 343.0**2) * (1e-3) ** 3
+    assert abs(e0 - want) <= 1e-12 * want
+    s.run(steps=40, track_energy=True, energy_sample_interval=10)
+    hist = s.get_energy_history()
+    assert len(hist) == 5 and 0.5 < hist[-1][2] / hist[0][2] < 1.5       # closed rigid box conserves energy
+    s.reset()
+    assert s.step_count == 0 and s.time == 0.0 and not np.any(s.get_field("p"))
+
+
+def test_no_cuda_fallback_message():
+    import strata_fdtd_b200 as sb
+    with pytest.raises(ValueError):
+        sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3, backend="python")
