@@ -74,7 +74,7 @@ typedef struct sb_stats {
 enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, SB_KERNEL_TMA = 3 };
 enum { SB_FIELD_P = 0, SB_FIELD_VX = 1, SB_FIELD_VY = 2, SB_FIELD_VZ = 3 };
 enum { SB_OPT_KERNEL = 0, SB_OPT_ROWS_PER_THREAD = 1, SB_OPT_WARPS_J = 2, SB_OPT_WARPS_K = 3,
-       SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5 };
+       SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5, SB_OPT_PROFILE = 6 };
 
 const char *sb_last_error(void);
 int sb_abi_version(void);
@@ -172,6 +172,9 @@ int sb_energy(sb_solver *h, double rho, double c, double dV, double *out);
 int sb_reset(sb_solver *h);                      /* zero fields, J, counters (solver.py:2781-2800) */
 int sb_set_option(sb_solver *h, int option, int value);
 int sb_query(sb_solver *h, sb_stats *out);
+/* With SB_OPT_PROFILE=1 every launch of the fused step kernel is bracketed by CUDA events on the
+ * handle's stream; this returns (and clears) mean / min duration in ms and the launch count.   */
+int sb_profile_read(sb_solver *h, double *mean_ms, double *min_ms, int *n_launches);
 int sb_synchronize(sb_solver *h);
 
 #ifdef __cplusplus

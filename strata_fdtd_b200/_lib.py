@@ -74,7 +74,7 @@ class Stats(C.Structure):
 
 
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_TMA = 0, 1, 2, 3
-OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH = range(6)
+OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH, OPT_PROFILE = range(7)
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _fp = C.POINTER(C.c_float)
@@ -108,6 +108,7 @@ SIGNATURES = {
     "sb_reset": (_i, [_vp]),
     "sb_set_option": (_i, [_vp, _i, _i]),
     "sb_query": (_i, [_vp, C.POINTER(Stats)]),
+    "sb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "sb_synchronize": (_i, [_vp]),
 }
 

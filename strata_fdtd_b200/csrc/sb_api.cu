@@ -80,6 +80,9 @@ struct sb_solver {
     long long steps_done = 0, kernels_launched = 0;
     int last_variant = 0;
     DBuf<double> d_energy;
+    // optional per-launch timing of the fused step kernel (SB_OPT_PROFILE)
+    int opt_profile = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
 };
 
 static void drop_graphs(sb_solver *h)
@@ -515,7 +518,13 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
         k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
         h->kernels_launched++;
     }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->opt_profile) {
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, h->stream);
+    }
     if (launch_step_kernel(h, P)) return 1;
+    if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.emplace_back(ev0, ev1); }
     if (h->have_ade) {
         const int nb = (h->ade.n_cells + 255) / 256;
         StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx;
@@ -556,7 +565,7 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     if (h->n_src_cells && !src_dev) return fail("source values required");
     if ((h->n_probes + h->n_mics) && !rec_dev) return fail("record buffer required");
     CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
-    if (h->opt_graph && n_steps > 1) {
+    if (h->opt_graph && n_steps > 1 && !h->opt_profile) {
         // graphs are keyed on (n_steps, starting set); pointers src_dev/rec_dev must be the internal staging buffers
         const bool internal = (src_dev == h->d_src_vals.p || !src_dev) && (rec_dev == h->d_record.p || !rec_dev);
         if (internal) {
@@ -671,6 +680,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
         case SB_OPT_CHUNK_I: if (value < 0) return fail("chunk_i must be >= 0"); h->opt_chunk_i = value; break;
         case SB_OPT_USE_GRAPH: h->opt_graph = value ? 1 : 0; break;
+        case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
         default: return fail("unknown option %d", option);
     }
     drop_graphs(h);
@@ -693,6 +703,23 @@ extern "C" int sb_query(sb_solver *h, sb_stats *out)
     out->algorithmic_bytes_per_cell = b;
     out->kernel_variant = h->last_variant;
     out->pitch = h->d.pitch;
+    return 0;
+}
+
+extern "C" int sb_profile_read(sb_solver *h, double *mean_ms, double *min_ms, int *n_launches)
+{
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    double sum = 0.0, mn = 1e300; int n = 0;
+    for (auto &pr : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { sum += ms; mn = std::min(mn, (double)ms); n++; }
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    h->prof.clear();
+    if (mean_ms) *mean_ms = n ? sum / n : 0.0;
+    if (min_ms) *min_ms = n ? mn : 0.0;
+    if (n_launches) *n_launches = n;
     return 0;
 }
 

@@ -125,7 +125,7 @@ class ResultWriter:
             for name, probe in s._probes.items():
                 self._attr(f"probes/{name}", "position", list(probe.position))
                 self._attr(f"probes/{name}", "units", "Pa")
-        self._dataset("materials/geometry", s._geometry.astype(np.uint8))
+        self._dataset("materials/geometry", np.asarray(s.geometry).astype(np.uint8))
 
     def _dataset(self, name: str, data):
         if self.use_h5:

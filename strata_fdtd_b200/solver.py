@@ -49,10 +49,12 @@ class _DeviceState:
         self.desc.pitch = pitch.value
         self.pitch = pitch.value
         with torch.cuda.device(self.index):
-            self.stream = torch.cuda.current_stream()
+            # a dedicated non-default stream: the legacy default stream cannot be captured into CUDA graphs
+            self.stream = torch.cuda.Stream(device=self.device)
             # two ping-pong sets of {p, vx, vy, vz}; planes -1 and nx are the slab ghosts
             self.sets = [[torch.zeros((nx + 2, ny, self.pitch), dtype=torch.float32, device=self.device)
                           for _ in range(4)] for _ in range(2)]
+            torch.cuda.synchronize(self.device)
             handle = C.c_void_p()
             _lib.check(self.lib.sb_create(C.byref(self.desc), self.index, C.c_void_p(self.stream.cuda_stream),
                                           C.byref(handle)))
@@ -87,18 +89,27 @@ class FDTDSolver:
 
     def __init__(self, shape=None, resolution=None, grid=None, c: float = 343.0, rho: float = 1.2,
                  courant: float = 0.95, backend: str = "b200", warn_energy_drift: bool = False,
-                 energy_drift_threshold: float = 0.01, device: int | None = None, chunk_steps: int = 256):
+                 energy_drift_threshold: float = 0.01, device: int | None = None, chunk_steps: int = 256,
+                 slab: tuple[int, int] | None = None):
         if backend not in ("b200", "auto"):
             raise ValueError(f"strata_fdtd_b200 provides backend='b200' only (got {backend!r}); "
                              "use the reference package for 'native' / 'python'")
         if grid is not None:
             self._grid = grid
-            self.shape = tuple(grid.shape)
+            self.global_shape = tuple(int(n) for n in grid.shape)
         elif shape is not None and resolution is not None:
             self._grid = UniformGrid(shape=shape, resolution=resolution)
-            self.shape = tuple(int(n) for n in shape)
+            self.global_shape = tuple(int(n) for n in shape)
         else:
             raise ValueError("Must provide either 'grid' or both 'shape' and 'resolution'")
+        # A slab [i0, i1) of the grid along axis 0 (multi-GPU decomposition); the default is the whole grid.
+        # Everything the caller passes (positions, geometry) is global; storage and kernels are local.
+        self._i0, self._i1 = (0, self.global_shape[0]) if slab is None else (int(slab[0]), int(slab[1]))
+        if not 0 <= self._i0 < self._i1 <= self.global_shape[0]:
+            raise ValueError(f"bad slab range {slab} for nx={self.global_shape[0]}")
+        self._has_lower = int(self._i0 > 0)
+        self._has_upper = int(self._i1 < self.global_shape[0])
+        self.shape = (self._i1 - self._i0, self.global_shape[1], self.global_shape[2])
         self.dx = self._grid.min_spacing
         self.c, self.rho = c, rho
         self.backend = "b200"
@@ -115,7 +126,7 @@ class FDTDSolver:
         self._host = {f: np.zeros(self.shape, dtype=np.float32) for f in _FIELDS}
         self._host_stale: set[str] = set()     # device holds newer data
         self._host_dirty: set[str] = set()     # host may hold newer data (array was handed out)
-        self._geometry = np.ones(self.shape, dtype=bool)
+        self._geometry = None                  # None = all air; materialised on first access
         self._rigid = False                    # face zeroing only after set_geometry (solver.py:1779-1780)
 
         self._sources: list = []
@@ -135,6 +146,8 @@ class FDTDSolver:
         self._energy_sample_interval = 1
         self._materials: dict = {}
         self._material_id = np.zeros(self.shape, dtype=np.uint8)
+        self._local_probes: list = []
+        self._geometry_ext = None
 
         self._device_index = device
         self._chunk_steps = int(chunk_steps)
@@ -178,15 +191,33 @@ class FDTDSolver:
 
     @property
     def geometry(self):
+        if self._geometry is None:
+            self._geometry_ext = np.ones((self.shape[0] + self._has_lower + self._has_upper,) + self.shape[1:], dtype=bool)
+            self._geometry = self._geometry_ext[self._has_lower: self._has_lower + self.shape[0]]
         self._dirty |= {"geometry", "sources"}  # may be edited in place by the caller
         return self._geometry
 
     @geometry.setter
     def geometry(self, value):
-        value = np.asarray(value)
-        if value.shape != self.shape:
-            raise ValueError(f"Geometry shape {value.shape} doesn't match solver shape {self.shape}")
-        self._geometry = value.astype(bool)
+        self._store_geometry(value)
+
+    def _store_geometry(self, mask) -> None:
+        """Keep the owned planes (``_geometry``) and, on a slab, the live ghost planes next to them
+        (``_geometry_ext``: the rigid-face test of the first/last owned plane looks across the cut).
+        ``mask`` is a global array or, for grids too large to materialise, ``f(i_lo, i_hi) -> bool planes``."""
+        lo, hi = self._i0 - self._has_lower, self._i1 + self._has_upper
+        if callable(mask):
+            ext = np.asarray(mask(lo, hi))
+            want = (hi - lo,) + self.global_shape[1:]
+            if ext.shape != want:
+                raise ValueError(f"Geometry shape {ext.shape} doesn't match solver shape {want}")
+        else:
+            mask = np.asarray(mask)
+            if mask.shape != self.global_shape:
+                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.global_shape}")
+            ext = mask[lo:hi]
+        self._geometry_ext = np.ascontiguousarray(ext.astype(bool))
+        self._geometry = self._geometry_ext[self._has_lower: self._has_lower + self.shape[0]]
         self._dirty |= {"geometry", "sources"}
 
     # ------------------------------------------------------------------ set-up API
@@ -194,9 +225,7 @@ class FDTDSolver:
         """bool array (True = air), an SDF primitive, or a MaterializedGeometry (solver.py:1682-1780)."""
         if hasattr(geometry, "voxelize_with_materials"):
             mask, ids = geometry.voxelize_with_materials(self.grid)
-            if mask.shape != self.shape:
-                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.shape}")
-            self._geometry = np.ascontiguousarray(mask, dtype=bool)
+            self._store_geometry(mask)
             for mat_id, material in geometry.get_material_table().items():
                 if mat_id == 0:
                     continue
@@ -206,25 +235,20 @@ class FDTDSolver:
                 if np.any(region):
                     self.set_material_region(region, material_id=mat_id)
         elif hasattr(geometry, "voxelize"):
-            mask = geometry.voxelize(self.grid)
-            if mask.shape != self.shape:
-                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.shape}")
-            self._geometry = np.ascontiguousarray(mask, dtype=bool)
+            self._store_geometry(geometry.voxelize(self.grid))
             self._material_id.fill(0)
             self._dirty.add("ade")
         else:
-            mask = np.asarray(geometry)
-            if mask.shape != self.shape:
-                raise ValueError(f"Geometry shape {mask.shape} doesn't match solver shape {self.shape}")
-            self._geometry = np.ascontiguousarray(mask.astype(bool))
+            self._store_geometry(geometry)
         self._rigid = True
         self._dirty |= {"geometry", "sources"}
 
     def _to_index(self, pos, what: str):
         """metres -> int(round(pos/dx)) when any entry is a float below max(shape) (solver.py:1818-1839)."""
-        if isinstance(pos, tuple) and len(pos) == 3 and any(isinstance(q, float) and q < max(self.shape) for q in pos):
+        gs = self.global_shape
+        if isinstance(pos, tuple) and len(pos) == 3 and any(isinstance(q, float) and q < max(gs) for q in pos):
             idx = tuple(int(round(q / self.dx)) for q in pos)
-            for a, (i, n) in enumerate(zip(idx, self.shape)):
+            for a, (i, n) in enumerate(zip(idx, gs)):
                 if not 0 <= i < n:
                     raise ValueError(f"{what} {'xyz'[a]} position {pos[a]:.4f}m (index {i}) is outside grid (0-{n-1})")
             return idx
@@ -315,10 +339,10 @@ class FDTDSolver:
 
     def _ensure_device(self) -> _DeviceState:
         if self._dev is None:
-            self._dev = _DeviceState(self.shape, self._device_index)
+            self._dev = _DeviceState(self.shape, self._device_index,
+                                     slab=(self._has_lower, self._has_upper, self.global_shape[0], self._i0))
             for opt, val in self._options.items():
                 _lib.check(self._dev.lib.sb_set_option(self._dev.handle, opt, val))
-            self._host_dirty = set(_FIELDS)
         return self._dev
 
     def _download(self, name: str) -> None:
@@ -328,36 +352,52 @@ class FDTDSolver:
 
     def _coefficient_tables(self):
         """fp32 per-face velocity coefficients and per-cell inverse spacings (see strata_b200.h)."""
-        nx, ny, nz = self.shape
+        nx, ny, nz = self.global_shape
         if self._grid.is_uniform:
             cv = np.float32(self._coeff_v)
-            return [np.full(n, cv, dtype=np.float32) for n in (nx, ny, nz)], [None] * 3, np.float32(self._coeff_p)
-        sa = self._spacing_arrays
-        cvb = np.float32(self._coeff_v_base)
-        faces = []
-        for a, n in zip("xyz", (nx, ny, nz)):
-            t = np.zeros(n, dtype=np.float32)
-            t[: n - 1] = cvb * sa[f"inv_d{a}_face"]          # one rounded fp32 multiply (fdtd_step.cpp:263)
-            faces.append(t)
-        cells = [np.ascontiguousarray(sa[f"inv_d{a}_cell"], dtype=np.float32) for a in "xyz"]
-        return faces, cells, np.float32(self._coeff_p_base)
+            faces = [np.full(n, cv, dtype=np.float32) for n in (nx, ny, nz)]
+            cells, cp = [None] * 3, np.float32(self._coeff_p)
+        else:
+            sa = self._spacing_arrays
+            cvb = np.float32(self._coeff_v_base)
+            faces = []
+            for a, n in zip("xyz", (nx, ny, nz)):
+                t = np.zeros(n, dtype=np.float32)
+                t[: n - 1] = cvb * sa[f"inv_d{a}_face"]      # one rounded fp32 multiply (fdtd_step.cpp:263)
+                faces.append(t)
+            cells = [np.ascontiguousarray(sa[f"inv_d{a}_cell"], dtype=np.float32) for a in "xyz"]
+            cp = np.float32(self._coeff_p_base)
+        faces[0] = self._x_slice(faces[0])
+        if cells[0] is not None:
+            cells[0] = self._x_slice(cells[0])
+        return faces, cells, cp
+
+    def _x_slice(self, table):
+        """Axis-0 table restricted to this slab's planes, live lower ghost first (see strata_b200.h)."""
+        return np.ascontiguousarray(table[self._i0 - self._has_lower: self._i1])
 
     def _build_source_table(self):
         """CSR over cells: (cell, [source id, field, weight]...) in source order (solver.py:2386-2433)."""
         nx, ny, nz = self.shape
         cells, sids, flds, wts = [], [], [], []
-        g = self._geometry
+        g = self._geometry if self._geometry is not None else np.broadcast_to(np.True_, self.shape)
         for sid, src in enumerate(self._sources):
             kind = getattr(src, "source_type", "point")
             if kind == "point":
                 i, j, k = src.position
-                if g[i, j, k]:
+                i -= self._i0                                  # local plane; other slabs own the rest
+                if 0 <= i < nx and g[i, j, k]:
                     cells.append(np.array([(i * ny + j) * nz + k], dtype=np.int64))
                     wts.append(np.ones(1)); flds.append(np.zeros(1, dtype=np.int32))
                     sids.append(np.full(1, sid, dtype=np.int32))
             elif kind == "plane":
                 sel = [slice(None)] * 3
-                sel[src.position["axis"]] = src.position["index"]
+                axis, index = src.position["axis"], src.position["index"]
+                if axis == 0:
+                    index -= self._i0
+                    if not 0 <= index < nx:
+                        continue
+                sel[axis] = index
                 m = np.zeros(self.shape, dtype=bool)
                 m[tuple(sel)] = g[tuple(sel)]
                 idx = np.flatnonzero(m)
@@ -368,10 +408,10 @@ class FDTDSolver:
                     src._check_grid_alignment(self._grid)
                     src._cached_weights = src.get_injection_weights(self._grid)
                     src._cached_mask = src._cached_weights > 0
-                m = src._cached_mask & g
+                m = src._cached_mask[self._i0:self._i1] & g
                 idx = np.flatnonzero(m)
                 fld = 0 if src.injection_type == "pressure" else 1 + "xyz".index(src.normal_axis)
-                cells.append(idx); wts.append(np.asarray(src._cached_weights, dtype=np.float64)[m])
+                cells.append(idx); wts.append(np.asarray(src._cached_weights, dtype=np.float64)[self._i0:self._i1][m])
                 flds.append(np.full(idx.size, fld, dtype=np.int32)); sids.append(np.full(idx.size, sid, dtype=np.int32))
             else:
                 raise ValueError(f"unknown source_type {kind!r}")
@@ -414,23 +454,30 @@ class FDTDSolver:
             _lib.check(lib.sb_set_coefficients(h, *(_lib.ptr(t) for t in faces), *(_lib.ptr(t) for t in cells),
                                                float(cp)))
         if "geometry" in self._dirty:
-            g = np.ascontiguousarray(self._geometry, dtype=np.uint8)
-            _lib.check(lib.sb_set_geometry(h, _lib.ptr(g), int(self._rigid)))
+            if self._geometry is None:
+                _lib.check(lib.sb_set_geometry(h, None, 0))
+            else:
+                g = np.ascontiguousarray(self._geometry_ext, dtype=np.uint8)   # owned planes + live ghosts
+                _lib.check(lib.sb_set_geometry(h, _lib.ptr(g), int(self._rigid)))
         if "sponges" in self._dirty:
             _lib.check(lib.sb_clear_sponges(h))
             for b in self._boundaries:                       # application order = list order (solver.py:2044-2047)
                 tabs = sponge_tables(b, self)
                 if tabs is not None:
+                    tabs = (None if tabs[0] is None else self._x_slice(tabs[0]), tabs[1], tabs[2])
                     _lib.check(lib.sb_add_sponge(h, *(_lib.ptr(t) for t in tabs)))
         if "sources" in self._dirty:
             cells, start, sids, flds, wts = self._build_source_table()
             _lib.check(lib.sb_set_sources(h, len(self._sources), len(cells), _lib.ptr(cells), _lib.ptr(start),
                                           _lib.ptr(sids), _lib.ptr(flds), _lib.ptr(wts)))
         if "records" in self._dirty:
-            flat = np.array([(i * ny + j) * nz + k for (i, j, k) in (pr.position for pr in self._probes.values())],
-                            dtype=np.int64)
+            self._local_probes = [pr for pr in self._probes.values() if self._i0 <= pr.position[0] < self._i1]
+            flat = np.array([((i - self._i0) * ny + j) * nz + k
+                             for (i, j, k) in (pr.position for pr in self._local_probes)], dtype=np.int64)
             _lib.check(lib.sb_set_probes(h, len(flat), _lib.ptr(flat) if len(flat) else None))
             mics = list(self._microphones.values())
+            if mics and (self._has_lower or self._has_upper):
+                raise NotImplementedError("microphones on decomposed slabs are not supported yet")
             if mics:
                 gp = np.array([q for m in mics for q in m._grid_position], dtype=np.float32)   # fp32 store, solver.py:2502-2509
                 idx8 = np.zeros(8 * len(mics), dtype=np.int64)
@@ -477,9 +524,9 @@ class FDTDSolver:
     def _advance(self, n_steps: int, callback=None, writer=None, snapshot_interval=None) -> None:
         dev = self._sync_to_device()
         lib, h = dev.lib, dev.handle
-        n_rec = len(self._probes) + len(self._microphones)
-        probes = list(self._probes.values())
+        probes = self._local_probes
         mics = list(self._microphones.values())
+        n_rec = len(probes) + len(mics)
         done = 0
         while done < n_steps:
             m = min(self._chunk_steps, n_steps - done)

@@ -29,9 +29,9 @@ def time_steps(s, n_steps, reps=3):
     best = 1e30
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(dev.stream)
         _lib.check(lib.sb_step_n_async(h, n_steps, src.data_ptr(), rec.data_ptr()))
-        e1.record()
+        e1.record(dev.stream)
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / n_steps)
     return best
