@@ -63,6 +63,11 @@ def workload_case(name: str, n_gpus: int) -> tuple[dict, str]:
         return c2_case(200, steps=0), "c2_200: 200^3 uniform 1 mm, PML(10), 1 point source, 1 probe"
     if name == "c1_100":
         return c1_case(0), "c1_100: 100^3 uniform 1 mm, PML(10), 1 kHz pulse, 1 probe"
+    if name == "c4_enclosure":
+        from cases import c4_case
+        return (c4_case((1024, 512, 512), steps=0, materialise=False),
+                "c4_enclosure: 1024x512x512 nonuniform (axis 0 stretched 1.002 from the centre), ported-enclosure "
+                f"rigid masks, PML(10), 1 source, 8 probes ({n_gpus} slab(s), strong scaling)")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -179,16 +184,8 @@ def run_b200_arm(a):
         s = build_b200_solver(case, device=local_rank, chunk_steps=max(K, W))
         slab, drv = s, None
     else:
-        from strata_fdtd_b200 import GaussianPulse, PML
-        from strata_fdtd_b200.multi import DistributedFDTDSolver
-        drv = DistributedFDTDSolver(shape=case["shape"], resolution=case["resolution"], device=local_rank,
-                                    chunk_steps=max(K, W))
-        for b in case["pml"]:
-            drv.add_boundary(PML(depth=b["depth"]))
-        for src in case["sources"]:
-            drv.add_source(GaussianPulse(position=src["position"], frequency=src["frequency"]))
-        for name, pos in case["probes"]:
-            drv.add_probe(name, pos)
+        from util import build_distributed_solver
+        drv = build_distributed_solver(case, device=local_rank, chunk_steps=max(K, W))
         slab = drv.slab
     for opt, val in ((_lib.OPT_ROWS_PER_THREAD, a.rows), (_lib.OPT_WARPS_J, a.warps_j), (_lib.OPT_WARPS_K, a.warps_k),
                      (_lib.OPT_CHUNK_I, a.chunk_i)):
@@ -276,7 +273,8 @@ def run_b200_arm(a):
         traffic_file = ROOT / "profiles" / "k1_dram_traffic.json"
         traffic = json.loads(traffic_file.read_text()).get(a.workload) if traffic_file.exists() else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dev_ms / K, "higher_is_better": True,
+                "scaling": "weak" if a.workload == "c5_weak" else "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": label, "cells_per_gpu": cells_rank, "l2_policy": "fields (34 GB/GPU) >> L2, no flush needed"
                            if a.workload == "c5_weak" else "inputs larger than L2 for >=200^3; small grids are L2-resident by nature",

@@ -113,6 +113,33 @@ def main():
     for name, case in make_cases().items():
         run_case(name, case, out_dir)
     run_case("c1_100cubed_1000", c1_case(1000), out_dir)
+    run_membrane_case(out_dir)
+
+
+def run_membrane_case(out_dir: Path):
+    """Membrane sources (solver.py:210-755, injection :2389-2412) through the reference's own classes.
+    The injection-weight arrays they produce are stored too, so the case can be rebuilt without the reference."""
+    from cases import MEMBRANE_SPEC, membrane_case
+    import numpy as _np
+    placeholder = [_np.zeros(MEMBRANE_SPEC["shape"]) for _ in MEMBRANE_SPEC["membranes"]]
+    case = membrane_case(placeholder)
+    s = R.build_reference_solver(case)
+    for _ in range(case["steps"]):
+        s.step()
+    out = {"dt": np.float64(s.dt), "steps": np.int64(case["steps"])}
+    for q, src in enumerate(s._sources):
+        w = np.asarray(src._cached_weights, dtype=np.float64)
+        nz_idx = np.flatnonzero(w)
+        out[f"weights_idx_{q}"] = nz_idx.astype(np.int64)
+        out[f"weights_val_{q}"] = w.ravel()[nz_idx]
+    for pname, probe in s._probes.items():
+        out["probe_" + pname] = probe.get_data()
+    for f in ("p", "vx", "vy", "vz"):
+        out["sha_" + f] = np.array(digest(getattr(s, f)))
+        out["final_" + f] = getattr(s, f)
+    np.savez_compressed(out_dir / "membranes.npz", **out)
+    print(f"membranes: |p|max={float(np.abs(s.p).max()):.3e} nnz weights "
+          f"{[int(len(out[f'weights_idx_{q}'])) for q in range(len(s._sources))]}")
 
 
 if __name__ == "__main__":

@@ -332,6 +332,13 @@ class OracleSolver:
                 view = self.p[tuple(sl)]
                 m = self.geometry[tuple(sl)]
                 view[m] = (view[m].astype(np.float64) + w).astype(np.float32)
+            elif kind == "weighted":
+                # membrane sources, solver.py:2389-2412: field[mask] += w * weights[mask], mask = weights>0 & air,
+                # float64 product and sum, float32 store
+                wt = np.asarray(s["weights"], dtype=np.float64)
+                m = (wt > 0) & self.geometry
+                fld = getattr(self, s.get("field", "p"))
+                fld[m] = (fld[m].astype(np.float64) + w * wt[m]).astype(np.float32)
             else:
                 raise ValueError(kind)
 

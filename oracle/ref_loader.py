@@ -105,6 +105,9 @@ def build_reference_solver(case: dict):
                            max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
     for src in case.get("sources", []):
         kind = src.get("kind", "point")
+        if kind == "weighted":
+            s.add_source(_reference_membrane(src["spec"]))
+            continue
         pos = src["position"] if kind == "point" else {"axis": src["axis"], "index": src["index"]}
         s.add_source(GaussianPulse(position=pos, frequency=src["frequency"], bandwidth=src.get("bandwidth"),
                                    amplitude=src.get("amplitude", 1.0), source_type=kind))
@@ -115,6 +118,17 @@ def build_reference_solver(case: dict):
     if case.get("materials"):
         _install_fixed_native_ade(s, case)
     return s
+
+
+def _reference_membrane(m: dict):
+    """The reference's own membrane source object for a tests/cases.py MEMBRANE_SPEC entry."""
+    from strata_fdtd.core.solver import CircularMembraneSource, GaussianPulse, RectangularMembraneSource
+    wf = GaussianPulse(position=(0, 0, 0), frequency=m["frequency"], amplitude=m["amplitude"])
+    if m["shape"] == "circular":
+        return CircularMembraneSource(center=m["center"], radius=m["radius"], normal_axis=m["normal_axis"],
+                                      waveform=wf, mode=tuple(m["mode"]), injection_type=m["injection_type"])
+    return RectangularMembraneSource(center=m["center"], size=tuple(m["size"]), normal_axis=m["normal_axis"],
+                                     waveform=wf, mode=tuple(m["mode"]), injection_type=m["injection_type"])
 
 
 def _install_fixed_native_ade(s, case: dict):

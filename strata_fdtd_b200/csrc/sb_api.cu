@@ -73,7 +73,7 @@ struct sb_solver {
     AdeTable ade{};
     DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat; DBuf<float> ade_J, ade_Jp;
     // options
-    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 2, opt_wj = 8, opt_wk = 1, opt_chunk_i = 0, opt_graph = 0;
+    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 2, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
     // graph cache: key = (n_steps, starting set)
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
     // stats
@@ -483,7 +483,13 @@ static int launch_step_kernel(sb_solver *h, StepParams &P)
         if (P.mask) k0_step_naive<true><<<grd, blk, 0, h->stream>>>(P);
         else        k0_step_naive<false><<<grd, blk, 0, h->stream>>>(P);
     } else {
-        const int rj = h->opt_rj, wj = h->opt_wj, wk = h->opt_wk;
+        const int rj = h->opt_rj, wk = h->opt_wk;
+        int wj = h->opt_wj;
+        if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
+            wj = std::max(1, 8 / wk);
+            while (wj > 1 && (long long)((d.nz + 128 * wk - 1) / (128 * wk)) * ((d.ny + rj * wj - 1) / (rj * wj)) *
+                                 ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
+        }
         if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
         const int gx = (d.nz + 128 * wk - 1) / (128 * wk), gy = (d.ny + rj * wj - 1) / (rj * wj);
         int chunk = h->opt_chunk_i;
@@ -565,7 +571,9 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     if (h->n_src_cells && !src_dev) return fail("source values required");
     if ((h->n_probes + h->n_mics) && !rec_dev) return fail("record buffer required");
     CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
-    if (h->opt_graph && n_steps > 1 && !h->opt_profile) {
+    const bool want_graph = h->opt_graph == 1 ||
+        (h->opt_graph < 0 && n_steps >= 4 && (long long)h->d.nx * h->d.ny * h->d.nz <= (32LL << 20));
+    if (want_graph && n_steps > 1 && !h->opt_profile) {
         // graphs are keyed on (n_steps, starting set); pointers src_dev/rec_dev must be the internal staging buffers
         const bool internal = (src_dev == h->d_src_vals.p || !src_dev) && (rec_dev == h->d_record.p || !rec_dev);
         if (internal) {
@@ -610,8 +618,10 @@ extern "C" int sb_step_n(sb_solver *h, int n_steps, const double *src_host, floa
     if (n_steps <= 0) return n_steps == 0 ? 0 : fail("negative step count");
     const int n_rec = h->n_probes + h->n_mics;
     if (h->n_sources && h->n_src_cells && !src_host) return fail("source values required");
+    const void *old_src = h->d_src_vals.p, *old_rec = h->d_record.p;
     if (h->d_src_vals.alloc((size_t)std::max(1, n_steps * std::max(1, h->n_sources)))) return 1;
     if (h->d_record.alloc((size_t)std::max(1, n_steps * std::max(1, n_rec)))) return 1;
+    if (old_src != h->d_src_vals.p || old_rec != h->d_record.p) drop_graphs(h);   // cached graphs hold these pointers
     if (h->n_sources && src_host)
         CU(cudaMemcpyAsync(h->d_src_vals.p, src_host, (size_t)n_steps * h->n_sources * sizeof(double),
                            cudaMemcpyHostToDevice, h->stream));
@@ -676,10 +686,10 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
     switch (option) {
         case SB_OPT_KERNEL: if (value < 0 || value > 3) return fail("bad kernel variant"); h->opt_kernel = value; break;
         case SB_OPT_ROWS_PER_THREAD: if (value != 1 && value != 2 && value != 4) return fail("rows_per_thread must be 1, 2 or 4"); h->opt_rj = value; break;
-        case SB_OPT_WARPS_J: if (value < 1 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
+        case SB_OPT_WARPS_J: if (value < 0 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
         case SB_OPT_CHUNK_I: if (value < 0) return fail("chunk_i must be >= 0"); h->opt_chunk_i = value; break;
-        case SB_OPT_USE_GRAPH: h->opt_graph = value ? 1 : 0; break;
+        case SB_OPT_USE_GRAPH: h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); break;
         case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
         default: return fail("unknown option %d", option);
     }

@@ -109,6 +109,14 @@ __device__ __forceinline__ float4 mul4s(float4 a, float s) { return make_float4(
 __device__ __forceinline__ float4 sel4(bool cx, bool cy, bool cz, bool cw, float4 a, float4 b)
 { return make_float4(cx ? a.x : b.x, cy ? a.y : b.y, cz ? a.z : b.z, cw ? a.w : b.w); }
 
+// keep element e of v iff byte e of the packed mask word has `bit` set, else +0.0f (boundaries.cpp:66-89)
+__device__ __forceinline__ float4 keep4(float4 v, unsigned w, unsigned bit)
+{
+    return make_float4((w & bit) ? v.x : 0.0f, (w & (bit << 8)) ? v.y : 0.0f,
+                       (w & (bit << 16)) ? v.z : 0.0f, (w & (bit << 24)) ? v.w : 0.0f);
+}
+constexpr unsigned ALL_OPEN = 0x0F0F0F0Fu;      // four cells: air, all three faces open
+
 template <int RJ, bool GEOM>
 __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
 {
@@ -165,10 +173,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             if (have_prev && row_ok[r + 1] && lane_ok) {
                 const long long cm = base - P.plane + (long long)r * P.pitch;
                 v = add4(ld4(P.vx_in + cm), mul4s(sub4(pc[r + 1], ld4(P.p_in + cm)), cx));
-                if (GEOM) {
-                    const uchar4 m = *reinterpret_cast<const uchar4 *>(P.mask + cm);
-                    v = sel4(m.x & M_XOPEN, m.y & M_XOPEN, m.z & M_XOPEN, m.w & M_XOPEN, v, z4);
-                }
+                if (GEOM) v = keep4(v, *reinterpret_cast<const unsigned *>(P.mask + cm), M_XOPEN);
                 if (ib == 0) {                                   // maintain the lower ghost plane of vx
                     float4 o = v;
                     for (int s = 0; s < P.n_sponge; s++) o = mul4s(o, P.decx[s][-1]);
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
 
         // loads (all issued before use)
         float4 pn[RJ], vx[RJ], vy[RJ + 1], vz[RJ];
-        uchar4 mk[RJ + 1];
+        unsigned mk[RJ + 1];
         float p_hi[RJ], p_lo[RJ], vz_lo[RJ];
         uint8_t m_lo[RJ];
 #pragma unroll
@@ -202,14 +207,24 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             p_hi[r] = (edge_hi && row_ok[r + 1]) ? P.p_in[c + 4] : 0.0f;
             p_lo[r] = (edge_lo && row_ok[r + 1]) ? P.p_in[c - 1] : 0.0f;
             vz_lo[r] = (edge_lo && row_ok[r + 1]) ? P.vz_in[c - 1] : 0.0f;
-            if (GEOM) m_lo[r] = (edge_lo && row_ok[r + 1]) ? P.mask[c - 1] : (uint8_t)0;
+            if (GEOM) m_lo[r] = (edge_lo && row_ok[r + 1]) ? P.mask[c - 1] : (uint8_t)0x0F;
         }
 #pragma unroll
         for (int r = -1; r < RJ; r++) {
             const bool ok = row_ok[r + 1] && lane_ok;
             const long long c = base + (long long)r * P.pitch;
             vy[r + 1] = ok ? ld4(P.vy_in + c) : z4;
-            if (GEOM) mk[r + 1] = ok ? *reinterpret_cast<const uchar4 *>(P.mask + c) : make_uchar4(0, 0, 0, 0);
+            if (GEOM) mk[r + 1] = ok ? *reinterpret_cast<const unsigned *>(P.mask + c) : ALL_OPEN;
+        }
+        // warp-uniform fast path: nothing solid or rigid in this warp's cells of this plane
+        bool masked = false;
+        if (GEOM) {
+            bool open = true;
+#pragma unroll
+            for (int r = -1; r < RJ; r++) open = open && (mk[r + 1] == ALL_OPEN);
+#pragma unroll
+            for (int r = 0; r < RJ; r++) open = open && (m_lo[r] == 0x0F);
+            masked = !__all_sync(FULL, open);
         }
         pc[0] = (row_ok[0] && lane_ok) ? ld4(P.p_in + base - P.pitch) : z4;
         pc[RJ + 1] = (row_ok[RJ + 1] && lane_ok) ? ld4(P.p_in + base + (long long)RJ * P.pitch) : z4;
@@ -221,10 +236,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             float4 v = vy[r + 1];
             if (row_ok[r + 1] && (j0 + r < ny - 1)) {
                 v = add4(v, mul4s(sub4(pc[r + 2], pc[r + 1]), cvy[r + 1]));
-                if (GEOM) {
-                    const uchar4 m = mk[r + 1];
-                    v = sel4(m.x & M_YOPEN, m.y & M_YOPEN, m.z & M_YOPEN, m.w & M_YOPEN, v, z4);
-                }
+                if (GEOM && masked) v = keep4(v, mk[r + 1], M_YOPEN);
             }
             vyn[r + 1] = v;                                      // row -1 outside the grid stays 0
         }
@@ -236,10 +248,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             float4 vxn = vx[r];
             if (upd_x) {
                 vxn = add4(vxn, mul4s(sub4(pn[r], p), cx));
-                if (GEOM) {
-                    const uchar4 m = mk[r + 1];
-                    vxn = sel4(m.x & M_XOPEN, m.y & M_XOPEN, m.z & M_XOPEN, m.w & M_XOPEN, vxn, z4);
-                }
+                if (GEOM && masked) vxn = keep4(vxn, mk[r + 1], M_XOPEN);
             }
             // z faces: p[k+1] from the next lane (or the next strip)
             float p_next = __shfl_down_sync(FULL, p.x, 1);
@@ -249,10 +258,10 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             {
                 const float4 upd = add4(vzn, mul4(sub4(pk1, p), cvz4));
                 vzn = sel4(u0, u1, u2, u3, upd, vzn);
-                if (GEOM) {
-                    const uchar4 m = mk[r + 1];
-                    vzn = sel4(!u0 || (m.x & M_ZOPEN), !u1 || (m.y & M_ZOPEN), !u2 || (m.z & M_ZOPEN),
-                               !u3 || (m.w & M_ZOPEN), vzn, z4);
+                if (GEOM && masked) {      // only updated faces are zeroed; the last face keeps its value
+                    const unsigned m = mk[r + 1] | (u0 ? 0u : 0x08u) | (u1 ? 0u : 0x0800u) | (u2 ? 0u : 0x080000u) |
+                                       (u3 ? 0u : 0x08000000u);
+                    vzn = keep4(vzn, m, M_ZOPEN);
                 }
             }
             // z face k0-1: previous lane's .w, or recomputed from the previous strip's values
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
                 vz_prev = 0.0f;
                 if (edge_lo) {
                     vz_prev = vz_lo[r] + cvz_lo * (p.x - p_lo[r]);
-                    if (GEOM && !(m_lo[r] & M_ZOPEN)) vz_prev = 0.0f;
+                    if (GEOM && masked && !(m_lo[r] & M_ZOPEN)) vz_prev = 0.0f;
                 }
             }
             const float4 vzm = make_float4(vz_prev, vzn.x, vzn.y, vzn.z);
@@ -271,10 +280,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             float4 ddz = sub4(vzn, vzm);
             if (P.icx) { ddx = mul4s(ddx, icx); ddy = mul4s(ddy, icy[r]); ddz = mul4(ddz, icz4); }
             float4 pnew = add4(p, mul4s(add4(add4(ddx, ddy), ddz), P.cp));
-            if (GEOM) {
-                const uchar4 m = mk[r + 1];
-                pnew = sel4(m.x & M_AIR, m.y & M_AIR, m.z & M_AIR, m.w & M_AIR, pnew, z4);
-            }
+            if (GEOM && masked) pnew = keep4(pnew, mk[r + 1], M_AIR);
             // sponge
             float4 ox = vxn, oy = vyn[r + 1], oz = vzn;
             if (P.n_sponge > 0) {

@@ -126,6 +126,89 @@ def make_cases() -> dict:
     return C
 
 
+MEMBRANE_SPEC = dict(
+    shape=(28, 24, 26), resolution=1e-3, steps=220,
+    geometry_block=((12, 0, 0), (16, 6, 26)),
+    pml=[dict(depth=4)],
+    membranes=[
+        dict(shape="circular", center=(0.020, 0.012, 0.008), radius=0.005, normal_axis="z", mode=(0, 1),
+             injection_type="pressure", frequency=18e3, amplitude=1.0),
+        dict(shape="rectangular", center=(0.006, 0.014, 0.016), size=(0.008, 0.006), normal_axis="x", mode=(1, 1),
+             injection_type="velocity", frequency=14e3, amplitude=1e-3),
+    ],
+    probes=[("a", (20, 12, 16)), ("b", (8, 14, 16)), ("c", (3, 3, 3))],
+)
+
+
+def membrane_case(weights: list) -> dict:
+    """The membrane case with the injection-weight arrays (taken from the reference via the fixture)."""
+    sp = MEMBRANE_SPEC
+    lo, hi = sp["geometry_block"]
+    srcs = []
+    for m, w in zip(sp["membranes"], weights):
+        fld = "p" if m["injection_type"] == "pressure" else "v" + m["normal_axis"]
+        srcs.append(dict(kind="weighted", weights=np.asarray(w, dtype=np.float64), field=fld, spec=m,
+                         frequency=m["frequency"], amplitude=m["amplitude"]))
+    return dict(shape=sp["shape"], resolution=sp["resolution"], steps=sp["steps"],
+                geometry=_block_geometry(sp["shape"], lo, hi), pml=sp["pml"], sources=srcs, probes=sp["probes"])
+
+
+def enclosure_air_mask(X, Y, Z, extent):
+    """Air mask (True = air) of a ported loudspeaker enclosure filling the central 60 % of the domain.
+
+    Own closed-form construction with the proportions of the reference's CSG example
+    (examples/sdf_csg/ported_enclosure.py:34-121: 200x200x300 mm box, 18 mm walls, 130 mm driver cut-out,
+    50 mm flared port through the front wall), evaluated at cell centres X, Y, Z (metres; any sub-range of
+    planes along X) so that slabs can voxelise only what they own.  Box axis = grid axis 0, front wall at low x.
+    """
+    Lx, Ly, Lz = extent
+    cx, cy, cz = Lx / 2, Ly / 2, Lz / 2
+    hx, hy, hz = 0.3 * Lx, 0.3 * Ly, 0.3 * Lz                    # half sizes of the outer box
+    t = 0.06 * 2 * min(hx, hy, hz)                               # wall thickness (18/300 of the smallest side)
+    x = np.asarray(X)[:, None, None]; y = np.asarray(Y)[None, :, None]; z = np.asarray(Z)[None, None, :]
+    outer = (np.abs(x - cx) <= hx) & (np.abs(y - cy) <= hy) & (np.abs(z - cz) <= hz)
+    inner = (np.abs(x - cx) < hx - t) & (np.abs(y - cy) < hy - t) & (np.abs(z - cz) < hz - t)
+    solid = outer & ~inner
+    depth = x - (cx - hx)                                        # distance behind the front face
+    in_front_wall = (depth >= 0) & (depth <= t)
+    r_driver = 0.325 * 2 * hy
+    r2_d = (y - cy) ** 2 + (z - cz) ** 2
+    solid &= ~(in_front_wall & (r2_d < r_driver ** 2))
+    r_port = 0.125 * 2 * hy
+    flare = 1.5 * r_port - 0.5 * r_port * np.clip(depth / (1.6667 * t), 0.0, 1.0)   # 30 mm flare vs 18 mm wall
+    r2_p = (y - cy) ** 2 + (z - (cz + 0.6 * hz)) ** 2
+    solid &= ~(in_front_wall & (r2_p < flare ** 2))
+    return ~solid
+
+
+def c4_case(shape=(1024, 512, 512), steps: int = 1000, stretch_x: float = 1.002, materialise: bool = True) -> dict:
+    """BASELINE config 4: nonuniform grid (axis 0 stretched from the centre), ported-enclosure
+    rigid geometry, PML(10), source inside the box, 8 probes.  ``materialise=False`` returns the geometry as a
+    callable f(i_lo, i_hi) for grids too large to voxelise in one piece."""
+    from strata_fdtd_b200.grid import NonuniformGrid
+    g = NonuniformGrid.from_stretch(shape=shape, base_resolution=1e-3, stretch_x=stretch_x, center_fine=True)
+    extent = g.physical_extent()
+    X, Y, Z = g.x_coords, g.y_coords, g.z_coords
+
+    def geom(i_lo, i_hi, _chunk=16):
+        out = np.empty((i_hi - i_lo,) + tuple(shape[1:]), dtype=bool)
+        for a in range(i_lo, i_hi, _chunk):
+            b = min(a + _chunk, i_hi)
+            out[a - i_lo:b - i_lo] = enclosure_air_mask(X[a:b], Y, Z, extent)
+        return out
+
+    nx, ny, nz = shape
+    probes = [("in_centre", (nx // 2, ny // 2, nz // 2)), ("in_back", (int(0.72 * nx), ny // 2, nz // 2)),
+              ("in_corner", (int(0.3 * nx), int(0.3 * ny), int(0.3 * nz))),
+              ("driver_mouth", (int(0.19 * nx), ny // 2, nz // 2)), ("port_mouth", (int(0.19 * nx), ny // 2, int(0.68 * nz))),
+              ("front_far", (int(0.08 * nx), ny // 2, nz // 2)), ("side", (nx // 2, int(0.1 * ny), nz // 2)),
+              ("behind", (int(0.92 * nx), ny // 2, nz // 2))]
+    return dict(nonuniform=dict(x_coords=X, y_coords=Y, z_coords=Z), shape=tuple(shape), steps=steps,
+                geometry=geom(0, nx) if materialise else geom, pml=[dict(depth=10)],
+                sources=[dict(kind="point", position=(int(0.6 * nx), ny // 2, nz // 2), frequency=2000.0)],
+                probes=probes)
+
+
 def c1_case(steps: int = 1000) -> dict:
     """BASELINE config 1 as worded: 100^3, 1 mm, PML 10, 1 kHz Gaussian pulse, 1 probe."""
     return dict(shape=(100, 100, 100), resolution=1e-3, steps=steps, pml=[dict(depth=10)],

@@ -86,3 +86,17 @@ def test_ade_changes_the_answer():
     with_mat.run_steps(150); without.run_steps(150)
     a, b = with_mat.probe_array("behind"), without.probe_array("behind")
     assert np.abs(a - b).max() > 1e-3 * np.abs(b).max()
+
+
+def test_oracle_membrane_sources_match_reference_fixture():
+    """Pressure- and velocity-injecting membrane sources (solver.py:2389-2412) vs the reference's output."""
+    from util import load_membrane_case
+    case, g = load_membrane_case()
+    o = O.OracleSolver(case)
+    assert float(o.dt) == float(g["dt"])
+    o.run_steps(case["steps"])
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(getattr(o, f), g["final_" + f]), f
+    for n, _ in o.probes:
+        assert np.array_equal(o.probe_array(n), g["probe_" + n])
+    assert np.abs(g["probe_a"]).max() > 0 and np.abs(g["probe_b"]).max() > 0

@@ -140,3 +140,48 @@ def test_no_cuda_fallback_message():
     import strata_fdtd_b200 as sb
     with pytest.raises(ValueError):
         sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3, backend="python")
+
+
+def test_membrane_sources_pressure_and_velocity_injection():
+    """Weighted region sources into p and into vx (reference membranes) -- vs the reference fixture and the oracle."""
+    from util import load_membrane_case
+    case, g = load_membrane_case()
+    s = build_b200_solver(case, chunk_steps=50)
+    s.run(steps=case["steps"])
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(s.get_field(f), g["final_" + f]), f
+    for n in s._probes:
+        assert np.array_equal(s.get_probe_data(n)[n], g["probe_" + n])
+    o = O.OracleSolver(case); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, "membranes")
+
+
+def test_result_writer_and_callbacks(tmp_path):
+    """run(output_file=..., snapshot_interval=..., callback=...) -- traces in the file equal the probe data,
+    one callback per step, snapshots at the reference's steps (solver.py:2572-2584, io/hdf5.py:164-207)."""
+    case = CASES["uniform_pml"]
+    s = build_b200_solver(case, chunk_steps=16)
+    seen = []
+    out = tmp_path / "res.h5"
+    s.enable_snapshots(25)
+    s.run(steps=60, output_file=str(out), snapshot_interval=20, callback=seen.append, script_content="# test")
+    assert seen == list(range(60))
+    assert [round(t / s.dt) for t, _ in s.get_snapshots()] == [0, 25, 50]
+    o = O.OracleSolver(case)
+    for n in range(60):
+        o.step()
+        if n == 50:
+            assert np.array_equal(s.get_snapshots()[2][1], o.p)
+    from strata_fdtd_b200 import io as sbio
+    if sbio.HAVE_H5PY:
+        import h5py
+        with h5py.File(out, "r") as f:
+            assert np.array_equal(f["probes/a"][:], o.probe_array("a"))
+            assert f["fields/pressure"].shape[0] == 3 and f["simulation"].attrs["num_steps"] == 60
+    else:
+        z = np.load(str(out) + ".npz", allow_pickle=False)
+        assert np.array_equal(z["probes/a"], o.probe_array("a"))
+        assert z["fields/pressure"].shape == (3,) + tuple(case["shape"])
+        import json
+        attrs = json.loads(str(z["__attrs__"]))
+        assert attrs["simulation@num_steps"] == 60 and attrs["metadata@backend"] == "b200"

@@ -10,6 +10,39 @@ def sha(a) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def load_membrane_case():
+    """Membrane case rebuilt from the fixture (weights produced by the reference's own membrane classes)."""
+    from pathlib import Path
+    from cases import MEMBRANE_SPEC, membrane_case
+    g = np.load(Path(__file__).parent / "golden" / "membranes.npz")
+    weights = []
+    for q in range(len(MEMBRANE_SPEC["membranes"])):
+        w = np.zeros(int(np.prod(MEMBRANE_SPEC["shape"])), dtype=np.float64)
+        w[g[f"weights_idx_{q}"]] = g[f"weights_val_{q}"]
+        weights.append(w.reshape(MEMBRANE_SPEC["shape"]))
+    return membrane_case(weights), g
+
+
+class FixtureMembrane:
+    """Duck-typed stand-in for the reference's MembraneSource (solver.py:210-370): what the solver touches."""
+    source_type = "membrane"
+
+    def __init__(self, src: dict):
+        import strata_fdtd_b200 as sb
+        m = src["spec"]
+        self.center, self.normal_axis, self.injection_type = m["center"], m["normal_axis"], m["injection_type"]
+        self.waveform = sb.GaussianPulse(position=(0, 0, 0), frequency=src["frequency"], amplitude=src["amplitude"])
+        self._weights = src["weights"]
+        self._cached_weights = None
+        self._cached_mask = None
+
+    def _check_grid_alignment(self, grid):
+        pass
+
+    def get_injection_weights(self, grid):
+        return self._weights
+
+
 def build_b200_solver(case: dict, **solver_kw):
     import strata_fdtd_b200 as sb
     kw = dict(c=case.get("c", 343.0), rho=case.get("rho", 1.2), courant=case.get("courant", 0.95), backend="b200")
@@ -20,13 +53,17 @@ def build_b200_solver(case: dict, **solver_kw):
     else:
         s = sb.FDTDSolver(grid=sb.NonuniformGrid(nu["x_coords"], nu["y_coords"], nu["z_coords"]), **kw)
     if case.get("geometry") is not None:
-        s.set_geometry(np.asarray(case["geometry"], dtype=bool))
+        g = case["geometry"]
+        s.set_geometry(g if callable(g) else np.asarray(g, dtype=bool))
     for b in case.get("pml", []):
         axes = tuple(b.get("axes", ("x", "y", "z")))
         s.add_boundary(sb.PML(depth=b.get("depth", 10), axis="all" if axes == ("x", "y", "z") else axes,
                               max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
     for src in case.get("sources", []):
         kind = src.get("kind", "point")
+        if kind == "weighted":
+            s.add_source(FixtureMembrane(src))
+            continue
         pos = src["position"] if kind == "point" else {"axis": src["axis"], "index": src["index"]}
         s.add_source(sb.GaussianPulse(position=pos, frequency=src["frequency"], bandwidth=src.get("bandwidth"),
                                       amplitude=src.get("amplitude", 1.0), source_type=kind))
@@ -66,3 +103,31 @@ def assert_same_as_oracle(s, o, what=""):
     for name, _ in o.mics:
         a, b = s.microphones[name].get_waveform(), o.mic_array(name)
         assert np.array_equal(a, b), f"{what}: mic {name} differs (max|d|={np.abs(a - b).max():.3e})"
+
+
+def build_distributed_solver(case: dict, **kw):
+    """DistributedFDTDSolver (one slab per rank, torch.distributed already initialised) from a case dict."""
+    import strata_fdtd_b200 as sb
+    from strata_fdtd_b200.multi import DistributedFDTDSolver
+    base = dict(c=case.get("c", 343.0), rho=case.get("rho", 1.2), courant=case.get("courant", 0.95))
+    base.update(kw)
+    nu = case.get("nonuniform")
+    if nu is None:
+        d = DistributedFDTDSolver(shape=tuple(case["shape"]), resolution=case["resolution"], **base)
+    else:
+        d = DistributedFDTDSolver(grid=sb.NonuniformGrid(nu["x_coords"], nu["y_coords"], nu["z_coords"]), **base)
+    if case.get("geometry") is not None:
+        g = case["geometry"]
+        d.set_geometry(g if callable(g) else np.asarray(g, dtype=bool))
+    for b in case.get("pml", []):
+        axes = tuple(b.get("axes", ("x", "y", "z")))
+        d.add_boundary(sb.PML(depth=b.get("depth", 10), axis="all" if axes == ("x", "y", "z") else axes,
+                              max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
+    for src in case.get("sources", []):
+        kind = src.get("kind", "point")
+        pos = src["position"] if kind == "point" else {"axis": src["axis"], "index": src["index"]}
+        d.add_source(sb.GaussianPulse(position=pos, frequency=src["frequency"], bandwidth=src.get("bandwidth"),
+                                      amplitude=src.get("amplitude", 1.0), source_type=kind))
+    for name, pos in case.get("probes", []):
+        d.add_probe(name, position=pos)
+    return d

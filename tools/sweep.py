@@ -43,14 +43,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--geometry", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--graph", action="store_true")
     ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
     a = ap.parse_args()
     case = c2_case(a.n, steps=0, with_geometry=a.geometry)
     s = build_b200_solver(case)
+    if a.graph:
+        s.set_kernel_option(_lib.OPT_USE_GRAPH, 1)
     cells = a.n ** 3
     rows = []
     combos = [("naive", 0, 0, 0, 0)]
     rjs, wjs, wks, chunks = ([2], [8], [1], [0]) if a.quick else ([1, 2, 4], [2, 4, 8], [1, 2, 4], [0, 16, 64])
+    if a.small:
+        rjs, wjs, wks, chunks = [1, 2], [1, 2, 4, 8], [1], [0, 2, 4, 8, 16, 32]
     for rj, wj, wk, ch in itertools.product(rjs, wjs, wks, chunks):
         if wj * wk > 8:
             continue
