@@ -185,7 +185,7 @@ def run_b200_arm(a):
         slab, drv = s, None
     else:
         from util import build_distributed_solver
-        drv = build_distributed_solver(case, device=local_rank, chunk_steps=max(K, W))
+        drv = build_distributed_solver(case, device=local_rank, chunk_steps=max(K, W), halo=a.halo)
         slab = drv.slab
     for opt, val in ((_lib.OPT_ROWS_PER_THREAD, a.rows), (_lib.OPT_WARPS_J, a.warps_j), (_lib.OPT_WARPS_K, a.warps_k),
                      (_lib.OPT_CHUNK_I, a.chunk_i)):
@@ -203,6 +203,7 @@ def run_b200_arm(a):
 
     # ---- e2e: the public API call, host buffers in, host traces out, every chunk --------------------
     run(W)                                   # warm-up (also builds device state, uploads tables)
+    run(K)                                   # untimed pass at the timed chunk length (instantiates its CUDA graph)
     barrier()
     t0 = time.perf_counter()
     run(K)
@@ -236,9 +237,12 @@ def run_b200_arm(a):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(dev.stream)
-        for _ in range(K):
-            slab.enqueue_step()
-            drv._exchange()
+        if drv.halo == "p2p":
+            slab.enqueue_steps(K)                # halos travel inside the step kernels (NVLink peer stores)
+        else:
+            for _ in range(K):
+                slab.enqueue_step()
+                drv._exchange()
         e1.record(dev.stream)
         barrier()
         dev_ms = e0.elapsed_time(e1)
@@ -255,8 +259,11 @@ def run_b200_arm(a):
         _lib.check(lib.sb_step_n_async(h, kp, src.data_ptr(), rec.data_ptr()))
     else:
         slab.begin_chunk(kp)
-        for _ in range(kp):
-            slab.enqueue_step(); drv._exchange()
+        if drv.halo == "p2p":
+            slab.enqueue_steps(kp)
+        else:
+            for _ in range(kp):
+                slab.enqueue_step(); drv._exchange()
         slab.end_chunk()
     import ctypes as C
     mean_ms, min_ms, n_l = C.c_double(), C.c_double(), C.c_int()
@@ -279,7 +286,8 @@ def run_b200_arm(a):
                 "config": {"workload": label, "cells_per_gpu": cells_rank, "l2_policy": "fields (34 GB/GPU) >> L2, no flush needed"
                            if a.workload == "c5_weak" else "inputs larger than L2 for >=200^3; small grids are L2-resident by nature",
                            "kernel": {0: "auto", 1: "naive", 2: "march", 3: "tma"}[st1["kernel_variant"]],
-                           "parallelism": f"slab{world}" if world > 1 else "single"},
+                           "parallelism": f"slab{world}" if world > 1 else "single",
+                           "halo": (drv.halo if drv is not None else None)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k1_step_march",
                              "kernel_ms_mean": mean_ms.value, "kernel_ms_min": min_ms.value, "launches_timed": n_l.value,
@@ -309,6 +317,7 @@ def main():
     ap.add_argument("--warps-k", type=int, default=None)
     ap.add_argument("--chunk-i", type=int, default=None)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -166,6 +166,18 @@ int sb_step_n_async(sb_solver *h, int n_steps, const double *src_values_dev, flo
 int sb_halo_planes(sb_solver *h, float **send_lo, float **send_hi, float **recv_lo, float **recv_hi,
                    int64_t *plane_elems);
 
+/* Peer-to-peer halo over NVLink (optional; replaces the host-driven exchange of sb_halo_planes).
+ * lo_p_sets / hi_p_sets: base addresses of the lower / upper neighbour's two p buffers (set 0, set 1), mapped
+ * into this process (CUDA IPC / symmetric memory); lo_nx = the lower neighbour's slab extent.
+ * my_flags: int[2] in peer-visible memory of THIS rank ([0] written by the lower, [1] by the upper neighbour);
+ * lo_flag = address of the lower neighbour's my_flags[1], hi_flag = address of the upper neighbour's
+ * my_flags[0].  From then on the fused step kernel stores its first / last p plane straight into the
+ * neighbours' ghost planes, the blocks that touch a cut first wait (bounded) until the neighbour has
+ * completed the previous step, and the last kernel of every step publishes this rank's step count.
+ * All flags must be zero and all ranks at the same step count when this is called; my_flags == NULL disables. */
+int sb_set_peers(sb_solver *h, float *const lo_p_sets[2], float *const hi_p_sets[2], int lo_nx,
+                 int *my_flags, int *lo_flag, int *hi_flag);
+
 /* 0.5*sum(p^2)/(rho c^2)*dV + 0.5*rho*sum(v^2)*dV over air cells (core/solver.py:2689-2706). */
 int sb_energy(sb_solver *h, double rho, double c, double dV, double *out);
 

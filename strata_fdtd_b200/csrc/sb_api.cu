@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 using namespace sb;
@@ -74,12 +75,24 @@ struct sb_solver {
     DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat; DBuf<float> ade_J, ade_Jp;
     // options
     int opt_kernel = SB_KERNEL_AUTO, opt_rj = 2, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
-    // graph cache: key = (n_steps, starting set)
-    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    // graph cache: key = (n_steps, starting set, source-table pointer, record pointer)
+    struct GraphKey {
+        int n, cur; const void *src, *rec;
+        bool operator<(const GraphKey &o) const {
+            return std::tie(n, cur, src, rec) < std::tie(o.n, o.cur, o.src, o.rec);
+        }
+    };
+    std::map<GraphKey, cudaGraphExec_t> graphs;
     // stats
     long long steps_done = 0, kernels_launched = 0;
     int last_variant = 0;
     DBuf<double> d_energy;
+    // peer-to-peer halo (sb_set_peers)
+    bool have_peers = false;
+    float *peer_lo_set[2] = {nullptr, nullptr}, *peer_hi_set[2] = {nullptr, nullptr};   // neighbours' p buffers (base)
+    int *my_flags = nullptr, *sig_lo = nullptr, *sig_hi = nullptr;
+    int peer_lo_nx = 0;
+    DBuf<int> d_step_global, d_err;
     // optional per-launch timing of the fused step kernel (SB_OPT_PROFILE)
     int opt_profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
@@ -129,6 +142,9 @@ extern "C" int sb_create(const sb_grid_desc *desc, int device, void *stream, sb_
     h->elems = sb_field_elems(&h->d);
     if (h->d_step_ctr.alloc(1)) { delete h; return 1; }
     if (h->d_energy.alloc(2)) { delete h; return 1; }
+    if (h->d_step_global.alloc(1) || h->d_err.alloc(1)) { delete h; return 1; }
+    cudaMemset(h->d_step_global.p, 0, sizeof(int));
+    cudaMemset(h->d_err.p, 0, sizeof(int));
     *out = h;
     return 0;
 }
@@ -143,7 +159,7 @@ extern "C" int sb_destroy(sb_solver *h)
     h->mask.release(); h->src_off.release(); h->src_start.release(); h->src_id.release(); h->src_field.release();
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
     h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release();
-    h->d_energy.release();
+    h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
     delete h;
     return 0;
 }
@@ -462,6 +478,23 @@ static void fill_params(sb_solver *h, StepParams &P)
     P.nx = d.nx; P.ny = d.ny; P.nz = d.nz; P.pitch = d.pitch; P.plane = h->plane;
     P.has_lower = d.has_lower; P.has_upper = d.has_upper;
     P.i_begin = 0; P.i_end = d.nx; P.chunk_i = d.nx;
+    P.peer_lo_p = P.peer_hi_p = nullptr; P.flag_lo = P.flag_hi = nullptr;
+    P.step_global = h->d_step_global.p; P.err_flag = h->d_err.p; P.permute_chunks = 0;
+    if (h->have_peers) {
+        if (d.has_lower) { P.peer_lo_p = h->peer_lo_set[out] + (long long)(h->peer_lo_nx + 1) * h->plane; P.flag_lo = h->my_flags; }
+        if (d.has_upper) { P.peer_hi_p = h->peer_hi_set[out]; P.flag_hi = h->my_flags + 1; }
+        P.permute_chunks = 1;
+    }
+}
+
+static PeerLink peer_link(sb_solver *h, const StepParams &P)
+{
+    PeerLink L{};
+    L.peer_lo_p = P.peer_lo_p; L.peer_hi_p = P.peer_hi_p;
+    L.sig_lo = h->have_peers && h->d.has_lower ? h->sig_lo : nullptr;
+    L.sig_hi = h->have_peers && h->d.has_upper ? h->sig_hi : nullptr;
+    L.step_global = h->d_step_global.p; L.nx = h->d.nx; L.plane = h->plane;
+    return L;
 }
 
 template <int RJ>
@@ -475,7 +508,7 @@ static int launch_step_kernel(sb_solver *h, StepParams &P)
 {
     const sb_grid_desc &d = h->d;
     int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
-    if (variant == SB_KERNEL_TMA) variant = SB_KERNEL_MARCH;
+    if (variant == SB_KERNEL_TMA || h->have_peers) variant = SB_KERNEL_MARCH;   // only K1 pushes halos to peers
     h->last_variant = variant;
     if (variant == SB_KERNEL_NAIVE) {
         P.i_begin = d.has_lower ? -1 : 0; P.i_end = d.nx;
@@ -539,14 +572,15 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
     }
     const int n_rec = h->n_probes + h->n_mics;
     SourceTable T{h->n_sources, h->n_src_cells, h->src_off.p, h->src_start.p, h->src_id.p, h->src_field.p, h->src_weight.p};
+    const PeerLink L = peer_link(h, P);
     if (h->n_src_cells <= 4096 && n_rec <= 4096) {
         k3_small<<<1, 1024, 0, h->stream>>>(T, P.p_out, P.vx_out, P.vy_out, P.vz_out, src_dev, h->n_probes,
-                                            h->probe_off.p, h->n_mics, h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p);
+                                            h->probe_off.p, h->n_mics, h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p, L);
         h->kernels_launched++;
     } else {
         if (h->n_src_cells) {
             k3_inject<<<(h->n_src_cells + 255) / 256, 256, 0, h->stream>>>(T, P.p_out, P.vx_out, P.vy_out, P.vz_out,
-                                                                            src_dev, h->d_step_ctr.p);
+                                                                            src_dev, h->d_step_ctr.p, L);
             h->kernels_launched++;
         }
         if (n_rec) {
@@ -554,7 +588,7 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
                                                                   h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p);
             h->kernels_launched++;
         }
-        k3_advance<<<1, 1, 0, h->stream>>>(h->d_step_ctr.p);
+        k3_advance<<<1, 1, 0, h->stream>>>(h->d_step_ctr.p, L);
         h->kernels_launched++;
     }
     h->cur = 1 - h->cur;
@@ -574,10 +608,9 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     const bool want_graph = h->opt_graph == 1 ||
         (h->opt_graph < 0 && n_steps >= 4 && (long long)h->d.nx * h->d.ny * h->d.nz <= (32LL << 20));
     if (want_graph && n_steps > 1 && !h->opt_profile) {
-        // graphs are keyed on (n_steps, starting set); pointers src_dev/rec_dev must be the internal staging buffers
-        const bool internal = (src_dev == h->d_src_vals.p || !src_dev) && (rec_dev == h->d_record.p || !rec_dev);
-        if (internal) {
-            auto key = std::make_pair(n_steps, h->cur);
+        {
+            sb_solver::GraphKey key{n_steps, h->cur, src_dev, rec_dev};
+            if (h->graphs.size() > 64) drop_graphs(h);
             auto it = h->graphs.find(key);
             if (it == h->graphs.end()) {
                 cudaGraph_t g;
@@ -648,6 +681,26 @@ extern "C" int sb_halo_planes(sb_solver *h, float **send_lo, float **send_hi, fl
     return 0;
 }
 
+extern "C" int sb_set_peers(sb_solver *h, float *const lo_p_sets[2], float *const hi_p_sets[2], int lo_nx,
+                            int *my_flags, int *lo_flag, int *hi_flag)
+{
+    CHECK_H(h);
+    drop_graphs(h);
+    if (!my_flags) { h->have_peers = false; return 0; }
+    if (h->d.has_lower && (!lo_p_sets || !lo_p_sets[0] || !lo_p_sets[1] || !lo_flag)) return fail("lower neighbour pointers missing");
+    if (h->d.has_upper && (!hi_p_sets || !hi_p_sets[0] || !hi_p_sets[1] || !hi_flag)) return fail("upper neighbour pointers missing");
+    for (int q = 0; q < 2; q++) {
+        h->peer_lo_set[q] = h->d.has_lower ? lo_p_sets[q] : nullptr;
+        h->peer_hi_set[q] = h->d.has_upper ? hi_p_sets[q] : nullptr;
+    }
+    h->peer_lo_nx = lo_nx; h->my_flags = my_flags; h->sig_lo = lo_flag; h->sig_hi = hi_flag;
+    CU(cudaMemsetAsync(h->d_step_global.p, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_peers = true;
+    return 0;
+}
+
 extern "C" int sb_energy(sb_solver *h, double rho, double c, double dV, double *out)
 {
     CHECK_H(h);
@@ -675,6 +728,7 @@ extern "C" int sb_reset(sb_solver *h)
         CU(cudaMemsetAsync(h->ade_J.p, 0, h->ade_J.n * 4, h->stream));
         CU(cudaMemsetAsync(h->ade_Jp.p, 0, h->ade_Jp.n * 4, h->stream));
     }
+    CU(cudaMemsetAsync(h->d_step_global.p, 0, sizeof(int), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->steps_done = 0;
     return 0;
@@ -738,5 +792,10 @@ extern "C" int sb_synchronize(sb_solver *h)
     CHECK_H(h);
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    if (h->have_peers) {
+        int err = 0;
+        CU(cudaMemcpy(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail("timed out waiting for a neighbour slab's step flag (peer-to-peer halo)");
+    }
     return 0;
 }

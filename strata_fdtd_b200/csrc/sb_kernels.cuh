@@ -33,7 +33,37 @@ struct StepParams {
     long long plane;
     int has_lower, has_upper;
     int i_begin, i_end, chunk_i;
+    // peer-to-peer halo (multi-GPU, NVLink): K1 stores its first / last p plane straight into the neighbour's
+    // ghost plane and the blocks that touch a cut wait for the neighbour's "step done" flag first.
+    float *peer_lo_p, *peer_hi_p;        // neighbour ghost planes of the set being written, or nullptr
+    const int *flag_lo, *flag_hi;        // my flags: number of steps the lower / upper neighbour has completed
+    const int *step_global;              // index of the step being executed (device counter)
+    int *err_flag;
+    int permute_chunks;                  // schedule the two cut chunks in the middle of the grid order
 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one lane per warp polls; bounded so that a dead neighbour cannot hang the GPU
+__device__ __forceinline__ void wait_neighbour(const int *flag, int target, int *err)
+{
+    if ((threadIdx.x & 31) == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) < target) {
+            __nanosleep(100);
+            if (clock64() - t0 > (6LL << 30)) { atomicExch(err, 1); break; }      // ~3 s
+        }
+    }
+    __syncwarp();
+}
 
 // ------------------------------------------------------------------------------------------
 // K0: one thread per cell, every face velocity recomputed from the "in" set.  Reference
@@ -126,9 +156,16 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
     const int strip_k0 = (blockIdx.x * (blockDim.x >> 5) + warp_k) * 128;
     const int k0 = strip_k0 + lane * 4;
     const int j0 = (blockIdx.y * blockDim.y + threadIdx.y) * RJ;
-    const int ib = P.i_begin + (int)blockIdx.z * P.chunk_i;
+    int chunk = (int)blockIdx.z;
+    if (P.permute_chunks && gridDim.z > 2) {                    // order: 1..m, 0, C-1, m+1..C-2
+        const int C = (int)gridDim.z, m = (C - 2) / 2, z = (int)blockIdx.z;
+        chunk = z < m ? z + 1 : (z == m ? 0 : (z == m + 1 ? C - 1 : z - 1));
+    }
+    const int ib = P.i_begin + chunk * P.chunk_i;
     const int ie = min(ib + P.chunk_i, P.i_end);
     if (strip_k0 >= P.nz || j0 >= P.ny || ib >= ie) return;     // warp-uniform exit
+    if (P.flag_lo && ib == 0) wait_neighbour(P.flag_lo, *P.step_global, P.err_flag);
+    if (P.flag_hi && ie == P.nx) wait_neighbour(P.flag_hi, *P.step_global, P.err_flag);
     const bool lane_ok = k0 < P.nz;
     const int nz = P.nz, ny = P.ny;
     // per-element validity and "z face is updated" flags
@@ -296,7 +333,10 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             }
             if (row_ok[r + 1] && lane_ok) {
                 const long long c = base + (long long)r * P.pitch;
-                st4(P.p_out + c, sel4(e0, e1, e2, e3, pnew, z4));
+                const float4 pst = sel4(e0, e1, e2, e3, pnew, z4);
+                st4(P.p_out + c, pst);
+                if (P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
+                if (P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
                 st4(P.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
                 st4(P.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
                 st4(P.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
@@ -337,6 +377,29 @@ __global__ void k_build_mask(const uint8_t *geom, uint8_t *mask, int nx, int ny,
 // microphones.cpp:82-116).  `step_ctr` is a device counter so the kernels can live in a
 // replayed CUDA graph; the recording kernel advances it.
 // ------------------------------------------------------------------------------------------
+// what K3 needs to keep the neighbours' ghosts and flags current (all nullptr on a single GPU)
+struct PeerLink {
+    float *peer_lo_p, *peer_hi_p;        // neighbour ghost planes of the set just written
+    int *sig_lo, *sig_hi;                // neighbours' flags to bump once this step is complete
+    int *step_global;                    // device counter of completed steps
+    int nx; long long plane;
+};
+__device__ __forceinline__ void mirror_injection(const PeerLink &L, int field, long long off, float v)
+{
+    if (field != 0) return;
+    const long long i = off / L.plane, rem = off - i * L.plane;
+    if (L.peer_lo_p && i == 0) L.peer_lo_p[rem] = v;
+    if (L.peer_hi_p && i == L.nx - 1) L.peer_hi_p[rem] = v;
+}
+__device__ __forceinline__ void signal_step_done(const PeerLink &L)
+{
+    const int done = *L.step_global + 1;
+    __threadfence_system();
+    if (L.sig_lo) st_release_sys(L.sig_lo, done);
+    if (L.sig_hi) st_release_sys(L.sig_hi, done);
+    *L.step_global = done;
+}
+
 struct SourceTable {
     int n_sources, n_cells;
     const long long *cell_off;          // padded-layout offset of each cell
@@ -345,7 +408,7 @@ struct SourceTable {
 };
 
 __global__ void k3_inject(SourceTable T, float *p, float *vx, float *vy, float *vz,
-                          const double *src_vals, const int *step_ctr)
+                          const double *src_vals, const int *step_ctr, PeerLink L)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= T.n_cells) return;
@@ -354,7 +417,9 @@ __global__ void k3_inject(SourceTable T, float *p, float *vx, float *vy, float *
     for (int e = T.start[u]; e < T.start[u + 1]; e++) {
         float *f = T.field[e] == 0 ? p : (T.field[e] == 1 ? vx : (T.field[e] == 2 ? vy : vz));
         // float64 add, float32 store (solver.py:2421); w*weight is one fp64 multiply (solver.py:2404)
-        f[off] = (float)((double)f[off] + __dmul_rn(w[T.src_id[e]], T.weight[e]));
+        const float v = (float)((double)f[off] + __dmul_rn(w[T.src_id[e]], T.weight[e]));
+        f[off] = v;
+        mirror_injection(L, T.field[e], off, v);
     }
 }
 
@@ -376,13 +441,13 @@ __global__ void k3_record(const float *p, int n_probes, const long long *probe_o
     }
 }
 
-__global__ void k3_advance(int *step_ctr) { *step_ctr += 1; }
+__global__ void k3_advance(int *step_ctr, PeerLink L) { *step_ctr += 1; signal_step_done(L); }
 
 // Small-problem variant: one block does inject -> record -> advance (saves two launches).
 __global__ void __launch_bounds__(1024) k3_small(SourceTable T, float *p, float *vx, float *vy, float *vz,
                                                  const double *src_vals, int n_probes, const long long *probe_off,
                                                  int n_mics, const long long *mic_off8, const float *mic_w8,
-                                                 float *record_out, int *step_ctr)
+                                                 float *record_out, int *step_ctr, PeerLink L)
 {
     const int step = *step_ctr;
     for (int u = threadIdx.x; u < T.n_cells; u += blockDim.x) {
@@ -390,7 +455,9 @@ __global__ void __launch_bounds__(1024) k3_small(SourceTable T, float *p, float 
         const long long off = T.cell_off[u];
         for (int e = T.start[u]; e < T.start[u + 1]; e++) {
             float *f = T.field[e] == 0 ? p : (T.field[e] == 1 ? vx : (T.field[e] == 2 ? vy : vz));
-            f[off] = (float)((double)f[off] + __dmul_rn(w[T.src_id[e]], T.weight[e]));
+            const float v = (float)((double)f[off] + __dmul_rn(w[T.src_id[e]], T.weight[e]));
+            f[off] = v;
+            mirror_injection(L, T.field[e], off, v);
         }
     }
     __syncthreads();
@@ -407,7 +474,7 @@ __global__ void __launch_bounds__(1024) k3_small(SourceTable T, float *p, float 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) *step_ctr = step + 1;
+    if (threadIdx.x == 0) { *step_ctr = step + 1; signal_step_done(L); }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -75,6 +75,13 @@ class SlabSolver(FDTDSolver):
                                            self._rec_dev.data_ptr() + q * max(1, self._n_rec) * 4))
         self._chunk_q += 1
 
+    def enqueue_steps(self, m: int) -> None:
+        """All remaining steps of the chunk in one call (peer-to-peer halo mode: no host work between steps)."""
+        dev, q = self._dev, self._chunk_q
+        _lib.check(dev.lib.sb_step_n_async(dev.handle, m, self._W_dev.data_ptr() + q * self._n_src * 8,
+                                           self._rec_dev.data_ptr() + q * max(1, self._n_rec) * 4))
+        self._chunk_q += m
+
     def end_chunk(self) -> None:
         dev, m = self._dev, self._chunk_m
         with dev.torch.cuda.stream(dev.stream):
@@ -110,10 +117,12 @@ class DistributedFDTDSolver:
     """
 
     def __init__(self, shape=None, resolution=None, grid=None, c=343.0, rho=1.2, courant=0.95,
-                 backend="b200", device=None, chunk_steps=64, group=None):
+                 backend="b200", device=None, chunk_steps=64, group=None, halo="auto"):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if halo not in ("auto", "p2p", "nccl"):
+            raise ValueError("halo must be 'auto', 'p2p' or 'nccl'")
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         nx = int((grid.shape if grid is not None else shape)[0])
@@ -122,6 +131,60 @@ class DistributedFDTDSolver:
                                backend=backend, device=device, chunk_steps=chunk_steps, slab=self.ranges[self.rank])
         self.chunk_steps = int(chunk_steps)
         self._ghosts_fresh = False
+        self.halo = "nccl"
+        self._symm = []                          # keeps symmetric allocations / handles alive
+        if halo in ("auto", "p2p") and self.world > 1 and dist.get_backend(group) == "nccl":
+            try:
+                self._setup_p2p()
+                self.halo = "p2p"
+            except Exception as e:               # symmetric memory unavailable -> host-driven NCCL exchange
+                if halo == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"peer-to-peer halo unavailable ({type(e).__name__}: {e}); using NCCL send/recv")
+                self.slab._p_allocator = None
+
+    def _setup_p2p(self):
+        """Fused halo: K1 stores its cut planes of p straight into the neighbours' ghost planes over NVLink.
+
+        The two p buffers and a small flag array live in torch symmetric memory, so every rank can map its
+        neighbours' copies; the addresses go to the C ABI (sb_set_peers) and no collective remains in the step."""
+        import ctypes as C
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        dist, s = self.dist, self.slab
+        group = self.group if self.group is not None else dist.group.WORLD
+        max_planes = max(hi - lo for lo, hi in self.ranges) + 2
+        made = []
+
+        def alloc(planes, ny, pitch, device):
+            t = symm.empty((max_planes, ny, pitch), dtype=torch.float32, device=device)
+            t.zero_()
+            made.append(t)
+            return t
+
+        s._p_allocator = alloc
+        dev = s._ensure_device()
+        flags = symm.empty(8, dtype=torch.int32, device=dev.device)
+        flags.zero_()
+        torch.cuda.synchronize(dev.device)
+        handles = [symm.rendezvous(t, group) for t in made]
+        fh = symm.rendezvous(flags, group)
+        self._symm = [made, flags, handles, fh]
+
+        def peer_ptr(h, t, r):
+            return h.get_buffer(r, tuple(t.shape), t.dtype, 0).data_ptr()
+
+        lo, hi = self.rank - 1, self.rank + 1
+        lo_sets = (C.c_void_p * 2)(*[peer_ptr(h, t, lo) if lo >= 0 else None for h, t in zip(handles, made)])
+        hi_sets = (C.c_void_p * 2)(*[peer_ptr(h, t, hi) if hi < self.world else None for h, t in zip(handles, made)])
+        lo_nx = (self.ranges[lo][1] - self.ranges[lo][0]) if lo >= 0 else 0
+        lo_flag = peer_ptr(fh, flags, lo) + 4 if lo >= 0 else None          # lower neighbour's flags[1]
+        hi_flag = peer_ptr(fh, flags, hi) if hi < self.world else None       # upper neighbour's flags[0]
+        _lib.check(dev.lib.sb_set_peers(dev.handle, lo_sets, hi_sets, lo_nx, C.c_void_p(flags.data_ptr()),
+                                        C.c_void_p(lo_flag) if lo_flag else None,
+                                        C.c_void_p(hi_flag) if hi_flag else None))
+        dist.barrier(group)
 
     # ---- delegated set-up (global coordinates; every rank makes the same calls) -----------------
     shape = property(lambda self: self.slab.global_shape)
@@ -180,13 +243,22 @@ class DistributedFDTDSolver:
         s = self.slab
         s._sync_to_device()
         if not self._ghosts_fresh:               # ghosts of p and vx after host-side edits / first use
+            if self.halo == "p2p":
+                _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
+                self.dist.barrier(self.group)    # nobody is still pushing into the ghosts we are about to fill
             self._exchange(include_vx_ghost=True)
+            if self.halo == "p2p":
+                _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
+                self.dist.barrier(self.group)
             self._ghosts_fresh = True
         for m in _chunks(steps, self.chunk_steps):
             s.begin_chunk(m)
-            for _ in range(m):
-                s.enqueue_step()
-                self._exchange()
+            if self.halo == "p2p":               # the kernels exchange halos themselves: enqueue the whole chunk
+                s.enqueue_steps(m)
+            else:
+                for _ in range(m):
+                    s.enqueue_step()
+                    self._exchange()
             s.end_chunk()
 
     def step(self):
@@ -229,13 +301,36 @@ class LocalSlabGroup:
     exchange order) where only one GPU is available; peer copies become device-to-device copies.
     """
 
-    def __init__(self, n_slabs: int, shape=None, resolution=None, grid=None, device=None, chunk_steps=32, **kw):
+    def __init__(self, n_slabs: int, shape=None, resolution=None, grid=None, device=None, chunk_steps=32,
+                 halo="copy", **kw):
         nx = int((grid.shape if grid is not None else shape)[0])
         self.ranges = slab_ranges(nx, n_slabs)
         self.slabs = [SlabSolver(shape=shape, resolution=resolution, grid=grid, device=device,
                                  chunk_steps=chunk_steps, slab=r, **kw) for r in self.ranges]
         self.chunk_steps = int(chunk_steps)
         self._ghosts_fresh = False
+        self.halo = halo
+        self._flags = []
+
+    def _setup_p2p(self):
+        """Same peer-store / flag protocol as the distributed path, with the 'peers' on the same device."""
+        import ctypes as C
+        if self._flags:
+            return
+        devs = [s._ensure_device() for s in self.slabs]
+        torch = devs[0].torch
+        self._flags = [torch.zeros(8, dtype=torch.int32, device=d.device) for d in devs]
+        torch.cuda.synchronize()
+        n = len(self.slabs)
+        for r, (s, d) in enumerate(zip(self.slabs, devs)):
+            lo, hi = r - 1, r + 1
+            lo_sets = (C.c_void_p * 2)(*[devs[lo].sets[q][0].data_ptr() if lo >= 0 else None for q in range(2)])
+            hi_sets = (C.c_void_p * 2)(*[devs[hi].sets[q][0].data_ptr() if hi < n else None for q in range(2)])
+            lo_nx = self.slabs[lo].shape[0] if lo >= 0 else 0
+            lo_flag = C.c_void_p(self._flags[lo].data_ptr() + 4) if lo >= 0 else None
+            hi_flag = C.c_void_p(self._flags[hi].data_ptr()) if hi < n else None
+            _lib.check(d.lib.sb_set_peers(d.handle, lo_sets, hi_sets, lo_nx, C.c_void_p(self._flags[r].data_ptr()),
+                                          lo_flag, hi_flag))
 
     def for_all(self, fn):
         for s in self.slabs:
@@ -261,13 +356,19 @@ class LocalSlabGroup:
         if not self._ghosts_fresh:
             self._exchange(include_vx_ghost=True)
             self._ghosts_fresh = True
+        if self.halo == "p2p":
+            self._setup_p2p()
         for m in _chunks(steps, self.chunk_steps):
             for s in self.slabs:
                 s.begin_chunk(m)
-            for _ in range(m):
+            if self.halo == "p2p":
                 for s in self.slabs:
-                    s.enqueue_step()
-                self._exchange()
+                    s.enqueue_steps(m)
+            else:
+                for _ in range(m):
+                    for s in self.slabs:
+                        s.enqueue_step()
+                    self._exchange()
             for s in self.slabs:
                 s.end_chunk()
 

@@ -32,7 +32,7 @@ _FIELDS = ("p", "vx", "vy", "vz")
 class _DeviceState:
     """Owns the torch buffers and the sb_solver handle of one slab."""
 
-    def __init__(self, shape, device_index: int | None, slab=None):
+    def __init__(self, shape, device_index: int | None, slab=None, p_allocator=None):
         import torch
         if not torch.cuda.is_available():
             raise _lib.B200BackendError("backend='b200' needs a CUDA device; none is visible (no CPU fallback)")
@@ -54,6 +54,10 @@ class _DeviceState:
             # two ping-pong sets of {p, vx, vy, vz}; planes -1 and nx are the slab ghosts
             self.sets = [[torch.zeros((nx + 2, ny, self.pitch), dtype=torch.float32, device=self.device)
                           for _ in range(4)] for _ in range(2)]
+            if p_allocator is not None:
+                # peer-visible p buffers (symmetric memory) for the NVLink halo path; may be over-sized
+                for q in range(2):
+                    self.sets[q][0] = p_allocator(nx + 2, ny, self.pitch, self.device)
             torch.cuda.synchronize(self.device)
             handle = C.c_void_p()
             _lib.check(self.lib.sb_create(C.byref(self.desc), self.index, C.c_void_p(self.stream.cuda_stream),
@@ -70,7 +74,7 @@ class _DeviceState:
     def field_view(self, name: str):
         """torch view [nx, ny, nz] of the current device field (no copy)."""
         t = self.sets[self.current_set()][_FIELDS.index(name)]
-        return t[1:-1, :, : self.desc.nz]
+        return t[1:self.desc.nx + 1, :, : self.desc.nz]
 
     def close(self):
         if self.handle:
@@ -340,7 +344,8 @@ class FDTDSolver:
     def _ensure_device(self) -> _DeviceState:
         if self._dev is None:
             self._dev = _DeviceState(self.shape, self._device_index,
-                                     slab=(self._has_lower, self._has_upper, self.global_shape[0], self._i0))
+                                     slab=(self._has_lower, self._has_upper, self.global_shape[0], self._i0),
+                                     p_allocator=getattr(self, "_p_allocator", None))
             for opt, val in self._options.items():
                 _lib.check(self._dev.lib.sb_set_option(self._dev.handle, opt, val))
         return self._dev

@@ -27,15 +27,16 @@ def test_slab_ranges_cover_and_balance():
         slab_ranges(3, 4)
 
 
-def _group_from_case(case, n_slabs, opts):
+def _group_from_case(case, n_slabs, opts, halo="copy"):
     import strata_fdtd_b200 as sb
     kw = dict(c=case.get("c", 343.0), rho=case.get("rho", 1.2), courant=case.get("courant", 0.95))
     nu = case.get("nonuniform")
     if nu is None:
-        g = LocalSlabGroup(n_slabs, shape=tuple(case["shape"]), resolution=case["resolution"], chunk_steps=16, **kw)
+        g = LocalSlabGroup(n_slabs, shape=tuple(case["shape"]), resolution=case["resolution"], chunk_steps=16,
+                           halo=halo, **kw)
     else:
         g = LocalSlabGroup(n_slabs, grid=sb.NonuniformGrid(nu["x_coords"], nu["y_coords"], nu["z_coords"]),
-                           chunk_steps=16, **kw)
+                           chunk_steps=16, halo=halo, **kw)
     for s in g.slabs:
         if case.get("geometry") is not None:
             g_ = case["geometry"]
@@ -104,7 +105,8 @@ from strata_fdtd_b200.multi import DistributedFDTDSolver
 rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 case = make_cases()["block_pml"]
-d = DistributedFDTDSolver(shape=case["shape"], resolution=case["resolution"], chunk_steps=16)
+d = DistributedFDTDSolver(shape=case["shape"], resolution=case["resolution"], chunk_steps=16, halo={halo!r})
+print("HALO", d.halo)
 d.set_geometry(case["geometry"])
 d.add_boundary(sb.PML(depth=8))
 for s in case["sources"]:
@@ -129,16 +131,18 @@ dist.barrier(); dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_two_ranks_nccl_equal_single_gpu(tmp_path):
+@pytest.mark.parametrize("halo", ["nccl", "p2p"])
+def test_two_ranks_nccl_equal_single_gpu(tmp_path, halo):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "two_rank.py"
-    script.write_text(_TWO_RANK.format(root=str(ROOT)))
+    script.write_text(_TWO_RANK.format(root=str(ROOT), halo=halo))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                          capture_output=True, text=True, timeout=600)
     assert "TWO_RANK_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert f"HALO {halo}" in res.stdout
 
 
 @pytest.mark.gpu
@@ -166,3 +170,24 @@ def test_c4_enclosure_nonuniform_scaled_down():
         for pname in one._probes:
             assert np.array_equal(tr[pname], one.get_probe_data(pname)[pname]), pname
         grp.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_slabs", [2, 3])
+@pytest.mark.parametrize("name", ["block_pml", "partial_pml_plane", "nonuniform_block_pml"])
+def test_peer_store_halo_protocol_on_one_device(name, n_slabs):
+    """The fused halo path (K1 peer stores + neighbour flags, sb_set_peers) with the peers on one device:
+    whole chunks are enqueued per slab with no host work between steps, results equal the single domain."""
+    case = dict(CASES[name]); case.pop("mics", None)
+    steps = 70
+    one = build_b200_solver(case)
+    one.set_kernel_option(_lib.OPT_CHUNK_I, 4)
+    grp = _group_from_case(case, n_slabs, {_lib.OPT_CHUNK_I: 4}, halo="p2p")
+    one.run(steps=steps)
+    grp.run(steps)
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(grp.get_field(f), one.get_field(f)), (name, f)
+    tr = grp.get_probe_data()
+    for pname in one._probes:
+        assert np.array_equal(tr[pname], one.get_probe_data(pname)[pname]), pname
+    grp.close(); one.close()
