@@ -59,6 +59,9 @@ def workload_case(name: str, n_gpus: int) -> tuple[dict, str]:
         return c, "c3_512: 512^3 uniform 1 mm, PML(10), 1 point source, 64 probes (no material)"
     if name == "c3_512_ade":
         return c3_case(512, steps=0), "c3_512_ade: 512^3, PML(10), ADE sphere r=51 (2 Debye + 1 Lorentz), 64 probes"
+    if name == "c3_512_ade_slab":
+        return (c3_case(512, steps=0, slab=True),
+                "c3_512_ade_slab: 512^3, PML(10), ADE material in the upper quarter (33.5 M cells, 2 Debye + 1 Lorentz), 64 probes")
     if name == "c2_200":
         return c2_case(200, steps=0), "c2_200: 200^3 uniform 1 mm, PML(10), 1 point source, 1 probe"
     if name == "c1_100":
@@ -225,6 +228,7 @@ def run_b200_arm(a):
         src.copy_(torch.from_numpy(np.ascontiguousarray(s._waveform_table(times)[:, :max(1, n_src)])).reshape(-1))
         torch.cuda.synchronize()
         _lib.check(lib.sb_step_n_async(h, W, src.data_ptr(), rec.data_ptr()))
+        _lib.check(lib.sb_step_n_async(h, K, src.data_ptr(), rec.data_ptr()))   # untimed: instantiates the K-step graph
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(dev.stream)

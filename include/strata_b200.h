@@ -126,6 +126,14 @@ int sb_sponge_decay(const float *sigma, int n, float dt, float *decay_out);
 int sb_clear_sponges(sb_solver *h);
 int sb_add_sponge(sb_solver *h, const float *decay_x, const float *decay_y, const float *decay_z);
 
+/* One-plane boundary updates applied to p after the sponges, in the order added (core/solver.py:2046-2047):
+ * kind 0 = first-order Mur ABC (boundaries/_boundaries.py:476-513, mur = (c dt - dx)/(c dt + dx)),
+ * kind 1 = RadiationImpedance (boundaries/_boundaries.py:700-760, R = reflection coefficient;
+ * weak_r != 0 when the reference holds R as a Python float, which NumPy multiplies in fp32).
+ * axis 0/1/2, side 0 = low face, 1 = high face.  The previous-plane state lives in the library.       */
+int sb_clear_plane_ops(sb_solver *h);
+int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, double mur, double R, int weak_r);
+
 /* ADE materials.  material_id_host: uint8 [nx][ny][nz] (slab only).  rho_inf / K_inf are
  * indexed by material id (n_ids entries).  dt and inv_dx are the fp32 scalars the reference
  * passes (kernels.cpp:786-787, 834).  Replaces ADEMaterialData + update_ade_* + apply_ade_* +
@@ -146,6 +154,10 @@ int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const int64_t *cell
  * microphones.hpp:30-32.  Record slots: probes first, then microphones.                  */
 int sb_set_probes(sb_solver *h, int n_probes, const int64_t *flat_idx);
 int sb_set_mics(sb_solver *h, int n_mics, const int64_t *idx8, const float *w8);
+/* General form of sb_set_mics: every record slot gathers 8 weighted corners of field[t] (SB_FIELD_*).
+ * Used for directional microphones, which sample p and the three velocity components with the
+ * weights of the reference's Python path (core/solver.py:1004-1100); the host combines them.       */
+int sb_set_gathers(sb_solver *h, int n, const int32_t *field, const int64_t *idx8, const float *w8);
 /* Same tables the reference derives from grid positions (microphones.cpp:16-80). */
 int sb_mic_tables(const float *grid_positions, int n_mics, int ny, int nz, int64_t *idx8, float *w8);
 

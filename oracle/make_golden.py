@@ -52,6 +52,8 @@ def run_case(name: str, case: dict, out_dir: Path):
         for key, arr in s._spacing_arrays.items():
             out["sp_" + key] = arr
     for bi, b in enumerate(s._boundaries):
+        if not hasattr(b, "_max_sigma"):
+            continue                       # Mur / RadiationImpedance: nothing tabulated
         out[f"pml{bi}_max_sigma"] = np.float64(b._max_sigma)
         for a, sig in zip("xyz", (b._sigma_x, b._sigma_y, b._sigma_z)):
             if sig is not None:

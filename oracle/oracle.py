@@ -204,6 +204,7 @@ class OracleSolver:
         self.sponges = []
         for b in case.get("pml", []):
             self.sponges.append(self._init_sponge(b))
+        self.plane_ops = self._init_plane_ops(case.get("plane_bcs", []))
         # sources / probes / mics
         self.sources = []
         for s in case.get("sources", []):
@@ -214,7 +215,7 @@ class OracleSolver:
         self.probes = [(name, resolve_position(pos, self.shape, self.dx)) for name, pos in case.get("probes", [])]
         self.probe_data = {name: [] for name, _ in self.probes}
         self.mics = list(case.get("mics", []))
-        self.mic_data = {name: [] for name, _ in self.mics}
+        self.mic_data = {m[0]: [] for m in self.mics}
         self._mic_tables = None
         # materials
         self.materials = case.get("materials", [])
@@ -310,12 +311,53 @@ class OracleSolver:
             L.orc_sponge_velocity(_fp(self.vx), _fp(self.vy), _fp(self.vz), *dims, *(_fp(d) for d in sp["decay"]))
         for sp in self.sponges:                                     # solver.py:2046-2047
             L.orc_sponge_pressure(_fp(self.p), *dims, *(_fp(d) for d in sp["decay"]))
+        for op in self.plane_ops:                                   # Mur / RadiationImpedance planes, same phase
+            self._apply_plane_op(op)
         self._inject()
         for name, (i, j, k) in self.probes:                         # solver.py:2435-2439
             self.probe_data[name].append(float(self.p[i, j, k]))
         self._record_mics()
         self.step_count += 1
         self.time += self.dt                                        # solver.py:2071-2072
+
+    def _init_plane_ops(self, specs):
+        """boundaries/_boundaries.py:420-526 (Mur) and :529-793 (RadiationImpedance), in list order."""
+        mur = (self.c * self.dt - self.dx) / (self.c * self.dt + self.dx)          # np.float64
+        ops = []
+        for b in specs:
+            if b["kind"] == "mur":
+                for a, name in enumerate("xyz"):
+                    if name in b.get("axes", ("x", "y", "z")):
+                        for side in (0, 1):
+                            ops.append(dict(kind="mur", axis=a, side=side, mur=mur))
+            else:
+                if b.get("reflection_coeff") is not None:
+                    R = b["reflection_coeff"]                                        # Python float
+                else:
+                    ka = (2 * np.pi * 1000 / self.c) * b["pipe_radius"]
+                    z = (ka ** 2) / 4
+                    R = min(abs((z - 1) / (z + 1)), 0.95)
+                ops.append(dict(kind="radiation", axis="xyz".index(b["axis"]), side=0 if b["side"] == "low" else 1,
+                                mur=mur, R=R))
+        for op in ops:
+            shp = tuple(n for q, n in enumerate(self.shape) if q != op["axis"])
+            op["prev"] = np.zeros(shp, dtype=np.float32)
+        return ops
+
+    def _apply_plane_op(self, op):
+        """The reference's NumPy expressions verbatim in type behaviour: fp32 difference, float64 coefficient
+        (np.float64 scalar), Python-float R multiplies in fp32 (NEP 50 weak scalar), one rounding on store."""
+        sl_b = [slice(None)] * 3; sl_i = [slice(None)] * 3
+        sl_b[op["axis"]] = -1 if op["side"] else 0
+        sl_i[op["axis"]] = -2 if op["side"] else 1
+        p_b, p_i = self.p[tuple(sl_b)], self.p[tuple(sl_i)]
+        abc = op["prev"] + op["mur"] * (p_i - p_b)
+        if op["kind"] == "mur":
+            p_b[...] = abc
+        else:
+            R = op["R"]
+            p_b[...] = R * p_i + (1 - R) * abc
+        op["prev"] = p_i.copy()
 
     def _inject(self):
         """solver.py:2386-2433: float64 add, float32 store."""
@@ -342,13 +384,63 @@ class OracleSolver:
             else:
                 raise ValueError(kind)
 
+    # ---- directional microphones: the reference's Python path (core/solver.py:1004-1173) ----------
+    _PATTERN_K = {"omni": 0.0, "subcardioid": 0.3, "cardioid": 0.5, "supercardioid": 0.63,
+                  "hypercardioid": 0.75, "figure8": 1.0}
+
+    @staticmethod
+    def _tri(gx, gy, gz):
+        """solver.py:962-1002 in float64."""
+        i0, j0, k0 = int(gx), int(gy), int(gz)
+        fx, fy, fz = gx - i0, gy - j0, gz - k0
+        w = [(1 - fx) * (1 - fy) * (1 - fz), fx * (1 - fy) * (1 - fz), (1 - fx) * fy * (1 - fz), fx * fy * (1 - fz),
+             (1 - fx) * (1 - fy) * fz, fx * (1 - fy) * fz, (1 - fx) * fy * fz, fx * fy * fz]
+        idx = [(i0 + (c & 1), j0 + ((c >> 1) & 1), k0 + ((c >> 2) & 1)) for c in range(8)]
+        return idx, w
+
+    def _record_mics_python(self):
+        nx, ny, nz = self.shape
+        for m in self.mics:
+            name, pos = m[0], m[1]
+            opt = m[2] if len(m) > 2 else {}
+            g = tuple(q / self.dx for q in pos)
+            pressure = 0.0
+            for (i, j, k), w in zip(*self._tri(*g)):
+                pressure += w * self.p[i, j, k]                      # float64 weight * fp32 -> fp32 (NEP 50)
+            pattern = opt.get("pattern", "omni")
+            if pattern == "omni":
+                self.mic_data[name].append(pressure)
+                continue
+            vel = []
+            for axis, fld in enumerate((self.vx, self.vy, self.vz)):  # solver.py:1060-1100
+                gg = list(g)
+                gg[axis] -= 0.5
+                gg = [max(0.0, min(q, n - 1.001)) for q, n in zip(gg, self.shape)]
+                v = 0.0
+                for (i, j, k), w in zip(*self._tri(*gg)):
+                    v += w * fld[min(i, nx - 1), min(j, ny - 1), min(k, nz - 1)]
+                vel.append(v)
+            d = np.array(opt.get("direction", (1.0, 0.0, 0.0)), dtype=np.float64)
+            d = d / np.linalg.norm(d)
+            v_dot_d = vel[0] * d[0] + vel[1] * d[1] + vel[2] * d[2]
+            if callable(pattern):
+                v_mag = np.sqrt(vel[0] ** 2 + vel[1] ** 2 + vel[2] ** 2)
+                theta = np.arccos(np.clip(v_dot_d / v_mag, -1.0, 1.0)) if v_mag > 1e-20 else 0.0
+                out = pressure * pattern(theta)
+            else:
+                k_ = self._PATTERN_K[pattern]
+                out = (1 - k_) * pressure + k_ * (self.rho * self.c) * v_dot_d
+            self.mic_data[name].append(out)
+
     def _record_mics(self):
         if not self.mics:
             return
+        if any(len(m) > 2 and m[2].get("pattern", "omni") != "omni" for m in self.mics):
+            return self._record_mics_python()                      # solver.py:2453-2461: Python path for all
         nx, ny, nz = self.shape
         if self._mic_tables is None:                                # solver.py:2496-2518
             gp = np.zeros(3 * len(self.mics), dtype=np.float32)
-            for m, (_, pos) in enumerate(self.mics):
+            for m, (_, pos, *_opt) in enumerate(self.mics):
                 for a in range(3):
                     gp[3 * m + a] = pos[a] / self.dx                # solver.py:941-943 then fp32 store :2507-2509
             idx = np.zeros(8 * len(self.mics), dtype=np.int64)
@@ -358,7 +450,7 @@ class OracleSolver:
         idx, w = self._mic_tables
         out = np.zeros(len(self.mics), dtype=np.float32)
         lib().orc_mic_record(_fp(self.p), idx.ctypes.data_as(_i64p), _fp(w), I(len(self.mics)), _fp(out))
-        for m, (name, _) in enumerate(self.mics):
+        for m, (name, *_rest) in enumerate(self.mics):
             self.mic_data[name].append(float(out[m]))
 
     def run_steps(self, n: int):

@@ -103,6 +103,14 @@ def build_reference_solver(case: dict):
         axes = tuple(b.get("axes", ("x", "y", "z")))
         s.add_boundary(PML(depth=b.get("depth", 10), axis="all" if axes == ("x", "y", "z") else axes,
                            max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
+    for b in case.get("plane_bcs", []):
+        from strata_fdtd.boundaries import ABCFirstOrder, RadiationImpedance
+        if b["kind"] == "mur":
+            s.add_boundary(ABCFirstOrder(axis=tuple(b.get("axes", ("x", "y", "z")))))
+        else:
+            s.add_boundary(RadiationImpedance(axis=b["axis"], side=b["side"],
+                                              reflection_coeff=b.get("reflection_coeff"),
+                                              pipe_radius=b.get("pipe_radius")))
     for src in case.get("sources", []):
         kind = src.get("kind", "point")
         if kind == "weighted":
@@ -113,8 +121,8 @@ def build_reference_solver(case: dict):
                                    amplitude=src.get("amplitude", 1.0), source_type=kind))
     for name, pos in case.get("probes", []):
         s.add_probe(name, position=pos)
-    for name, pos in case.get("mics", []):
-        s.add_microphone(position=pos, name=name)
+    for name, pos, *opt in case.get("mics", []):
+        s.add_microphone(position=pos, name=name, **(opt[0] if opt else {}))
     if case.get("materials"):
         _install_fixed_native_ade(s, case)
     return s

@@ -96,10 +96,13 @@ SIGNATURES = {
     "sb_sponge_decay": (_i, [_vp, _i, C.c_float, _vp]),
     "sb_clear_sponges": (_i, [_vp]),
     "sb_add_sponge": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_clear_plane_ops": (_i, [_vp]),
+    "sb_add_plane_op": (_i, [_vp, _i, _i, _i, C.c_double, C.c_double, _i]),
     "sb_set_ade": (_i, [_vp, C.POINTER(Pole), _i, _vp, _vp, _vp, _i, C.c_float, C.c_float]),
     "sb_set_sources": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sb_set_probes": (_i, [_vp, _i, _vp]),
     "sb_set_mics": (_i, [_vp, _i, _vp, _vp]),
+    "sb_set_gathers": (_i, [_vp, _i, _vp, _vp, _vp]),
     "sb_mic_tables": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sb_step_n": (_i, [_vp, _i, _vp, _vp]),
     "sb_step_n_async": (_i, [_vp, _i, _vp, _vp]),

@@ -107,6 +107,87 @@ class PML:
         return self._initialized
 
 
+class ABCFirstOrder:
+    """First-order Mur absorbing boundary on the chosen axes (reference _boundaries.py:420-526).
+
+    On this backend the six plane updates run on the device after the sponges (k4_plane_op); the
+    previous-plane state is kept there, so ``apply_pressure`` is a no-op."""
+
+    def __init__(self, axis="all"):
+        self.axes = _AXES if axis == "all" else ((axis,) if isinstance(axis, str) else tuple(axis))
+        self._solver = None
+        self._coeff = 0.0
+
+    def initialize(self, solver) -> None:
+        self._solver = solver
+        self._coeff = (solver.c * solver.dt - solver.dx) / (solver.c * solver.dt + solver.dx)   # reference :461-463
+
+    def apply_velocity(self, solver) -> None: ...
+    def apply_pressure(self, solver) -> None: ...
+    def reset(self) -> None: ...
+
+
+class RadiationImpedance:
+    """Partially reflecting open end on one face (reference _boundaries.py:529-793):
+    p_b = R*p_i + (1-R)*(prev + mur*(p_i - p_b)); R constant or from the pipe radius (ka ~ 1 kHz, clamped 0.95)."""
+
+    def __init__(self, axis, side, reflection_coeff: float | None = None, pipe_radius: float | None = None):
+        self.axis, self.side = axis, side
+        if reflection_coeff is not None:
+            if not 0.0 <= reflection_coeff <= 1.0:
+                raise ValueError("reflection_coeff must be in [0, 1]")
+            self._reflection_coeff, self._frequency_dependent = reflection_coeff, False
+        elif pipe_radius is not None:
+            if pipe_radius <= 0:
+                raise ValueError("pipe_radius must be positive")
+            self._pipe_radius, self._frequency_dependent, self._reflection_coeff = pipe_radius, True, None
+        else:
+            raise ValueError("Must specify either reflection_coeff or pipe_radius")
+        self._solver = None
+        self._initialized = False
+        self._coeff_a = self._coeff_b = 0.0
+
+    def initialize(self, solver) -> None:
+        self._solver = solver
+        c, dt, dx = solver.c, solver.dt, solver.dx
+        mur = (c * dt - dx) / (c * dt + dx)
+        if not self._frequency_dependent:
+            R = self._reflection_coeff
+        else:                                            # reference :650-663
+            ka = (2 * np.pi * 1000 / c) * self._pipe_radius
+            z_ratio = (ka ** 2) / 4
+            R = min(abs((z_ratio - 1) / (z_ratio + 1)), 0.95)
+        self._coeff_a, self._coeff_b = (1 - R) * mur, R
+        self._initialized = True
+
+    def apply_velocity(self, solver) -> None: ...
+    def apply_pressure(self, solver) -> None: ...
+    def reset(self) -> None: ...
+
+    @property
+    def reflection_coefficient(self) -> float:
+        return self._coeff_b
+
+    @property
+    def is_initialized(self) -> bool:
+        return self._initialized
+
+
+def plane_ops(boundary, solver):
+    """[(axis, side, kind, mur, R, weak_r)] for a Mur / RadiationImpedance object (ours or the reference's),
+    in the order the reference applies them; None if the object is not of that family."""
+    name = type(boundary).__name__
+    mur = (solver.c * solver.dt - solver.dx) / (solver.c * solver.dt + solver.dx)
+    if name == "ABCFirstOrder":
+        return [("xyz".index(a), side, 0, float(boundary._coeff), 0.0, 0)
+                for a in "xyz" if a in boundary.axes for side in (0, 1)]
+    if name == "RadiationImpedance":
+        R = boundary._coeff_b
+        weak = isinstance(R, float) and not isinstance(R, np.floating)     # Python float -> NumPy multiplies in fp32
+        return [("xyz".index(boundary.axis), 0 if boundary.side == "low" else 1, 1, float(mur), float(R), int(weak))]
+    return None
+
+
 def decay_table(sigma: np.ndarray, dt) -> np.ndarray:
     """``expf(-sigma*float(dt))`` through the host libm, as pml.cpp:13-45 computes it."""
     sigma = np.ascontiguousarray(sigma, dtype=np.float32)

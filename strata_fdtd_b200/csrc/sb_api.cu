@@ -49,6 +49,7 @@ template <typename T> struct DBuf {
 };
 
 struct Sponge { DBuf<float> x, y, z; };
+struct PlaneOpHost { PlaneOp op; DBuf<float> prev; };
 
 struct sb_solver {
     sb_grid_desc d{};
@@ -63,11 +64,12 @@ struct sb_solver {
     float cp = 0.f;
     DBuf<uint8_t> mask; bool have_mask = false;
     std::vector<Sponge *> sponges;
+    std::vector<PlaneOpHost *> plane_ops;
     // sources / records
     int n_sources = 0, n_src_cells = 0;
     DBuf<long long> src_off; DBuf<int> src_start, src_id, src_field; DBuf<double> src_weight;
     int n_probes = 0, n_mics = 0;
-    DBuf<long long> probe_off, mic_off; DBuf<float> mic_w;
+    DBuf<long long> probe_off, mic_off; DBuf<float> mic_w; DBuf<int> mic_field; bool have_mic_field = false;
     DBuf<double> d_src_vals; DBuf<float> d_record; DBuf<int> d_step_ctr;
     // ADE
     bool have_ade = false;
@@ -155,6 +157,7 @@ extern "C" int sb_destroy(sb_solver *h)
     cudaSetDevice(h->device);
     drop_graphs(h);
     for (auto *s : h->sponges) { s->x.release(); s->y.release(); s->z.release(); delete s; }
+    for (auto *po : h->plane_ops) { po->prev.release(); delete po; }
     for (DBuf<float> *b : {&h->cvx, &h->cvy, &h->cvz, &h->icx, &h->icy, &h->icz, &h->mic_w, &h->d_record, &h->ade_J, &h->ade_Jp}) b->release();
     h->mask.release(); h->src_off.release(); h->src_start.release(); h->src_id.release(); h->src_field.release();
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
@@ -301,6 +304,33 @@ extern "C" int sb_add_sponge(sb_solver *h, const float *dx, const float *dy, con
     return 0;
 }
 
+extern "C" int sb_clear_plane_ops(sb_solver *h)
+{
+    CHECK_H(h);
+    for (auto *po : h->plane_ops) { po->prev.release(); delete po; }
+    h->plane_ops.clear();
+    drop_graphs(h);
+    return 0;
+}
+
+extern "C" int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, double mur, double R, int weak_r)
+{
+    CHECK_H(h);
+    if (axis < 0 || axis > 2 || side < 0 || side > 1 || kind < 0 || kind > 1) return fail("bad plane-op arguments");
+    if (h->d.has_lower || h->d.has_upper) return fail("Mur / radiation planes are not supported on decomposed slabs yet");
+    const int n[3] = {h->d.nx, h->d.ny, h->d.nz};
+    if (n[axis] < 3) return fail("plane op needs at least 3 cells along its axis");
+    PlaneOpHost *po = new PlaneOpHost();
+    const size_t cells = (size_t)n[axis == 0 ? 1 : 0] * n[axis == 2 ? 1 : 2];
+    if (po->prev.alloc(cells)) { delete po; return 1; }
+    CU(cudaMemsetAsync(po->prev.p, 0, cells * 4, h->stream));
+    po->op.axis = axis; po->op.side = side; po->op.kind = kind; po->op.weak_r = weak_r ? 1 : 0;
+    po->op.mur = mur; po->op.R = R; po->op.one_minus_R = 1 - R; po->op.r32 = (float)R; po->op.prev = po->prev.p;
+    h->plane_ops.push_back(po);
+    drop_graphs(h);
+    return 0;
+}
+
 static inline long long dense_to_off(const sb_solver *h, long long dense)
 {
     const sb_grid_desc &d = h->d;
@@ -346,10 +376,22 @@ extern "C" int sb_set_probes(sb_solver *h, int n_probes, const int64_t *flat_idx
     return n_probes ? h->probe_off.upload(off, h->stream) : 0;
 }
 
+extern "C" int sb_set_gathers(sb_solver *h, int n, const int32_t *field, const int64_t *idx8, const float *w8)
+{
+    if (sb_set_mics(h, n, idx8, w8)) return 1;
+    h->have_mic_field = false;
+    if (!n || !field) return 0;
+    for (int t = 0; t < n; t++) if (field[t] < 0 || field[t] > 3) return fail("gather %d: bad field", t);
+    if (h->mic_field.upload(field, (size_t)n, h->stream)) return 1;
+    h->have_mic_field = true;
+    return 0;
+}
+
 extern "C" int sb_set_mics(sb_solver *h, int n_mics, const int64_t *idx8, const float *w8)
 {
     CHECK_H(h);
     drop_graphs(h);
+    h->have_mic_field = false;
     const long long ncell = (long long)h->d.nx * h->d.ny * h->d.nz;
     std::vector<long long> off((size_t)n_mics * 8);
     for (int t = 0; t < n_mics * 8; t++) {
@@ -570,12 +612,20 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
         k2b_fixup<<<nb, 256, 0, h->stream>>>(Q, h->ade);
         h->kernels_launched++;
     }
+    for (auto *po : h->plane_ops) {                        // Mur / radiation planes, sequential by construction
+        const int n[3] = {h->d.nx, h->d.ny, h->d.nz};
+        const int na = n[po->op.axis == 0 ? 1 : 0], nb = n[po->op.axis == 2 ? 1 : 2];
+        dim3 blk(128), grd((nb + 127) / 128, na);
+        k4_plane_op<<<grd, blk, 0, h->stream>>>(po->op, P.p_out, h->d.nx, h->d.ny, h->d.nz, h->d.pitch, h->plane);
+        h->kernels_launched++;
+    }
     const int n_rec = h->n_probes + h->n_mics;
     SourceTable T{h->n_sources, h->n_src_cells, h->src_off.p, h->src_start.p, h->src_id.p, h->src_field.p, h->src_weight.p};
     const PeerLink L = peer_link(h, P);
     if (h->n_src_cells <= 4096 && n_rec <= 4096) {
         k3_small<<<1, 1024, 0, h->stream>>>(T, P.p_out, P.vx_out, P.vy_out, P.vz_out, src_dev, h->n_probes,
-                                            h->probe_off.p, h->n_mics, h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p, L);
+                                            h->probe_off.p, h->n_mics, h->have_mic_field ? h->mic_field.p : nullptr, h->mic_off.p,
+                                            h->mic_w.p, rec_dev, h->d_step_ctr.p, L);
         h->kernels_launched++;
     } else {
         if (h->n_src_cells) {
@@ -584,7 +634,9 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
             h->kernels_launched++;
         }
         if (n_rec) {
-            k3_record<<<(n_rec + 255) / 256, 256, 0, h->stream>>>(P.p_out, h->n_probes, h->probe_off.p, h->n_mics,
+            const FieldPtrs F{{P.p_out, P.vx_out, P.vy_out, P.vz_out}};
+            k3_record<<<(n_rec + 255) / 256, 256, 0, h->stream>>>(F, h->n_probes, h->probe_off.p, h->n_mics,
+                                                                  h->have_mic_field ? h->mic_field.p : nullptr,
                                                                   h->mic_off.p, h->mic_w.p, rec_dev, h->d_step_ctr.p);
             h->kernels_launched++;
         }
@@ -631,7 +683,7 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
             }
             CU(cudaGraphLaunch(it->second, h->stream));
             // bookkeeping equivalent to n_steps enqueues
-            const int per_step = (h->have_ade ? 2 : 0) + 1 + ((h->n_src_cells <= 4096 && (h->n_probes + h->n_mics) <= 4096) ? 1 :
+            const int per_step = (h->have_ade ? 2 : 0) + 1 + (int)h->plane_ops.size() + ((h->n_src_cells <= 4096 && (h->n_probes + h->n_mics) <= 4096) ? 1 :
                                  ((h->n_src_cells ? 1 : 0) + ((h->n_probes + h->n_mics) ? 1 : 0) + 1));
             h->kernels_launched += (long long)per_step * n_steps;
             h->steps_done += n_steps;
@@ -728,6 +780,7 @@ extern "C" int sb_reset(sb_solver *h)
         CU(cudaMemsetAsync(h->ade_J.p, 0, h->ade_J.n * 4, h->stream));
         CU(cudaMemsetAsync(h->ade_Jp.p, 0, h->ade_Jp.n * 4, h->stream));
     }
+    for (auto *po : h->plane_ops) CU(cudaMemsetAsync(po->prev.p, 0, po->prev.n * 4, h->stream));
     CU(cudaMemsetAsync(h->d_step_global.p, 0, sizeof(int), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->steps_done = 0;

@@ -373,6 +373,49 @@ __global__ void k_build_mask(const uint8_t *geom, uint8_t *mask, int nx, int ny,
 }
 
 // ------------------------------------------------------------------------------------------
+// K4: one-plane boundary updates applied to p after the sponge, in boundary-list order:
+//   first-order Mur ABC        boundaries/_boundaries.py:476-513   p_b = prev + c*(p_i - p_b); prev = p_i
+//   RadiationImpedance         boundaries/_boundaries.py:700-760   abc as above; p_b = R*p_i + (1-R)*abc
+// Mixed precision exactly as NumPy evaluates the reference expressions: the difference is fp32, the
+// Mur coefficient and (1-R) are float64, R*p_i is fp32 when R is a Python float ("weak" scalar) and
+// float64 when it is a NumPy float64; the sum is rounded to fp32 once on store.
+// ------------------------------------------------------------------------------------------
+struct PlaneOp {
+    int axis, side;              // axis 0/1/2, side 0 = low face, 1 = high face
+    int kind;                    // 0 = Mur, 1 = radiation impedance
+    int weak_r;                  // R is a Python float -> fp32 product
+    double mur, R, one_minus_R;
+    float r32;
+    float *prev;                 // previous interior-neighbour plane, n_a * n_b floats
+};
+
+__global__ void k4_plane_op(PlaneOp op, float *p, int nx, int ny, int nz, int pitch, long long plane)
+{
+    const int n[3] = {nx, ny, nz};
+    const int a_ax = op.axis == 0 ? 1 : 0, b_ax = op.axis == 2 ? 1 : 2;      // the two in-plane axes
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= n[b_ax] || a >= n[a_ax]) return;
+    int c[3];
+    c[a_ax] = a; c[b_ax] = b;
+    c[op.axis] = op.side ? n[op.axis] - 1 : 0;
+    const long long ib = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
+    c[op.axis] = op.side ? n[op.axis] - 2 : 1;
+    const long long ii = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
+    const long long t = (long long)a * n[b_ax] + b;
+    const float pb = p[ib], pi = p[ii];
+    const double abc = __dadd_rn((double)op.prev[t], __dmul_rn(op.mur, (double)(pi - pb)));
+    float out;
+    if (op.kind == 0) {
+        out = (float)abc;
+    } else {
+        const double rigid = op.weak_r ? (double)(op.r32 * pi) : __dmul_rn(op.R, (double)pi);
+        out = (float)__dadd_rn(rigid, __dmul_rn(op.one_minus_R, abc));
+    }
+    p[ib] = out;
+    op.prev[t] = pi;
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: source injection and probe / microphone recording (core/solver.py:2386-2439,
 // microphones.cpp:82-116).  `step_ctr` is a device counter so the kernels can live in a
 // replayed CUDA graph; the recording kernel advances it.
@@ -423,21 +466,30 @@ __global__ void k3_inject(SourceTable T, float *p, float *vx, float *vy, float *
     }
 }
 
-__global__ void k3_record(const float *p, int n_probes, const long long *probe_off,
-                          int n_mics, const long long *mic_off8, const float *mic_w8,
+// 8-point weighted gather of one field (trilinear microphone sample): sum = 0; sum += w[c]*f[idx[c]], fp32,
+// corner order of microphones.hpp:30-32 (microphones.cpp:82-116; Python path core/solver.py:1027-1034, 1085-1099)
+struct FieldPtrs { const float *f[4]; };
+__device__ __forceinline__ float gather8(const FieldPtrs &F, const int *mic_field, const long long *mic_off8,
+                                         const float *mic_w8, int m)
+{
+    const float *f = F.f[mic_field ? mic_field[m] : 0];
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * f[mic_off8[8 * m + c]];
+    return sum;
+}
+
+__global__ void k3_record(FieldPtrs F, int n_probes, const long long *probe_off,
+                          int n_mics, const int *mic_field, const long long *mic_off8, const float *mic_w8,
                           float *record_out, int *step_ctr)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_rec = n_probes + n_mics;
     const int step = *step_ctr;
     if (t < n_probes) {
-        record_out[(long long)step * n_rec + t] = p[probe_off[t]];
+        record_out[(long long)step * n_rec + t] = F.f[0][probe_off[t]];
     } else if (t < n_rec) {
-        const int m = t - n_probes;
-        float sum = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * p[mic_off8[8 * m + c]];
-        record_out[(long long)step * n_rec + t] = sum;
+        record_out[(long long)step * n_rec + t] = gather8(F, mic_field, mic_off8, mic_w8, t - n_probes);
     }
 }
 
@@ -446,8 +498,8 @@ __global__ void k3_advance(int *step_ctr, PeerLink L) { *step_ctr += 1; signal_s
 // Small-problem variant: one block does inject -> record -> advance (saves two launches).
 __global__ void __launch_bounds__(1024) k3_small(SourceTable T, float *p, float *vx, float *vy, float *vz,
                                                  const double *src_vals, int n_probes, const long long *probe_off,
-                                                 int n_mics, const long long *mic_off8, const float *mic_w8,
-                                                 float *record_out, int *step_ctr, PeerLink L)
+                                                 int n_mics, const int *mic_field, const long long *mic_off8,
+                                                 const float *mic_w8, float *record_out, int *step_ctr, PeerLink L)
 {
     const int step = *step_ctr;
     for (int u = threadIdx.x; u < T.n_cells; u += blockDim.x) {
@@ -466,11 +518,8 @@ __global__ void __launch_bounds__(1024) k3_small(SourceTable T, float *p, float 
         if (t < n_probes) {
             record_out[(long long)step * n_rec + t] = p[probe_off[t]];
         } else {
-            const int m = t - n_probes;
-            float sum = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * p[mic_off8[8 * m + c]];
-            record_out[(long long)step * n_rec + t] = sum;
+            const FieldPtrs F{{p, vx, vy, vz}};
+            record_out[(long long)step * n_rec + t] = gather8(F, mic_field, mic_off8, mic_w8, t - n_probes);
         }
     }
     __syncthreads();

@@ -22,7 +22,7 @@ from collections.abc import Callable
 import numpy as np
 
 from . import _lib
-from .boundaries import sponge_tables
+from .boundaries import plane_ops, sponge_tables
 from .grid import NonuniformGrid, UniformGrid
 from .sources import Microphone, Probe
 
@@ -151,6 +151,7 @@ class FDTDSolver:
         self._materials: dict = {}
         self._material_id = np.zeros(self.shape, dtype=np.uint8)
         self._local_probes: list = []
+        self._mic_slots: list = []
         self._geometry_ext = None
 
         self._device_index = device
@@ -279,8 +280,9 @@ class FDTDSolver:
     def add_microphone(self, position, name=None, pattern="omni", direction=None, up=None):
         if hasattr(position, "_initialize"):
             mic = position
-            if mic.is_directional():
-                raise NotImplementedError("directional microphones are not on the b200 device path yet")
+            if not hasattr(mic, "_gather_tables"):            # a reference Microphone object: rebuild as ours
+                mic = Microphone(position=mic.position, name=mic.name, pattern=mic.pattern,
+                                 direction=tuple(mic._direction), up=tuple(mic._up))
         else:
             mic = Microphone(position=position, name=name, pattern=pattern, direction=direction, up=up)
         mic.name = mic.name or f"mic_{len(self._microphones)}"
@@ -293,9 +295,16 @@ class FDTDSolver:
 
     def add_boundary(self, boundary) -> None:
         boundary.initialize(self)
-        if sponge_tables(boundary, self) is None and type(boundary).__name__ != "RigidBoundary":
-            raise NotImplementedError(f"{type(boundary).__name__} is not on the b200 device path yet "
-                                      "(PML / RigidBoundary are)")
+        is_plane = plane_ops(boundary, self) is not None
+        if not is_plane and sponge_tables(boundary, self) is None and type(boundary).__name__ != "RigidBoundary":
+            raise NotImplementedError(f"{type(boundary).__name__} is not on the b200 device path "
+                                      "(PML, ABCFirstOrder, RadiationImpedance, RigidBoundary are)")
+        if not is_plane and any(plane_ops(b, self) is not None for b in self._boundaries) \
+                and sponge_tables(boundary, self) is not None:
+            # the sponge is fused into the step kernel and therefore always runs before the plane updates
+            raise NotImplementedError("add PML boundaries before ABCFirstOrder / RadiationImpedance")
+        if is_plane and (self._has_lower or self._has_upper):
+            raise NotImplementedError("ABCFirstOrder / RadiationImpedance are not supported on decomposed slabs yet")
         self._boundaries.append(boundary)
         self._dirty.add("sponges")
 
@@ -466,6 +475,10 @@ class FDTDSolver:
                 _lib.check(lib.sb_set_geometry(h, _lib.ptr(g), int(self._rigid)))
         if "sponges" in self._dirty:
             _lib.check(lib.sb_clear_sponges(h))
+            _lib.check(lib.sb_clear_plane_ops(h))
+            for b in self._boundaries:
+                for op in plane_ops(b, self) or []:
+                    _lib.check(lib.sb_add_plane_op(h, *op))
             for b in self._boundaries:                       # application order = list order (solver.py:2044-2047)
                 tabs = sponge_tables(b, self)
                 if tabs is not None:
@@ -483,12 +496,26 @@ class FDTDSolver:
             mics = list(self._microphones.values())
             if mics and (self._has_lower or self._has_upper):
                 raise NotImplementedError("microphones on decomposed slabs are not supported yet")
-            if mics:
+            self._mic_slots = []                              # per microphone: its record slots after the probes
+            if mics and any(m.is_directional() for m in mics):
+                # one directional microphone switches the reference to its Python path for ALL microphones
+                # (solver.py:2453-2461): p (+ vx, vy, vz) gathers with that path's weights, combined on the host
+                fields, idx_all, w_all = [], [], []
+                for m in mics:
+                    tabs = m._gather_tables(self.shape)
+                    self._mic_slots.append(list(range(len(fields), len(fields) + len(tabs))))
+                    for f, idx8, w8 in tabs:
+                        fields.append(f); idx_all.append(idx8); w_all.append(w8)
+                fields = np.array(fields, dtype=np.int32)
+                idx_all, w_all = np.concatenate(idx_all), np.concatenate(w_all)
+                _lib.check(lib.sb_set_gathers(h, len(fields), _lib.ptr(fields), _lib.ptr(idx_all), _lib.ptr(w_all)))
+            elif mics:
                 gp = np.array([q for m in mics for q in m._grid_position], dtype=np.float32)   # fp32 store, solver.py:2502-2509
                 idx8 = np.zeros(8 * len(mics), dtype=np.int64)
                 w8 = np.zeros(8 * len(mics), dtype=np.float32)
                 _lib.check(lib.sb_mic_tables(_lib.ptr(gp), len(mics), ny, nz, _lib.ptr(idx8), _lib.ptr(w8)))
                 self._mic_tables = (idx8, w8)
+                self._mic_slots = [[q] for q in range(len(mics))]
                 _lib.check(lib.sb_set_mics(h, len(mics), _lib.ptr(idx8), _lib.ptr(w8)))
             else:
                 _lib.check(lib.sb_set_mics(h, 0, None, None))
@@ -531,7 +558,7 @@ class FDTDSolver:
         lib, h = dev.lib, dev.handle
         probes = self._local_probes
         mics = list(self._microphones.values())
-        n_rec = len(probes) + len(mics)
+        n_rec = len(probes) + sum(len(sl) for sl in self._mic_slots)
         done = 0
         while done < n_steps:
             m = min(self._chunk_steps, n_steps - done)
@@ -555,8 +582,9 @@ class FDTDSolver:
             self._host_stale = set(_FIELDS)
             for q, pr in enumerate(probes):
                 pr.data.extend(rec[:, q].tolist())
-            for q, mic in enumerate(mics):
-                mic._data.extend(rec[:, len(probes) + q].tolist())
+            for mic, slots in zip(mics, self._mic_slots):
+                cols = [rec[:, len(probes) + q] for q in slots]
+                mic._data.extend(mic._combine(cols[0], cols[1:]).tolist())
                 mic._times.extend(times.tolist())
             last_idx = self._step_count + m - 1
             self._step_count += m

@@ -55,29 +55,68 @@ class Probe:
         self.data.clear()
 
 
-class Microphone:
-    """Omnidirectional virtual microphone at a physical position, trilinear in p
-    (reference solver.py:797-1002; weights as microphones.cpp:16-80).
+POLAR_PATTERNS = {"omni": 0.0, "subcardioid": 0.3, "cardioid": 0.5, "supercardioid": 0.63,
+                  "hypercardioid": 0.75, "figure8": 1.0}           # S(theta) = (1-k) + k cos(theta)
 
-    Directional patterns need the velocity field per step and are not on the device path yet.
-    """
+
+def trilinear_tables(g, shape, clamp: bool = False):
+    """8 corner indices and float64 weights of the reference's Python path (solver.py:962-1002), corner
+    order (i0,j0,k0),(i1,j0,k0),(i0,j1,k0),(i1,j1,k0),(i0,j0,k1),...; ``clamp`` as in solver.py:1093-1097."""
+    gx, gy, gz = g
+    i0, j0, k0 = int(gx), int(gy), int(gz)
+    fx, fy, fz = gx - i0, gy - j0, gz - k0
+    idx, wts = [], []
+    for c in range(8):
+        bx, by, bz = c & 1, (c >> 1) & 1, (c >> 2) & 1
+        i, j, k = i0 + bx, j0 + by, k0 + bz
+        if clamp:
+            i, j, k = min(i, shape[0] - 1), min(j, shape[1] - 1), min(k, shape[2] - 1)
+        idx.append((i * shape[1] + j) * shape[2] + k)
+        wts.append((fx if bx else 1 - fx) * (fy if by else 1 - fy) * (fz if bz else 1 - fz))
+    return idx, wts
+
+
+class Microphone:
+    """Virtual microphone at a physical position, trilinear in the fields (reference solver.py:797-1439).
+
+    Omnidirectional microphones are gathered on the device with the native backend's fp32 weights
+    (microphones.cpp:16-116).  Directional patterns (cardioid ... figure-8, or a callable gain(theta)) follow the
+    reference's Python path (solver.py:1004-1173): the device gathers p and the three velocity components with
+    that path's weights, the host applies (1-k) p + k rho c (v . d) in the same mixed precision."""
 
     def __init__(self, position, name=None, pattern="omni", direction=None, up=None):
-        if pattern != "omni":
-            raise NotImplementedError(
-                "the b200 backend records omnidirectional microphones only (pattern='omni'); "
-                "directional patterns are listed under 'next' in DESIGN.md")
         self.position = position
         self.name = name
+        if isinstance(pattern, str):
+            if pattern not in POLAR_PATTERNS:
+                raise ValueError(f"Unknown pattern '{pattern}'. Valid patterns: {list(POLAR_PATTERNS.keys())}")
+            self._pattern_name, self._pattern_k, self._custom_pattern = pattern, POLAR_PATTERNS[pattern], None
+        elif callable(pattern):
+            self._pattern_name, self._pattern_k, self._custom_pattern = "custom", None, pattern
+        else:
+            raise TypeError(f"pattern must be str or callable, got {type(pattern).__name__}")
         self.pattern = pattern
-        self._pattern_name = "omni"
+        d = np.array((1.0, 0.0, 0.0) if direction is None else direction, dtype=np.float64)
+        if np.linalg.norm(d) < 1e-10:
+            raise ValueError("direction vector cannot be zero")
+        self._direction = d / np.linalg.norm(d)
+        u = np.array((0.0, 0.0, 1.0) if up is None else up, dtype=np.float64)
+        if np.linalg.norm(u) < 1e-10:
+            raise ValueError("up vector cannot be zero")
+        self._up = u / np.linalg.norm(u)
+        if abs(np.dot(self._direction, self._up)) > 0.999:
+            raise ValueError("direction and up vectors cannot be parallel")
         self._data: list = []
         self._times: list = []
         self._grid_position = None
-        self._solver_dt = None
+        self._solver_dt = self._solver_rho = self._solver_c = None
+
+    @property
+    def direction(self):
+        return tuple(self._direction)
 
     def is_directional(self) -> bool:
-        return False
+        return self._pattern_name != "omni"
 
     def _initialize(self, solver) -> None:
         g = tuple(q / solver.dx for q in self.position)          # reference :941-943
@@ -86,15 +125,53 @@ class Microphone:
             raise ValueError(f"Microphone position {self.position} is outside simulation domain. "
                              f"Valid range: (0, 0, 0) to ({hi[0]:.4f}, {hi[1]:.4f}, {hi[2]:.4f})")
         self._grid_position = g
-        self._solver_dt = solver.dt
+        self._solver_dt, self._solver_rho, self._solver_c = solver.dt, solver.rho, solver.c
 
-    def get_waveform(self) -> np.ndarray:
+    # ---- Python-path sampling tables (used whenever any microphone of the solver is directional) ----
+    def _gather_tables(self, shape):
+        """[(field, idx8, w8 float32)]: p, then vx, vy, vz for a directional microphone.  The reference multiplies
+        a float64 weight with an fp32 sample, which NumPy evaluates in fp32 -> the weight is rounded first."""
+        out = [(0, *trilinear_tables(self._grid_position, shape))]
+        if self.is_directional():
+            for axis in range(3):                                 # staggered positions, solver.py:1073-1090
+                g = list(self._grid_position)
+                g[axis] -= 0.5
+                g = [max(0.0, min(q, n - 1.001)) for q, n in zip(g, shape)]
+                out.append((1 + axis, *trilinear_tables(g, shape, clamp=True)))
+        return [(f, np.array(i, dtype=np.int64), np.array(w, dtype=np.float64).astype(np.float32)) for f, i, w in out]
+
+    def _combine(self, pressure, vel):
+        """Directional output from fp32 samples (solver.py:1102-1173); arrays in, float64 array out."""
+        if not self.is_directional():
+            return pressure
+        vx, vy, vz = vel
+        d = self._direction
+        v_dot_d = vx * d[0] + vy * d[1] + vz * d[2]               # fp32 * np.float64 -> float64
+        if self._custom_pattern is not None:
+            out = np.empty(len(pressure), dtype=np.float64)
+            for q in range(len(pressure)):
+                v_mag = np.sqrt(vx[q] ** 2 + vy[q] ** 2 + vz[q] ** 2)
+                if v_mag > 1e-20:
+                    theta = np.arccos(np.clip(v_dot_d[q] / v_mag, -1.0, 1.0))
+                else:
+                    theta = 0.0
+                out[q] = pressure[q] * self._custom_pattern(theta)
+            return out
+        k = self._pattern_k
+        Z = self._solver_rho * self._solver_c
+        return (1 - k) * pressure + k * Z * v_dot_d               # fp32 term + float64 term
+
+    def get_waveform(self, weighting=None) -> np.ndarray:
+        if weighting not in ("Z", None):
+            raise NotImplementedError("frequency weighting is post-processing; use strata_fdtd.analysis on the raw waveform")
         return np.array(self._data, dtype=np.float32)
 
     def get_time_axis(self) -> np.ndarray:
         return np.array(self._times, dtype=np.float64)
 
     def get_sample_rate(self) -> float:
+        if self._solver_dt is None:
+            raise RuntimeError("Microphone not initialized. Add to solver first.")
         return 1.0 / self._solver_dt
 
     def clear(self) -> None:

@@ -123,7 +123,45 @@ def make_cases() -> dict:
                    dict(id=7, rho_inf=1.1, K_inf=1.1 * 350.0 ** 2, poles=SECOND_POLES)],
         material_id=mid2,
     )
+    # --- first-order Mur ABC on every face (edges/corners depend on the x,y,z application order)
+    C["mur_all"] = dict(
+        shape=(22, 26, 24), resolution=1e-3, steps=200,
+        plane_bcs=[dict(kind="mur", axes=("x", "y", "z"))],
+        sources=[dict(kind="point", position=(7, 13, 12), frequency=20e3)],
+        probes=[("corner", (0, 0, 0)), ("edge", (21, 13, 0)), ("face", (0, 13, 12)), ("mid", (15, 13, 12))],
+    )
+
+    # --- open pipe: sponge on y/z first, then radiation impedance at both x ends (constant R and
+    #     pipe-radius R) and a Mur plane pair on y; solid block inside
+    C["pml_radiation_mur"] = dict(
+        shape=(40, 18, 20), resolution=1e-3, steps=220,
+        geometry=_block_geometry((40, 18, 20), (18, 0, 0), (22, 7, 20)),
+        pml=[dict(depth=4, axes=("z",))],
+        plane_bcs=[dict(kind="radiation", axis="x", side="high", reflection_coeff=0.7),
+                   dict(kind="radiation", axis="x", side="low", pipe_radius=0.01),
+                   dict(kind="mur", axes=("y",))],
+        sources=[dict(kind="point", position=(8, 9, 10), frequency=15e3)],
+        probes=[("hi_end", (39, 9, 10)), ("lo_end", (0, 9, 10)), ("ywall", (30, 0, 10)), ("mid", (30, 9, 10))],
+    )
+    # --- directional microphones (cardioid / figure-8 / custom gain(theta)) next to an omni one: the reference
+    #     then records every microphone through its Python path (solver.py:2453-2461)
+    C["directional_mics"] = dict(
+        shape=(26, 24, 22), resolution=1e-3, steps=180,
+        geometry=_block_geometry((26, 24, 22), (15, 0, 0), (18, 9, 22)),
+        pml=[dict(depth=4)],
+        sources=[dict(kind="point", position=(6, 12, 11), frequency=16e3)],
+        probes=[("p", (20, 12, 11))],
+        mics=[("omni", (0.0123, 0.0101, 0.0107)),
+              ("card", (0.0123, 0.0101, 0.0107), dict(pattern="cardioid", direction=(1.0, 0.0, 0.0))),
+              ("fig8", (0.0201, 0.0152, 0.0093), dict(pattern="figure8", direction=(0.0, 1.0, 1.0))),
+              ("hyper_edge", (0.0003, 0.0004, 0.0208), dict(pattern="hypercardioid", direction=(-1.0, 0.5, 0.0))),
+              ("custom", (0.0180, 0.0120, 0.0110), dict(pattern=_subcardioid_gain, direction=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0)))],
+    )
     return C
+
+
+def _subcardioid_gain(theta):
+    return 0.7 + 0.3 * np.cos(theta)
 
 
 MEMBRANE_SPEC = dict(

@@ -58,6 +58,8 @@ def test_sponge_tables_and_indices_match_golden():
     g = np.load(GOLDEN / "partial_pml_plane.npz")
     s = build_b200_solver(case)
     for bi, b in enumerate(s._boundaries):
+        if not hasattr(b, "_max_sigma"):
+            continue
         assert float(b._max_sigma) == float(g[f"pml{bi}_max_sigma"])
         for a, sig, dec in zip("xyz", (b._sigma_x, b._sigma_y, b._sigma_z), b._decay):
             if sig is None:

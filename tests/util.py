@@ -59,6 +59,13 @@ def build_b200_solver(case: dict, **solver_kw):
         axes = tuple(b.get("axes", ("x", "y", "z")))
         s.add_boundary(sb.PML(depth=b.get("depth", 10), axis="all" if axes == ("x", "y", "z") else axes,
                               max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
+    for b in case.get("plane_bcs", []):
+        if b["kind"] == "mur":
+            s.add_boundary(sb.boundaries.ABCFirstOrder(axis=tuple(b.get("axes", ("x", "y", "z")))))
+        else:
+            s.add_boundary(sb.boundaries.RadiationImpedance(axis=b["axis"], side=b["side"],
+                                                            reflection_coeff=b.get("reflection_coeff"),
+                                                            pipe_radius=b.get("pipe_radius")))
     for src in case.get("sources", []):
         kind = src.get("kind", "point")
         if kind == "weighted":
@@ -69,8 +76,8 @@ def build_b200_solver(case: dict, **solver_kw):
                                       amplitude=src.get("amplitude", 1.0), source_type=kind))
     for name, pos in case.get("probes", []):
         s.add_probe(name, position=pos)
-    for name, pos in case.get("mics", []):
-        s.add_microphone(position=pos, name=name)
+    for name, pos, *opt in case.get("mics", []):
+        s.add_microphone(position=pos, name=name, **(opt[0] if opt else {}))
     for m in case.get("materials", []):
         poles = []
         for p in m["poles"]:
@@ -100,7 +107,7 @@ def assert_same_as_oracle(s, o, what=""):
     for name, _ in o.probes:
         a, b = s.get_probe_data(name)[name], o.probe_array(name)
         assert np.array_equal(a, b), f"{what}: probe {name} differs (max|d|={np.abs(a - b).max():.3e})"
-    for name, _ in o.mics:
+    for name, *_ in o.mics:
         a, b = s.microphones[name].get_waveform(), o.mic_array(name)
         assert np.array_equal(a, b), f"{what}: mic {name} differs (max|d|={np.abs(a - b).max():.3e})"
 
