@@ -114,7 +114,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline (reference kernels)
-def cpu_reference_sample(steps: int = 10, warmup: int = 2, shape=(256, 256, 256)):
+def cpu_reference_sample(steps: int = 60, warmup: int = 2, shape=(512, 512, 512)):
     """The reference's compiled C++/OpenMP kernels (oracle/_ref) on the host cores, same path (PML + source +
     probe), on a bounded sub-grid of the workload.  Falls back to the oracle port if _ref is not built."""
     from oracle import oracle as O
@@ -230,6 +230,7 @@ def run_b200_arm(a):
         _lib.check(lib.sb_step_n_async(h, W, src.data_ptr(), rec.data_ptr()))
         _lib.check(lib.sb_step_n_async(h, K, src.data_ptr(), rec.data_ptr()))   # untimed: instantiates the K-step graph
         barrier()
+        st0 = slab.device_stats()                # launches are counted over the timed region only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(dev.stream)
         _lib.check(lib.sb_step_n_async(h, K, src.data_ptr(), rec.data_ptr()))
@@ -325,7 +326,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
-        a.steps = 10 if a.steps is None else min(a.steps, 40)
+        a.steps = 60 if a.steps is None else a.steps
         a.warmup = 2 if a.warmup is None else a.warmup
         run_reference_arm(a)
     else:
