@@ -1,0 +1,97 @@
+"""Run scripts written for ``strata_fdtd`` unchanged on a box that only has this package.
+
+``install_as_strata_fdtd()`` registers importable modules named ``strata_fdtd``, ``strata_fdtd.boundaries``
+and ``strata_fdtd.materials`` whose names resolve to this package's mirrors, with ``FDTDSolver`` defaulting to
+``backend="b200"`` ("auto", "native" and "python" requests are mapped to it as well, with a note, because no
+other backend exists here).  When the real reference package is importable it is used instead and only gains
+the extra backend (``shim.install_into_reference``), so geometry/SDF, the material library, DSP etc. keep working.
+
+``python -m strata_fdtd_b200 script.py [args...]`` executes a script under that arrangement -- the stand-in
+for ``fdtd-compute`` on the GPU box (the reference CLI itself needs ``grid.num_cells``, which the shim adds).
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+import warnings
+
+
+def _reference_available() -> bool:
+    if "strata_fdtd" in sys.modules and not getattr(sys.modules["strata_fdtd"], "_b200_alias", False):
+        return True
+    try:
+        spec = importlib.util.find_spec("strata_fdtd")
+    except (ImportError, ValueError):
+        spec = None
+    return spec is not None
+
+
+def install_as_strata_fdtd(force_alias: bool = False):
+    """Make ``import strata_fdtd`` work; returns the module that scripts will see."""
+    if not force_alias and _reference_available():
+        try:
+            import strata_fdtd
+            from .shim import install_into_reference
+            os.environ.setdefault("STRATA_FDTD_BACKEND", "b200")
+            return install_into_reference(strata_fdtd)
+        except Exception as e:                       # e.g. h5py missing: fall back to the alias
+            warnings.warn(f"reference package present but not importable ({e}); using the b200 mirrors")
+            for k in [k for k in sys.modules if k == "strata_fdtd" or k.startswith("strata_fdtd.")]:
+                del sys.modules[k]
+    import strata_fdtd_b200 as sb
+    from . import boundaries, materials
+
+    class FDTDSolver(sb.FDTDSolver):
+        __doc__ = sb.FDTDSolver.__doc__
+
+        def __init__(self, *args, backend="auto", **kw):
+            if backend not in ("b200", "auto"):
+                warnings.warn(f"backend={backend!r} is not available in this installation; using 'b200'", stacklevel=2)
+            super().__init__(*args, backend="b200", **kw)
+
+    root = types.ModuleType("strata_fdtd")
+    root.__doc__ = "strata_fdtd API served by strata_fdtd_b200 (backend='b200')"
+    root._b200_alias = True
+    root.__path__ = []                               # lets 'import strata_fdtd.materials' resolve via sys.modules
+    names = dict(FDTDSolver=FDTDSolver, GaussianPulse=sb.GaussianPulse, Probe=sb.Probe, Microphone=sb.Microphone,
+                 PML=sb.PML, RigidBoundary=sb.RigidBoundary, ABCFirstOrder=boundaries.ABCFirstOrder,
+                 RadiationImpedance=boundaries.RadiationImpedance, UniformGrid=sb.UniformGrid,
+                 NonuniformGrid=sb.NonuniformGrid, Pole=sb.Pole, PoleType=sb.PoleType, SimpleMaterial=sb.SimpleMaterial,
+                 has_native_kernels=lambda: False, has_gpu_backend=lambda: True,
+                 get_native_info=lambda: {"available": False, "version": None, "has_openmp": False, "num_threads": 1},
+                 __version__=sb.__version__)
+    for k, v in names.items():
+        setattr(root, k, v)
+    b = types.ModuleType("strata_fdtd.boundaries")
+    for k in ("PML", "RigidBoundary", "ABCFirstOrder", "RadiationImpedance"):
+        setattr(b, k, getattr(boundaries, k))
+    m = types.ModuleType("strata_fdtd.materials")
+    for k in ("Pole", "PoleType", "SimpleMaterial", "PoleMaterial"):
+        setattr(m, k, getattr(materials, k))
+    core = types.ModuleType("strata_fdtd.core")
+    core.__path__ = []
+    solver_mod = types.ModuleType("strata_fdtd.core.solver")
+    for k in ("FDTDSolver", "GaussianPulse", "Probe", "Microphone"):
+        setattr(solver_mod, k, names[k])
+    grid_mod = types.ModuleType("strata_fdtd.core.grid")
+    grid_mod.UniformGrid, grid_mod.NonuniformGrid = sb.UniformGrid, sb.NonuniformGrid
+    core.solver, core.grid = solver_mod, grid_mod
+    root.boundaries, root.materials, root.core = b, m, core
+    sys.modules.update({"strata_fdtd": root, "strata_fdtd.boundaries": b, "strata_fdtd.materials": m,
+                        "strata_fdtd.core": core, "strata_fdtd.core.solver": solver_mod,
+                        "strata_fdtd.core.grid": grid_mod})
+    return root
+
+
+def run_script(path: str, argv: list[str] | None = None) -> dict:
+    """Execute ``path`` as __main__ with ``strata_fdtd`` importable; returns the script's globals."""
+    import runpy
+    install_as_strata_fdtd()
+    old_argv = sys.argv
+    sys.argv = [path] + list(argv or [])
+    try:
+        return runpy.run_path(path, run_name="__main__")
+    finally:
+        sys.argv = old_argv

@@ -24,7 +24,7 @@ import numpy as np
 
 try:
     import h5py
-    HAVE_H5PY = True
+    HAVE_H5PY = hasattr(h5py, "File")     # a stub module may be registered under this name
 except ImportError:      # pragma: no cover - depends on the image
     h5py = None
     HAVE_H5PY = False
@@ -48,7 +48,8 @@ class _NpzTree:
     def close(self):
         payload = dict(self.data)
         payload["__attrs__"] = np.array(json.dumps(self.attrs, default=str))
-        np.savez_compressed(self.path, **payload)
+        with open(self.path, "wb") as fh:            # a file object keeps the exact name (no ".npz" appended)
+            np.savez_compressed(fh, **payload)
 
 
 class ResultWriter:
@@ -64,7 +65,7 @@ class ResultWriter:
         if self.use_h5:
             self.file = h5py.File(self.filename, "w")
         else:
-            self.filename = self.filename.with_suffix(self.filename.suffix + ".npz")
+            # same path the caller asked for (scripts stat / upload it afterwards); the content is an .npz archive
             self.file = _NpzTree(self.filename)
         self._metadata(script_content)
         self._q: queue.Queue = queue.Queue(maxsize=8)

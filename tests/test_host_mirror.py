@@ -188,3 +188,42 @@ def test_shim_registers_backend_with_reference():
     r = ref.FDTDSolver(shape=(12, 12, 12), resolution=1e-3, backend="native")
     assert r.using_native and r.grid.num_cells == 12 ** 3
     r.step()
+
+
+def test_result_writer_schema_without_device(tmp_path):
+    """The asynchronous writer (io.ResultWriter) against a stub solver: reference schema, chunked appends."""
+    import json, types
+    from strata_fdtd_b200 import io as sbio
+    solver = types.SimpleNamespace(shape=(4, 5, 6), dx=1e-3, dt=1.6e-6, c=343.0, rho=1.2, step_count=7, time=7 * 1.6e-6,
+                                   grid=sb.UniformGrid((4, 5, 6), 1e-3), geometry=np.ones((4, 5, 6), bool),
+                                   _sources=[sb.GaussianPulse(position=(1, 2, 3), frequency=1e3)],
+                                   _probes={"a": sb.Probe("a", (1, 1, 1)), "b": sb.Probe("b", (2, 2, 2))})
+    out = tmp_path / "r.h5"
+    w = sbio.ResultWriter(out, solver, script_content="print(1)")
+    blk = np.arange(14, dtype=np.float32).reshape(7, 2)
+    w.append_probe_block(["a", "b"], blk[:3]); w.append_probe_block(["a", "b"], blk[3:])
+    w.write_snapshot(np.full((4, 5, 6), 2.0, np.float32))
+    w.finalize(runtime=0.5, backend="b200", num_threads=0)
+    if sbio.HAVE_H5PY:
+        import h5py
+        with h5py.File(out, "r") as f:
+            assert np.array_equal(f["probes/b"][:], blk[:, 1]) and f["fields/pressure"].shape == (1, 4, 5, 6)
+            assert f["metadata"].attrs["backend"] == "b200" and f["simulation"].attrs["num_steps"] == 7
+    else:
+        z = np.load(out)
+        assert np.array_equal(z["probes/a"], blk[:, 0]) and np.array_equal(z["probes/b"], blk[:, 1])
+        assert z["fields/pressure"].shape == (1, 4, 5, 6) and z["materials/geometry"].dtype == np.uint8
+        attrs = json.loads(str(z["__attrs__"]))
+        assert attrs["metadata@backend"] == "b200" and attrs["simulation@num_steps"] == 7
+        assert attrs["grid@shape"] == [4, 5, 6] and attrs["sources/source_0@frequency"] == 1e3
+
+
+def test_strata_fdtd_alias_resolves_names():
+    import subprocess, sys
+    code = ("from strata_fdtd_b200.compat import install_as_strata_fdtd; install_as_strata_fdtd(force_alias=True); "
+            "from strata_fdtd import FDTDSolver, PML, GaussianPulse, NonuniformGrid; "
+            "from strata_fdtd.materials import Pole, PoleType, SimpleMaterial; "
+            "from strata_fdtd.boundaries import RadiationImpedance; "
+            "s = FDTDSolver(shape=(6,6,6), resolution=1e-3); print(s.backend, s.using_native)")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
+    assert res.stdout.strip() == "b200 False", res.stderr
