@@ -74,7 +74,8 @@ class Stats(C.Structure):
 
 
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_TMA = 0, 1, 2, 3
-OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH, OPT_PROFILE = range(7)
+(OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH, OPT_PROFILE,
+ OPT_FUSE_K3) = range(8)
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _fp = C.POINTER(C.c_float)

@@ -68,6 +68,10 @@ struct sb_solver {
     // sources / records
     int n_sources = 0, n_src_cells = 0;
     DBuf<long long> src_off; DBuf<int> src_start, src_id, src_field; DBuf<double> src_weight;
+    // host copy of small source tables: enables the single-kernel step (injection inside K1)
+    int n_src_entries = 0; bool inline_ok = false;
+    int inl_i[8], inl_j[8], inl_k[8], inl_src[8]; double inl_weight[8];
+    int opt_fuse_k3 = 1;
     int n_probes = 0, n_mics = 0;
     DBuf<long long> probe_off, mic_off; DBuf<float> mic_w; DBuf<int> mic_field; bool have_mic_field = false;
     DBuf<double> d_src_vals; DBuf<float> d_record; DBuf<int> d_step_ctr;
@@ -84,7 +88,8 @@ struct sb_solver {
             return std::tie(n, cur, src, rec) < std::tie(o.n, o.cur, o.src, o.rec);
         }
     };
-    std::map<GraphKey, cudaGraphExec_t> graphs;
+    struct GraphVal { cudaGraphExec_t exec; long long launches; };
+    std::map<GraphKey, GraphVal> graphs;
     // stats
     long long steps_done = 0, kernels_launched = 0;
     int last_variant = 0;
@@ -102,7 +107,7 @@ struct sb_solver {
 
 static void drop_graphs(sb_solver *h)
 {
-    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
 }
 
@@ -345,6 +350,7 @@ extern "C" int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const in
     CHECK_H(h);
     drop_graphs(h);
     h->n_sources = n_sources; h->n_src_cells = n_cells;
+    h->n_src_entries = 0; h->inline_ok = true;
     if (n_cells == 0) return 0;
     if (!cell_idx || !start || !src_id || !field || !weight) return fail("null source table");
     const long long ncell = (long long)h->d.nx * h->d.ny * h->d.nz;
@@ -356,6 +362,16 @@ extern "C" int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const in
     const int n_ent = start[n_cells];
     for (int e = 0; e < n_ent; e++)
         if (src_id[e] < 0 || src_id[e] >= n_sources || field[e] < 0 || field[e] > 3) return fail("bad source entry %d", e);
+    h->n_src_entries = n_ent;
+    h->inline_ok = n_ent <= 8;
+    for (int u = 0; u < n_cells && h->inline_ok; u++)
+        for (int e = start[u]; e < start[u + 1]; e++) {
+            if (field[e] != 0) { h->inline_ok = false; break; }
+            const long long dn = cell_idx[u];
+            h->inl_k[e] = (int)(dn % h->d.nz); h->inl_j[e] = (int)((dn / h->d.nz) % h->d.ny);
+            h->inl_i[e] = (int)(dn / ((long long)h->d.nz * h->d.ny));
+            h->inl_src[e] = src_id[e]; h->inl_weight[e] = weight[e];
+        }
     if (h->src_off.upload(off, h->stream) || h->src_start.upload(start, (size_t)n_cells + 1, h->stream) ||
         h->src_id.upload(src_id, (size_t)n_ent, h->stream) || h->src_field.upload(field, (size_t)n_ent, h->stream) ||
         h->src_weight.upload(weight, (size_t)n_ent, h->stream)) return 1;
@@ -522,6 +538,8 @@ static void fill_params(sb_solver *h, StepParams &P)
     P.i_begin = 0; P.i_end = d.nx; P.chunk_i = d.nx;
     P.peer_lo_p = P.peer_hi_p = nullptr; P.flag_lo = P.flag_hi = nullptr;
     P.step_global = h->d_step_global.p; P.err_flag = h->d_err.p; P.permute_chunks = 0;
+    P.n_inline = 0; P.src_row = nullptr; P.rec_prev = 0; P.n_probes = P.n_mics = 0;
+    P.probe_off = P.mic_off8 = nullptr; P.mic_field = nullptr; P.mic_w8 = nullptr; P.rec_row = nullptr;
     if (h->have_peers) {
         if (d.has_lower) { P.peer_lo_p = h->peer_lo_set[out] + (long long)(h->peer_lo_nx + 1) * h->plane; P.flag_lo = h->my_flags; }
         if (d.has_upper) { P.peer_hi_p = h->peer_hi_set[out]; P.flag_hi = h->my_flags + 1; }
@@ -590,10 +608,33 @@ static int launch_step_kernel(sb_solver *h, StepParams &P)
     return 0;
 }
 
-static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
+// single-kernel step: point sources injected inside K1, previous step's records taken from K1's input set
+static bool fused_k3(const sb_solver *h)
+{
+    const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
+    return h->opt_fuse_k3 && h->inline_ok && !h->have_peers && !h->have_ade && h->plane_ops.empty() &&
+           (variant == SB_KERNEL_MARCH || variant == SB_KERNEL_TMA);
+}
+
+static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev, int step, bool last)
 {
     StepParams P;
     fill_params(h, P);
+    const int n_rec_all = h->n_probes + h->n_mics;
+    const bool fused = fused_k3(h);
+    if (fused) {
+        P.n_inline = h->n_src_entries;
+        for (int e = 0; e < h->n_src_entries; e++) {
+            P.inl_i[e] = h->inl_i[e]; P.inl_j[e] = h->inl_j[e]; P.inl_k[e] = h->inl_k[e];
+            P.inl_src[e] = h->inl_src[e]; P.inl_weight[e] = h->inl_weight[e];
+        }
+        P.src_row = src_dev ? src_dev + (long long)step * h->n_sources : nullptr;
+        P.rec_prev = (step > 0 && n_rec_all > 0) ? 1 : 0;
+        P.n_probes = h->n_probes; P.n_mics = h->n_mics;
+        P.probe_off = h->probe_off.p; P.mic_off8 = h->mic_off.p; P.mic_w8 = h->mic_w.p;
+        P.mic_field = h->have_mic_field ? h->mic_field.p : nullptr;
+        P.rec_row = rec_dev ? rec_dev + (long long)(step - 1) * n_rec_all : nullptr;
+    }
     if (h->have_ade) {
         const int nb = (h->ade.n_cells + 255) / 256;
         k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
@@ -622,7 +663,16 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev)
     const int n_rec = h->n_probes + h->n_mics;
     SourceTable T{h->n_sources, h->n_src_cells, h->src_off.p, h->src_start.p, h->src_id.p, h->src_field.p, h->src_weight.p};
     const PeerLink L = peer_link(h, P);
-    if (h->n_src_cells <= 4096 && n_rec <= 4096) {
+    if (fused) {
+        if (last && n_rec) {                               // the chunk's last step has no successor to record it
+            const FieldPtrs F{{P.p_out, P.vx_out, P.vy_out, P.vz_out}};
+            k3_record_row<<<(n_rec + 255) / 256, 256, 0, h->stream>>>(F, h->n_probes, h->probe_off.p, h->n_mics,
+                                                                      h->have_mic_field ? h->mic_field.p : nullptr,
+                                                                      h->mic_off.p, h->mic_w.p,
+                                                                      rec_dev + (long long)step * n_rec);
+            h->kernels_launched++;
+        }
+    } else if (h->n_src_cells <= 4096 && n_rec <= 4096) {
         k3_small<<<1, 1024, 0, h->stream>>>(T, P.p_out, P.vx_out, P.vy_out, P.vz_out, src_dev, h->n_probes,
                                             h->probe_off.p, h->n_mics, h->have_mic_field ? h->mic_field.p : nullptr, h->mic_off.p,
                                             h->mic_w.p, rec_dev, h->d_step_ctr.p, L);
@@ -669,7 +719,7 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
                 const long long k0 = h->kernels_launched; const int cur0 = h->cur; const long long s0 = h->steps_done;
                 CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                 int rc = 0;
-                for (int s = 0; s < n_steps && !rc; s++) rc = enqueue_one_step(h, src_dev, rec_dev);
+                for (int s = 0; s < n_steps && !rc; s++) rc = enqueue_one_step(h, src_dev, rec_dev, s, s == n_steps - 1);
                 cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
                 h->cur = cur0; h->steps_done = s0;
                 const long long per_launch = h->kernels_launched - k0; h->kernels_launched = k0;
@@ -678,21 +728,17 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
                 cudaGraphExec_t ge;
                 CU(cudaGraphInstantiate(&ge, g, 0));
                 cudaGraphDestroy(g);
-                it = h->graphs.emplace(key, ge).first;
-                (void)per_launch;
+                it = h->graphs.emplace(key, sb_solver::GraphVal{ge, per_launch}).first;
             }
-            CU(cudaGraphLaunch(it->second, h->stream));
-            // bookkeeping equivalent to n_steps enqueues
-            const int per_step = (h->have_ade ? 2 : 0) + 1 + (int)h->plane_ops.size() + ((h->n_src_cells <= 4096 && (h->n_probes + h->n_mics) <= 4096) ? 1 :
-                                 ((h->n_src_cells ? 1 : 0) + ((h->n_probes + h->n_mics) ? 1 : 0) + 1));
-            h->kernels_launched += (long long)per_step * n_steps;
+            CU(cudaGraphLaunch(it->second.exec, h->stream));
+            h->kernels_launched += it->second.launches;    // bookkeeping equivalent to n_steps enqueues
             h->steps_done += n_steps;
             if (n_steps & 1) h->cur = 1 - h->cur;
             return 0;
         }
     }
     for (int s = 0; s < n_steps; s++)
-        if (enqueue_one_step(h, src_dev, rec_dev)) return 1;
+        if (enqueue_one_step(h, src_dev, rec_dev, s, s == n_steps - 1)) return 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -798,6 +844,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
         case SB_OPT_CHUNK_I: if (value < 0) return fail("chunk_i must be >= 0"); h->opt_chunk_i = value; break;
         case SB_OPT_USE_GRAPH: h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); break;
         case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
+        case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value ? 1 : 0; break;
         default: return fail("unknown option %d", option);
     }
     drop_graphs(h);

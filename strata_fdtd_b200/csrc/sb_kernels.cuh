@@ -40,7 +40,33 @@ struct StepParams {
     const int *step_global;              // index of the step being executed (device counter)
     int *err_flag;
     int permute_chunks;                  // schedule the two cut chunks in the middle of the grid order
+    // single-kernel step ("fused K3"): a handful of point sources are injected by the thread that owns the cell
+    // right before it stores p, and the probes / microphones of the PREVIOUS step are recorded from the input set
+    // by the first warp of block 0 (they are final there); a tail launch records the last step of a chunk.
+    int n_inline;                        // 0 = off
+    int inl_i[8], inl_j[8], inl_k[8], inl_src[8];
+    double inl_weight[8];
+    const double *src_row;               // this step's waveform samples [n_sources]
+    int rec_prev;                        // 1 = record the previous step's slots in this launch
+    int n_probes, n_mics;
+    const long long *probe_off, *mic_off8;
+    const int *mic_field;
+    const float *mic_w8;
+    float *rec_row;                      // record slots of the previous step [n_probes + n_mics]
 };
+
+// 8-point weighted gather of one field (trilinear microphone sample): sum = 0; sum += w[c]*f[idx[c]], fp32,
+// corner order of microphones.hpp:30-32 (microphones.cpp:82-116; Python path core/solver.py:1027-1034, 1085-1099)
+struct FieldPtrs { const float *f[4]; };
+__device__ __forceinline__ float gather8(const FieldPtrs &F, const int *mic_field, const long long *mic_off8,
+                                         const float *mic_w8, int m)
+{
+    const float *f = F.f[mic_field ? mic_field[m] : 0];
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * f[mic_off8[8 * m + c]];
+    return sum;
+}
 
 __device__ __forceinline__ int ld_acquire_sys(const int *p)
 {
@@ -166,6 +192,17 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
     if (strip_k0 >= P.nz || j0 >= P.ny || ib >= ie) return;     // warp-uniform exit
     if (P.flag_lo && ib == 0) wait_neighbour(P.flag_lo, *P.step_global, P.err_flag);
     if (P.flag_hi && ie == P.nx) wait_neighbour(P.flag_hi, *P.step_global, P.err_flag);
+    if (P.rec_prev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 32) {
+        // probes / microphones of the previous step: its output set is this launch's (read-only) input set
+        const FieldPtrs F{{P.p_in, P.vx_in, P.vy_in, P.vz_in}};
+        for (int t = lane; t < P.n_probes + P.n_mics; t += 32)
+            P.rec_row[t] = t < P.n_probes ? P.p_in[P.probe_off[t]]
+                                          : gather8(F, P.mic_field, P.mic_off8, P.mic_w8, t - P.n_probes);
+    }
+    unsigned inl_mask = 0;                                       // inline point sources inside this thread's column
+    for (int q = 0; q < P.n_inline; q++)
+        if (P.inl_j[q] >= j0 && P.inl_j[q] < j0 + RJ && P.inl_k[q] >= k0 && P.inl_k[q] < k0 + 4 &&
+            P.inl_i[q] >= ib && P.inl_i[q] < ie) inl_mask |= 1u << q;
     const bool lane_ok = k0 < P.nz;
     const int nz = P.nz, ny = P.ny;
     // per-element validity and "z face is updated" flags
@@ -333,7 +370,18 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             }
             if (row_ok[r + 1] && lane_ok) {
                 const long long c = base + (long long)r * P.pitch;
-                const float4 pst = sel4(e0, e1, e2, e3, pnew, z4);
+                float4 pst = sel4(e0, e1, e2, e3, pnew, z4);
+                if (inl_mask) {                                  // float64 add, fp32 store (solver.py:2421), list order
+                    for (int q = 0; q < P.n_inline; q++)
+                        if (((inl_mask >> q) & 1u) && P.inl_i[q] == i && P.inl_j[q] == j0 + r) {
+                            const double w = __dmul_rn(P.src_row[P.inl_src[q]], P.inl_weight[q]);
+                            const int e = P.inl_k[q] - k0;
+                            if (e == 0) pst.x = (float)((double)pst.x + w);
+                            else if (e == 1) pst.y = (float)((double)pst.y + w);
+                            else if (e == 2) pst.z = (float)((double)pst.z + w);
+                            else pst.w = (float)((double)pst.w + w);
+                        }
+                }
                 st4(P.p_out + c, pst);
                 if (P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
                 if (P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
@@ -466,19 +514,6 @@ __global__ void k3_inject(SourceTable T, float *p, float *vx, float *vy, float *
     }
 }
 
-// 8-point weighted gather of one field (trilinear microphone sample): sum = 0; sum += w[c]*f[idx[c]], fp32,
-// corner order of microphones.hpp:30-32 (microphones.cpp:82-116; Python path core/solver.py:1027-1034, 1085-1099)
-struct FieldPtrs { const float *f[4]; };
-__device__ __forceinline__ float gather8(const FieldPtrs &F, const int *mic_field, const long long *mic_off8,
-                                         const float *mic_w8, int m)
-{
-    const float *f = F.f[mic_field ? mic_field[m] : 0];
-    float sum = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 8; c++) sum = sum + mic_w8[8 * m + c] * f[mic_off8[8 * m + c]];
-    return sum;
-}
-
 __global__ void k3_record(FieldPtrs F, int n_probes, const long long *probe_off,
                           int n_mics, const int *mic_field, const long long *mic_off8, const float *mic_w8,
                           float *record_out, int *step_ctr)
@@ -491,6 +526,15 @@ __global__ void k3_record(FieldPtrs F, int n_probes, const long long *probe_off,
     } else if (t < n_rec) {
         record_out[(long long)step * n_rec + t] = gather8(F, mic_field, mic_off8, mic_w8, t - n_probes);
     }
+}
+
+// records one step into an explicit row (tail of a chunk in single-kernel-step mode)
+__global__ void k3_record_row(FieldPtrs F, int n_probes, const long long *probe_off, int n_mics, const int *mic_field,
+                              const long long *mic_off8, const float *mic_w8, float *rec_row)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_probes) rec_row[t] = F.f[0][probe_off[t]];
+    else if (t < n_probes + n_mics) rec_row[t] = gather8(F, mic_field, mic_off8, mic_w8, t - n_probes);
 }
 
 __global__ void k3_advance(int *step_ctr, PeerLink L) { *step_ctr += 1; signal_step_done(L); }

@@ -143,6 +143,19 @@ def make_cases() -> dict:
         sources=[dict(kind="point", position=(8, 9, 10), frequency=15e3)],
         probes=[("hi_end", (39, 9, 10)), ("lo_end", (0, 9, 10)), ("ywall", (30, 0, 10)), ("mid", (30, 9, 10))],
     )
+    # --- odd extents WITH geometry and sponge: rows end inside a float4 / mask word, solids touch the outer faces
+    g_odd = _block_geometry((19, 21, 13), (7, 0, 5), (12, 9, 13))
+    g_odd[0:3, 15:21, 0:4] = False
+    g_odd[18, :, 6] = False
+    C["odd_geometry_pml"] = dict(
+        shape=(19, 21, 13), resolution=1e-3, steps=220,
+        geometry=g_odd,
+        pml=[dict(depth=3)],
+        sources=[dict(kind="point", position=(4, 12, 8), frequency=20e3), dict(kind="point", position=(9, 4, 9), frequency=9e3)],
+        probes=[("a", (15, 15, 3)), ("in_solid", (9, 4, 9)), ("edge", (18, 20, 12))],
+        mics=[("m", (0.0141, 0.0122, 0.0031))],
+    )
+
     # --- directional microphones (cardioid / figure-8 / custom gain(theta)) next to an omni one: the reference
     #     then records every microphone through its Python path (solver.py:2453-2461)
     C["directional_mics"] = dict(

@@ -21,6 +21,9 @@ VARIANTS = {
     "march_r4_chunk5": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 4, _lib.OPT_CHUNK_I: 5,
                         _lib.OPT_WARPS_J: 2},
     "march_r2_graph": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_USE_GRAPH: 1},
+    "march_r2_separate_k3": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_FUSE_K3: 0},
+    "march_r1_nograph_wk2": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_USE_GRAPH: 0,
+                             _lib.OPT_WARPS_K: 2, _lib.OPT_WARPS_J: 2},
 }
 
 
@@ -207,3 +210,38 @@ def test_example_scripts_run_unchanged_through_the_alias(tmp_path):
                          cwd=tmp_path, capture_output=True, text=True, timeout=300,
                          env={**__import__("os").environ, "PYTHONPATH": str(root)})
     assert res.returncode == 0 and "64 probes" in res.stdout, res.stderr[-2000:]
+
+
+def test_lifecycle_reset_rerun_late_additions_and_inplace_geometry():
+    """reset() reproduces the first run; sources / probes added after stepping take effect; geometry edited in
+    place WITHOUT set_geometry zeroes p in solids but leaves faces open, as the native backend does
+    (boundary lists exist only after set_geometry, core/solver.py:1779-1780, 2094)."""
+    case = CASES["block_pml"]
+    s = build_b200_solver(case, chunk_steps=33)
+    s.run(steps=90)
+    first = {f: s.get_field(f) for f in ("p", "vx", "vy", "vz")}
+    tr = s.get_probe_data("shadow")["shadow"].copy()
+    s.reset()
+    assert len(s.get_probe_data("shadow")["shadow"]) == 0
+    s.run(steps=45); s.run(steps=45)
+    for f in first:
+        assert np.array_equal(s.get_field(f), first[f]), f
+    assert np.array_equal(s.get_probe_data("shadow")["shadow"], tr)
+    # late additions
+    import strata_fdtd_b200 as sb
+    o = O.OracleSolver(case); o.run_steps(90)
+    s.add_source(sb.GaussianPulse(position=(40, 30, 10), frequency=12e3))
+    s.add_probe("late", (41, 30, 10))
+    o.sources.append(dict(kind="point", position=(40, 30, 10), frequency=12e3)); o.probes.append(("late", (41, 30, 10)))
+    o.probe_data["late"] = []
+    s.run(steps=40); o.run_steps(40)
+    assert_same_as_oracle(s, o, "late additions")
+    # in-place geometry edit without set_geometry
+    plain = dict(shape=(20, 18, 22), resolution=1e-3, steps=0, pml=[dict(depth=3)],
+                 sources=[dict(kind="point", position=(5, 9, 11), frequency=20e3)], probes=[("q", (15, 9, 11))])
+    s2 = build_b200_solver(plain); o2 = O.OracleSolver(plain)
+    s2.geometry[9:12, 6:12, 8:14] = False
+    o2.geometry[9:12, 6:12, 8:14] = False
+    s2.run(steps=80); o2.run_steps(80)
+    assert not o2.rigid
+    assert_same_as_oracle(s2, o2, "in-place geometry")
