@@ -61,7 +61,7 @@ struct sb_solver {
     // tables
     DBuf<float> cvx, cvy, cvz, icx, icy, icz;
     bool nonuniform = false, have_coeffs = false;
-    float cp = 0.f;
+    float cp = 0.f, cv_uni = 0.f;
     DBuf<uint8_t> mask; bool have_mask = false;
     std::vector<Sponge *> sponges;
     std::vector<PlaneOpHost *> plane_ops;
@@ -247,6 +247,12 @@ extern "C" int sb_set_coefficients(sb_solver *h, const float *cv_x, const float 
         if (upload_table(h->icz, ic_z, d.nz, d.pitch + 4, 1.0f, h->stream)) return 1;
     }
     h->nonuniform = nu; h->cp = cp; h->have_coeffs = true;
+    h->cv_uni = cv_x[0];
+    if (!nu) {                                   // the UNI kernels use one scalar: the tables must really be constant
+        for (int q = 0; q < gx; q++) if (cv_x[q] != cv_x[0]) return fail("uniform grid needs a constant cv table");
+        for (int q = 0; q < d.ny; q++) if (cv_y[q] != cv_x[0]) return fail("uniform grid needs a constant cv table");
+        for (int q = 0; q < d.nz; q++) if (cv_z[q] != cv_x[0]) return fail("uniform grid needs a constant cv table");
+    }
     drop_graphs(h);
     return 0;
 }
@@ -537,13 +543,13 @@ static void fill_params(sb_solver *h, StepParams &P)
     P.has_lower = d.has_lower; P.has_upper = d.has_upper;
     P.i_begin = 0; P.i_end = d.nx; P.chunk_i = d.nx;
     P.peer_lo_p = P.peer_hi_p = nullptr; P.flag_lo = P.flag_hi = nullptr;
-    P.step_global = h->d_step_global.p; P.err_flag = h->d_err.p; P.permute_chunks = 0;
+    P.step_global = h->d_step_global.p; P.err_flag = h->d_err.p; P.two_range = 0;
+    P.cv_uni = h->cv_uni;
     P.n_inline = 0; P.src_row = nullptr; P.rec_prev = 0; P.n_probes = P.n_mics = 0;
     P.probe_off = P.mic_off8 = nullptr; P.mic_field = nullptr; P.mic_w8 = nullptr; P.rec_row = nullptr;
     if (h->have_peers) {
         if (d.has_lower) { P.peer_lo_p = h->peer_lo_set[out] + (long long)(h->peer_lo_nx + 1) * h->plane; P.flag_lo = h->my_flags; }
         if (d.has_upper) { P.peer_hi_p = h->peer_hi_set[out]; P.flag_hi = h->my_flags + 1; }
-        P.permute_chunks = 1;
     }
 }
 
@@ -557,14 +563,31 @@ static PeerLink peer_link(sb_solver *h, const StepParams &P)
     return L;
 }
 
-template <int RJ>
-static void launch_march(sb_solver *h, const StepParams &P, dim3 grd, dim3 blk)
+// ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE> ------------------------------
+template <int RJ, bool GEOM, bool UNI, bool PEER>
+static void launch_march3(bool fuse, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
-    if (P.mask) k1_step_march<RJ, true><<<grd, blk, 0, h->stream>>>(P);
-    else        k1_step_march<RJ, false><<<grd, blk, 0, h->stream>>>(P);
+    if (fuse) k1_step_march<RJ, GEOM, UNI, PEER, true><<<grd, blk, 0, st>>>(P);
+    else      k1_step_march<RJ, GEOM, UNI, PEER, false><<<grd, blk, 0, st>>>(P);
+}
+template <int RJ, bool GEOM>
+static void launch_march2(bool uni, bool peer, bool fuse, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+{
+    if (uni) { if (peer) launch_march3<RJ, GEOM, true, true>(fuse, P, grd, blk, st);
+               else      launch_march3<RJ, GEOM, true, false>(fuse, P, grd, blk, st); }
+    else     { if (peer) launch_march3<RJ, GEOM, false, true>(fuse, P, grd, blk, st);
+               else      launch_march3<RJ, GEOM, false, false>(fuse, P, grd, blk, st); }
+}
+static void launch_march(int rj, bool peer, bool fuse, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+{
+    const bool geom = P.mask != nullptr, uni = P.icx == nullptr;
+    if (rj == 1) { if (geom) launch_march2<1, true>(uni, peer, fuse, P, grd, blk, st);
+                   else      launch_march2<1, false>(uni, peer, fuse, P, grd, blk, st); }
+    else         { if (geom) launch_march2<2, true>(uni, peer, fuse, P, grd, blk, st);
+                   else      launch_march2<2, false>(uni, peer, fuse, P, grd, blk, st); }
 }
 
-static int launch_step_kernel(sb_solver *h, StepParams &P)
+static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
 {
     const sb_grid_desc &d = h->d;
     int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
@@ -575,36 +598,54 @@ static int launch_step_kernel(sb_solver *h, StepParams &P)
         dim3 blk(128), grd((d.nz + 127) / 128, d.ny, P.i_end - P.i_begin);
         if (P.mask) k0_step_naive<true><<<grd, blk, 0, h->stream>>>(P);
         else        k0_step_naive<false><<<grd, blk, 0, h->stream>>>(P);
-    } else {
-        const int rj = h->opt_rj, wk = h->opt_wk;
-        int wj = h->opt_wj;
-        if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
-            wj = std::max(1, 8 / wk);
-            while (wj > 1 && (long long)((d.nz + 128 * wk - 1) / (128 * wk)) * ((d.ny + rj * wj - 1) / (rj * wj)) *
-                                 ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
-        }
-        if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
-        const int gx = (d.nz + 128 * wk - 1) / (128 * wk), gy = (d.ny + rj * wj - 1) / (rj * wj);
-        int chunk = h->opt_chunk_i;
-        if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
-            const long long want = 148LL * 8;
-            long long nchunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
-            nchunks = std::max(1LL, std::min<long long>(nchunks, (d.nx + 7) / 8));
-            chunk = (int)((d.nx + nchunks - 1) / nchunks);
-            chunk = std::max(chunk, std::min(d.nx, 8));
-            chunk = std::min(chunk, 64);
-        }
-        P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-        dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
-        if (grd.z > 65535) return fail("too many i-chunks");
-        switch (rj) {
-            case 1: launch_march<1>(h, P, grd, blk); break;
-            case 2: launch_march<2>(h, P, grd, blk); break;
-            case 4: launch_march<4>(h, P, grd, blk); break;
-            default: return fail("rows_per_thread must be 1, 2 or 4");
-        }
+        h->kernels_launched++;
+        return 0;
     }
-    h->kernels_launched++;
+    const int rj = h->opt_rj, wk = h->opt_wk;
+    if (rj != 1 && rj != 2) return fail("rows_per_thread must be 1 or 2");
+    int wj = h->opt_wj;
+    if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
+        wj = std::max(1, 8 / wk);
+        while (wj > 1 && (long long)((d.nz + 128 * wk - 1) / (128 * wk)) * ((d.ny + rj * wj - 1) / (rj * wj)) *
+                             ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
+    }
+    if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
+    const int gx = (d.nz + 128 * wk - 1) / (128 * wk), gy = (d.ny + rj * wj - 1) / (rj * wj);
+    int chunk = h->opt_chunk_i;
+    if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
+        const long long want = 148LL * 8;
+        long long nchunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
+        nchunks = std::max(1LL, std::min<long long>(nchunks, (d.nx + 7) / 8));
+        chunk = (int)((d.nx + nchunks - 1) / nchunks);
+        chunk = std::max(chunk, std::min(d.nx, 8));
+        chunk = std::min(chunk, 64);
+    }
+    const dim3 blk(32 * wk, wj);
+    if (!h->have_peers) {
+        P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
+        const dim3 grd(gx, gy, (d.nx + chunk - 1) / chunk);
+        if (grd.z > 65535) return fail("too many i-chunks");
+        launch_march(rj, false, fuse, P, grd, blk, h->stream);
+        h->kernels_launched++;
+        return 0;
+    }
+    // Multi-GPU: the planes next to a cut go through the PEER variant (neighbour flags, NVLink peer stores); the
+    // interior runs the lean variant first, so the neighbours' flags have arrived long before they are polled.
+    const int cb = std::min(8, chunk);
+    if (d.nx >= 4 * cb) {
+        StepParams Q = P;
+        Q.peer_lo_p = Q.peer_hi_p = nullptr; Q.flag_lo = Q.flag_hi = nullptr;
+        Q.i_begin = cb; Q.i_end = d.nx - cb; Q.chunk_i = chunk;
+        const dim3 grd(gx, gy, (Q.i_end - Q.i_begin + chunk - 1) / chunk);
+        launch_march(rj, false, false, Q, grd, blk, h->stream);
+        P.two_range = 1; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = cb;
+        launch_march(rj, true, false, P, dim3(gx, gy, 2), blk, h->stream);
+        h->kernels_launched += 2;
+    } else {                                // thin slab: everything through the PEER variant
+        P.two_range = 0; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
+        launch_march(rj, true, false, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
+        h->kernels_launched++;
+    }
     return 0;
 }
 
@@ -612,8 +653,10 @@ static int launch_step_kernel(sb_solver *h, StepParams &P)
 static bool fused_k3(const sb_solver *h)
 {
     const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
-    return h->opt_fuse_k3 && h->inline_ok && !h->have_peers && !h->have_ade && h->plane_ops.empty() &&
-           (variant == SB_KERNEL_MARCH || variant == SB_KERNEL_TMA);
+    // worth it where a launch is a visible fraction of a step: <= 32 M cells unless forced (opt_fuse_k3 == 2)
+    const bool small = (long long)h->d.nx * h->d.ny * h->d.nz <= (32LL << 20);
+    return h->opt_fuse_k3 && (small || h->opt_fuse_k3 == 2) && h->inline_ok && !h->have_peers && !h->have_ade &&
+           h->plane_ops.empty() && (variant == SB_KERNEL_MARCH || variant == SB_KERNEL_TMA);
 }
 
 static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev, int step, bool last)
@@ -645,7 +688,7 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, h->stream);
     }
-    if (launch_step_kernel(h, P)) return 1;
+    if (launch_step_kernel(h, P, fused)) return 1;
     if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.emplace_back(ev0, ev1); }
     if (h->have_ade) {
         const int nb = (h->ade.n_cells + 255) / 256;
@@ -838,13 +881,13 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
     if (!h) return fail("null handle");
     switch (option) {
         case SB_OPT_KERNEL: if (value < 0 || value > 3) return fail("bad kernel variant"); h->opt_kernel = value; break;
-        case SB_OPT_ROWS_PER_THREAD: if (value != 1 && value != 2 && value != 4) return fail("rows_per_thread must be 1, 2 or 4"); h->opt_rj = value; break;
+        case SB_OPT_ROWS_PER_THREAD: if (value != 1 && value != 2) return fail("rows_per_thread must be 1 or 2"); h->opt_rj = value; break;
         case SB_OPT_WARPS_J: if (value < 0 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
         case SB_OPT_CHUNK_I: if (value < 0) return fail("chunk_i must be >= 0"); h->opt_chunk_i = value; break;
         case SB_OPT_USE_GRAPH: h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); break;
         case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
-        case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value ? 1 : 0; break;
+        case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value < 0 ? 0 : std::min(value, 2); break;
         default: return fail("unknown option %d", option);
     }
     drop_graphs(h);

@@ -39,7 +39,8 @@ struct StepParams {
     const int *flag_lo, *flag_hi;        // my flags: number of steps the lower / upper neighbour has completed
     const int *step_global;              // index of the step being executed (device counter)
     int *err_flag;
-    int permute_chunks;                  // schedule the two cut chunks in the middle of the grid order
+    int two_range;                       // PEER launch over the two cut ranges [0,chunk_i) and [nx-chunk_i,nx)
+    float cv_uni;                        // UNI kernels: the one velocity coefficient of a uniform grid
     // single-kernel step ("fused K3"): a handful of point sources are injected by the thread that owns the cell
     // right before it stores p, and the probes / microphones of the PREVIOUS step are recorded from the input set
     // by the first warp of block 0 (they are final there); a tail launch records the last step of a chunk.
@@ -173,7 +174,11 @@ __device__ __forceinline__ float4 keep4(float4 v, unsigned w, unsigned bit)
 }
 constexpr unsigned ALL_OPEN = 0x0F0F0F0Fu;      // four cells: air, all three faces open
 
-template <int RJ, bool GEOM>
+// Compile-time variants keep the common path lean (the kernel is register-bound at 128 regs / 2 blocks per SM):
+//   UNI  uniform grid: one scalar velocity coefficient, no inverse-cell multiplies
+//   PEER multi-GPU: neighbour flags + peer stores (launched only over the chunks that touch a cut)
+//   FUSE single-kernel step: inline point-source injection + deferred probe recording (small grids)
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE>
 __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
 {
     const unsigned FULL = 0xffffffffu;
@@ -182,17 +187,15 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
     const int strip_k0 = (blockIdx.x * (blockDim.x >> 5) + warp_k) * 128;
     const int k0 = strip_k0 + lane * 4;
     const int j0 = (blockIdx.y * blockDim.y + threadIdx.y) * RJ;
-    int chunk = (int)blockIdx.z;
-    if (P.permute_chunks && gridDim.z > 2) {                    // order: 1..m, 0, C-1, m+1..C-2
-        const int C = (int)gridDim.z, m = (C - 2) / 2, z = (int)blockIdx.z;
-        chunk = z < m ? z + 1 : (z == m ? 0 : (z == m + 1 ? C - 1 : z - 1));
-    }
-    const int ib = P.i_begin + chunk * P.chunk_i;
+    int ib = P.i_begin + (int)blockIdx.z * P.chunk_i;
+    if (PEER && P.two_range) ib = blockIdx.z ? P.nx - P.chunk_i : 0;
     const int ie = min(ib + P.chunk_i, P.i_end);
     if (strip_k0 >= P.nz || j0 >= P.ny || ib >= ie) return;     // warp-uniform exit
-    if (P.flag_lo && ib == 0) wait_neighbour(P.flag_lo, *P.step_global, P.err_flag);
-    if (P.flag_hi && ie == P.nx) wait_neighbour(P.flag_hi, *P.step_global, P.err_flag);
-    if (P.rec_prev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 32) {
+    if (PEER) {
+        if (P.flag_lo && ib == 0) wait_neighbour(P.flag_lo, *P.step_global, P.err_flag);
+        if (P.flag_hi && ie == P.nx) wait_neighbour(P.flag_hi, *P.step_global, P.err_flag);
+    }
+    if (FUSE && P.rec_prev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 32) {
         // probes / microphones of the previous step: its output set is this launch's (read-only) input set
         const FieldPtrs F{{P.p_in, P.vx_in, P.vy_in, P.vz_in}};
         for (int t = lane; t < P.n_probes + P.n_mics; t += 32)
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
                                           : gather8(F, P.mic_field, P.mic_off8, P.mic_w8, t - P.n_probes);
     }
     unsigned inl_mask = 0;                                       // inline point sources inside this thread's column
-    for (int q = 0; q < P.n_inline; q++)
+    for (int q = 0; FUSE && q < P.n_inline; q++)
         if (P.inl_j[q] >= j0 && P.inl_j[q] < j0 + RJ && P.inl_k[q] >= k0 && P.inl_k[q] < k0 + 4 &&
             P.inl_i[q] >= ib && P.inl_i[q] < ie) inl_mask |= 1u << q;
     const bool lane_ok = k0 < P.nz;
@@ -213,20 +216,20 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
     const float4 z4 = f4(0.0f);
 
     // k tables (hoisted)
-    const float4 cvz4 = lane_ok ? ld4(P.cvz + k0) : z4;
-    const float4 icz4 = (P.icz && lane_ok) ? ld4(P.icz + k0) : f4(1.0f);
+    const float4 cvz4 = UNI ? f4(P.cv_uni) : (lane_ok ? ld4(P.cvz + k0) : z4);
+    const float4 icz4 = (!UNI && lane_ok) ? ld4(P.icz + k0) : f4(1.0f);
     const float4 dz0 = (P.n_sponge > 0 && lane_ok) ? ld4(P.decz[0] + k0) : f4(1.0f);
-    const float cvz_lo = edge_lo ? P.cvz[k0 - 1] : 0.0f;
+    const float cvz_lo = UNI ? P.cv_uni : (edge_lo ? P.cvz[k0 - 1] : 0.0f);
     // j tables (hoisted); row index r = -1 .. RJ-1 stored at [r+1]
     float cvy[RJ + 1], icy[RJ], dy0[RJ];
     bool row_ok[RJ + 2];                                       // rows -1 .. RJ
 #pragma unroll
     for (int r = -1; r <= RJ; r++) row_ok[r + 1] = (j0 + r >= 0) && (j0 + r < ny);
 #pragma unroll
-    for (int r = -1; r < RJ; r++) cvy[r + 1] = (row_ok[r + 1] && j0 + r < ny - 1) ? P.cvy[j0 + r] : 0.0f;
+    for (int r = -1; r < RJ; r++) cvy[r + 1] = UNI ? P.cv_uni : ((row_ok[r + 1] && j0 + r < ny - 1) ? P.cvy[j0 + r] : 0.0f);
 #pragma unroll
     for (int r = 0; r < RJ; r++) {
-        icy[r] = (P.icy && row_ok[r + 1]) ? P.icy[j0 + r] : 1.0f;
+        icy[r] = (!UNI && row_ok[r + 1]) ? P.icy[j0 + r] : 1.0f;
         dy0[r] = (P.n_sponge > 0 && row_ok[r + 1]) ? P.decy[0][j0 + r] : 1.0f;
     }
     const long long col = (long long)j0 * P.pitch + k0;         // offset of (row 0, k0) inside a plane
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
         for (int r = 0; r < RJ; r++)
             pc[r + 1] = (row_ok[r + 1] && lane_ok) ? ld4(P.p_in + base + (long long)r * P.pitch) : z4;
         const bool have_prev = (ib > 0) || P.has_lower;
-        const float cx = have_prev ? P.cvx[ib - 1] : 0.0f;
+        const float cx = UNI ? P.cv_uni : (have_prev ? P.cvx[ib - 1] : 0.0f);
 #pragma unroll
         for (int r = 0; r < RJ; r++) {
             float4 v = z4;
@@ -262,8 +265,8 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
     for (int i = ib; i < ie; i++) {
         const long long base = (long long)i * P.plane + col;
         const bool upd_x = (i < P.nx - 1) || P.has_upper;
-        const float cx = upd_x ? P.cvx[i] : 0.0f;
-        const float icx = P.icx ? P.icx[i] : 1.0f;
+        const float cx = UNI ? P.cv_uni : (upd_x ? P.cvx[i] : 0.0f);
+        const float icx = UNI ? 1.0f : P.icx[i];
         const float dx0 = (P.n_sponge > 0) ? P.decx[0][i] : 1.0f;
 
         // loads (all issued before use)
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             float4 ddx = sub4(vxn, vxp[r]);
             float4 ddy = sub4(vyn[r + 1], vyn[r]);
             float4 ddz = sub4(vzn, vzm);
-            if (P.icx) { ddx = mul4s(ddx, icx); ddy = mul4s(ddy, icy[r]); ddz = mul4(ddz, icz4); }
+            if (!UNI) { ddx = mul4s(ddx, icx); ddy = mul4s(ddy, icy[r]); ddz = mul4(ddz, icz4); }
             float4 pnew = add4(p, mul4s(add4(add4(ddx, ddy), ddz), P.cp));
             if (GEOM && masked) pnew = keep4(pnew, mk[r + 1], M_AIR);
             // sponge
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             if (row_ok[r + 1] && lane_ok) {
                 const long long c = base + (long long)r * P.pitch;
                 float4 pst = sel4(e0, e1, e2, e3, pnew, z4);
-                if (inl_mask) {                                  // float64 add, fp32 store (solver.py:2421), list order
+                if (FUSE && inl_mask) {                          // float64 add, fp32 store (solver.py:2421), list order
                     for (int q = 0; q < P.n_inline; q++)
                         if (((inl_mask >> q) & 1u) && P.inl_i[q] == i && P.inl_j[q] == j0 + r) {
                             const double w = __dmul_rn(P.src_row[P.inl_src[q]], P.inl_weight[q]);
@@ -383,8 +386,8 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
                         }
                 }
                 st4(P.p_out + c, pst);
-                if (P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
-                if (P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
+                if (PEER && P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
+                if (PEER && P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
                 st4(P.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
                 st4(P.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
                 st4(P.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));

@@ -18,8 +18,8 @@ VARIANTS = {
     "naive": {_lib.OPT_KERNEL: _lib.KERNEL_NAIVE},
     "march_r1": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1},
     "march_r2": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2},
-    "march_r4_chunk5": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 4, _lib.OPT_CHUNK_I: 5,
-                        _lib.OPT_WARPS_J: 2},
+    "march_r1_chunk5_fused": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 5,
+                              _lib.OPT_WARPS_J: 2, _lib.OPT_FUSE_K3: 2},
     "march_r2_graph": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_USE_GRAPH: 1},
     "march_r2_separate_k3": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_FUSE_K3: 0},
     "march_r1_nograph_wk2": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_USE_GRAPH: 0,

@@ -1,0 +1,72 @@
+// A/B timing harness for the fused step kernel: compile against different revisions of sb_kernels.cuh
+// (-I<dir> -DKV=<1|2|3>) and compare on the same GPU.  Usage: k1_ab <nx> <ny> <nz> <steps> [rj] [chunk]
+#include "sb_kernels.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+using namespace sb;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+int main(int argc, char **argv)
+{
+    int nx = argc > 1 ? atoi(argv[1]) : 512, ny = argc > 2 ? atoi(argv[2]) : 512, nz = argc > 3 ? atoi(argv[3]) : 512;
+    int steps = argc > 4 ? atoi(argv[4]) : 20, rj = argc > 5 ? atoi(argv[5]) : 2, chunk = argc > 6 ? atoi(argv[6]) : 64;
+    int var = argc > 7 ? atoi(argv[7]) : 0;      // KV>=4: 0 UNI lean, 1 tables (non-UNI), 2 UNI+PEER, 3 UNI+FUSE
+    int pitch = (nz + 31) / 32 * 32;
+    long long plane = (long long)ny * pitch, elems = (long long)(nx + 2) * plane;
+    float *buf[8];
+    for (int q = 0; q < 8; q++) { CK(cudaMalloc(&buf[q], elems * 4)); CK(cudaMemset(buf[q], 0, elems * 4)); }
+    auto table = [&](int n, float v) { std::vector<float> h(n + 8, v); float *d; CK(cudaMalloc(&d, (n + 8) * 4));
+                                       CK(cudaMemcpy(d, h.data(), (n + 8) * 4, cudaMemcpyHostToDevice)); return d; };
+    StepParams P;
+    memset(&P, 0, sizeof P);
+    P.cvx = table(nx + 2, -1e-3f) + 1; P.cvy = table(ny, -1e-3f); P.cvz = table(pitch, -1e-3f);
+    P.n_sponge = 1; P.decx[0] = table(nx + 2, 0.999f) + 1; P.decy[0] = table(ny, 0.999f); P.decz[0] = table(pitch, 0.999f);
+    P.cp = -100.f; P.nx = nx; P.ny = ny; P.nz = nz; P.pitch = pitch; P.plane = plane;
+    P.i_begin = 0; P.i_end = nx; P.chunk_i = chunk;
+#if KV >= 4
+    P.cv_uni = -1e-3f;
+    if (var == 1) { P.icx = table(nx + 2, 1.0f) + 1; P.icy = table(ny, 1.0f); P.icz = table(pitch, 1.0f); }
+#endif
+#if KV >= 2
+    int *ctr; CK(cudaMalloc(&ctr, 8)); CK(cudaMemset(ctr, 0, 8));
+    P.step_global = ctr; P.err_flag = ctr + 1;
+#endif
+    int wj = 8;
+    dim3 blk(32, wj), grd((nz + 127) / 128, (ny + rj * wj - 1) / (rj * wj), (nx + chunk - 1) / chunk);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f, sum = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        for (int s = 0; s < steps; s++) {
+            int in = s & 1;
+            P.p_in = buf[in * 4] + plane; P.vx_in = buf[in * 4 + 1] + plane; P.vy_in = buf[in * 4 + 2] + plane; P.vz_in = buf[in * 4 + 3] + plane;
+            int o = 1 - in;
+            P.p_out = buf[o * 4] + plane; P.vx_out = buf[o * 4 + 1] + plane; P.vy_out = buf[o * 4 + 2] + plane; P.vz_out = buf[o * 4 + 3] + plane;
+#if KV >= 4
+            if (rj == 1) {
+                if (var == 0) k1_step_march<1, false, true, false, false><<<grd, blk>>>(P);
+                else if (var == 1) k1_step_march<1, false, false, false, false><<<grd, blk>>>(P);
+                else if (var == 2) k1_step_march<1, false, true, true, false><<<grd, blk>>>(P);
+                else k1_step_march<1, false, true, false, true><<<grd, blk>>>(P);
+            } else {
+                if (var == 0) k1_step_march<2, false, true, false, false><<<grd, blk>>>(P);
+                else if (var == 1) k1_step_march<2, false, false, false, false><<<grd, blk>>>(P);
+                else if (var == 2) k1_step_march<2, false, true, true, false><<<grd, blk>>>(P);
+                else k1_step_march<2, false, true, false, true><<<grd, blk>>>(P);
+            }
+#else
+            if (rj == 1) k1_step_march<1, false><<<grd, blk>>>(P);
+            else if (rj == 2) k1_step_march<2, false><<<grd, blk>>>(P);
+            else k1_step_march<4, false><<<grd, blk>>>(P);
+#endif
+        }
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= steps;
+        if (rep) { best = ms < best ? ms : best; sum += ms; }
+    }
+    double cells = (double)nx * ny * nz;
+    printf("KV=%d var=%d %dx%dx%d rj=%d chunk=%d  best %.4f ms  mean %.4f ms  %.1f Gcell/s  %.3f of 6540.8 GB/s\n", KV, var, nx, ny, nz, rj, chunk,
+           best, sum / 4, cells / best / 1e6, cells * 32 / (best * 1e-3) / 6540.8e9);
+    return 0;
+}
