@@ -80,7 +80,7 @@ struct sb_solver {
     AdeTable ade{};
     DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat; DBuf<float> ade_J, ade_Jp;
     // options
-    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 2, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
+    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 1, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
     // graph cache: key = (n_steps, starting set, source-table pointer, record pointer)
     struct GraphKey {
         int n, cur; const void *src, *rec;
@@ -653,8 +653,9 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
 static bool fused_k3(const sb_solver *h)
 {
     const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
-    // worth it where a launch is a visible fraction of a step: <= 32 M cells unless forced (opt_fuse_k3 == 2)
-    const bool small = (long long)h->d.nx * h->d.ny * h->d.nz <= (32LL << 20);
+    // worth it where a launch is a visible fraction of a step (the FUSE variant of K1 is ~9 % slower, a K3 launch
+    // costs ~3 us): <= 4 M cells unless forced (opt_fuse_k3 == 2)
+    const bool small = (long long)h->d.nx * h->d.ny * h->d.nz <= (4LL << 20);
     return h->opt_fuse_k3 && (small || h->opt_fuse_k3 == 2) && h->inline_ok && !h->have_peers && !h->have_ade &&
            h->plane_ops.empty() && (variant == SB_KERNEL_MARCH || variant == SB_KERNEL_TMA);
 }
