@@ -275,6 +275,8 @@ def run_b200_arm(a):
     _lib.check(lib.sb_profile_read(h, C.byref(mean_ms), C.byref(min_ms), C.byref(n_l)))
     slab.set_kernel_option(_lib.OPT_PROFILE, 0)
     barrier()
+    shape4, tuned_ms = (C.c_int32 * 4)(), C.c_float()
+    _lib.check(lib.sb_tuned(h, shape4, C.byref(tuned_ms)))
     peak, peak_src = measured_peak_gbs()
     cells_rank = int(np.prod(slab.shape, dtype=np.int64))
     achieved = ALGO_BYTES_PER_CELL * cells_rank / (mean_ms.value * 1e-3) / 1e9
@@ -291,6 +293,8 @@ def run_b200_arm(a):
                 "config": {"workload": label, "cells_per_gpu": cells_rank, "l2_policy": "fields (34 GB/GPU) >> L2, no flush needed"
                            if a.workload == "c5_weak" else "inputs larger than L2 for >=200^3; small grids are L2-resident by nature",
                            "kernel": {0: "auto", 1: "naive", 2: "march", 3: "tma"}[st1["kernel_variant"]],
+                           "launch_shape": {"rows_per_thread": shape4[0], "warps_j": shape4[1], "warps_k": shape4[2],
+                                            "chunk_planes": shape4[3], "source": "library autotune" if a.rows is None else "flag"},
                            "parallelism": f"slab{world}" if world > 1 else "single",
                            "halo": (drv.halo if drv is not None else None)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

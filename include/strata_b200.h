@@ -199,6 +199,9 @@ int sb_query(sb_solver *h, sb_stats *out);
 /* With SB_OPT_PROFILE=1 every launch of the fused step kernel is bracketed by CUDA events on the
  * handle's stream; this returns (and clears) mean / min duration in ms and the launch count.   */
 int sb_profile_read(sb_solver *h, double *mean_ms, double *min_ms, int *n_launches);
+/* Launch shape chosen by the library's autotuner for the current configuration (rows per thread, warps along j,
+ * warps along k, planes per chunk; 0 = heuristic) and the K1 time it measured; all shapes give identical results. */
+int sb_tuned(sb_solver *h, int32_t shape_out[4], float *ms_out);
 int sb_synchronize(sb_solver *h);
 
 #ifdef __cplusplus

@@ -114,6 +114,7 @@ SIGNATURES = {
     "sb_set_option": (_i, [_vp, _i, _i]),
     "sb_query": (_i, [_vp, C.POINTER(Stats)]),
     "sb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
+    "sb_tuned": (_i, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "sb_synchronize": (_i, [_vp]),
 }
 

@@ -72,6 +72,7 @@ struct sb_solver {
     int n_src_entries = 0; bool inline_ok = false;
     int inl_i[8], inl_j[8], inl_k[8], inl_src[8]; double inl_weight[8];
     int opt_fuse_k3 = 1;
+    int tuned[4] = {1, 0, 1, 0}, tuned_key = -1; float tuned_ms = 0.f;
     int n_probes = 0, n_mics = 0;
     DBuf<long long> probe_off, mic_off; DBuf<float> mic_w; DBuf<int> mic_field; bool have_mic_field = false;
     DBuf<double> d_src_vals; DBuf<float> d_record; DBuf<int> d_step_ctr;
@@ -80,7 +81,7 @@ struct sb_solver {
     AdeTable ade{};
     DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat; DBuf<float> ade_J, ade_Jp;
     // options
-    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 1, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
+    int opt_kernel = SB_KERNEL_AUTO, opt_rj = 0, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
     // graph cache: key = (n_steps, starting set, source-table pointer, record pointer)
     struct GraphKey {
         int n, cur; const void *src, *rec;
@@ -107,6 +108,7 @@ struct sb_solver {
 
 static void drop_graphs(sb_solver *h)
 {
+    h->tuned_key = -1;                       // configuration changed: re-measure the launch shape as well
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
 }
@@ -601,9 +603,12 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         h->kernels_launched++;
         return 0;
     }
-    const int rj = h->opt_rj, wk = h->opt_wk;
+    int rj = h->opt_rj, wk = h->opt_wk;
+    int wj = h->opt_wj, chunk_opt = h->opt_chunk_i;
+    if (rj == 0) {                          // auto: the configuration measured by autotune() for this variant
+        rj = h->tuned[0]; wj = h->tuned[1]; wk = h->tuned[2]; chunk_opt = h->tuned[3];
+    }
     if (rj != 1 && rj != 2) return fail("rows_per_thread must be 1 or 2");
-    int wj = h->opt_wj;
     if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
         wj = std::max(1, 8 / wk);
         while (wj > 1 && (long long)((d.nz + 128 * wk - 1) / (128 * wk)) * ((d.ny + rj * wj - 1) / (rj * wj)) *
@@ -611,7 +616,7 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
     }
     if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
     const int gx = (d.nz + 128 * wk - 1) / (128 * wk), gy = (d.ny + rj * wj - 1) / (rj * wj);
-    int chunk = h->opt_chunk_i;
+    int chunk = chunk_opt;
     if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
         const long long want = 148LL * 8;
         long long nchunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
@@ -646,6 +651,46 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         launch_march(rj, true, false, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
         h->kernels_launched++;
     }
+    return 0;
+}
+
+// Launch-shape autotuning.  The best (rows per thread, warps per block, chunk length) depends on the variant
+// (uniform / tables, geometry) and on the grid; all shapes give bit-identical results, so the library simply times
+// a handful on the live buffers: K1 reads the current set and writes the other one, and without flipping `cur`
+// every trial recomputes the same next state, which the real step then overwrites.
+static int autotune(sb_solver *h)
+{
+    static const int cand[][4] = {{1, 8, 1, 64}, {1, 8, 1, 16}, {1, 4, 1, 16}, {1, 2, 2, 16},
+                                  {2, 8, 1, 64}, {2, 8, 1, 16}, {2, 4, 1, 16}, {2, 4, 1, 0}, {1, 0, 1, 0}};
+    const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->have_peers ? 64 : 0);
+    if (h->tuned_key == key) return 0;
+    const int save_rj = h->opt_rj, save_wj = h->opt_wj, save_wk = h->opt_wk, save_ch = h->opt_chunk_i;
+    const bool save_peers = h->have_peers;
+    const long long k0 = h->kernels_launched;
+    h->have_peers = false;                                  // time the lean interior variant
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f; int best_c = 0;
+    for (int c = 0; c < (int)(sizeof cand / sizeof cand[0]); c++) {
+        h->opt_rj = cand[c][0]; h->opt_wj = cand[c][1]; h->opt_wk = cand[c][2]; h->opt_chunk_i = cand[c][3];
+        float t_min = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            StepParams P; fill_params(h, P);
+            cudaEventRecord(e0, h->stream);
+            if (launch_step_kernel(h, P, false)) { h->have_peers = save_peers; return 1; }
+            cudaEventRecord(e1, h->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep) t_min = std::min(t_min, ms);
+        }
+        if (t_min < best) { best = t_min; best_c = c; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int q = 0; q < 4; q++) h->tuned[q] = cand[best_c][q];
+    h->tuned_ms = best; h->tuned_key = key;
+    h->opt_rj = save_rj; h->opt_wj = save_wj; h->opt_wk = save_wk; h->opt_chunk_i = save_ch;
+    h->have_peers = save_peers; h->kernels_launched = k0;
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -750,6 +795,10 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     if (!h->have_coeffs) return fail("coefficients not set");
     if (h->n_src_cells && !src_dev) return fail("source values required");
     if ((h->n_probes + h->n_mics) && !rec_dev) return fail("record buffer required");
+    if (h->opt_rj == 0 && n_steps > 0) {
+        const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
+        if (variant != SB_KERNEL_NAIVE && autotune(h)) return 1;
+    }
     CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
     const bool want_graph = h->opt_graph == 1 ||
         (h->opt_graph < 0 && n_steps >= 4 && (long long)h->d.nx * h->d.ny * h->d.nz <= (32LL << 20));
@@ -882,7 +931,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
     if (!h) return fail("null handle");
     switch (option) {
         case SB_OPT_KERNEL: if (value < 0 || value > 3) return fail("bad kernel variant"); h->opt_kernel = value; break;
-        case SB_OPT_ROWS_PER_THREAD: if (value != 1 && value != 2) return fail("rows_per_thread must be 1 or 2"); h->opt_rj = value; break;
+        case SB_OPT_ROWS_PER_THREAD: if (value < 0 || value > 2) return fail("rows_per_thread must be 0 (auto), 1 or 2"); h->opt_rj = value; break;
         case SB_OPT_WARPS_J: if (value < 0 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
         case SB_OPT_CHUNK_I: if (value < 0) return fail("chunk_i must be >= 0"); h->opt_chunk_i = value; break;
@@ -928,6 +977,14 @@ extern "C" int sb_profile_read(sb_solver *h, double *mean_ms, double *min_ms, in
     if (mean_ms) *mean_ms = n ? sum / n : 0.0;
     if (min_ms) *min_ms = n ? mn : 0.0;
     if (n_launches) *n_launches = n;
+    return 0;
+}
+
+extern "C" int sb_tuned(sb_solver *h, int32_t shape_out[4], float *ms_out)
+{
+    if (!h || !shape_out) return fail("null argument");
+    for (int q = 0; q < 4; q++) shape_out[q] = h->tuned[q];
+    if (ms_out) *ms_out = h->tuned_key >= 0 ? h->tuned_ms : 0.f;
     return 0;
 }
 
