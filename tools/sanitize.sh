@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# compute-sanitizer pass over a few small parity cases (memcheck + racecheck + initcheck); writes gpurun_out/sanitizer_*.log
+set -u
+mkdir -p gpurun_out
+SEL='test_matches_oracle_and_golden and (odd_geometry_pml or ade_two or directional or pml_radiation) and (march_r2_separate_k3 or march_r1_chunk5_fused or naive)'
+for tool in memcheck racecheck initcheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 --target-processes all \
+      python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool exit=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_$tool.log | tr '\n' ' ')"
+done
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k "peer_store and block_pml" > gpurun_out/sanitizer_memcheck_p2p.log 2>&1
+echo "memcheck-p2p exit=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_memcheck_p2p.log | tr '\n' ' ')"
