@@ -2,6 +2,7 @@
 // Host side only: table upload, list building, launch sequencing, CUDA-graph caching.
 #include "../../include/strata_b200.h"
 #include "sb_kernels.cuh"
+#include "sb_resident.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -101,9 +102,16 @@ struct sb_solver {
     int *my_flags = nullptr, *sig_lo = nullptr, *sig_hi = nullptr;
     int peer_lo_nx = 0;
     DBuf<int> d_step_global, d_err;
-    // optional per-launch timing of the fused step kernel (SB_OPT_PROFILE)
+    // optional per-launch timing of the fused step kernel (SB_OPT_PROFILE); a resident launch covers `steps` steps
     int opt_profile = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+    struct ProfEntry { cudaEvent_t e0, e1; int steps; };
+    std::vector<ProfEntry> prof;
+    // shared-memory-resident kernel (K5, sb_resident.cuh)
+    int n_sm = 0; long long smem_optin = 0;
+    int opt_res_split = 1, opt_res_min_steps = 4;
+    std::vector<int> probe_ijk_host; DBuf<int> d_probe_ijk, d_res_flags;
+    bool resident_used = false;
+    int res_nbi = 0, res_nbj = 0;
 };
 
 static void drop_graphs(sb_solver *h)
@@ -154,6 +162,9 @@ extern "C" int sb_create(const sb_grid_desc *desc, int device, void *stream, sb_
     if (h->d_step_global.alloc(1) || h->d_err.alloc(1)) { delete h; return 1; }
     cudaMemset(h->d_step_global.p, 0, sizeof(int));
     cudaMemset(h->d_err.p, 0, sizeof(int));
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) h->n_sm = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess) h->smem_optin = v;
     *out = h;
     return 0;
 }
@@ -170,6 +181,7 @@ extern "C" int sb_destroy(sb_solver *h)
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
     h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release();
     h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
+    h->d_probe_ijk.release(); h->d_res_flags.release();
     delete h;
     return 0;
 }
@@ -397,7 +409,15 @@ extern "C" int sb_set_probes(sb_solver *h, int n_probes, const int64_t *flat_idx
         off[t] = dense_to_off(h, flat_idx[t]);
     }
     h->n_probes = n_probes;
-    return n_probes ? h->probe_off.upload(off, h->stream) : 0;
+    h->probe_ijk_host.assign((size_t)n_probes * 3, 0);
+    for (int t = 0; t < n_probes; t++) {
+        const long long dn = flat_idx[t];
+        h->probe_ijk_host[3 * t] = (int)(dn / ((long long)h->d.nz * h->d.ny));
+        h->probe_ijk_host[3 * t + 1] = (int)((dn / h->d.nz) % h->d.ny);
+        h->probe_ijk_host[3 * t + 2] = (int)(dn % h->d.nz);
+    }
+    if (!n_probes) return 0;
+    return h->probe_off.upload(off, h->stream) || h->d_probe_ijk.upload(h->probe_ijk_host, h->stream);
 }
 
 extern "C" int sb_set_gathers(sb_solver *h, int n, const int32_t *field, const int64_t *idx8, const float *w8)
@@ -735,7 +755,7 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
         cudaEventRecord(ev0, h->stream);
     }
     if (launch_step_kernel(h, P, fused)) return 1;
-    if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.emplace_back(ev0, ev1); }
+    if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, 1}); }
     if (h->have_ade) {
         const int nb = (h->ade.n_cells + 255) / 256;
         StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx;
@@ -787,6 +807,81 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
     return 0;
 }
 
+// ---- K5: shared-memory-resident chunk (sb_resident.cuh) ---------------------------------------------------
+// 0 = not applicable (why_not says why), 1 = plan filled in
+static int resident_plan(sb_solver *h, ResParams &R, const char **why_not)
+{
+    const sb_grid_desc &d = h->d;
+    *why_not = nullptr;
+    if (d.has_lower || d.has_upper || h->have_peers) *why_not = "decomposed slab";
+    else if (h->have_ade) *why_not = "ADE materials";
+    else if (!h->plane_ops.empty()) *why_not = "Mur / radiation planes";
+    else if (h->n_mics) *why_not = "microphones";
+    else if (h->n_src_cells && !h->inline_ok) *why_not = "more than 8 source cells or velocity sources";
+    else if (h->n_probes > K5_MAX_PROBES) *why_not = "too many probes";
+    else if (h->n_sm <= 0 || h->smem_optin <= 0) *why_not = "device attributes unavailable";
+    if (*why_not) return 0;
+    int nbi = 0, nbj = 0;
+    if (!res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, &nbi, &nbj)) {
+        *why_not = "grid does not fit in shared memory";
+        return 0;
+    }
+    StepParams P;
+    fill_params(h, P);
+    R = ResParams{};
+    for (int q = 0; q < 2; q++) for (int f = 0; f < 4; f++) R.set[q][f] = plane0(h, q, f);
+    R.cur = h->cur;
+    R.mask = P.mask;
+    R.cvx = P.cvx; R.cvy = P.cvy; R.cvz = P.cvz; R.icx = P.icx; R.icy = P.icy; R.icz = P.icz;
+    R.n_sponge = P.n_sponge;
+    for (int q = 0; q < MAX_SPONGES; q++) { R.decx[q] = P.decx[q]; R.decy[q] = P.decy[q]; R.decz[q] = P.decz[q]; }
+    R.cp = h->cp;
+    R.nx = d.nx; R.ny = d.ny; R.nz = d.nz; R.pitch = d.pitch; R.plane = h->plane;
+    R.nbi = nbi; R.nbj = nbj; R.LI = (d.nx + nbi - 1) / nbi; R.LJ = (d.ny + nbj - 1) / nbj; R.kp = (d.nz + 3) / 4 * 4;
+    R.n_inline = h->n_src_cells ? h->n_src_entries : 0;
+    for (int e = 0; e < R.n_inline; e++) {
+        R.inl_i[e] = h->inl_i[e]; R.inl_j[e] = h->inl_j[e]; R.inl_k[e] = h->inl_k[e];
+        R.inl_src[e] = h->inl_src[e]; R.inl_weight[e] = h->inl_weight[e];
+    }
+    R.n_sources = h->n_sources;
+    R.n_probes = h->n_probes; R.n_rec = h->n_probes; R.probe_ijk = h->d_probe_ijk.p;
+    R.err_flag = h->d_err.p; R.split = h->opt_res_split;
+    return 1;
+}
+
+template <bool GEOM>
+static int launch_resident_t(sb_solver *h, ResParams &R, size_t smem)
+{
+    CU(cudaFuncSetAttribute(k5_resident<GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_resident<GEOM>, K5_NT, smem));
+    if ((long long)per_sm * h->n_sm < (long long)R.nbi * R.nbj) return fail("resident kernel: %d boxes cannot be co-resident", R.nbi * R.nbj);
+    void *args[] = {&R};
+    CU(cudaLaunchCooperativeKernel((const void *)k5_resident<GEOM>, dim3(R.nbi * R.nbj), dim3(K5_NT), args, smem, h->stream));
+    return 0;
+}
+
+static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double *src_dev, float *rec_dev)
+{
+    const int nb = R.nbi * R.nbj;
+    R.n_steps = n_steps; R.src_vals = src_dev; R.rec = rec_dev;
+    if (h->d_res_flags.alloc((size_t)nb)) return 1;
+    R.flags = h->d_res_flags.p;
+    CU(cudaMemsetAsync(R.flags, 0, (size_t)nb * sizeof(int), h->stream));
+    const size_t smem = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, R.n_probes);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->opt_profile) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, h->stream); }
+    if (R.mask ? launch_resident_t<true>(h, R, smem) : launch_resident_t<false>(h, R, smem)) return 1;
+    if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, n_steps}); }
+    h->kernels_launched++;
+    h->steps_done += n_steps;
+    if (n_steps & 1) h->cur = 1 - h->cur;
+    h->last_variant = SB_KERNEL_RESIDENT;
+    h->resident_used = true;
+    h->res_nbi = R.nbi; h->res_nbj = R.nbj;
+    return 0;
+}
+
 extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev, float *rec_dev)
 {
     CHECK_H(h);
@@ -795,6 +890,12 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     if (!h->have_coeffs) return fail("coefficients not set");
     if (h->n_src_cells && !src_dev) return fail("source values required");
     if ((h->n_probes + h->n_mics) && !rec_dev) return fail("record buffer required");
+    if (n_steps > 0 && (h->opt_kernel == SB_KERNEL_RESIDENT ||
+                        (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps))) {
+        ResParams R; const char *why_not = nullptr;
+        if (resident_plan(h, R, &why_not)) return launch_resident(h, R, n_steps, src_dev, rec_dev);
+        if (h->opt_kernel == SB_KERNEL_RESIDENT) return fail("resident kernel not applicable: %s", why_not);
+    }
     if (h->opt_rj == 0 && n_steps > 0) {
         const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
         if (variant != SB_KERNEL_NAIVE && autotune(h)) return 1;
@@ -855,6 +956,7 @@ extern "C" int sb_step_n(sb_solver *h, int n_steps, const double *src_host, floa
                            cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    if (h->resident_used) return sb_synchronize(h);
     return 0;
 }
 
@@ -930,7 +1032,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
 {
     if (!h) return fail("null handle");
     switch (option) {
-        case SB_OPT_KERNEL: if (value < 0 || value > 3) return fail("bad kernel variant"); h->opt_kernel = value; break;
+        case SB_OPT_KERNEL: if (value < 0 || value > 4) return fail("bad kernel variant"); h->opt_kernel = value; break;
         case SB_OPT_ROWS_PER_THREAD: if (value < 0 || value > 2) return fail("rows_per_thread must be 0 (auto), 1 or 2"); h->opt_rj = value; break;
         case SB_OPT_WARPS_J: if (value < 0 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
@@ -938,6 +1040,8 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
         case SB_OPT_USE_GRAPH: h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); break;
         case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
         case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value < 0 ? 0 : std::min(value, 2); break;
+        case SB_OPT_RESIDENT_SPLIT: h->opt_res_split = value ? 1 : 0; break;
+        case SB_OPT_RESIDENT_MIN_STEPS: h->opt_res_min_steps = std::max(1, value); break;
         default: return fail("unknown option %d", option);
     }
     drop_graphs(h);
@@ -968,10 +1072,10 @@ extern "C" int sb_profile_read(sb_solver *h, double *mean_ms, double *min_ms, in
     CHECK_H(h);
     CU(cudaStreamSynchronize(h->stream));
     double sum = 0.0, mn = 1e300; int n = 0;
-    for (auto &pr : h->prof) {
+    for (auto &pr : h->prof) {                  // per step: a resident launch is divided by the steps it covers
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { sum += ms; mn = std::min(mn, (double)ms); n++; }
-        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        if (cudaEventElapsedTime(&ms, pr.e0, pr.e1) == cudaSuccess) { sum += ms; mn = std::min(mn, (double)ms / pr.steps); n += pr.steps; }
+        cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1);
     }
     h->prof.clear();
     if (mean_ms) *mean_ms = n ? sum / n : 0.0;
@@ -993,9 +1097,10 @@ extern "C" int sb_synchronize(sb_solver *h)
     CHECK_H(h);
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
-    if (h->have_peers) {
+    if (h->have_peers || h->resident_used) {
         int err = 0;
         CU(cudaMemcpy(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err == 2) return fail("resident kernel: timed out waiting for a neighbour box's step flag");
         if (err) return fail("timed out waiting for a neighbour slab's step flag (peer-to-peer halo)");
     }
     return 0;

@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// helpers shared with the host-side lockstep emulation of the resident kernel (tests/emu): plain arithmetic only
+#define SB_HD __host__ __device__ __forceinline__
+
 namespace sb {
 
 constexpr int MAX_SPONGES = 4;
@@ -156,18 +159,18 @@ __global__ void __launch_bounds__(256) k0_step_naive(StepParams P)
 // No shared memory, no block barrier: warps are independent; the block only groups strips
 // that are adjacent in j so that their halo rows hit in L1.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
-__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
-__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float4 mul4s(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
-__device__ __forceinline__ float4 sel4(bool cx, bool cy, bool cz, bool cw, float4 a, float4 b)
+SB_HD float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+SB_HD void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+SB_HD float4 f4(float a) { return make_float4(a, a, a, a); }
+SB_HD float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+SB_HD float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+SB_HD float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+SB_HD float4 mul4s(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+SB_HD float4 sel4(bool cx, bool cy, bool cz, bool cw, float4 a, float4 b)
 { return make_float4(cx ? a.x : b.x, cy ? a.y : b.y, cz ? a.z : b.z, cw ? a.w : b.w); }
 
 // keep element e of v iff byte e of the packed mask word has `bit` set, else +0.0f (boundaries.cpp:66-89)
-__device__ __forceinline__ float4 keep4(float4 v, unsigned w, unsigned bit)
+SB_HD float4 keep4(float4 v, unsigned w, unsigned bit)
 {
     return make_float4((w & bit) ? v.x : 0.0f, (w & (bit << 8)) ? v.y : 0.0f,
                        (w & (bit << 16)) ? v.z : 0.0f, (w & (bit << 24)) ? v.w : 0.0f);

@@ -1,0 +1,461 @@
+// sb_resident.cuh -- K5: shared-memory-resident persistent step kernel (sm_100a).
+//
+// For grids small enough that the four fields fit in the aggregate shared memory of the GPU
+// (148 SMs x 227 KB = 33 MB, about 1.3 M cells: BASELINE config 1 and every 100^3-class example
+// script of the reference) a step is latency-bound, not bandwidth-bound: K1 streams the grid
+// through L2 once per launch and pays a launch + ramp + tail per step.  K5 instead keeps the grid
+// ON CHIP for a whole chunk of steps:
+//
+//   * the grid is cut into nbi x nbj boxes (full rows along k), one CTA per box, at most one CTA per
+//     SM, all co-resident (cooperative launch);
+//   * every CTA loads its box of {p,vx,vy,vz} into shared memory once, advances it n_steps times in
+//     place (velocity phase, barrier, pressure phase, barrier) and stores it back once -- HBM/L2 see
+//     2 x 16 B per cell per CHUNK instead of 32 B per cell per STEP;
+//   * per step only the four p faces of a box cross CTAs.  They go through L2 (the p buffers of the
+//     two ping-pong sets double as the exchange area, indexed by step parity) with one release/acquire
+//     flag per CTA -- point-to-point, no grid-wide barrier.  The face velocities on the low sides
+//     (vx at i0-1, vy at j0-1) are kept redundantly in the box, updated with the owner's exact
+//     operations (the same trick as the multi-GPU slabs), so nothing but p travels;
+//   * the part of the velocity phase that needs no halo value runs while the neighbours' faces are in
+//     flight (R.split).
+//
+// Arithmetic is the contract of sb_kernels.cuh: separately rounded fp32 operations in the reference's
+// order (fdtd_step.cpp:34-80, 109-211 / 235-439; boundaries.cpp:66-89; pml.cpp:47-149;
+// core/solver.py:2386-2439).  The sponge multiply of the velocities is deferred to their next use (the
+// pressure update reads them undamped, exactly as the reference applies the sponge after both updates),
+// which performs the same operations on the same values.
+//
+// The phase functions are __host__ __device__ so that tests/emu/ can run the box decomposition in
+// lockstep on the CPU against the oracle (index logic, halos, deferred damping); the product only ever
+// calls them from k5_resident.
+#pragma once
+#include "sb_kernels.cuh"
+
+#ifdef __CUDA_ARCH__
+#define SB_LDG(ptr) __ldg(ptr)
+#define SB_DMUL(a, b) __dmul_rn((a), (b))
+#else
+#define SB_LDG(ptr) (*(ptr))
+#define SB_DMUL(a, b) ((a) * (b))
+#endif
+
+namespace sb {
+
+constexpr int K5_NT = 512;                 // threads per CTA
+constexpr int K5_MAX_PROBES = 1024;
+
+struct ResParams {
+    float *set[2][4];                      // plane-0 pointers of both ping-pong sets; set[cur] holds the state on entry
+    int cur, n_steps;
+    const uint8_t *mask;                   // plane-0 pointer of the face-mask bytes, or nullptr (all air)
+    const float *cvx, *cvy, *cvz;          // per-face velocity coefficients
+    const float *icx, *icy, *icz;          // per-cell inverse spacing, or nullptr (uniform grid)
+    const float *decx[MAX_SPONGES], *decy[MAX_SPONGES], *decz[MAX_SPONGES];
+    int n_sponge;
+    float cp;
+    int nx, ny, nz, pitch;
+    long long plane;
+    int nbi, nbj, LI, LJ, kp;              // box grid, largest box extents, shared-memory row pitch (floats, multiple of 4)
+    int n_inline;                          // point sources (p field), list order
+    int inl_i[8], inl_j[8], inl_k[8], inl_src[8];
+    double inl_weight[8];
+    const double *src_vals;                // [n_steps][n_sources]
+    int n_sources;
+    int n_probes, n_rec;
+    const int *probe_ijk;                  // 3 ints per probe
+    float *rec;                            // [n_steps][n_rec]
+    int *flags;                            // one per CTA: number of steps whose p faces are published (zero on entry)
+    int *err_flag;
+    int split;                             // 1 = overlap the halo-free part of the velocity phase with the exchange
+};
+
+// shared-memory layout, float offsets; p carries a one-cell halo on all four sides, vx / vy a low-side ghost
+struct ResMap {
+    int kp, LI, LJ, o_vx, o_vy, o_vz, o_end;
+    SB_HD explicit ResMap(const ResParams &R) : kp(R.kp), LI(R.LI), LJ(R.LJ)
+    {
+        o_vx = (LI + 2) * (LJ + 2) * kp;
+        o_vy = o_vx + (LI + 1) * LJ * kp;
+        o_vz = o_vy + LI * (LJ + 1) * kp;
+        o_end = o_vz + LI * LJ * kp;
+    }
+    SB_HD int p(int li, int lj) const { return ((li + 1) * (LJ + 2) + (lj + 1)) * kp; }     // li -1..LI, lj -1..LJ
+    SB_HD int vx(int li, int lj) const { return o_vx + ((li + 1) * LJ + lj) * kp; }          // li -1..LI-1
+    SB_HD int vy(int li, int lj) const { return o_vy + (li * (LJ + 1) + (lj + 1)) * kp; }    // lj -1..LJ-1
+    SB_HD int vz(int li, int lj) const { return o_vz + (li * LJ + lj) * kp; }
+};
+
+static inline long long res_smem_bytes(int LI, int LJ, int kp, int n_probes)
+{
+    const long long fl = (long long)(LI + 2) * (LJ + 2) * kp + (long long)(LI + 1) * LJ * kp +
+                         (long long)LI * (LJ + 1) * kp + (long long)LI * LJ * kp;
+    return fl * 4 + (long long)(2 * n_probes + 4) * 4;
+}
+
+// Box grid for a given SM count and shared-memory limit: fewest items per thread, then least shared memory.
+// Returns false when the grid does not fit on chip.
+static inline bool res_choose_partition(int nx, int ny, int nz, int n_sm, long long smem_limit, int n_probes,
+                                        int *nbi_out, int *nbj_out)
+{
+    const int kp = (nz + 3) / 4 * 4, K4 = kp / 4;
+    long long best_cost = -1;
+    for (int nbi = 1; nbi <= nx && nbi <= n_sm; nbi++) {
+        const int nbj = ny < n_sm / nbi ? ny : n_sm / nbi;
+        if (nbj < 1) break;
+        const int LI = (nx + nbi - 1) / nbi, LJ = (ny + nbj - 1) / nbj;
+        if ((long long)LJ * K4 > K5_NT) continue;                     // one thread per (row, float4) column at least
+        const long long bytes = res_smem_bytes(LI, LJ, kp, n_probes);
+        if (bytes > smem_limit) continue;
+        const int G = K5_NT / (LJ * K4);
+        const long long iters = (LI + G - 1) / G;
+        const long long cost = iters * (1LL << 32) + bytes;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; *nbi_out = nbi; *nbj_out = nbj; }
+    }
+    return best_cost >= 0;
+}
+
+struct ResBlock { int bi, bj, i0, j0, li_n, lj_n; };
+
+SB_HD ResBlock res_block(const ResParams &R, int b)
+{
+    ResBlock B;
+    B.bi = b / R.nbj; B.bj = b - B.bi * R.nbj;
+    B.i0 = (int)((long long)B.bi * R.nx / R.nbi);
+    B.li_n = (int)((long long)(B.bi + 1) * R.nx / R.nbi) - B.i0;
+    B.j0 = (int)((long long)B.bj * R.ny / R.nbj);
+    B.lj_n = (int)((long long)(B.bj + 1) * R.ny / R.nbj) - B.j0;
+    return B;
+}
+
+// Per-thread constants: a thread owns one (row, float4) column of the box and every G-th plane of it.
+struct ResThread {
+    int tid, g, G, lj, gj, k0;
+    bool active;
+    bool e0, e1, e2, e3, u0, u1, u2, u3;   // element inside the grid / its z face is updated
+    float cvy, icy, dy0;
+    float4 cvz4, icz4, dz0;
+    unsigned inl_mask;
+};
+
+SB_HD ResThread res_thread(const ResParams &R, const ResBlock &B, int tid)
+{
+    ResThread T;
+    const int K4 = R.kp >> 2, ncol = B.lj_n * K4;
+    T.tid = tid;
+    T.G = K5_NT / ncol;
+    T.g = tid / ncol;
+    const int c = tid - T.g * ncol;
+    T.active = T.g < T.G;
+    T.lj = c / K4; T.k0 = 4 * (c - T.lj * K4); T.gj = B.j0 + T.lj;
+    T.e0 = T.k0 < R.nz; T.e1 = T.k0 + 1 < R.nz; T.e2 = T.k0 + 2 < R.nz; T.e3 = T.k0 + 3 < R.nz;
+    T.u0 = T.k0 < R.nz - 1; T.u1 = T.k0 + 1 < R.nz - 1; T.u2 = T.k0 + 2 < R.nz - 1; T.u3 = T.k0 + 3 < R.nz - 1;
+    T.cvy = 0.0f; T.icy = 1.0f; T.dy0 = 1.0f;
+    T.cvz4 = f4(0.0f); T.icz4 = f4(1.0f); T.dz0 = f4(1.0f);
+    T.inl_mask = 0;
+    if (!T.active) return T;
+    if (T.gj < R.ny - 1) T.cvy = SB_LDG(R.cvy + T.gj);
+    T.cvz4 = ld4(R.cvz + T.k0);
+    if (R.icx) { T.icy = SB_LDG(R.icy + T.gj); T.icz4 = ld4(R.icz + T.k0); }
+    if (R.n_sponge > 0) { T.dy0 = SB_LDG(R.decy[0] + T.gj); T.dz0 = ld4(R.decz[0] + T.k0); }
+    for (int q = 0; q < R.n_inline; q++)
+        if (R.inl_j[q] == T.gj && R.inl_k[q] >= T.k0 && R.inl_k[q] < T.k0 + 4 &&
+            R.inl_i[q] >= B.i0 && R.inl_i[q] < B.i0 + B.li_n) T.inl_mask |= 1u << q;
+    return T;
+}
+
+SB_HD unsigned res_mask_word(const ResParams &R, int gi, int gj, int k0)
+{
+    return SB_LDG(reinterpret_cast<const unsigned *>(R.mask + (long long)gi * R.plane + (long long)gj * R.pitch + k0));
+}
+
+// ---- box <-> global --------------------------------------------------------------------------------
+SB_HD void res_load(const ResParams &R, const ResBlock &B, float *sm, int tid)
+{
+    const ResMap M(R);
+    const int K4 = R.kp >> 2;
+    const float4 z4 = f4(0.0f);
+    float *const *F = R.set[R.cur];
+    {   // p with its halo
+        const int nj = B.lj_n + 2, n = (B.li_n + 2) * nj * K4;
+        for (int idx = tid; idx < n; idx += K5_NT) {
+            const int k4 = idx % K4, r = idx / K4, lj = r % nj - 1, li = r / nj - 1;
+            const int gi = B.i0 + li, gj = B.j0 + lj;
+            const bool in = gi >= 0 && gi < R.nx && gj >= 0 && gj < R.ny;
+            st4(sm + M.p(li, lj) + 4 * k4, in ? ld4(F[0] + (long long)gi * R.plane + (long long)gj * R.pitch + 4 * k4) : z4);
+        }
+    }
+    {   // vx with the plane below
+        const int n = (B.li_n + 1) * B.lj_n * K4;
+        for (int idx = tid; idx < n; idx += K5_NT) {
+            const int k4 = idx % K4, r = idx / K4, lj = r % B.lj_n, li = r / B.lj_n - 1;
+            const int gi = B.i0 + li, gj = B.j0 + lj;
+            st4(sm + M.vx(li, lj) + 4 * k4, gi >= 0 ? ld4(F[1] + (long long)gi * R.plane + (long long)gj * R.pitch + 4 * k4) : z4);
+        }
+    }
+    {   // vy with the row below
+        const int nj = B.lj_n + 1, n = B.li_n * nj * K4;
+        for (int idx = tid; idx < n; idx += K5_NT) {
+            const int k4 = idx % K4, r = idx / K4, lj = r % nj - 1, li = r / nj;
+            const int gi = B.i0 + li, gj = B.j0 + lj;
+            st4(sm + M.vy(li, lj) + 4 * k4, gj >= 0 ? ld4(F[2] + (long long)gi * R.plane + (long long)gj * R.pitch + 4 * k4) : z4);
+        }
+    }
+    {
+        const int n = B.li_n * B.lj_n * K4;
+        for (int idx = tid; idx < n; idx += K5_NT) {
+            const int k4 = idx % K4, r = idx / K4, lj = r % B.lj_n, li = r / B.lj_n;
+            st4(sm + M.vz(li, lj) + 4 * k4, ld4(F[3] + (long long)(B.i0 + li) * R.plane + (long long)(B.j0 + lj) * R.pitch + 4 * k4));
+        }
+    }
+}
+
+// final state -> set[(cur + n_steps) & 1]; the sponge multiply of the last step's velocities happens here
+SB_HD void res_store(const ResParams &R, const ResBlock &B, const float *sm, int tid)
+{
+    const ResMap M(R);
+    const int K4 = R.kp >> 2, n = B.li_n * B.lj_n * K4;
+    float *const *F = R.set[(R.cur + R.n_steps) & 1];
+    const float4 z4 = f4(0.0f);
+    for (int idx = tid; idx < n; idx += K5_NT) {
+        const int k4 = idx % K4, r = idx / K4, lj = r % B.lj_n, li = r / B.lj_n, k0 = 4 * k4;
+        const int gi = B.i0 + li, gj = B.j0 + lj;
+        const bool e0 = k0 < R.nz, e1 = k0 + 1 < R.nz, e2 = k0 + 2 < R.nz, e3 = k0 + 3 < R.nz;
+        float4 vx = ld4(sm + M.vx(li, lj) + k0), vy = ld4(sm + M.vy(li, lj) + k0), vz = ld4(sm + M.vz(li, lj) + k0);
+        if (R.n_steps > 0)
+            for (int q = 0; q < R.n_sponge; q++) {
+                vx = mul4s(vx, SB_LDG(R.decx[q] + gi)); vy = mul4s(vy, SB_LDG(R.decy[q] + gj)); vz = mul4(vz, ld4(R.decz[q] + k0));
+            }
+        const long long c = (long long)gi * R.plane + (long long)gj * R.pitch + k0;
+        st4(F[0] + c, sel4(e0, e1, e2, e3, ld4(sm + M.p(li, lj) + k0), z4));
+        st4(F[1] + c, sel4(e0, e1, e2, e3, vx, z4));
+        st4(F[2] + c, sel4(e0, e1, e2, e3, vy, z4));
+        st4(F[3] + c, sel4(e0, e1, e2, e3, vz, z4));
+    }
+}
+
+// one p face of a neighbour (published after its step s-1) -> halo; face 0: i0-1, 1: i0+li_n, 2: j0-1, 3: j0+lj_n
+template <typename LoadF>
+SB_HD void res_halo_load(const ResParams &R, const ResBlock &B, float *sm, int face, int t, int nt, int s, LoadF load4)
+{
+    const ResMap M(R);
+    const int K4 = R.kp >> 2;
+    const float *pb = R.set[(R.cur + s) & 1][0];
+    if (face < 2) {
+        const int li = face == 0 ? -1 : B.li_n, n = B.lj_n * K4;
+        for (int idx = t; idx < n; idx += nt) {
+            const int lj = idx / K4, k0 = 4 * (idx - lj * K4);
+            st4(sm + M.p(li, lj) + k0, load4(pb + (long long)(B.i0 + li) * R.plane + (long long)(B.j0 + lj) * R.pitch + k0));
+        }
+    } else {
+        const int lj = face == 2 ? -1 : B.lj_n, n = B.li_n * K4;
+        for (int idx = t; idx < n; idx += nt) {
+            const int li = idx / K4, k0 = 4 * (idx - li * K4);
+            st4(sm + M.p(li, lj) + k0, load4(pb + (long long)(B.i0 + li) * R.plane + (long long)(B.j0 + lj) * R.pitch + k0));
+        }
+    }
+}
+
+SB_HD int res_neighbour(const ResParams &R, const ResBlock &B, int face)
+{
+    if (face == 0) return B.bi > 0 ? (B.bi - 1) * R.nbj + B.bj : -1;
+    if (face == 1) return B.bi < R.nbi - 1 ? (B.bi + 1) * R.nbj + B.bj : -1;
+    if (face == 2) return B.bj > 0 ? B.bi * R.nbj + B.bj - 1 : -1;
+    return B.bj < R.nbj - 1 ? B.bi * R.nbj + B.bj + 1 : -1;
+}
+
+// ---- velocity phase: v += cv * grad p on the box and on its two low-side ghost faces ---------------
+// pass 0: the items that read no halo value; pass 1: the others and the ghost faces; pass 2: everything
+template <bool GEOM>
+SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T, float *sm, int s, int pass)
+{
+    const ResMap M(R);
+    const int sti = (R.LJ + 2) * R.kp;                                 // plane stride of the p array
+    const bool damp = s > 0 && R.n_sponge > 0;                         // sponge of the previous step, applied on first use
+    if (T.active) {
+        for (int li = T.g; li < B.li_n; li += T.G) {
+            const int gi = B.i0 + li;
+            const bool upd_x = gi < R.nx - 1, upd_y = T.gj < R.ny - 1;
+            const bool halo = (upd_x && li == B.li_n - 1) || (upd_y && T.lj == B.lj_n - 1);
+            if (pass != 2 && halo != (pass == 1)) continue;
+            const float *pp = sm + M.p(li, T.lj) + T.k0;
+            float *qx = sm + M.vx(li, T.lj) + T.k0, *qy = sm + M.vy(li, T.lj) + T.k0, *qz = sm + M.vz(li, T.lj) + T.k0;
+            const float4 p = ld4(pp);
+            float4 vx = ld4(qx), vy = ld4(qy), vz = ld4(qz);
+            if (damp) {                                                // pml.cpp:47-98
+                vx = mul4s(vx, SB_LDG(R.decx[0] + gi)); vy = mul4s(vy, T.dy0); vz = mul4(vz, T.dz0);
+                for (int q = 1; q < R.n_sponge; q++) {
+                    vx = mul4s(vx, SB_LDG(R.decx[q] + gi)); vy = mul4s(vy, SB_LDG(R.decy[q] + T.gj));
+                    vz = mul4(vz, ld4(R.decz[q] + T.k0));
+                }
+            }
+            unsigned mk = ALL_OPEN;
+            if (GEOM) mk = res_mask_word(R, gi, T.gj, T.k0);
+            if (upd_x) {                                               // fdtd_step.cpp:34-47 / 255-269
+                vx = add4(vx, mul4s(sub4(ld4(pp + sti), p), SB_LDG(R.cvx + gi)));
+                if (GEOM) vx = keep4(vx, mk, M_XOPEN);                 // boundaries.cpp:66-89
+            }
+            if (upd_y) {                                               // fdtd_step.cpp:53-64 / 272-288
+                vy = add4(vy, mul4s(sub4(ld4(pp + R.kp), p), T.cvy));
+                if (GEOM) vy = keep4(vy, mk, M_YOPEN);
+            }
+            {                                                          // fdtd_step.cpp:71-81 / 291-306
+                const float p_next = T.u3 ? pp[4] : 0.0f;
+                const float4 upd = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, p_next), p), T.cvz4));
+                vz = sel4(T.u0, T.u1, T.u2, T.u3, upd, vz);
+                if (GEOM) {                                            // only updated faces are zeroed
+                    const unsigned m = mk | (T.u0 ? 0u : 0x08u) | (T.u1 ? 0u : 0x0800u) | (T.u2 ? 0u : 0x080000u) |
+                                       (T.u3 ? 0u : 0x08000000u);
+                    vz = keep4(vz, m, M_ZOPEN);
+                }
+            }
+            st4(qx, vx); st4(qy, vy); st4(qz, vz);
+        }
+    }
+    if (pass == 0) return;
+    if (B.i0 > 0 && T.active && T.g == 0) {                            // vx of plane i0-1, redundant with its owner
+        const int gi = B.i0 - 1;
+        float *q = sm + M.vx(-1, T.lj) + T.k0;
+        float4 v = ld4(q);
+        if (damp) for (int w = 0; w < R.n_sponge; w++) v = mul4s(v, SB_LDG(R.decx[w] + gi));
+        v = add4(v, mul4s(sub4(ld4(sm + M.p(0, T.lj) + T.k0), ld4(sm + M.p(-1, T.lj) + T.k0)), SB_LDG(R.cvx + gi)));
+        if (GEOM) v = keep4(v, res_mask_word(R, gi, T.gj, T.k0), M_XOPEN);
+        st4(q, v);
+    }
+    if (B.j0 > 0) {                                                    // vy of row j0-1, redundant with its owner
+        const int K4 = R.kp >> 2, gj = B.j0 - 1, n = B.li_n * K4;
+        const float cy = SB_LDG(R.cvy + gj);
+        for (int idx = T.tid; idx < n; idx += K5_NT) {
+            const int li = idx / K4, k0 = 4 * (idx - li * K4);
+            float *q = sm + M.vy(li, -1) + k0;
+            float4 v = ld4(q);
+            if (damp) for (int w = 0; w < R.n_sponge; w++) v = mul4s(v, SB_LDG(R.decy[w] + gj));
+            v = add4(v, mul4s(sub4(ld4(sm + M.p(li, 0) + k0), ld4(sm + M.p(li, -1) + k0)), cy));
+            if (GEOM) v = keep4(v, res_mask_word(R, B.i0 + li, gj, k0), M_YOPEN);
+            st4(q, v);
+        }
+    }
+}
+
+// ---- pressure phase: p += cp * div v, solids, sponge, point sources; publishes the box faces ----------
+template <bool GEOM>
+SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T, float *sm, int s)
+{
+    if (!T.active) return;
+    const ResMap M(R);
+    float *pex = R.set[(R.cur + s + 1) & 1][0];
+    const float4 z4 = f4(0.0f);
+    for (int li = T.g; li < B.li_n; li += T.G) {
+        const int gi = B.i0 + li;
+        float *pp = sm + M.p(li, T.lj) + T.k0;
+        const float *qz = sm + M.vz(li, T.lj) + T.k0;
+        const float4 vx = ld4(sm + M.vx(li, T.lj) + T.k0), vy = ld4(sm + M.vy(li, T.lj) + T.k0), vz = ld4(qz);
+        float4 ddx = vx, ddy = vy;                                     // fdtd_step.cpp:109-211: zero ghost at index 0
+        if (gi > 0) ddx = sub4(vx, ld4(sm + M.vx(li - 1, T.lj) + T.k0));
+        if (T.gj > 0) ddy = sub4(vy, ld4(sm + M.vy(li, T.lj - 1) + T.k0));
+        const float vz_prev = T.k0 > 0 ? qz[-1] : 0.0f;
+        float4 ddz = sub4(vz, make_float4(vz_prev, vz.x, vz.y, vz.z));
+        if (R.icx) { ddx = mul4s(ddx, SB_LDG(R.icx + gi)); ddy = mul4s(ddy, T.icy); ddz = mul4(ddz, T.icz4); }
+        float4 pn = add4(ld4(pp), mul4s(add4(add4(ddx, ddy), ddz), R.cp));
+        if (GEOM) pn = keep4(pn, res_mask_word(R, gi, T.gj, T.k0), M_AIR);
+        if (R.n_sponge > 0) {                                          // pml.cpp:100-149
+            pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[0] + gi)), T.dy0), T.dz0);
+            for (int q = 1; q < R.n_sponge; q++)
+                pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[q] + gi)), SB_LDG(R.decy[q] + T.gj)), ld4(R.decz[q] + T.k0));
+        }
+        pn = sel4(T.e0, T.e1, T.e2, T.e3, pn, z4);
+        if (T.inl_mask) {                                              // float64 add, fp32 store (solver.py:2421), list order
+            for (int q = 0; q < R.n_inline; q++)
+                if (((T.inl_mask >> q) & 1u) && R.inl_i[q] == gi) {
+                    const double w = SB_DMUL(R.src_vals[(long long)s * R.n_sources + R.inl_src[q]], R.inl_weight[q]);
+                    const int e = R.inl_k[q] - T.k0;
+                    if (e == 0) pn.x = (float)((double)pn.x + w);
+                    else if (e == 1) pn.y = (float)((double)pn.y + w);
+                    else if (e == 2) pn.z = (float)((double)pn.z + w);
+                    else pn.w = (float)((double)pn.w + w);
+                }
+        }
+        st4(pp, pn);
+        const bool face = (li == 0 && gi > 0) || (li == B.li_n - 1 && gi < R.nx - 1) ||
+                          (T.lj == 0 && T.gj > 0) || (T.lj == B.lj_n - 1 && T.gj < R.ny - 1);
+        if (face) st4(pex + (long long)gi * R.plane + (long long)T.gj * R.pitch + T.k0, pn);
+    }
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+struct LoadCg {                            // L2 load: the same addresses were read two steps earlier, L1 may hold that line
+    SB_HD float4 operator()(const float *p) const
+    {
+#ifdef __CUDA_ARCH__
+        return __ldcg(reinterpret_cast<const float4 *>(p));
+#else
+        return ld4(p);
+#endif
+    }
+};
+
+template <bool GEOM>
+__global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ ResParams R)
+{
+    extern __shared__ float4 k5_smem4[];
+    float *sm = reinterpret_cast<float *>(k5_smem4);
+    const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
+    const ResBlock B = res_block(R, b);
+    const ResThread T = res_thread(R, B, tid);
+    const ResMap M(R);
+    int *spr = reinterpret_cast<int *>(sm + M.o_end);                  // [0] = probes owned, then (slot, offset) pairs
+    if (tid == 0) spr[0] = 0;
+    res_load(R, B, sm, tid);
+    __syncthreads();
+    for (int t = tid; t < R.n_probes; t += K5_NT) {
+        const int i = R.probe_ijk[3 * t] - B.i0, j = R.probe_ijk[3 * t + 1] - B.j0, k = R.probe_ijk[3 * t + 2];
+        if (i >= 0 && i < B.li_n && j >= 0 && j < B.lj_n) {
+            const int q = atomicAdd(&spr[0], 1);
+            spr[1 + 2 * q] = t; spr[2 + 2 * q] = M.p(i, j) + k;
+        }
+    }
+    __syncthreads();
+    const int n_own = spr[0];
+    bool dead = false;                                                 // a wait timed out: stop waiting, finish, report
+
+    for (int s = 0; s < R.n_steps; s++) {
+        if (s > 0) {
+            if (R.split) res_phase_v<GEOM>(R, B, T, sm, s, 0);         // overlaps the neighbours' publication
+            if (warp < 4) {                                            // warp w receives face w
+                const int nb = res_neighbour(R, B, warp);
+                if (nb >= 0) {
+                    if (lane == 0 && !dead) {
+                        const long long t0 = clock64();
+                        while (ld_acquire_gpu(R.flags + nb) < s)
+                            if (clock64() - t0 > (2LL << 30)) { atomicExch(R.err_flag, 2); dead = true; break; }   // ~1 s: never hang the GPU
+                    }
+                    __syncwarp();
+                    res_halo_load(R, B, sm, warp, lane, 32, s, LoadCg());
+                }
+            }
+            __syncthreads();
+            res_phase_v<GEOM>(R, B, T, sm, s, R.split ? 1 : 2);
+        } else {
+            res_phase_v<GEOM>(R, B, T, sm, 0, 2);
+        }
+        __syncthreads();
+        res_phase_p<GEOM>(R, B, T, sm, s);
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release_gpu(R.flags + b, s + 1); }
+        for (int q = tid - 32; q >= 0 && q < n_own; q += K5_NT - 32)   // core/solver.py:2435-2439
+            R.rec[(long long)s * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];
+    }
+    res_store(R, B, sm, tid);
+}
+#endif  // __CUDACC__
+
+}  // namespace sb

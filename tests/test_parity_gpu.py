@@ -245,3 +245,84 @@ def test_lifecycle_reset_rerun_late_additions_and_inplace_geometry():
     s2.run(steps=80); o2.run_steps(80)
     assert not o2.rigid
     assert_same_as_oracle(s2, o2, "in-place geometry")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K5: shared-memory-resident chunk kernel (csrc/sb_resident.cuh).  The same cases the CPU emulation checks
+# (tests/test_resident_emulation.py), now with the real barriers / step flags / cooperative launch.
+def _resident_cases():
+    from test_resident_emulation import EMU_CASES
+    return EMU_CASES
+
+
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("name", sorted(_resident_cases()))
+def test_resident_kernel_matches_oracle(name, split):
+    case = _resident_cases()[name]
+    s = _with_options(build_b200_solver(case, chunk_steps=37),
+                      {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT, _lib.OPT_RESIDENT_SPLIT: split})
+    o = O.OracleSolver(case)
+    s.run(steps=case["steps"]); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"resident/{name}/split{split}")
+    st = s.device_stats()
+    assert st["kernel_variant"] == _lib.KERNEL_RESIDENT
+    assert st["kernels_launched"] <= -(-case["steps"] // 37) + 2, "one launch per chunk"
+    s.close()
+
+
+def test_resident_is_the_automatic_choice_for_config_1_and_matches_the_reference_fixture():
+    """BASELINE config 1 (100^3, 1000 steps): AUTO keeps the grid in shared memory; output == the reference's."""
+    g = np.load(GOLDEN / "c1_100cubed_1000.npz")
+    s = build_b200_solver(c1_case(1000))
+    s.run(steps=1000)
+    assert s.device_stats()["kernel_variant"] == _lib.KERNEL_RESIDENT
+    assert s.kernel_launches() <= 6
+    assert np.array_equal(s.get_probe_data("probe")["probe"], g["probe_probe"])
+    for f in ("p", "vx", "vy", "vz"):
+        assert sha(s.get_field(f)) == str(g["sha_" + f])
+    # a single step() afterwards goes through K1 and must continue from the stored state
+    m = _with_options(build_b200_solver(c1_case(1000)), {_lib.OPT_KERNEL: _lib.KERNEL_MARCH})
+    m.run(steps=1000)
+    s.step(); m.step()
+    assert s.device_stats()["kernel_variant"] == _lib.KERNEL_MARCH
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(s.get_field(f), m.get_field(f)), f
+
+
+@pytest.mark.parametrize("shape", [(150, 7, 9), (5, 300, 12), (3, 3, 3), (40, 40, 1), (97, 101, 103), (2, 2, 600)])
+def test_resident_equals_march_on_awkward_shapes(shape):
+    """Two independent implementations (K1 streams through L2, K5 stays in shared memory) on shapes that
+    stress the box partition: more SMs than planes, one-cell axes, extents that no box count divides."""
+    nx, ny, nz = shape
+    geom = np.ones(shape, dtype=bool)
+    geom[nx // 3: nx // 3 + 2, ny // 2:, : max(1, nz // 3)] = False
+    case = dict(shape=shape, resolution=1e-3, steps=120, geometry=geom,
+                pml=[dict(depth=min(3, max(1, min(shape) // 3)))] if min(shape) >= 3 else [],
+                sources=[dict(kind="point", position=(nx // 2, ny // 4, nz // 2), frequency=30e3),
+                         dict(kind="point", position=(0, 0, 0), frequency=12e3, amplitude=0.3)],
+                probes=[("a", (nx - 1, ny - 1, nz - 1)), ("b", (nx // 2, ny // 2, nz // 2)), ("c", (0, ny - 1, 0))])
+    a = _with_options(build_b200_solver(case, chunk_steps=50), {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT})
+    b = _with_options(build_b200_solver(case, chunk_steps=50), {_lib.OPT_KERNEL: _lib.KERNEL_MARCH})
+    a.run(steps=120); b.run(steps=120)
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(a.get_field(f), b.get_field(f)), f
+    for n in ("a", "b", "c"):
+        assert np.array_equal(a.get_probe_data(n)[n], b.get_probe_data(n)[n]), n
+    assert np.abs(a.get_field("p")).max() > 0
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_RESIDENT
+
+
+def test_resident_refuses_what_it_cannot_do_and_auto_falls_back_to_k1():
+    case = CASES["uniform_pml"]                               # has microphones: trilinear gathers cross boxes
+    s = _with_options(build_b200_solver(case), {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT})
+    with pytest.raises(_lib.B200BackendError, match="resident kernel not applicable: microphones"):
+        s.run(steps=8)
+    s.close()
+    big = _with_options(build_b200_solver(c2_case(200, steps=0)), {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT})
+    with pytest.raises(_lib.B200BackendError, match="does not fit in shared memory"):
+        big.run(steps=8)
+    big.close()
+    a = build_b200_solver(case)
+    a.run(steps=16)
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_MARCH
+    a.close()
