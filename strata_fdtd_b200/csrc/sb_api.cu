@@ -109,7 +109,8 @@ struct sb_solver {
     // shared-memory-resident kernel (K5, sb_resident.cuh)
     int n_sm = 0; long long smem_optin = 0;
     int opt_res_split = 1, opt_res_min_steps = 4;
-    std::vector<int> probe_ijk_host; DBuf<int> d_probe_ijk, d_res_flags;
+    std::vector<int> probe_ijk_host; DBuf<int> d_probe_ijk; DBuf<uint4> d_res_xch;
+    unsigned res_epoch = 0;                // step tags of the face exchange keep growing across launches
     bool resident_used = false;
     int res_nbi = 0, res_nbj = 0;
 };
@@ -181,7 +182,7 @@ extern "C" int sb_destroy(sb_solver *h)
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
     h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release();
     h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
-    h->d_probe_ijk.release(); h->d_res_flags.release();
+    h->d_probe_ijk.release(); h->d_res_xch.release();
     delete h;
     return 0;
 }
@@ -865,9 +866,15 @@ static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double
 {
     const int nb = R.nbi * R.nbj;
     R.n_steps = n_steps; R.src_vals = src_dev; R.rec = rec_dev;
-    if (h->d_res_flags.alloc((size_t)nb)) return 1;
-    R.flags = h->d_res_flags.p;
-    CU(cudaMemsetAsync(R.flags, 0, (size_t)nb * sizeof(int), h->stream));
+    R.xch_face = std::max(R.LI, R.LJ) * R.kp / 2;
+    const size_t need = (size_t)2 * nb * 4 * R.xch_face;
+    if (h->d_res_xch.n < need || !h->d_res_xch.p || h->res_epoch > 0xF0000000u) {   // (re)start the tags at zero
+        if (h->d_res_xch.alloc(need)) return 1;
+        CU(cudaMemsetAsync(h->d_res_xch.p, 0, h->d_res_xch.n * sizeof(uint4), h->stream));
+        h->res_epoch = 0;
+    }
+    R.xch = h->d_res_xch.p; R.tag_base = h->res_epoch;
+    h->res_epoch += (unsigned)n_steps;
     const size_t smem = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, R.n_probes);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->opt_profile) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, h->stream); }

@@ -11,11 +11,14 @@
 //   * every CTA loads its box of {p,vx,vy,vz} into shared memory once, advances it n_steps times in
 //     place (velocity phase, barrier, pressure phase, barrier) and stores it back once -- HBM/L2 see
 //     2 x 16 B per cell per CHUNK instead of 32 B per cell per STEP;
-//   * per step only the four p faces of a box cross CTAs.  They go through L2 (the p buffers of the
-//     two ping-pong sets double as the exchange area, indexed by step parity) with one release/acquire
-//     flag per CTA -- point-to-point, no grid-wide barrier.  The face velocities on the low sides
-//     (vx at i0-1, vy at j0-1) are kept redundantly in the box, updated with the owner's exact
-//     operations (the same trick as the multi-GPU slabs), so nothing but p travels;
+//   * per step only the four p faces of a box cross CTAs.  They go through an exchange area in L2 as
+//     (value, step tag) pairs in 8-byte units, two per 16-byte volatile store -- the receiver polls the
+//     data itself until the tag is the step it needs, so there is no flag, no fence and no grid-wide
+//     barrier on the path (the "LL" protocol of NCCL, here between SMs of one GPU).  Slots are double
+//     buffered by step parity; a box can only be one step ahead of a neighbour, which makes that enough.
+//     The face velocities on the low sides (vx at i0-1, vy at j0-1) are kept redundantly in the box,
+//     updated with the owner's exact operations (the same trick as the multi-GPU slabs, DESIGN.md
+//     section 5), so nothing but p travels;
 //   * the part of the velocity phase that needs no halo value runs while the neighbours' faces are in
 //     flight (R.split).
 //
@@ -30,6 +33,7 @@
 // calls them from k5_resident.
 #pragma once
 #include "sb_kernels.cuh"
+#include <string.h>
 
 #ifdef __CUDA_ARCH__
 #define SB_LDG(ptr) __ldg(ptr)
@@ -64,7 +68,9 @@ struct ResParams {
     int n_probes, n_rec;
     const int *probe_ijk;                  // 3 ints per probe
     float *rec;                            // [n_steps][n_rec]
-    int *flags;                            // one per CTA: number of steps whose p faces are published (zero on entry)
+    uint4 *xch;                            // exchange area [2 parities][boxes][4 faces][xch_face] of (value, tag) pairs
+    int xch_face;                          // uint4 per face slot = max(LI, LJ) * kp / 2
+    unsigned tag_base;                     // p after step s of this launch travels with tag tag_base + s + 1 (never 0)
     int *err_flag;
     int split;                             // 1 = overlap the halo-free part of the velocity phase with the exchange
 };
@@ -233,34 +239,69 @@ SB_HD void res_store(const ResParams &R, const ResBlock &B, const float *sm, int
     }
 }
 
-// one p face of a neighbour (published after its step s-1) -> halo; face 0: i0-1, 1: i0+li_n, 2: j0-1, 3: j0+lj_n
-template <typename LoadF>
-SB_HD void res_halo_load(const ResParams &R, const ResBlock &B, float *sm, int face, int t, int nt, int s, LoadF load4)
+// ---- exchange of p faces between boxes ------------------------------------------------------------
+// face 0: plane li = 0, 1: plane li = li_n-1, 2: row lj = 0, 3: row lj = lj_n-1 of the publishing box
+SB_HD long long res_xch_slot(const ResParams &R, int parity, int box, int face)
 {
-    const ResMap M(R);
-    const int K4 = R.kp >> 2;
-    const float *pb = R.set[(R.cur + s) & 1][0];
-    if (face < 2) {
-        const int li = face == 0 ? -1 : B.li_n, n = B.lj_n * K4;
-        for (int idx = t; idx < n; idx += nt) {
-            const int lj = idx / K4, k0 = 4 * (idx - lj * K4);
-            st4(sm + M.p(li, lj) + k0, load4(pb + (long long)(B.i0 + li) * R.plane + (long long)(B.j0 + lj) * R.pitch + k0));
-        }
-    } else {
-        const int lj = face == 2 ? -1 : B.lj_n, n = B.li_n * K4;
-        for (int idx = t; idx < n; idx += nt) {
-            const int li = idx / K4, k0 = 4 * (idx - li * K4);
-            st4(sm + M.p(li, lj) + k0, load4(pb + (long long)(B.i0 + li) * R.plane + (long long)(B.j0 + lj) * R.pitch + k0));
-        }
-    }
+    return (((long long)parity * (R.nbi * R.nbj) + box) * 4 + face) * R.xch_face;
 }
 
-SB_HD int res_neighbour(const ResParams &R, const ResBlock &B, int face)
+SB_HD unsigned res_bits(float f)
 {
-    if (face == 0) return B.bi > 0 ? (B.bi - 1) * R.nbj + B.bj : -1;
-    if (face == 1) return B.bi < R.nbi - 1 ? (B.bi + 1) * R.nbj + B.bj : -1;
-    if (face == 2) return B.bj > 0 ? B.bi * R.nbj + B.bj - 1 : -1;
-    return B.bj < R.nbj - 1 ? B.bi * R.nbj + B.bj + 1 : -1;
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    unsigned u; memcpy(&u, &f, 4); return u;
+#endif
+}
+
+SB_HD void res_publish(uint4 *dst, float4 v, unsigned tag)
+{
+    const uint4 a = make_uint4(res_bits(v.x), tag, res_bits(v.y), tag);
+    const uint4 b = make_uint4(res_bits(v.z), tag, res_bits(v.w), tag);
+#ifdef __CUDA_ARCH__
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 1), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+#else
+    dst[0] = a; dst[1] = b;
+#endif
+}
+
+// the neighbours' faces of p after step s-1 -> halo of the box; recv(src, tag) returns four values once their tags match
+template <typename RecvF>
+SB_HD void res_halo_recv(const ResParams &R, const ResBlock &B, float *sm, int t, int nt, int s, RecvF &recv)
+{
+    const ResMap M(R);
+    const int K4 = R.kp >> 2, K2 = R.kp >> 1, par = s & 1;
+    const unsigned tag = R.tag_base + (unsigned)s;
+    if (B.bi > 0) {                                                    // plane i0-1 = face 1 of the box below
+        const uint4 *src = R.xch + res_xch_slot(R, par, (B.bi - 1) * R.nbj + B.bj, 1);
+        for (int idx = t; idx < B.lj_n * K4; idx += nt) {
+            const int lj = idx / K4, k0 = 4 * (idx - lj * K4);
+            st4(sm + M.p(-1, lj) + k0, recv(src + lj * K2 + (k0 >> 1), tag));
+        }
+    }
+    if (B.bi < R.nbi - 1) {                                            // plane i0+li_n = face 0 of the box above
+        const uint4 *src = R.xch + res_xch_slot(R, par, (B.bi + 1) * R.nbj + B.bj, 0);
+        for (int idx = t; idx < B.lj_n * K4; idx += nt) {
+            const int lj = idx / K4, k0 = 4 * (idx - lj * K4);
+            st4(sm + M.p(B.li_n, lj) + k0, recv(src + lj * K2 + (k0 >> 1), tag));
+        }
+    }
+    if (B.bj > 0) {                                                    // row j0-1 = face 3 of the box to the left
+        const uint4 *src = R.xch + res_xch_slot(R, par, B.bi * R.nbj + B.bj - 1, 3);
+        for (int idx = t; idx < B.li_n * K4; idx += nt) {
+            const int li = idx / K4, k0 = 4 * (idx - li * K4);
+            st4(sm + M.p(li, -1) + k0, recv(src + li * K2 + (k0 >> 1), tag));
+        }
+    }
+    if (B.bj < R.nbj - 1) {                                            // row j0+lj_n = face 2 of the box to the right
+        const uint4 *src = R.xch + res_xch_slot(R, par, B.bi * R.nbj + B.bj + 1, 2);
+        for (int idx = t; idx < B.li_n * K4; idx += nt) {
+            const int li = idx / K4, k0 = 4 * (idx - li * K4);
+            st4(sm + M.p(li, B.lj_n) + k0, recv(src + li * K2 + (k0 >> 1), tag));
+        }
+    }
 }
 
 // ---- velocity phase: v += cv * grad p on the box and on its two low-side ghost faces ---------------
@@ -342,7 +383,9 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
 {
     if (!T.active) return;
     const ResMap M(R);
-    float *pex = R.set[(R.cur + s + 1) & 1][0];
+    const int K2 = R.kp >> 1;
+    const unsigned tag = R.tag_base + (unsigned)s + 1u;                // p after step s
+    uint4 *xo = R.xch + res_xch_slot(R, (s + 1) & 1, B.bi * R.nbj + B.bj, 0);
     const float4 z4 = f4(0.0f);
     for (int li = T.g; li < B.li_n; li += T.G) {
         const int gi = B.i0 + li;
@@ -375,31 +418,34 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
                 }
         }
         st4(pp, pn);
-        const bool face = (li == 0 && gi > 0) || (li == B.li_n - 1 && gi < R.nx - 1) ||
-                          (T.lj == 0 && T.gj > 0) || (T.lj == B.lj_n - 1 && T.gj < R.ny - 1);
-        if (face) st4(pex + (long long)gi * R.plane + (long long)T.gj * R.pitch + T.k0, pn);
+        if (li == 0 && gi > 0) res_publish(xo + T.lj * K2 + (T.k0 >> 1), pn, tag);
+        if (li == B.li_n - 1 && gi < R.nx - 1) res_publish(xo + R.xch_face + T.lj * K2 + (T.k0 >> 1), pn, tag);
+        if (T.lj == 0 && T.gj > 0) res_publish(xo + 2 * R.xch_face + li * K2 + (T.k0 >> 1), pn, tag);
+        if (T.lj == B.lj_n - 1 && T.gj < R.ny - 1) res_publish(xo + 3 * R.xch_face + li * K2 + (T.k0 >> 1), pn, tag);
     }
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ int ld_acquire_gpu(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-struct LoadCg {                            // L2 load: the same addresses were read two steps earlier, L1 may hold that line
-    SB_HD float4 operator()(const float *p) const
+// Receiver of one 16-byte pair of (value, tag) units: spins on the data until both tags are the wanted step.
+struct RecvPoll {
+    int *err_flag;
+    bool dead;                               // a wait timed out: stop waiting, finish the chunk, report
+    __device__ __forceinline__ uint4 poll(const uint4 *src, unsigned tag)
     {
-#ifdef __CUDA_ARCH__
-        return __ldcg(reinterpret_cast<const float4 *>(p));
-#else
-        return ld4(p);
-#endif
+        uint4 v;
+        long long t0 = 0;
+        for (;;) {
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+            if ((v.y == tag && v.w == tag) || dead) break;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > (2LL << 30)) { atomicExch(err_flag, 2); dead = true; }   // ~1 s: never hang the GPU
+        }
+        return v;
+    }
+    __device__ __forceinline__ float4 operator()(const uint4 *src, unsigned tag)
+    {
+        const uint4 a = poll(src, tag), b = poll(src + 1, tag);
+        return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
     }
 };
 
@@ -408,7 +454,7 @@ __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ 
 {
     extern __shared__ float4 k5_smem4[];
     float *sm = reinterpret_cast<float *>(k5_smem4);
-    const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, b = blockIdx.x;
     const ResBlock B = res_block(R, b);
     const ResThread T = res_thread(R, B, tid);
     const ResMap M(R);
@@ -425,33 +471,21 @@ __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ 
     }
     __syncthreads();
     const int n_own = spr[0];
-    bool dead = false;                                                 // a wait timed out: stop waiting, finish, report
+    RecvPoll recv{R.err_flag, false};
 
     for (int s = 0; s < R.n_steps; s++) {
         if (s > 0) {
-            if (R.split) res_phase_v<GEOM>(R, B, T, sm, s, 0);         // overlaps the neighbours' publication
-            if (warp < 4) {                                            // warp w receives face w
-                const int nb = res_neighbour(R, B, warp);
-                if (nb >= 0) {
-                    if (lane == 0 && !dead) {
-                        const long long t0 = clock64();
-                        while (ld_acquire_gpu(R.flags + nb) < s)
-                            if (clock64() - t0 > (2LL << 30)) { atomicExch(R.err_flag, 2); dead = true; break; }   // ~1 s: never hang the GPU
-                    }
-                    __syncwarp();
-                    res_halo_load(R, B, sm, warp, lane, 32, s, LoadCg());
-                }
-            }
+            if (R.split) res_phase_v<GEOM>(R, B, T, sm, s, 0);         // runs while the neighbours' faces are in flight
+            res_halo_recv(R, B, sm, tid, K5_NT, s, recv);
             __syncthreads();
             res_phase_v<GEOM>(R, B, T, sm, s, R.split ? 1 : 2);
         } else {
             res_phase_v<GEOM>(R, B, T, sm, 0, 2);
         }
         __syncthreads();
-        res_phase_p<GEOM>(R, B, T, sm, s);
+        res_phase_p<GEOM>(R, B, T, sm, s);                             // publishes the box faces as it goes
         __syncthreads();
-        if (tid == 0) { __threadfence(); st_release_gpu(R.flags + b, s + 1); }
-        for (int q = tid - 32; q >= 0 && q < n_own; q += K5_NT - 32)   // core/solver.py:2435-2439
+        for (int q = tid; q < n_own; q += K5_NT)                       // core/solver.py:2435-2439
             R.rec[(long long)s * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];
     }
     res_store(R, B, sm, tid);

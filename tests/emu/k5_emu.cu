@@ -27,8 +27,22 @@ template <typename T> struct Aligned {
 };
 
 
-template <bool GEOM> void run(ResParams &R, std::vector<float *> &smem)
+// host stand-in for RecvPoll: in lockstep the data is always there; a wrong tag is an indexing bug
+struct RecvHost {
+    int bad = 0;
+    float4 operator()(const uint4 *src, unsigned tag)
+    {
+        const uint4 a = src[0], b = src[1];
+        if (a.y != tag || a.w != tag || b.y != tag || b.w != tag) bad++;
+        float f[4]; const unsigned u[4] = {a.x, a.z, b.x, b.z};
+        memcpy(f, u, 16);
+        return make_float4(f[0], f[1], f[2], f[3]);
+    }
+};
+
+template <bool GEOM> int run(ResParams &R, std::vector<float *> &smem)
 {
+    RecvHost recv;
     const int nb = R.nbi * R.nbj;
     const ResMap M(R);
     std::vector<std::vector<int>> own(nb);                       // (slot, offset) pairs of the probes a box owns
@@ -53,9 +67,7 @@ template <bool GEOM> void run(ResParams &R, std::vector<float *> &smem)
             if (R.split) phase_v(s, 0);
             for (int b = 0; b < nb; b++) {
                 const ResBlock B = res_block(R, b);
-                for (int face = 0; face < 4; face++)
-                    if (res_neighbour(R, B, face) >= 0)
-                        for (int lane = 0; lane < 32; lane++) res_halo_load(R, B, smem[b], face, lane, 32, s, LoadCg());
+                for (int t = 0; t < K5_NT; t++) res_halo_recv(R, B, smem[b], t, K5_NT, s, recv);
             }
             phase_v(s, R.split ? 1 : 2);
         } else {
@@ -73,12 +85,14 @@ template <bool GEOM> void run(ResParams &R, std::vector<float *> &smem)
         const ResBlock B = res_block(R, b);
         for (int t = 0; t < K5_NT; t++) res_store(R, B, smem[b], t);
     }
+    return recv.bad;
 }
 }  // namespace
 
 // fields: 8 padded buffers [(nx+2)][ny][pitch] (set 0 then set 1; p, vx, vy, vz), updated in place.
 // x tables arrive with nx+2 entries (index -1 first), y tables with ny+4, z tables with pitch+4 -- the layouts
-// sb_api.cu uploads.  Returns 0, or 1 when the grid does not fit the given SM count / shared-memory limit.
+// sb_api.cu uploads.  Returns 0, 1 when the grid does not fit the given SM count / shared-memory limit, 2 when a
+// received face carried the wrong step tag.
 extern "C" int k5emu_run(int nx, int ny, int nz, int pitch, float **fields, int cur, int n_steps, const uint8_t *mask,
                          const float *cvx, const float *cvy, const float *cvz,
                          const float *icx, const float *icy, const float *icz,
@@ -118,17 +132,23 @@ extern "C" int k5emu_run(int nx, int ny, int nz, int pitch, float **fields, int 
     }
     R.src_vals = src_vals; R.n_sources = n_sources;
     R.n_probes = n_probes; R.n_rec = n_rec; R.probe_ijk = probe_ijk; R.rec = rec;
-    R.flags = nullptr; R.err_flag = nullptr; R.split = split;
+    R.err_flag = nullptr; R.split = split;
+    R.xch_face = (R.LI > R.LJ ? R.LI : R.LJ) * R.kp / 2;
+    static unsigned epoch = 0;                                  // tags keep growing across calls, as in the library
+    static Aligned<uint4> *xch = nullptr; static size_t xch_n = 0;
+    const size_t need = (size_t)2 * nbi * nbj * 4 * R.xch_face;
+    if (!xch || xch_n < need) { delete xch; xch = new Aligned<uint4>(need); xch_n = need; }
+    R.xch = xch->p; R.tag_base = epoch; epoch += (unsigned)n_steps;
     const size_t sm_floats = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, n_probes) / 4;
     std::vector<Aligned<float> *> S;
     std::vector<float *> smem;
     for (int b = 0; b < nbi * nbj; b++) { S.push_back(new Aligned<float>(sm_floats)); smem.push_back(S.back()->p); }
     // poison the shared memory so that a read of something never loaded shows up
     for (float *p : smem) for (size_t q = 0; q < sm_floats; q++) p[q] = 1.0e30f;
-    if (mask) run<true>(R, smem); else run<false>(R, smem);
+    const int bad = mask ? run<true>(R, smem) : run<false>(R, smem);
     for (int q = 0; q < 8; q++) std::memcpy(fields[q], F[q]->p, (size_t)elems * sizeof(float));
     for (auto *a : F) delete a;
     for (auto *a : D) delete a;
     for (auto *a : S) delete a;
-    return 0;
+    return bad ? 2 : 0;
 }

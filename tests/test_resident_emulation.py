@@ -99,6 +99,7 @@ def run_emulated(emu, case, n_steps, chunk=37, nbi=0, nbj=0, n_sm=148, smem_limi
         rc = emu.k5emu_run(nx, ny, nz, pitch, fptr, cur, m, vp(mask), vp(cvx), vp(cvy), vp(cvz), vp(ic[0]), vp(ic[1]), vp(ic[2]),
                            len(dec), dx_, dy_, dz_, C.c_float(float(cp)), len(w) - 1, vp(ijks), vp(w), vp(W), n_src,
                            len(names), vp(pijk), vp(rec), n_rec, nbi, nbj, n_sm, C.c_longlong(smem_limit), split, chosen)
+        assert rc != 2, "a box received a face with the wrong step tag"
         if rc != 0 and nbi > 0:
             pytest.skip("this forced partition needs more than 512 columns per box")
         assert rc == 0, "grid does not fit the emulated machine"

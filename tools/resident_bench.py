@@ -43,7 +43,7 @@ def main():
             for label, opts in (("march_graph", {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_USE_GRAPH: 1}),
                                 ("resident_nosplit", {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT, _lib.OPT_RESIDENT_SPLIT: 0}),
                                 ("resident_split", {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT, _lib.OPT_RESIDENT_SPLIT: 1})):
-                for chunk in (16, 256, 1000):
+                for chunk in (32, 512):
                     s = build_b200_solver(case)
                     for k, v in opts.items():
                         s.set_kernel_option(k, v)
