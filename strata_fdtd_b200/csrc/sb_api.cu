@@ -108,7 +108,7 @@ struct sb_solver {
     std::vector<ProfEntry> prof;
     // shared-memory-resident kernel (K5, sb_resident.cuh)
     int n_sm = 0; long long smem_optin = 0;
-    int opt_res_split = 1, opt_res_min_steps = 4;
+    int opt_res_split = 0, opt_res_min_steps = 4;
     std::vector<int> probe_ijk_host; DBuf<int> d_probe_ijk; DBuf<uint4> d_res_xch;
     unsigned res_epoch = 0;                // step tags of the face exchange keep growing across launches
     bool resident_used = false;
@@ -823,7 +823,7 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not)
     else if (h->n_sm <= 0 || h->smem_optin <= 0) *why_not = "device attributes unavailable";
     if (*why_not) return 0;
     int nbi = 0, nbj = 0;
-    if (!res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, &nbi, &nbj)) {
+    if (!res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, h->have_mask, &nbi, &nbj)) {
         *why_not = "grid does not fit in shared memory";
         return 0;
     }
@@ -850,17 +850,21 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not)
     return 1;
 }
 
-template <bool GEOM>
-static int launch_resident_t(sb_solver *h, ResParams &R, size_t smem)
-{
-    CU(cudaFuncSetAttribute(k5_resident<GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_resident<GEOM>, K5_NT, smem));
-    if ((long long)per_sm * h->n_sm < (long long)R.nbi * R.nbj) return fail("resident kernel: %d boxes cannot be co-resident", R.nbi * R.nbj);
-    void *args[] = {&R};
-    CU(cudaLaunchCooperativeKernel((const void *)k5_resident<GEOM>, dim3(R.nbi * R.nbj), dim3(K5_NT), args, smem, h->stream));
-    return 0;
-}
+struct ResidentLauncher {
+    sb_solver *h; ResParams &R; size_t smem;
+    template <bool GEOM, bool UNI, int NS> int run()
+    {
+        auto kern = k5_resident<GEOM, UNI, NS>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K5_NT, smem));
+        if ((long long)per_sm * h->n_sm < (long long)R.nbi * R.nbj)
+            return fail("resident kernel: %d boxes cannot be co-resident", R.nbi * R.nbj);
+        void *args[] = {&R};
+        CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(R.nbi * R.nbj), dim3(K5_NT), args, smem, h->stream));
+        return 0;
+    }
+};
 
 static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double *src_dev, float *rec_dev)
 {
@@ -875,10 +879,11 @@ static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double
     }
     R.xch = h->d_res_xch.p; R.tag_base = h->res_epoch;
     h->res_epoch += (unsigned)n_steps;
-    const size_t smem = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, R.n_probes);
+    const size_t smem = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, R.n_probes, R.mask != nullptr);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->opt_profile) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, h->stream); }
-    if (R.mask ? launch_resident_t<true>(h, R, smem) : launch_resident_t<false>(h, R, smem)) return 1;
+    ResidentLauncher launcher{h, R, smem};
+    if (res_dispatch(R.mask != nullptr, R.icx == nullptr, R.n_sponge, launcher)) return 1;
     if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, n_steps}); }
     h->kernels_launched++;
     h->steps_done += n_steps;

@@ -75,32 +75,39 @@ struct ResParams {
     int split;                             // 1 = overlap the halo-free part of the velocity phase with the exchange
 };
 
-// shared-memory layout, float offsets; p carries a one-cell halo on all four sides, vx / vy a low-side ghost
+// shared-memory layout, float offsets; p carries a one-cell halo on all four sides, vx / vy a low-side ghost;
+// the x tables (they vary along the planes a thread loops over) and the face-mask words live there too
 struct ResMap {
-    int kp, LI, LJ, o_vx, o_vy, o_vz, o_end;
-    SB_HD explicit ResMap(const ResParams &R) : kp(R.kp), LI(R.LI), LJ(R.LJ)
+    int kp, LI, LJ, o_vx, o_vy, o_vz, o_xt, o_mask, o_end;
+    SB_HD ResMap(int LI_, int LJ_, int kp_, bool geom) : kp(kp_), LI(LI_), LJ(LJ_)
     {
         o_vx = (LI + 2) * (LJ + 2) * kp;
         o_vy = o_vx + (LI + 1) * LJ * kp;
         o_vz = o_vy + LI * (LJ + 1) * kp;
-        o_end = o_vz + LI * LJ * kp;
+        o_xt = o_vz + LI * LJ * kp;
+        o_mask = o_xt + (3 * (LI + 1) + 3) / 4 * 4;
+        o_end = o_mask + (geom ? (LI + 2) * (LJ + 2) * (kp / 4) : 0);
     }
+    SB_HD explicit ResMap(const ResParams &R) : ResMap(R.LI, R.LJ, R.kp, R.mask != nullptr) {}
     SB_HD int p(int li, int lj) const { return ((li + 1) * (LJ + 2) + (lj + 1)) * kp; }     // li -1..LI, lj -1..LJ
     SB_HD int vx(int li, int lj) const { return o_vx + ((li + 1) * LJ + lj) * kp; }          // li -1..LI-1
     SB_HD int vy(int li, int lj) const { return o_vy + (li * (LJ + 1) + (lj + 1)) * kp; }    // lj -1..LJ-1
     SB_HD int vz(int li, int lj) const { return o_vz + (li * LJ + lj) * kp; }
+    SB_HD int cvx(int li) const { return o_xt + li + 1; }                                    // li -1..LI-1
+    SB_HD int icx(int li) const { return o_xt + (LI + 1) + li + 1; }
+    SB_HD int dx0(int li) const { return o_xt + 2 * (LI + 1) + li + 1; }
+    SB_HD int mw(int p_off) const { return o_mask + (p_off >> 2); }                          // mask word of the 4 cells at p_off
 };
 
-static inline long long res_smem_bytes(int LI, int LJ, int kp, int n_probes)
+static inline long long res_smem_bytes(int LI, int LJ, int kp, int n_probes, bool geom)
 {
-    const long long fl = (long long)(LI + 2) * (LJ + 2) * kp + (long long)(LI + 1) * LJ * kp +
-                         (long long)LI * (LJ + 1) * kp + (long long)LI * LJ * kp;
-    return fl * 4 + (long long)(2 * n_probes + 4) * 4;
+    const ResMap M(LI, LJ, kp, geom);
+    return (long long)M.o_end * 4 + (long long)(2 * n_probes + 4) * 4;
 }
 
 // Box grid for a given SM count and shared-memory limit: fewest items per thread, then least shared memory.
 // Returns false when the grid does not fit on chip.
-static inline bool res_choose_partition(int nx, int ny, int nz, int n_sm, long long smem_limit, int n_probes,
+static inline bool res_choose_partition(int nx, int ny, int nz, int n_sm, long long smem_limit, int n_probes, bool geom,
                                         int *nbi_out, int *nbj_out)
 {
     const int kp = (nz + 3) / 4 * 4, K4 = kp / 4;
@@ -110,10 +117,13 @@ static inline bool res_choose_partition(int nx, int ny, int nz, int n_sm, long l
         if (nbj < 1) break;
         const int LI = (nx + nbi - 1) / nbi, LJ = (ny + nbj - 1) / nbj;
         if ((long long)LJ * K4 > K5_NT) continue;                     // one thread per (row, float4) column at least
-        const long long bytes = res_smem_bytes(LI, LJ, kp, n_probes);
+        if ((long long)(LI + 2) * (LJ + 2) * kp * 2 >= (1LL << 30)) continue;
+        const long long bytes = res_smem_bytes(LI, LJ, kp, n_probes, geom);
         if (bytes > smem_limit) continue;
-        const int G = K5_NT / (LJ * K4);
-        const long long iters = (LI + G - 1) / G;
+        // work of the busiest thread: its share of the planes plus the ghost-face items handed to the idle ones
+        const int ncol = LJ * K4, G = K5_NT / ncol;
+        const long long items = (long long)LI * ncol + ncol + (long long)LI * K4;
+        const long long iters = (items + K5_NT - 1) / K5_NT > (LI + G - 1) / G ? (items + K5_NT - 1) / K5_NT : (LI + G - 1) / G;
         const long long cost = iters * (1LL << 32) + bytes;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; *nbi_out = nbi; *nbj_out = nbj; }
     }
@@ -136,8 +146,11 @@ SB_HD ResBlock res_block(const ResParams &R, int b)
 // Per-thread constants: a thread owns one (row, float4) column of the box and every G-th plane of it.
 struct ResThread {
     int tid, g, G, lj, gj, k0;
+    int op, ox, oy, oz;                    // shared-memory offsets of the thread's first item (plane li = g)
     bool active;
     bool e0, e1, e2, e3, u0, u1, u2, u3;   // element inside the grid / its z face is updated
+    bool upd_y, sub_y, up_i, low_i;        // y face updated; j > 0; a box above / below exists
+    bool pub_jlo, pub_jhi;                 // the column lies on a j face that a neighbour needs
     float cvy, icy, dy0;
     float4 cvz4, icz4, dz0;
     unsigned inl_mask;
@@ -146,6 +159,7 @@ struct ResThread {
 SB_HD ResThread res_thread(const ResParams &R, const ResBlock &B, int tid)
 {
     ResThread T;
+    const ResMap M(R);
     const int K4 = R.kp >> 2, ncol = B.lj_n * K4;
     T.tid = tid;
     T.G = K5_NT / ncol;
@@ -153,13 +167,17 @@ SB_HD ResThread res_thread(const ResParams &R, const ResBlock &B, int tid)
     const int c = tid - T.g * ncol;
     T.active = T.g < T.G;
     T.lj = c / K4; T.k0 = 4 * (c - T.lj * K4); T.gj = B.j0 + T.lj;
+    T.op = M.p(T.g, T.lj) + T.k0; T.ox = M.vx(T.g, T.lj) + T.k0; T.oy = M.vy(T.g, T.lj) + T.k0; T.oz = M.vz(T.g, T.lj) + T.k0;
     T.e0 = T.k0 < R.nz; T.e1 = T.k0 + 1 < R.nz; T.e2 = T.k0 + 2 < R.nz; T.e3 = T.k0 + 3 < R.nz;
     T.u0 = T.k0 < R.nz - 1; T.u1 = T.k0 + 1 < R.nz - 1; T.u2 = T.k0 + 2 < R.nz - 1; T.u3 = T.k0 + 3 < R.nz - 1;
+    T.upd_y = T.gj < R.ny - 1; T.sub_y = T.gj > 0;
+    T.up_i = B.i0 + B.li_n < R.nx; T.low_i = B.i0 > 0;
+    T.pub_jlo = T.lj == 0 && T.gj > 0; T.pub_jhi = T.lj == B.lj_n - 1 && T.gj < R.ny - 1;
     T.cvy = 0.0f; T.icy = 1.0f; T.dy0 = 1.0f;
     T.cvz4 = f4(0.0f); T.icz4 = f4(1.0f); T.dz0 = f4(1.0f);
     T.inl_mask = 0;
     if (!T.active) return T;
-    if (T.gj < R.ny - 1) T.cvy = SB_LDG(R.cvy + T.gj);
+    if (T.upd_y) T.cvy = SB_LDG(R.cvy + T.gj);
     T.cvz4 = ld4(R.cvz + T.k0);
     if (R.icx) { T.icy = SB_LDG(R.icy + T.gj); T.icz4 = ld4(R.icz + T.k0); }
     if (R.n_sponge > 0) { T.dy0 = SB_LDG(R.decy[0] + T.gj); T.dz0 = ld4(R.decz[0] + T.k0); }
@@ -169,11 +187,6 @@ SB_HD ResThread res_thread(const ResParams &R, const ResBlock &B, int tid)
     return T;
 }
 
-SB_HD unsigned res_mask_word(const ResParams &R, int gi, int gj, int k0)
-{
-    return SB_LDG(reinterpret_cast<const unsigned *>(R.mask + (long long)gi * R.plane + (long long)gj * R.pitch + k0));
-}
-
 // ---- box <-> global --------------------------------------------------------------------------------
 SB_HD void res_load(const ResParams &R, const ResBlock &B, float *sm, int tid)
 {
@@ -181,13 +194,16 @@ SB_HD void res_load(const ResParams &R, const ResBlock &B, float *sm, int tid)
     const int K4 = R.kp >> 2;
     const float4 z4 = f4(0.0f);
     float *const *F = R.set[R.cur];
-    {   // p with its halo
+    {   // p with its halo (and the face-mask words of the same cells)
         const int nj = B.lj_n + 2, n = (B.li_n + 2) * nj * K4;
+        unsigned *smw = reinterpret_cast<unsigned *>(sm);
         for (int idx = tid; idx < n; idx += K5_NT) {
             const int k4 = idx % K4, r = idx / K4, lj = r % nj - 1, li = r / nj - 1;
             const int gi = B.i0 + li, gj = B.j0 + lj;
             const bool in = gi >= 0 && gi < R.nx && gj >= 0 && gj < R.ny;
-            st4(sm + M.p(li, lj) + 4 * k4, in ? ld4(F[0] + (long long)gi * R.plane + (long long)gj * R.pitch + 4 * k4) : z4);
+            const long long c = (long long)gi * R.plane + (long long)gj * R.pitch + 4 * k4;
+            st4(sm + M.p(li, lj) + 4 * k4, in ? ld4(F[0] + c) : z4);
+            if (R.mask) smw[M.mw(M.p(li, lj) + 4 * k4)] = in ? *reinterpret_cast<const unsigned *>(R.mask + c) : 0u;
         }
     }
     {   // vx with the plane below
@@ -212,6 +228,12 @@ SB_HD void res_load(const ResParams &R, const ResBlock &B, float *sm, int tid)
             const int k4 = idx % K4, r = idx / K4, lj = r % B.lj_n, li = r / B.lj_n;
             st4(sm + M.vz(li, lj) + 4 * k4, ld4(F[3] + (long long)(B.i0 + li) * R.plane + (long long)(B.j0 + lj) * R.pitch + 4 * k4));
         }
+    }
+    for (int li = tid - 1; li < B.li_n; li += K5_NT) {                  // x tables of planes i0-1 .. i0+li_n-1
+        const int gi = B.i0 + li;
+        sm[M.cvx(li)] = gi >= 0 ? R.cvx[gi] : 0.0f;
+        sm[M.icx(li)] = (R.icx && gi >= 0) ? R.icx[gi] : 1.0f;
+        sm[M.dx0(li)] = (R.n_sponge > 0 && gi >= 0) ? R.decx[0][gi] : 1.0f;
     }
 }
 
@@ -304,38 +326,47 @@ SB_HD void res_halo_recv(const ResParams &R, const ResBlock &B, float *sm, int t
     }
 }
 
+// Compile-time variants: GEOM face masks; UNI uniform grid (no inverse-cell multiplies); NS sponge layers: 0, 1, or
+// 2 = any number (layers beyond the first read their tables from global memory)
+template <int NS>
+SB_HD void res_damp_v(const ResParams &R, const ResMap &M, const ResThread &T, const float *sm, int li, int gi,
+                      float4 &vx, float4 &vy, float4 &vz)
+{
+    if (NS == 0) return;
+    vx = mul4s(vx, sm[M.dx0(li)]); vy = mul4s(vy, T.dy0); vz = mul4(vz, T.dz0);               // pml.cpp:47-98
+    if (NS == 2)
+        for (int q = 1; q < R.n_sponge; q++) {
+            vx = mul4s(vx, SB_LDG(R.decx[q] + gi)); vy = mul4s(vy, SB_LDG(R.decy[q] + T.gj)); vz = mul4(vz, ld4(R.decz[q] + T.k0));
+        }
+}
+
 // ---- velocity phase: v += cv * grad p on the box and on its two low-side ghost faces ---------------
 // pass 0: the items that read no halo value; pass 1: the others and the ghost faces; pass 2: everything
-template <bool GEOM>
+template <bool GEOM, bool UNI, int NS>
 SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T, float *sm, int s, int pass)
 {
     const ResMap M(R);
     const int sti = (R.LJ + 2) * R.kp;                                 // plane stride of the p array
-    const bool damp = s > 0 && R.n_sponge > 0;                         // sponge of the previous step, applied on first use
+    const bool damp = s > 0;                                           // sponge of the previous step, applied on first use
+    const unsigned *smw = reinterpret_cast<const unsigned *>(sm);
     if (T.active) {
-        for (int li = T.g; li < B.li_n; li += T.G) {
-            const int gi = B.i0 + li;
-            const bool upd_x = gi < R.nx - 1, upd_y = T.gj < R.ny - 1;
-            const bool halo = (upd_x && li == B.li_n - 1) || (upd_y && T.lj == B.lj_n - 1);
+        const int dp = T.G * sti, dvx = T.G * R.LJ * R.kp, dvy = T.G * (R.LJ + 1) * R.kp;
+        int op = T.op, ox = T.ox, oy = T.oy, oz = T.oz;
+        for (int li = T.g; li < B.li_n; li += T.G, op += dp, ox += dvx, oy += dvy, oz += dvx) {
+            const bool upd_x = li < B.li_n - 1 || T.up_i;
+            const bool halo = (upd_x && li == B.li_n - 1) || T.pub_jhi;
             if (pass != 2 && halo != (pass == 1)) continue;
-            const float *pp = sm + M.p(li, T.lj) + T.k0;
-            float *qx = sm + M.vx(li, T.lj) + T.k0, *qy = sm + M.vy(li, T.lj) + T.k0, *qz = sm + M.vz(li, T.lj) + T.k0;
+            const float *pp = sm + op;
             const float4 p = ld4(pp);
-            float4 vx = ld4(qx), vy = ld4(qy), vz = ld4(qz);
-            if (damp) {                                                // pml.cpp:47-98
-                vx = mul4s(vx, SB_LDG(R.decx[0] + gi)); vy = mul4s(vy, T.dy0); vz = mul4(vz, T.dz0);
-                for (int q = 1; q < R.n_sponge; q++) {
-                    vx = mul4s(vx, SB_LDG(R.decx[q] + gi)); vy = mul4s(vy, SB_LDG(R.decy[q] + T.gj));
-                    vz = mul4(vz, ld4(R.decz[q] + T.k0));
-                }
-            }
+            float4 vx = ld4(sm + ox), vy = ld4(sm + oy), vz = ld4(sm + oz);
+            if (damp) res_damp_v<NS>(R, M, T, sm, li, B.i0 + li, vx, vy, vz);
             unsigned mk = ALL_OPEN;
-            if (GEOM) mk = res_mask_word(R, gi, T.gj, T.k0);
+            if (GEOM) mk = smw[M.mw(op)];
             if (upd_x) {                                               // fdtd_step.cpp:34-47 / 255-269
-                vx = add4(vx, mul4s(sub4(ld4(pp + sti), p), SB_LDG(R.cvx + gi)));
+                vx = add4(vx, mul4s(sub4(ld4(pp + sti), p), sm[M.cvx(li)]));
                 if (GEOM) vx = keep4(vx, mk, M_XOPEN);                 // boundaries.cpp:66-89
             }
-            if (upd_y) {                                               // fdtd_step.cpp:53-64 / 272-288
+            if (T.upd_y) {                                             // fdtd_step.cpp:53-64 / 272-288
                 vy = add4(vy, mul4s(sub4(ld4(pp + R.kp), p), T.cvy));
                 if (GEOM) vy = keep4(vy, mk, M_YOPEN);
             }
@@ -349,66 +380,75 @@ SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T
                     vz = keep4(vz, m, M_ZOPEN);
                 }
             }
-            st4(qx, vx); st4(qy, vy); st4(qz, vz);
+            st4(sm + ox, vx); st4(sm + oy, vy); st4(sm + oz, vz);
         }
     }
     if (pass == 0) return;
-    if (B.i0 > 0 && T.active && T.g == 0) {                            // vx of plane i0-1, redundant with its owner
+    // The two ghost faces go to the threads with the least work of their own: vx of plane i0-1 to the last group
+    // of columns, vy of row j0-1 to the threads counted from the top (the idle ones first).
+    if (T.low_i && T.active && T.g == T.G - 1) {                       // redundant with the owner of plane i0-1
         const int gi = B.i0 - 1;
         float *q = sm + M.vx(-1, T.lj) + T.k0;
         float4 v = ld4(q);
-        if (damp) for (int w = 0; w < R.n_sponge; w++) v = mul4s(v, SB_LDG(R.decx[w] + gi));
-        v = add4(v, mul4s(sub4(ld4(sm + M.p(0, T.lj) + T.k0), ld4(sm + M.p(-1, T.lj) + T.k0)), SB_LDG(R.cvx + gi)));
-        if (GEOM) v = keep4(v, res_mask_word(R, gi, T.gj, T.k0), M_XOPEN);
+        if (damp && NS > 0) {
+            v = mul4s(v, sm[M.dx0(-1)]);
+            if (NS == 2) for (int w = 1; w < R.n_sponge; w++) v = mul4s(v, SB_LDG(R.decx[w] + gi));
+        }
+        const int o0 = M.p(0, T.lj) + T.k0, om = M.p(-1, T.lj) + T.k0;
+        v = add4(v, mul4s(sub4(ld4(sm + o0), ld4(sm + om)), sm[M.cvx(-1)]));
+        if (GEOM) v = keep4(v, smw[M.mw(om)], M_XOPEN);
         st4(q, v);
     }
-    if (B.j0 > 0) {                                                    // vy of row j0-1, redundant with its owner
+    if (B.j0 > 0) {                                                    // redundant with the owner of row j0-1
         const int K4 = R.kp >> 2, gj = B.j0 - 1, n = B.li_n * K4;
         const float cy = SB_LDG(R.cvy + gj);
-        for (int idx = T.tid; idx < n; idx += K5_NT) {
+        for (int idx = K5_NT - 1 - T.tid; idx < n; idx += K5_NT) {
             const int li = idx / K4, k0 = 4 * (idx - li * K4);
             float *q = sm + M.vy(li, -1) + k0;
             float4 v = ld4(q);
-            if (damp) for (int w = 0; w < R.n_sponge; w++) v = mul4s(v, SB_LDG(R.decy[w] + gj));
-            v = add4(v, mul4s(sub4(ld4(sm + M.p(li, 0) + k0), ld4(sm + M.p(li, -1) + k0)), cy));
-            if (GEOM) v = keep4(v, res_mask_word(R, B.i0 + li, gj, k0), M_YOPEN);
+            if (damp && NS > 0) for (int w = 0; w < R.n_sponge; w++) v = mul4s(v, SB_LDG(R.decy[w] + gj));
+            const int o0 = M.p(li, 0) + k0, om = M.p(li, -1) + k0;
+            v = add4(v, mul4s(sub4(ld4(sm + o0), ld4(sm + om)), cy));
+            if (GEOM) v = keep4(v, smw[M.mw(om)], M_YOPEN);
             st4(q, v);
         }
     }
 }
 
 // ---- pressure phase: p += cp * div v, solids, sponge, point sources; publishes the box faces ----------
-template <bool GEOM>
+template <bool GEOM, bool UNI, int NS>
 SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T, float *sm, int s)
 {
     if (!T.active) return;
     const ResMap M(R);
     const int K2 = R.kp >> 1;
     const unsigned tag = R.tag_base + (unsigned)s + 1u;                // p after step s
-    uint4 *xo = R.xch + res_xch_slot(R, (s + 1) & 1, B.bi * R.nbj + B.bj, 0);
+    uint4 *xo = R.xch + res_xch_slot(R, (s + 1) & 1, B.bi * R.nbj + B.bj, 0) + (T.k0 >> 1);
     const float4 z4 = f4(0.0f);
-    for (int li = T.g; li < B.li_n; li += T.G) {
-        const int gi = B.i0 + li;
-        float *pp = sm + M.p(li, T.lj) + T.k0;
-        const float *qz = sm + M.vz(li, T.lj) + T.k0;
-        const float4 vx = ld4(sm + M.vx(li, T.lj) + T.k0), vy = ld4(sm + M.vy(li, T.lj) + T.k0), vz = ld4(qz);
+    const unsigned *smw = reinterpret_cast<const unsigned *>(sm);
+    const int sti = (R.LJ + 2) * R.kp, svx = R.LJ * R.kp;
+    const int dp = T.G * sti, dvx = T.G * svx, dvy = T.G * (R.LJ + 1) * R.kp;
+    int op = T.op, ox = T.ox, oy = T.oy, oz = T.oz;
+    for (int li = T.g; li < B.li_n; li += T.G, op += dp, ox += dvx, oy += dvy, oz += dvx) {
+        const float4 vx = ld4(sm + ox), vy = ld4(sm + oy), vz = ld4(sm + oz);
         float4 ddx = vx, ddy = vy;                                     // fdtd_step.cpp:109-211: zero ghost at index 0
-        if (gi > 0) ddx = sub4(vx, ld4(sm + M.vx(li - 1, T.lj) + T.k0));
-        if (T.gj > 0) ddy = sub4(vy, ld4(sm + M.vy(li, T.lj - 1) + T.k0));
-        const float vz_prev = T.k0 > 0 ? qz[-1] : 0.0f;
+        if (li > 0 || T.low_i) ddx = sub4(vx, ld4(sm + ox - svx));
+        if (T.sub_y) ddy = sub4(vy, ld4(sm + oy - R.kp));
+        const float vz_prev = T.k0 > 0 ? sm[oz - 1] : 0.0f;
         float4 ddz = sub4(vz, make_float4(vz_prev, vz.x, vz.y, vz.z));
-        if (R.icx) { ddx = mul4s(ddx, SB_LDG(R.icx + gi)); ddy = mul4s(ddy, T.icy); ddz = mul4(ddz, T.icz4); }
-        float4 pn = add4(ld4(pp), mul4s(add4(add4(ddx, ddy), ddz), R.cp));
-        if (GEOM) pn = keep4(pn, res_mask_word(R, gi, T.gj, T.k0), M_AIR);
-        if (R.n_sponge > 0) {                                          // pml.cpp:100-149
-            pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[0] + gi)), T.dy0), T.dz0);
-            for (int q = 1; q < R.n_sponge; q++)
-                pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[q] + gi)), SB_LDG(R.decy[q] + T.gj)), ld4(R.decz[q] + T.k0));
+        if (!UNI) { ddx = mul4s(ddx, sm[M.icx(li)]); ddy = mul4s(ddy, T.icy); ddz = mul4(ddz, T.icz4); }
+        float4 pn = add4(ld4(sm + op), mul4s(add4(add4(ddx, ddy), ddz), R.cp));
+        if (GEOM) pn = keep4(pn, smw[M.mw(op)], M_AIR);
+        if (NS > 0) {                                                  // pml.cpp:100-149
+            pn = mul4(mul4s(mul4s(pn, sm[M.dx0(li)]), T.dy0), T.dz0);
+            if (NS == 2)
+                for (int q = 1; q < R.n_sponge; q++)
+                    pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[q] + B.i0 + li)), SB_LDG(R.decy[q] + T.gj)), ld4(R.decz[q] + T.k0));
         }
         pn = sel4(T.e0, T.e1, T.e2, T.e3, pn, z4);
         if (T.inl_mask) {                                              // float64 add, fp32 store (solver.py:2421), list order
             for (int q = 0; q < R.n_inline; q++)
-                if (((T.inl_mask >> q) & 1u) && R.inl_i[q] == gi) {
+                if (((T.inl_mask >> q) & 1u) && R.inl_i[q] == B.i0 + li) {
                     const double w = SB_DMUL(R.src_vals[(long long)s * R.n_sources + R.inl_src[q]], R.inl_weight[q]);
                     const int e = R.inl_k[q] - T.k0;
                     if (e == 0) pn.x = (float)((double)pn.x + w);
@@ -417,12 +457,24 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
                     else pn.w = (float)((double)pn.w + w);
                 }
         }
-        st4(pp, pn);
-        if (li == 0 && gi > 0) res_publish(xo + T.lj * K2 + (T.k0 >> 1), pn, tag);
-        if (li == B.li_n - 1 && gi < R.nx - 1) res_publish(xo + R.xch_face + T.lj * K2 + (T.k0 >> 1), pn, tag);
-        if (T.lj == 0 && T.gj > 0) res_publish(xo + 2 * R.xch_face + li * K2 + (T.k0 >> 1), pn, tag);
-        if (T.lj == B.lj_n - 1 && T.gj < R.ny - 1) res_publish(xo + 3 * R.xch_face + li * K2 + (T.k0 >> 1), pn, tag);
+        st4(sm + op, pn);
+        if (li == 0 && T.low_i) res_publish(xo + T.lj * K2, pn, tag);
+        if (li == B.li_n - 1 && T.up_i) res_publish(xo + R.xch_face + T.lj * K2, pn, tag);
+        if (T.pub_jlo) res_publish(xo + 2 * R.xch_face + li * K2, pn, tag);
+        if (T.pub_jhi) res_publish(xo + 3 * R.xch_face + li * K2, pn, tag);
     }
+}
+
+// calls f.template run<GEOM, UNI, NS>() for the variant a configuration needs
+template <typename F> static inline int res_dispatch(bool geom, bool uni, int n_sponge, F &f)
+{
+    const int ns = n_sponge > 2 ? 2 : n_sponge;
+    if (geom) {
+        if (uni) return ns == 0 ? f.template run<true, true, 0>() : ns == 1 ? f.template run<true, true, 1>() : f.template run<true, true, 2>();
+        return ns == 0 ? f.template run<true, false, 0>() : ns == 1 ? f.template run<true, false, 1>() : f.template run<true, false, 2>();
+    }
+    if (uni) return ns == 0 ? f.template run<false, true, 0>() : ns == 1 ? f.template run<false, true, 1>() : f.template run<false, true, 2>();
+    return ns == 0 ? f.template run<false, false, 0>() : ns == 1 ? f.template run<false, false, 1>() : f.template run<false, false, 2>();
 }
 
 #ifdef __CUDACC__
@@ -449,7 +501,7 @@ struct RecvPoll {
     }
 };
 
-template <bool GEOM>
+template <bool GEOM, bool UNI, int NS>
 __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ ResParams R)
 {
     extern __shared__ float4 k5_smem4[];
@@ -475,15 +527,15 @@ __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ 
 
     for (int s = 0; s < R.n_steps; s++) {
         if (s > 0) {
-            if (R.split) res_phase_v<GEOM>(R, B, T, sm, s, 0);         // runs while the neighbours' faces are in flight
+            if (R.split) res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, 0); // runs while the neighbours' faces are in flight
             res_halo_recv(R, B, sm, tid, K5_NT, s, recv);
             __syncthreads();
-            res_phase_v<GEOM>(R, B, T, sm, s, R.split ? 1 : 2);
+            res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, R.split ? 1 : 2);
         } else {
-            res_phase_v<GEOM>(R, B, T, sm, 0, 2);
+            res_phase_v<GEOM, UNI, NS>(R, B, T, sm, 0, 2);
         }
         __syncthreads();
-        res_phase_p<GEOM>(R, B, T, sm, s);                             // publishes the box faces as it goes
+        res_phase_p<GEOM, UNI, NS>(R, B, T, sm, s);                    // publishes the box faces as it goes
         __syncthreads();
         for (int q = tid; q < n_own; q += K5_NT)                       // core/solver.py:2435-2439
             R.rec[(long long)s * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];

@@ -40,7 +40,12 @@ struct RecvHost {
     }
 };
 
-template <bool GEOM> int run(ResParams &R, std::vector<float *> &smem)
+struct Runner {
+    ResParams &R; std::vector<float *> &smem;
+    template <bool GEOM, bool UNI, int NS> int run();
+};
+
+template <bool GEOM, bool UNI, int NS> int Runner::run()
 {
     RecvHost recv;
     const int nb = R.nbi * R.nbj;
@@ -59,7 +64,7 @@ template <bool GEOM> int run(ResParams &R, std::vector<float *> &smem)
     auto phase_v = [&](int s, int pass) {
         for (int b = 0; b < nb; b++) {
             const ResBlock B = res_block(R, b);
-            for (int t = 0; t < K5_NT; t++) res_phase_v<GEOM>(R, B, thr[b][t], smem[b], s, pass);
+            for (int t = 0; t < K5_NT; t++) res_phase_v<GEOM, UNI, NS>(R, B, thr[b][t], smem[b], s, pass);
         }
     };
     for (int s = 0; s < R.n_steps; s++) {
@@ -75,7 +80,7 @@ template <bool GEOM> int run(ResParams &R, std::vector<float *> &smem)
         }
         for (int b = 0; b < nb; b++) {
             const ResBlock B = res_block(R, b);
-            for (int t = 0; t < K5_NT; t++) res_phase_p<GEOM>(R, B, thr[b][t], smem[b], s);
+            for (int t = 0; t < K5_NT; t++) res_phase_p<GEOM, UNI, NS>(R, B, thr[b][t], smem[b], s);
         }
         for (int b = 0; b < nb; b++)
             for (size_t q = 0; q + 1 < own[b].size(); q += 2)
@@ -102,7 +107,7 @@ extern "C" int k5emu_run(int nx, int ny, int nz, int pitch, float **fields, int 
                          int nbi, int nbj, int n_sm, long long smem_limit, int split, int *chosen)
 {
     const long long plane = (long long)ny * pitch, elems = (long long)(nx + 2) * plane;
-    if (nbi <= 0 && !res_choose_partition(nx, ny, nz, n_sm, smem_limit, n_probes, &nbi, &nbj)) return 1;
+    if (nbi <= 0 && !res_choose_partition(nx, ny, nz, n_sm, smem_limit, n_probes, mask != nullptr, &nbi, &nbj)) return 1;
     if (chosen) { chosen[0] = nbi; chosen[1] = nbj; }
     std::vector<Aligned<float> *> F;
     for (int q = 0; q < 8; q++) F.push_back(new Aligned<float>(fields[q], (size_t)elems));
@@ -139,13 +144,14 @@ extern "C" int k5emu_run(int nx, int ny, int nz, int pitch, float **fields, int 
     const size_t need = (size_t)2 * nbi * nbj * 4 * R.xch_face;
     if (!xch || xch_n < need) { delete xch; xch = new Aligned<uint4>(need); xch_n = need; }
     R.xch = xch->p; R.tag_base = epoch; epoch += (unsigned)n_steps;
-    const size_t sm_floats = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, n_probes) / 4;
+    const size_t sm_floats = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, n_probes, mask != nullptr) / 4;
     std::vector<Aligned<float> *> S;
     std::vector<float *> smem;
     for (int b = 0; b < nbi * nbj; b++) { S.push_back(new Aligned<float>(sm_floats)); smem.push_back(S.back()->p); }
     // poison the shared memory so that a read of something never loaded shows up
     for (float *p : smem) for (size_t q = 0; q < sm_floats; q++) p[q] = 1.0e30f;
-    const int bad = mask ? run<true>(R, smem) : run<false>(R, smem);
+    Runner runner{R, smem};
+    const int bad = res_dispatch(mask != nullptr, icx == nullptr, n_sponge, runner);
     for (int q = 0; q < 8; q++) std::memcpy(fields[q], F[q]->p, (size_t)elems * sizeof(float));
     for (auto *a : F) delete a;
     for (auto *a : D) delete a;
