@@ -14,7 +14,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 ROOT = _PKG.parent
-SO_PATH = _PKG / "lib" / "libstrata_b200.so"
+SO_PATH = Path(os.environ.get("STRATA_B200_LIB_OVERRIDE") or _PKG / "lib" / "libstrata_b200.so")   # override: kernel experiments
 SOURCES = [_PKG / "csrc" / "sb_api.cu", _PKG / "csrc" / "sb_kernels.cuh", _PKG / "csrc" / "sb_resident.cuh",
            ROOT / "include" / "strata_b200.h"]
 

@@ -45,7 +45,10 @@
 
 namespace sb {
 
-constexpr int K5_NT = 512;                 // threads per CTA
+#ifndef SB_K5_NT
+#define SB_K5_NT 512
+#endif
+constexpr int K5_NT = SB_K5_NT;            // threads per CTA
 constexpr int K5_MAX_PROBES = 1024;
 
 struct ResParams {
@@ -150,7 +153,7 @@ struct ResThread {
     bool active;
     bool e0, e1, e2, e3, u0, u1, u2, u3;   // element inside the grid / its z face is updated
     bool upd_y, sub_y, up_i, low_i;        // y face updated; j > 0; a box above / below exists
-    bool pub_jlo, pub_jhi;                 // the column lies on a j face that a neighbour needs
+    bool pub_jlo, pub_jhi, pub_j;          // the column lies on a j face that a neighbour needs
     float cvy, icy, dy0;
     float4 cvz4, icz4, dz0;
     unsigned inl_mask;
@@ -173,6 +176,7 @@ SB_HD ResThread res_thread(const ResParams &R, const ResBlock &B, int tid)
     T.upd_y = T.gj < R.ny - 1; T.sub_y = T.gj > 0;
     T.up_i = B.i0 + B.li_n < R.nx; T.low_i = B.i0 > 0;
     T.pub_jlo = T.lj == 0 && T.gj > 0; T.pub_jhi = T.lj == B.lj_n - 1 && T.gj < R.ny - 1;
+    T.pub_j = T.pub_jlo || T.pub_jhi;
     T.cvy = 0.0f; T.icy = 1.0f; T.dy0 = 1.0f;
     T.cvz4 = f4(0.0f); T.icz4 = f4(1.0f); T.dz0 = f4(1.0f);
     T.inl_mask = 0;
@@ -289,57 +293,37 @@ SB_HD void res_publish(uint4 *dst, float4 v, unsigned tag)
 #endif
 }
 
-// the neighbours' faces of p after step s-1 -> halo of the box; recv(src, tag) returns four values once their tags match
-template <typename RecvF>
-SB_HD void res_halo_recv(const ResParams &R, const ResBlock &B, float *sm, int t, int nt, int s, RecvF &recv)
-{
-    const ResMap M(R);
-    const int K4 = R.kp >> 2, K2 = R.kp >> 1, par = s & 1;
-    const unsigned tag = R.tag_base + (unsigned)s;
-    if (B.bi > 0) {                                                    // plane i0-1 = face 1 of the box below
-        const uint4 *src = R.xch + res_xch_slot(R, par, (B.bi - 1) * R.nbj + B.bj, 1);
-        for (int idx = t; idx < B.lj_n * K4; idx += nt) {
-            const int lj = idx / K4, k0 = 4 * (idx - lj * K4);
-            st4(sm + M.p(-1, lj) + k0, recv(src + lj * K2 + (k0 >> 1), tag));
-        }
+// Halo items of a box, flattened over its (up to four) faces so that they spread evenly over the threads:
+// item idx -> the 32-byte source in the publisher's slot (parity `par`) and the shared-memory offset it lands at.
+struct ResHalo {
+    int n0, n1, n2, n3, total;
+    SB_HD ResHalo(const ResParams &R, const ResBlock &B)
+    {
+        const int K4 = R.kp >> 2;
+        n0 = B.bi > 0 ? B.lj_n * K4 : 0;                               // plane i0-1      = face 1 of the box below
+        n1 = B.bi < R.nbi - 1 ? B.lj_n * K4 : 0;                       // plane i0+li_n   = face 0 of the box above
+        n2 = B.bj > 0 ? B.li_n * K4 : 0;                               // row j0-1        = face 3 of the box to the left
+        n3 = B.bj < R.nbj - 1 ? B.li_n * K4 : 0;                       // row j0+lj_n     = face 2 of the box to the right
+        total = n0 + n1 + n2 + n3;
     }
-    if (B.bi < R.nbi - 1) {                                            // plane i0+li_n = face 0 of the box above
-        const uint4 *src = R.xch + res_xch_slot(R, par, (B.bi + 1) * R.nbj + B.bj, 0);
-        for (int idx = t; idx < B.lj_n * K4; idx += nt) {
-            const int lj = idx / K4, k0 = 4 * (idx - lj * K4);
-            st4(sm + M.p(B.li_n, lj) + k0, recv(src + lj * K2 + (k0 >> 1), tag));
-        }
+    SB_HD void item(const ResParams &R, const ResBlock &B, const ResMap &M, int par, int idx, const uint4 *&src, int &dst) const
+    {
+        const int K4 = R.kp >> 2, K2 = R.kp >> 1;
+        int f = 0;
+        if (idx >= n0) { idx -= n0; f = 1;
+            if (idx >= n1) { idx -= n1; f = 2;
+                if (idx >= n2) { idx -= n2; f = 3; } } }
+        const int row = idx / K4, k0 = 4 * (idx - row * K4);
+        const int box = f == 0 ? (B.bi - 1) * R.nbj + B.bj : f == 1 ? (B.bi + 1) * R.nbj + B.bj
+                      : f == 2 ? B.bi * R.nbj + B.bj - 1 : B.bi * R.nbj + B.bj + 1;
+        const int their_face = f == 0 ? 1 : f == 1 ? 0 : f == 2 ? 3 : 2;
+        src = R.xch + res_xch_slot(R, par, box, their_face) + row * K2 + (k0 >> 1);
+        dst = (f == 0 ? M.p(-1, row) : f == 1 ? M.p(B.li_n, row) : f == 2 ? M.p(row, -1) : M.p(row, B.lj_n)) + k0;
     }
-    if (B.bj > 0) {                                                    // row j0-1 = face 3 of the box to the left
-        const uint4 *src = R.xch + res_xch_slot(R, par, B.bi * R.nbj + B.bj - 1, 3);
-        for (int idx = t; idx < B.li_n * K4; idx += nt) {
-            const int li = idx / K4, k0 = 4 * (idx - li * K4);
-            st4(sm + M.p(li, -1) + k0, recv(src + li * K2 + (k0 >> 1), tag));
-        }
-    }
-    if (B.bj < R.nbj - 1) {                                            // row j0+lj_n = face 2 of the box to the right
-        const uint4 *src = R.xch + res_xch_slot(R, par, B.bi * R.nbj + B.bj + 1, 2);
-        for (int idx = t; idx < B.li_n * K4; idx += nt) {
-            const int li = idx / K4, k0 = 4 * (idx - li * K4);
-            st4(sm + M.p(li, B.lj_n) + k0, recv(src + li * K2 + (k0 >> 1), tag));
-        }
-    }
-}
+};
 
 // Compile-time variants: GEOM face masks; UNI uniform grid (no inverse-cell multiplies); NS sponge layers: 0, 1, or
 // 2 = any number (layers beyond the first read their tables from global memory)
-template <int NS>
-SB_HD void res_damp_v(const ResParams &R, const ResMap &M, const ResThread &T, const float *sm, int li, int gi,
-                      float4 &vx, float4 &vy, float4 &vz)
-{
-    if (NS == 0) return;
-    vx = mul4s(vx, sm[M.dx0(li)]); vy = mul4s(vy, T.dy0); vz = mul4(vz, T.dz0);               // pml.cpp:47-98
-    if (NS == 2)
-        for (int q = 1; q < R.n_sponge; q++) {
-            vx = mul4s(vx, SB_LDG(R.decx[q] + gi)); vy = mul4s(vy, SB_LDG(R.decy[q] + T.gj)); vz = mul4(vz, ld4(R.decz[q] + T.k0));
-        }
-}
-
 // ---- velocity phase: v += cv * grad p on the box and on its two low-side ghost faces ---------------
 // pass 0: the items that read no halo value; pass 1: the others and the ghost faces; pass 2: everything
 template <bool GEOM, bool UNI, int NS>
@@ -359,7 +343,14 @@ SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T
             const float *pp = sm + op;
             const float4 p = ld4(pp);
             float4 vx = ld4(sm + ox), vy = ld4(sm + oy), vz = ld4(sm + oz);
-            if (damp) res_damp_v<NS>(R, M, T, sm, li, B.i0 + li, vx, vy, vz);
+            if (damp && NS > 0) {                                      // pml.cpp:47-98, sponge of the previous step
+                vx = mul4s(vx, sm[M.dx0(li)]); vy = mul4s(vy, T.dy0); vz = mul4(vz, T.dz0);
+                if (NS == 2)
+                    for (int q = 1; q < R.n_sponge; q++) {
+                        vx = mul4s(vx, SB_LDG(R.decx[q] + B.i0 + li)); vy = mul4s(vy, SB_LDG(R.decy[q] + T.gj));
+                        vz = mul4(vz, ld4(R.decz[q] + T.k0));
+                    }
+            }
             unsigned mk = ALL_OPEN;
             if (GEOM) mk = smw[M.mw(op)];
             if (upd_x) {                                               // fdtd_step.cpp:34-47 / 255-269
@@ -370,13 +361,14 @@ SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T
                 vy = add4(vy, mul4s(sub4(ld4(pp + R.kp), p), T.cvy));
                 if (GEOM) vy = keep4(vy, mk, M_YOPEN);
             }
-            {                                                          // fdtd_step.cpp:71-81 / 291-306
-                const float p_next = T.u3 ? pp[4] : 0.0f;
-                const float4 upd = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, p_next), p), T.cvz4));
+            if (T.u3) {                                                // fdtd_step.cpp:71-81 / 291-306, all four faces updated
+                vz = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, pp[4]), p), T.cvz4));
+                if (GEOM) vz = keep4(vz, mk, M_ZOPEN);
+            } else {                                                   // the float4 holding the last face / the row padding
+                const float4 upd = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, 0.0f), p), T.cvz4));
                 vz = sel4(T.u0, T.u1, T.u2, T.u3, upd, vz);
                 if (GEOM) {                                            // only updated faces are zeroed
-                    const unsigned m = mk | (T.u0 ? 0u : 0x08u) | (T.u1 ? 0u : 0x0800u) | (T.u2 ? 0u : 0x080000u) |
-                                       (T.u3 ? 0u : 0x08000000u);
+                    const unsigned m = mk | (T.u0 ? 0u : 0x08u) | (T.u1 ? 0u : 0x0800u) | (T.u2 ? 0u : 0x080000u) | 0x08000000u;
                     vz = keep4(vz, m, M_ZOPEN);
                 }
             }
@@ -424,7 +416,6 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
     const int K2 = R.kp >> 1;
     const unsigned tag = R.tag_base + (unsigned)s + 1u;                // p after step s
     uint4 *xo = R.xch + res_xch_slot(R, (s + 1) & 1, B.bi * R.nbj + B.bj, 0) + (T.k0 >> 1);
-    const float4 z4 = f4(0.0f);
     const unsigned *smw = reinterpret_cast<const unsigned *>(sm);
     const int sti = (R.LJ + 2) * R.kp, svx = R.LJ * R.kp;
     const int dp = T.G * sti, dvx = T.G * svx, dvy = T.G * (R.LJ + 1) * R.kp;
@@ -445,7 +436,7 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
                 for (int q = 1; q < R.n_sponge; q++)
                     pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[q] + B.i0 + li)), SB_LDG(R.decy[q] + T.gj)), ld4(R.decz[q] + T.k0));
         }
-        pn = sel4(T.e0, T.e1, T.e2, T.e3, pn, z4);
+        // (row padding is not masked here: no valid cell ever reads a padded element, and res_store writes zeros there)
         if (T.inl_mask) {                                              // float64 add, fp32 store (solver.py:2421), list order
             for (int q = 0; q < R.n_inline; q++)
                 if (((T.inl_mask >> q) & 1u) && R.inl_i[q] == B.i0 + li) {
@@ -458,10 +449,13 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
                 }
         }
         st4(sm + op, pn);
-        if (li == 0 && T.low_i) res_publish(xo + T.lj * K2, pn, tag);
-        if (li == B.li_n - 1 && T.up_i) res_publish(xo + R.xch_face + T.lj * K2, pn, tag);
-        if (T.pub_jlo) res_publish(xo + 2 * R.xch_face + li * K2, pn, tag);
-        if (T.pub_jhi) res_publish(xo + 3 * R.xch_face + li * K2, pn, tag);
+        const bool f_lo = li == 0 && T.low_i, f_hi = li == B.li_n - 1 && T.up_i;
+        if (f_lo || f_hi || T.pub_j) {                                 // a face some neighbour needs
+            if (f_lo) res_publish(xo + T.lj * K2, pn, tag);
+            if (f_hi) res_publish(xo + R.xch_face + T.lj * K2, pn, tag);
+            if (T.pub_jlo) res_publish(xo + 2 * R.xch_face + li * K2, pn, tag);
+            if (T.pub_jhi) res_publish(xo + 3 * R.xch_face + li * K2, pn, tag);
+        }
     }
 }
 
@@ -477,27 +471,48 @@ template <typename F> static inline int res_dispatch(bool geom, bool uni, int n_
     return ns == 0 ? f.template run<false, false, 0>() : ns == 1 ? f.template run<false, false, 1>() : f.template run<false, false, 2>();
 }
 
-#ifdef __CUDACC__
-// Receiver of one 16-byte pair of (value, tag) units: spins on the data until both tags are the wanted step.
+#if defined(__CUDACC__) && !defined(SB_RESIDENT_NO_KERNEL)
+// Receiver: the (value, tag) units of p after step s-1 that the neighbours published -> halo of the box.  A thread
+// issues the loads of all its items at once and only then looks at the tags, so a face that has already arrived
+// costs one L2 round trip, not one per item; units whose tag is not yet the wanted step are simply read again.
 struct RecvPoll {
     int *err_flag;
     bool dead;                               // a wait timed out: stop waiting, finish the chunk, report
-    __device__ __forceinline__ uint4 poll(const uint4 *src, unsigned tag)
+    static __device__ __forceinline__ uint4 ldv(const uint4 *src)
     {
         uint4 v;
-        long long t0 = 0;
-        for (;;) {
-            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
-            if ((v.y == tag && v.w == tag) || dead) break;
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > (2LL << 30)) { atomicExch(err_flag, 2); dead = true; }   // ~1 s: never hang the GPU
-        }
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
         return v;
     }
-    __device__ __forceinline__ float4 operator()(const uint4 *src, unsigned tag)
+    __device__ __forceinline__ void run(const ResParams &R, const ResBlock &B, const ResMap &M, const ResHalo &H,
+                                        float *sm, int tid, int s)
     {
-        const uint4 a = poll(src, tag), b = poll(src + 1, tag);
-        return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+        constexpr int Q = 4;
+        const unsigned tag = R.tag_base + (unsigned)s;
+        for (int base = tid; base < H.total; base += Q * K5_NT) {
+            const uint4 *src[Q]; int dst[Q]; uint4 a[Q], b[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const int idx = base + q * K5_NT;
+                src[q] = nullptr; dst[q] = 0;
+                if (idx < H.total) H.item(R, B, M, s & 1, idx, src[q], dst[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++)
+                if (src[q]) { a[q] = ldv(src[q]); b[q] = ldv(src[q] + 1); }
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                if (!src[q]) continue;
+                long long t0 = 0;
+                while (!(a[q].y == tag && a[q].w == tag && b[q].y == tag && b[q].w == tag) && !dead) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > (2LL << 30)) { atomicExch(err_flag, 2); dead = true; }   // ~1 s: never hang the GPU
+                    a[q] = ldv(src[q]); b[q] = ldv(src[q] + 1);
+                }
+                st4(sm + dst[q], make_float4(__uint_as_float(a[q].x), __uint_as_float(a[q].z),
+                                             __uint_as_float(b[q].x), __uint_as_float(b[q].z)));
+            }
+        }
     }
 };
 
@@ -524,22 +539,28 @@ __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ 
     __syncthreads();
     const int n_own = spr[0];
     RecvPoll recv{R.err_flag, false};
+    const ResHalo H(R, B);
 
     for (int s = 0; s < R.n_steps; s++) {
         if (s > 0) {
-            if (R.split) res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, 0); // runs while the neighbours' faces are in flight
-            res_halo_recv(R, B, sm, tid, K5_NT, s, recv);
-            __syncthreads();
-            res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, R.split ? 1 : 2);
-        } else {
-            res_phase_v<GEOM, UNI, NS>(R, B, T, sm, 0, 2);
+            if (R.split) {                                             // halo-free velocities while the faces are in flight
+                __syncthreads();
+                res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, 0);
+            }
+            recv.run(R, B, M, H, sm, tid, s);
         }
+        __syncthreads();                                               // p of step s-1 complete in the box, halo in place
+        if (s > 0)
+            for (int q = tid; q < n_own; q += K5_NT)                   // core/solver.py:2435-2439
+                R.rec[(long long)(s - 1) * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];
+        res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, (s > 0 && R.split) ? 1 : 2);
         __syncthreads();
         res_phase_p<GEOM, UNI, NS>(R, B, T, sm, s);                    // publishes the box faces as it goes
-        __syncthreads();
-        for (int q = tid; q < n_own; q += K5_NT)                       // core/solver.py:2435-2439
-            R.rec[(long long)s * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];
     }
+    __syncthreads();
+    if (R.n_steps > 0)
+        for (int q = tid; q < n_own; q += K5_NT)
+            R.rec[(long long)(R.n_steps - 1) * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];
     res_store(R, B, sm, tid);
 }
 #endif  // __CUDACC__

@@ -3,6 +3,7 @@
 // decomposition, halo indexing and deferred sponge against the oracle without a GPU.  Every "thread"
 // of every "CTA" runs each phase to completion before the next phase starts, which is what the
 // barriers and step flags of k5_resident guarantee on the device.  Never part of the product library.
+#define SB_RESIDENT_NO_KERNEL            // host emulation only: skip the __global__ kernel (and its 12 device variants)
 #include "../../strata_fdtd_b200/csrc/sb_resident.cuh"
 
 #include <cstdlib>
@@ -28,17 +29,22 @@ template <typename T> struct Aligned {
 
 
 // host stand-in for RecvPoll: in lockstep the data is always there; a wrong tag is an indexing bug
-struct RecvHost {
+static int recv_host(const ResParams &R, const ResBlock &B, float *sm, int s)
+{
+    const ResMap M(R);
+    const ResHalo H(R, B);
+    const unsigned tag = R.tag_base + (unsigned)s;
     int bad = 0;
-    float4 operator()(const uint4 *src, unsigned tag)
-    {
+    for (int idx = 0; idx < H.total; idx++) {
+        const uint4 *src; int dst;
+        H.item(R, B, M, s & 1, idx, src, dst);
         const uint4 a = src[0], b = src[1];
         if (a.y != tag || a.w != tag || b.y != tag || b.w != tag) bad++;
-        float f[4]; const unsigned u[4] = {a.x, a.z, b.x, b.z};
-        memcpy(f, u, 16);
-        return make_float4(f[0], f[1], f[2], f[3]);
+        const unsigned u[4] = {a.x, a.z, b.x, b.z};
+        memcpy(sm + dst, u, 16);
     }
-};
+    return bad;
+}
 
 struct Runner {
     ResParams &R; std::vector<float *> &smem;
@@ -47,7 +53,7 @@ struct Runner {
 
 template <bool GEOM, bool UNI, int NS> int Runner::run()
 {
-    RecvHost recv;
+    int bad = 0;
     const int nb = R.nbi * R.nbj;
     const ResMap M(R);
     std::vector<std::vector<int>> own(nb);                       // (slot, offset) pairs of the probes a box owns
@@ -72,7 +78,7 @@ template <bool GEOM, bool UNI, int NS> int Runner::run()
             if (R.split) phase_v(s, 0);
             for (int b = 0; b < nb; b++) {
                 const ResBlock B = res_block(R, b);
-                for (int t = 0; t < K5_NT; t++) res_halo_recv(R, B, smem[b], t, K5_NT, s, recv);
+                bad += recv_host(R, B, smem[b], s);
             }
             phase_v(s, R.split ? 1 : 2);
         } else {
@@ -90,7 +96,7 @@ template <bool GEOM, bool UNI, int NS> int Runner::run()
         const ResBlock B = res_block(R, b);
         for (int t = 0; t < K5_NT; t++) res_store(R, B, smem[b], t);
     }
-    return recv.bad;
+    return bad;
 }
 }  // namespace
 

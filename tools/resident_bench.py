@@ -36,14 +36,18 @@ def time_chunk(s, n_steps, reps=5):
 
 
 def main():
+    import os
     out = []
-    for n in (64, 100, 110):
-        for geometry in (False, True):
+    fast = os.environ.get("RB_FAST") == "1"          # one line per size: the default resident configuration only
+    for n in ((64, 100) if fast else (64, 100, 110)):
+        for geometry in ((False,) if fast else (False, True)):
             case = c2_case(n, steps=0, with_geometry=geometry)
             for label, opts in (("march_graph", {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_USE_GRAPH: 1}),
                                 ("resident_nosplit", {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT, _lib.OPT_RESIDENT_SPLIT: 0}),
                                 ("resident_split", {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT, _lib.OPT_RESIDENT_SPLIT: 1})):
-                for chunk in (32, 512):
+                if fast and label != "resident_nosplit":
+                    continue
+                for chunk in ((512,) if fast else (32, 512)):
                     s = build_b200_solver(case)
                     for k, v in opts.items():
                         s.set_kernel_option(k, v)
