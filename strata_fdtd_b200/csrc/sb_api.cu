@@ -343,9 +343,11 @@ extern "C" int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, doubl
 {
     CHECK_H(h);
     if (axis < 0 || axis > 2 || side < 0 || side > 1 || kind < 0 || kind > 1) return fail("bad plane-op arguments");
-    if (h->d.has_lower || h->d.has_upper) return fail("Mur / radiation planes are not supported on decomposed slabs yet");
+    // on a slab, an axis-0 face exists only where the slab touches the outer face of the grid
+    if (axis == 0 && ((side == 0 && h->d.has_lower) || (side == 1 && h->d.has_upper)))
+        return fail("this slab does not own the requested axis-0 face");
     const int n[3] = {h->d.nx, h->d.ny, h->d.nz};
-    if (n[axis] < 3) return fail("plane op needs at least 3 cells along its axis");
+    if (n[axis] < (axis == 0 && (h->d.has_lower || h->d.has_upper) ? 2 : 3)) return fail("plane op needs at least 3 cells along its axis");
     PlaneOpHost *po = new PlaneOpHost();
     const size_t cells = (size_t)n[axis == 0 ? 1 : 0] * n[axis == 2 ? 1 : 2];
     if (po->prev.alloc(cells)) { delete po; return 1; }
@@ -767,7 +769,8 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
         const int n[3] = {h->d.nx, h->d.ny, h->d.nz};
         const int na = n[po->op.axis == 0 ? 1 : 0], nb = n[po->op.axis == 2 ? 1 : 2];
         dim3 blk(128), grd((nb + 127) / 128, na);
-        k4_plane_op<<<grd, blk, 0, h->stream>>>(po->op, P.p_out, h->d.nx, h->d.ny, h->d.nz, h->d.pitch, h->plane);
+        k4_plane_op<<<grd, blk, 0, h->stream>>>(po->op, P.p_out, h->d.nx, h->d.ny, h->d.nz, h->d.pitch, h->plane,
+                                                peer_link(h, P));
         h->kernels_launched++;
     }
     const int n_rec = h->n_probes + h->n_mics;

@@ -426,54 +426,6 @@ __global__ void k_build_mask(const uint8_t *geom, uint8_t *mask, int nx, int ny,
     mask[c] = m;
 }
 
-// ------------------------------------------------------------------------------------------
-// K4: one-plane boundary updates applied to p after the sponge, in boundary-list order:
-//   first-order Mur ABC        boundaries/_boundaries.py:476-513   p_b = prev + c*(p_i - p_b); prev = p_i
-//   RadiationImpedance         boundaries/_boundaries.py:700-760   abc as above; p_b = R*p_i + (1-R)*abc
-// Mixed precision exactly as NumPy evaluates the reference expressions: the difference is fp32, the
-// Mur coefficient and (1-R) are float64, R*p_i is fp32 when R is a Python float ("weak" scalar) and
-// float64 when it is a NumPy float64; the sum is rounded to fp32 once on store.
-// ------------------------------------------------------------------------------------------
-struct PlaneOp {
-    int axis, side;              // axis 0/1/2, side 0 = low face, 1 = high face
-    int kind;                    // 0 = Mur, 1 = radiation impedance
-    int weak_r;                  // R is a Python float -> fp32 product
-    double mur, R, one_minus_R;
-    float r32;
-    float *prev;                 // previous interior-neighbour plane, n_a * n_b floats
-};
-
-__global__ void k4_plane_op(PlaneOp op, float *p, int nx, int ny, int nz, int pitch, long long plane)
-{
-    const int n[3] = {nx, ny, nz};
-    const int a_ax = op.axis == 0 ? 1 : 0, b_ax = op.axis == 2 ? 1 : 2;      // the two in-plane axes
-    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
-    if (b >= n[b_ax] || a >= n[a_ax]) return;
-    int c[3];
-    c[a_ax] = a; c[b_ax] = b;
-    c[op.axis] = op.side ? n[op.axis] - 1 : 0;
-    const long long ib = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
-    c[op.axis] = op.side ? n[op.axis] - 2 : 1;
-    const long long ii = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
-    const long long t = (long long)a * n[b_ax] + b;
-    const float pb = p[ib], pi = p[ii];
-    const double abc = __dadd_rn((double)op.prev[t], __dmul_rn(op.mur, (double)(pi - pb)));
-    float out;
-    if (op.kind == 0) {
-        out = (float)abc;
-    } else {
-        const double rigid = op.weak_r ? (double)(op.r32 * pi) : __dmul_rn(op.R, (double)pi);
-        out = (float)__dadd_rn(rigid, __dmul_rn(op.one_minus_R, abc));
-    }
-    p[ib] = out;
-    op.prev[t] = pi;
-}
-
-// ------------------------------------------------------------------------------------------
-// K3: source injection and probe / microphone recording (core/solver.py:2386-2439,
-// microphones.cpp:82-116).  `step_ctr` is a device counter so the kernels can live in a
-// replayed CUDA graph; the recording kernel advances it.
-// ------------------------------------------------------------------------------------------
 // what K3 needs to keep the neighbours' ghosts and flags current (all nullptr on a single GPU)
 struct PeerLink {
     float *peer_lo_p, *peer_hi_p;        // neighbour ghost planes of the set just written
@@ -497,6 +449,55 @@ __device__ __forceinline__ void signal_step_done(const PeerLink &L)
     *L.step_global = done;
 }
 
+// ------------------------------------------------------------------------------------------
+// K4: one-plane boundary updates applied to p after the sponge, in boundary-list order:
+//   first-order Mur ABC        boundaries/_boundaries.py:476-513   p_b = prev + c*(p_i - p_b); prev = p_i
+//   RadiationImpedance         boundaries/_boundaries.py:700-760   abc as above; p_b = R*p_i + (1-R)*abc
+// Mixed precision exactly as NumPy evaluates the reference expressions: the difference is fp32, the
+// Mur coefficient and (1-R) are float64, R*p_i is fp32 when R is a Python float ("weak" scalar) and
+// float64 when it is a NumPy float64; the sum is rounded to fp32 once on store.
+// ------------------------------------------------------------------------------------------
+struct PlaneOp {
+    int axis, side;              // axis 0/1/2, side 0 = low face, 1 = high face
+    int kind;                    // 0 = Mur, 1 = radiation impedance
+    int weak_r;                  // R is a Python float -> fp32 product
+    double mur, R, one_minus_R;
+    float r32;
+    float *prev;                 // previous interior-neighbour plane, n_a * n_b floats
+};
+
+__global__ void k4_plane_op(PlaneOp op, float *p, int nx, int ny, int nz, int pitch, long long plane, PeerLink L)
+{
+    const int n[3] = {nx, ny, nz};
+    const int a_ax = op.axis == 0 ? 1 : 0, b_ax = op.axis == 2 ? 1 : 2;      // the two in-plane axes
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= n[b_ax] || a >= n[a_ax]) return;
+    int c[3];
+    c[a_ax] = a; c[b_ax] = b;
+    c[op.axis] = op.side ? n[op.axis] - 1 : 0;
+    const long long ib = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
+    c[op.axis] = op.side ? n[op.axis] - 2 : 1;
+    const long long ii = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
+    const long long t = (long long)a * n[b_ax] + b;
+    const float pb = p[ib], pi = p[ii];
+    const double abc = __dadd_rn((double)op.prev[t], __dmul_rn(op.mur, (double)(pi - pb)));
+    float out;
+    if (op.kind == 0) {
+        out = (float)abc;
+    } else {
+        const double rigid = op.weak_r ? (double)(op.r32 * pi) : __dmul_rn(op.R, (double)pi);
+        out = (float)__dadd_rn(rigid, __dmul_rn(op.one_minus_R, abc));
+    }
+    p[ib] = out;
+    mirror_injection(L, 0, ib, out);          // a y / z face cell on a cut plane: keep the neighbour's ghost current
+    op.prev[t] = pi;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: source injection and probe / microphone recording (core/solver.py:2386-2439,
+// microphones.cpp:82-116).  `step_ctr` is a device counter so the kernels can live in a
+// replayed CUDA graph; the recording kernel advances it.
+// ------------------------------------------------------------------------------------------
 struct SourceTable {
     int n_sources, n_cells;
     const long long *cell_off;          // padded-layout offset of each cell

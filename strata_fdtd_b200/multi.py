@@ -41,6 +41,32 @@ def slab_ranges(nx: int, world: int) -> list[tuple[int, int]]:
     return out
 
 
+def combine_corner_samples(mics, gathers, corners: dict, times) -> None:
+    """Finish the microphones of a decomposed run: ``corners[(mic, gather, corner)]`` are the raw fp32 samples the
+    owning slabs recorded; each gather is summed exactly as microphones.cpp:82-116 / solver.py:1027-1034 do --
+    ``sum = 0; sum += w[c] * f[c]`` for c = 0..7 in fp32 -- and handed to the microphone's pattern."""
+    if len(times) == 0:
+        return
+    for mi, mic in enumerate(mics):
+        cols = []
+        for g, (_f, _idx8, w8) in enumerate(gathers[mi]):
+            acc = np.zeros(len(times), dtype=np.float32)
+            for c in range(8):
+                acc = acc + np.float32(w8[c]) * corners[(mi, g, c)]
+            cols.append(acc)
+        mic._data.extend(np.asarray(mic._combine(cols[0], cols[1:])).tolist())
+        mic._times.extend(np.asarray(times).tolist())
+
+
+def _drain_corner_samples(slab) -> tuple[dict, np.ndarray]:
+    """(corner traces recorded since the last drain, their time axis) of one slab."""
+    data = {k: np.concatenate(v) for k, v in slab._corner_data.items()}
+    times = np.concatenate(slab._corner_times) if slab._corner_times else np.zeros(0)
+    slab._corner_data.clear()
+    slab._corner_times.clear()
+    return data, times
+
+
 def owner_of(i: int, ranges: list[tuple[int, int]]) -> int:
     for r, (lo, hi) in enumerate(ranges):
         if lo <= i < hi:
@@ -63,7 +89,7 @@ class SlabSolver(FDTDSolver):
             t = t + self.dt
         self._chunk_times, self._chunk_t_end = times, t
         self._n_src = max(1, len(self._sources))
-        self._n_rec = len(self._local_probes)
+        self._n_rec = len(self._local_probes) + len(self._corner_keys)
         W = self._waveform_table(times) if self._sources else np.zeros((m, 1))
         with torch.cuda.stream(dev.stream):
             self._W_dev = torch.from_numpy(np.ascontiguousarray(W)).to(dev.device, non_blocking=False)
@@ -89,6 +115,7 @@ class SlabSolver(FDTDSolver):
         _lib.check(dev.lib.sb_synchronize(dev.handle))
         for q, pr in enumerate(self._local_probes):
             pr.data.extend(rec[:, q].tolist())
+        self._store_corner_samples(rec, len(self._local_probes), self._chunk_times)
         self._host_stale = set(_FIELDS)
         self._step_count += m
         self._time = self._chunk_t_end
@@ -206,8 +233,28 @@ class DistributedFDTDSolver:
     def add_probe(self, name, position):
         self.slab.add_probe(name, position)
 
+    def add_microphone(self, position, name=None, pattern="omni", direction=None, up=None):
+        return self.slab.add_microphone(position, name=name, pattern=pattern, direction=direction, up=up)
+
+    microphones = property(lambda self: self.slab.microphones)
+
     def set_kernel_option(self, opt, val):
         self.slab.set_kernel_option(opt, val)
+
+    def _finish_microphones(self):
+        """Collective: every rank receives the corner samples of all slabs and completes every microphone."""
+        mics = list(self.slab._microphones.values())
+        if not mics:
+            return
+        local, times = _drain_corner_samples(self.slab)
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, (local, times), group=self.group)
+        merged = {}
+        for part, t in parts:
+            merged.update(part)
+            if len(t):
+                times = t
+        combine_corner_samples(mics, self.slab._mic_gathers or self.slab.microphone_gathers(mics), merged, times)
 
     # ---- halo exchange ---------------------------------------------------------------------------
     def _exchange(self, fields=("p",), include_vx_ghost=False):
@@ -260,6 +307,7 @@ class DistributedFDTDSolver:
                     s.enqueue_step()
                     self._exchange()
             s.end_chunk()
+        self._finish_microphones()
 
     def step(self):
         self.run(steps=1)
@@ -371,6 +419,19 @@ class LocalSlabGroup:
                     self._exchange()
             for s in self.slabs:
                 s.end_chunk()
+        mics = list(self.slabs[0]._microphones.values())
+        if mics:                                  # every slab holds the same microphone objects' twins; finish slab 0's
+            merged, times = {}, np.zeros(0)
+            for s in self.slabs:
+                part, t = _drain_corner_samples(s)
+                merged.update(part)
+                times = t if len(t) else times
+            combine_corner_samples(mics, self.slabs[0]._mic_gathers, merged, times)
+
+    def add_microphone(self, position, name=None, **kw):
+        return [s.add_microphone(position, name=name, **kw) for s in self.slabs][0]
+
+    microphones = property(lambda self: self.slabs[0].microphones)
 
     def get_field(self, name: str) -> np.ndarray:
         return np.concatenate([s.get_field(name) for s in self.slabs], axis=0)

@@ -152,6 +152,10 @@ class FDTDSolver:
         self._material_id = np.zeros(self.shape, dtype=np.uint8)
         self._local_probes: list = []
         self._mic_slots: list = []
+        self._corner_keys: list = []
+        self._mic_gathers: list = []
+        self._corner_data: dict = {}
+        self._corner_times: list = []
         self._geometry_ext = None
 
         self._device_index = device
@@ -303,8 +307,6 @@ class FDTDSolver:
                 and sponge_tables(boundary, self) is not None:
             # the sponge is fused into the step kernel and therefore always runs before the plane updates
             raise NotImplementedError("add PML boundaries before ABCFirstOrder / RadiationImpedance")
-        if is_plane and (self._has_lower or self._has_upper):
-            raise NotImplementedError("ABCFirstOrder / RadiationImpedance are not supported on decomposed slabs yet")
         self._boundaries.append(boundary)
         self._dirty.add("sponges")
 
@@ -478,6 +480,9 @@ class FDTDSolver:
             _lib.check(lib.sb_clear_plane_ops(h))
             for b in self._boundaries:
                 for op in plane_ops(b, self) or []:
+                    axis, side = op[0], op[1]
+                    if axis == 0 and ((side == 0 and self._has_lower) or (side == 1 and self._has_upper)):
+                        continue                             # that face of the grid belongs to another slab
                     _lib.check(lib.sb_add_plane_op(h, *op))
             for b in self._boundaries:                       # application order = list order (solver.py:2044-2047)
                 tabs = sponge_tables(b, self)
@@ -494,10 +499,12 @@ class FDTDSolver:
                              for (i, j, k) in (pr.position for pr in self._local_probes)], dtype=np.int64)
             _lib.check(lib.sb_set_probes(h, len(flat), _lib.ptr(flat) if len(flat) else None))
             mics = list(self._microphones.values())
-            if mics and (self._has_lower or self._has_upper):
-                raise NotImplementedError("microphones on decomposed slabs are not supported yet")
             self._mic_slots = []                              # per microphone: its record slots after the probes
-            if mics and any(m.is_directional() for m in mics):
+            self._corner_keys = []                            # slab only: (mic, gather, corner) of each extra record slot
+            self._mic_gathers = []
+            if mics and (self._has_lower or self._has_upper):
+                self._set_corner_samples(mics, lib, h)
+            elif mics and any(m.is_directional() for m in mics):
                 # one directional microphone switches the reference to its Python path for ALL microphones
                 # (solver.py:2453-2461): p (+ vx, vy, vz) gathers with that path's weights, combined on the host
                 fields, idx_all, w_all = [], [], []
@@ -510,10 +517,7 @@ class FDTDSolver:
                 idx_all, w_all = np.concatenate(idx_all), np.concatenate(w_all)
                 _lib.check(lib.sb_set_gathers(h, len(fields), _lib.ptr(fields), _lib.ptr(idx_all), _lib.ptr(w_all)))
             elif mics:
-                gp = np.array([q for m in mics for q in m._grid_position], dtype=np.float32)   # fp32 store, solver.py:2502-2509
-                idx8 = np.zeros(8 * len(mics), dtype=np.int64)
-                w8 = np.zeros(8 * len(mics), dtype=np.float32)
-                _lib.check(lib.sb_mic_tables(_lib.ptr(gp), len(mics), ny, nz, _lib.ptr(idx8), _lib.ptr(w8)))
+                idx8, w8 = self._native_mic_tables(mics, lib)
                 self._mic_tables = (idx8, w8)
                 self._mic_slots = [[q] for q in range(len(mics))]
                 _lib.check(lib.sb_set_mics(h, len(mics), _lib.ptr(idx8), _lib.ptr(w8)))
@@ -533,6 +537,53 @@ class FDTDSolver:
                 _lib.check(lib.sb_upload_field(h, _FIELDS.index(name), _lib.ptr(self._host[name])))
         self._host_dirty.clear()
         return dev
+
+    def _native_mic_tables(self, mics, lib):
+        """Corner indices (global flat) and fp32 weights of the native path (microphones.cpp:16-80)."""
+        ny, nz = self.shape[1], self.shape[2]
+        gp = np.array([q for m in mics for q in m._grid_position], dtype=np.float32)   # fp32 store, solver.py:2502-2509
+        idx8 = np.zeros(8 * len(mics), dtype=np.int64)
+        w8 = np.zeros(8 * len(mics), dtype=np.float32)
+        _lib.check(lib.sb_mic_tables(_lib.ptr(gp), len(mics), ny, nz, _lib.ptr(idx8), _lib.ptr(w8)))
+        return idx8, w8
+
+    def microphone_gathers(self, mics, lib=None):
+        """Per microphone the list of (field, idx8 global flat, w8 fp32) the reference would gather (native tables when
+        every microphone is omnidirectional, the Python path's otherwise -- solver.py:2453-2461)."""
+        lib = lib or _lib.load()
+        if any(m.is_directional() for m in mics):
+            return [m._gather_tables(self.global_shape) for m in mics]
+        idx8, w8 = self._native_mic_tables(mics, lib)
+        return [[(0, idx8[8 * q: 8 * q + 8], w8[8 * q: 8 * q + 8])] for q in range(len(mics))]
+
+    def _set_corner_samples(self, mics, lib, h) -> None:
+        """Microphones on a slab: the eight corners of a trilinear gather can lie on two slabs, and the fp32 sum runs
+        over them in corner order.  Every slab therefore records the raw corner values it owns (one-hot gathers) and
+        the driver adds them up in the reference's order once all corners are known (multi.combine_corner_samples)."""
+        ny, nz = self.shape[1], self.shape[2]
+        n_cells = int(np.prod(self.global_shape, dtype=np.int64))
+        self._mic_gathers = self.microphone_gathers(mics, lib)
+        fields, idx_all = [], []
+        for mi, tabs in enumerate(self._mic_gathers):
+            for g, (f, idx8, _w) in enumerate(tabs):
+                for c, gidx in enumerate(idx8):
+                    gidx = int(gidx)
+                    if not 0 <= gidx < n_cells:
+                        raise _lib.B200BackendError(f"microphone corner {c} of '{mics[mi].name}' out of range")
+                    i = gidx // (ny * nz)
+                    if self._i0 <= i < self._i1:
+                        fields.append(f)
+                        idx_all.append(gidx - self._i0 * ny * nz)
+                        self._corner_keys.append((mi, g, c))
+        n = len(fields)
+        if n == 0:
+            _lib.check(lib.sb_set_mics(h, 0, None, None))
+            return
+        one_hot = np.zeros((n, 8), dtype=np.float32)
+        one_hot[:, 0] = 1.0
+        idx8 = np.repeat(np.array(idx_all, dtype=np.int64), 8)
+        fields = np.array(fields, dtype=np.int32)
+        _lib.check(lib.sb_set_gathers(h, n, _lib.ptr(fields), _lib.ptr(idx8), _lib.ptr(np.ascontiguousarray(one_hot))))
 
     # ------------------------------------------------------------------ time stepping
     def _waveform_table(self, times: np.ndarray) -> np.ndarray:
@@ -558,7 +609,7 @@ class FDTDSolver:
         lib, h = dev.lib, dev.handle
         probes = self._local_probes
         mics = list(self._microphones.values())
-        n_rec = len(probes) + sum(len(sl) for sl in self._mic_slots)
+        n_rec = len(probes) + sum(len(sl) for sl in self._mic_slots) + len(self._corner_keys)
         done = 0
         while done < n_steps:
             m = min(self._chunk_steps, n_steps - done)
@@ -586,6 +637,7 @@ class FDTDSolver:
                 cols = [rec[:, len(probes) + q] for q in slots]
                 mic._data.extend(mic._combine(cols[0], cols[1:]).tolist())
                 mic._times.extend(times.tolist())
+            self._store_corner_samples(rec, len(probes), times)
             last_idx = self._step_count + m - 1
             self._step_count += m
             self._time = t
@@ -604,6 +656,14 @@ class FDTDSolver:
                 for q in range(m):
                     callback(last_idx - (m - 1 - q))
             done += m
+
+    def _store_corner_samples(self, rec, first_slot: int, times) -> None:
+        """Slab only: keep the raw microphone corner values of a chunk until the driver combines them."""
+        if not self._corner_keys:
+            return
+        for q, key in enumerate(self._corner_keys):
+            self._corner_data.setdefault(key, []).append(np.array(rec[:, first_slot + q], dtype=np.float32))
+        self._corner_times.append(np.array(times, dtype=np.float64))
 
     def step(self) -> None:
         """Advance one time step (solver.py:2003-2077)."""
@@ -734,6 +794,8 @@ class FDTDSolver:
             pr.clear()
         for mic in self._microphones.values():
             mic.clear()
+        self._corner_data.clear()
+        self._corner_times.clear()
         for b in self._boundaries:
             b.reset()
 

@@ -120,8 +120,9 @@ class Microphone:
 
     def _initialize(self, solver) -> None:
         g = tuple(q / solver.dx for q in self.position)          # reference :941-943
-        if not all(0 <= gq < n - 1 for gq, n in zip(g, solver.shape)):
-            hi = tuple((n - 1) * solver.dx for n in solver.shape)
+        shape = getattr(solver, "global_shape", solver.shape)    # positions are global also on a slab
+        if not all(0 <= gq < n - 1 for gq, n in zip(g, shape)):
+            hi = tuple((n - 1) * solver.dx for n in shape)
             raise ValueError(f"Microphone position {self.position} is outside simulation domain. "
                              f"Valid range: (0, 0, 0) to ({hi[0]:.4f}, {hi[1]:.4f}, {hi[2]:.4f})")
         self._grid_position = g
