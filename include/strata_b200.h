@@ -139,7 +139,9 @@ int sb_add_sponge(sb_solver *h, const float *decay_x, const float *decay_y, cons
 int sb_clear_plane_ops(sb_solver *h);
 int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, double mur, double R, int weak_r);
 
-/* ADE materials.  material_id_host: uint8 [nx][ny][nz] (slab only).  rho_inf / K_inf are
+/* ADE materials.  material_id_host: uint8 [nx][ny][nz], on a slab PLUS its live ghost planes as for
+ * sb_set_geometry ([nx + has_lower + has_upper] planes, lower ghost first): the auxiliary density fields of the
+ * ghost cells are advanced redundantly so that no J plane has to be exchanged.  rho_inf / K_inf are
  * indexed by material id (n_ids entries).  dt and inv_dx are the fp32 scalars the reference
  * passes (kernels.cpp:786-787, 834).  Replaces ADEMaterialData + update_ade_* + apply_ade_* +
  * compute_divergence* (ade.cpp:25-692) in the order of core/solver.py:2135-2193.           */

@@ -475,7 +475,6 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
     h->have_ade = false;
     if (n_poles == 0 || !mat) return 0;
     if (n_poles > MAX_POLES) return fail("at most %d ADE poles", MAX_POLES);
-    if (h->d.has_lower || h->d.has_upper) return fail("ADE materials are not supported on decomposed slabs yet");
     const sb_grid_desc &d = h->d;
     bool used[256] = {false};
     AdeTable &A = h->ade;
@@ -490,32 +489,37 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
         Q.vcoef = -dt / rho_inf[s.material_id] * inv_dx;          // ade.cpp:242 (fp32, left to right)
         Q.pcoef = -K_inf[s.material_id] * dt;                     // ade.cpp:417
     }
-    // compact list of cells whose material carries poles, in dense order; neighbour slots via rolling plane maps
+    // Compact list of the cells whose material carries poles, in dense order, over the owned planes AND the live
+    // ghost planes of a slab: a ghost cell's density-pole J is advanced redundantly from the ghost p plane (same
+    // operations as its owner's), so the velocity correction across a cut needs no extra exchange.  Neighbour
+    // slots come from rolling plane maps.  `mat` arrives with the ghost planes, lower one first.
     const size_t pl = (size_t)d.ny * d.nz;
+    const int i_lo = -d.has_lower, i_hi = d.nx + d.has_upper;     // planes [i_lo, i_hi)
+    auto mplane = [&](int i) { return mat + (size_t)(i - i_lo) * pl; };
     std::vector<long long> off; std::vector<int> ijk; std::vector<uint8_t> cm;
-    std::vector<long long> plane_start((size_t)d.nx + 1, 0);
-    for (int i = 0; i < d.nx; i++) {
-        const uint8_t *m = mat + (size_t)i * pl;
+    std::vector<long long> plane_start((size_t)(i_hi - i_lo) + 1, 0);
+    for (int i = i_lo; i < i_hi; i++) {
+        const uint8_t *m = mplane(i);
         long long cnt = 0;
         for (size_t q = 0; q < pl; q++) cnt += used[m[q]];
-        plane_start[i + 1] = plane_start[i] + cnt;
+        plane_start[i - i_lo + 1] = plane_start[i - i_lo] + cnt;
     }
-    const long long n = plane_start[d.nx];
+    const long long n = plane_start[i_hi - i_lo];
     if (n == 0) return 0;
     if (n >= (1LL << 31)) return fail("too many material cells");
     off.resize((size_t)n); ijk.resize((size_t)n * 3); cm.resize((size_t)n);
     std::vector<int> nbr((size_t)n * 6, -1);
     std::vector<int> slot_prev(pl, -1), slot_cur(pl, -1), slot_next(pl, -1);
     auto fill_slots = [&](int i, std::vector<int> &slots) {
-        if (i < 0 || i >= d.nx) { std::fill(slots.begin(), slots.end(), -1); return; }
-        const uint8_t *m = mat + (size_t)i * pl;
-        int s = (int)plane_start[i];
+        if (i < i_lo || i >= i_hi) { std::fill(slots.begin(), slots.end(), -1); return; }
+        const uint8_t *m = mplane(i);
+        int s = (int)plane_start[i - i_lo];
         for (size_t q = 0; q < pl; q++) slots[q] = used[m[q]] ? s++ : -1;
     };
-    fill_slots(0, slot_cur); fill_slots(1, slot_next);
-    for (int i = 0; i < d.nx; i++) {
-        const uint8_t *m = mat + (size_t)i * pl;
-        const uint8_t *mp = i > 0 ? m - pl : nullptr, *mn = i + 1 < d.nx ? m + pl : nullptr;
+    fill_slots(i_lo, slot_cur); fill_slots(i_lo + 1, slot_next);
+    for (int i = i_lo; i < i_hi; i++) {
+        const uint8_t *m = mplane(i);
+        const uint8_t *mp = i > i_lo ? m - pl : nullptr, *mn = i + 1 < i_hi ? m + pl : nullptr;
         for (int j = 0; j < d.ny; j++)
             for (int k = 0; k < d.nz; k++) {
                 const size_t q = (size_t)j * d.nz + k;
@@ -747,11 +751,6 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
         P.mic_field = h->have_mic_field ? h->mic_field.p : nullptr;
         P.rec_row = rec_dev ? rec_dev + (long long)(step - 1) * n_rec_all : nullptr;
     }
-    if (h->have_ade) {
-        const int nb = (h->ade.n_cells + 255) / 256;
-        k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
-        h->kernels_launched++;
-    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->opt_profile) {
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -760,10 +759,13 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
     if (launch_step_kernel(h, P, fused)) return 1;
     if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, 1}); }
     if (h->have_ade) {
+        // after K1: on a slab the density poles of the ghost cells read the ghost p planes, and K1's cut blocks are
+        // the ones that wait for the neighbour's step flag (K2a only reads the input set, K1 never touches J)
         const int nb = (h->ade.n_cells + 255) / 256;
+        k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
         StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx;
         k2b_fixup<<<nb, 256, 0, h->stream>>>(Q, h->ade);
-        h->kernels_launched++;
+        h->kernels_launched += 2;
     }
     for (auto *po : h->plane_ops) {                        // Mur / radiation planes, sequential by construction
         const int n[3] = {h->d.nx, h->d.ny, h->d.nz};

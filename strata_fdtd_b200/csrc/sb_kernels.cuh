@@ -653,6 +653,7 @@ __global__ void k2b_fixup(StepParams P, AdeTable A)
     if (s >= A.n_cells) return;
     const long long c = A.cell_off[s];
     const int i = A.cell_ijk[3 * s], j = A.cell_ijk[3 * s + 1], k = A.cell_ijk[3 * s + 2];
+    if (i < 0 || i >= P.nx) return;          // ghost-plane cell of a slab: only its J is kept here (K2a), its owner does the rest
     const int mat = A.cell_mat[s];
     const int n = A.n_cells;
     const int sxp = A.nbr[s], syp = A.nbr[n + s], szp = A.nbr[2 * n + s];
@@ -663,8 +664,15 @@ __global__ void k2b_fixup(StepParams P, AdeTable A)
     const float vyn = upd_y ? ade_face(P, A, P.vy_in, P.cvy[j], c, c + P.pitch, s, syp, mat, M_YOPEN) : P.vy_in[c];
     const float vzn = upd_z ? ade_face(P, A, P.vz_in, P.cvz[k], c, c + 1, s, szp, mat, M_ZOPEN) : P.vz_in[c];
     float ddx = vxn, ddy = vyn, ddz = vzn;
-    if (i > 0 || P.has_lower)
-        ddx = vxn - ade_face(P, A, P.vx_in, P.cvx[i - 1], c - P.plane, c, sxm, s, mat, M_XOPEN);
+    if (i > 0 || P.has_lower) {
+        const float vxm = ade_face(P, A, P.vx_in, P.cvx[i - 1], c - P.plane, c, sxm, s, mat, M_XOPEN);
+        ddx = vxn - vxm;
+        if (i == 0 && sxm >= 0) {            // the redundantly kept ghost face vx[-1] carries the correction too
+            float og = vxm;
+            for (int sp = 0; sp < P.n_sponge; sp++) og = og * P.decx[sp][-1];
+            P.vx_out[c - P.plane] = og;
+        }
+    }
     if (j > 0)
         ddy = vyn - ade_face(P, A, P.vy_in, P.cvy[j - 1], c - P.pitch, c, sym, s, mat, M_YOPEN);
     if (k > 0)
@@ -698,6 +706,8 @@ __global__ void k2b_fixup(StepParams P, AdeTable A)
         pn = ((pn * dx) * dy) * dz;
     }
     P.p_out[c] = pn;
+    if (P.peer_lo_p && i == 0) P.peer_lo_p[c] = pn;                           // keep the neighbours' ghost planes current
+    if (P.peer_hi_p && i == P.nx - 1) P.peer_hi_p[c - (long long)i * P.plane] = pn;
     if (sxp >= 0 && upd_x) P.vx_out[c] = ox;       // only faces the ADE correction touched
     if (syp >= 0 && upd_y) P.vy_out[c] = oy;
     if (szp >= 0 && upd_z) P.vz_out[c] = oz;

@@ -238,6 +238,15 @@ class DistributedFDTDSolver:
 
     microphones = property(lambda self: self.slab.microphones)
 
+    def register_material(self, material, material_id=None):
+        return self.slab.register_material(material, material_id=material_id)
+
+    def set_material_region(self, mask, material_id):
+        self.slab.set_material_region(mask, material_id)
+
+    def set_material_box(self, material_id, x_range, y_range, z_range):
+        self.slab.set_material_box(material_id, x_range, y_range, z_range)
+
     def set_kernel_option(self, opt, val):
         self.slab.set_kernel_option(opt, val)
 
@@ -410,8 +419,13 @@ class LocalSlabGroup:
             for s in self.slabs:
                 s.begin_chunk(m)
             if self.halo == "p2p":
-                for s in self.slabs:
-                    s.enqueue_steps(m)
+                # One device runs every slab here, so a slab's spinning cut blocks wait for kernels of ANOTHER stream
+                # of the same GPU.  Submitting step by step, slab after slab, keeps every kernel a waiter depends on
+                # ahead of it in submission order (whole chunks per slab can leave the neighbour's kernels queued
+                # behind the spinner).  With one GPU per slab (DistributedFDTDSolver) no such dependency exists.
+                for _ in range(m):
+                    for s in self.slabs:
+                        s.enqueue_step()
             else:
                 for _ in range(m):
                     for s in self.slabs:

@@ -149,7 +149,9 @@ class FDTDSolver:
         self._track_energy = False
         self._energy_sample_interval = 1
         self._materials: dict = {}
-        self._material_id = np.zeros(self.shape, dtype=np.uint8)
+        # material ids of the owned planes plus, on a slab, the live ghost planes next to them (as the geometry)
+        self._material_ext = np.zeros((self.shape[0] + self._has_lower + self._has_upper,) + self.shape[1:], dtype=np.uint8)
+        self._material_id = self._material_ext[self._has_lower: self._has_lower + self.shape[0]]
         self._local_probes: list = []
         self._mic_slots: list = []
         self._corner_keys: list = []
@@ -245,7 +247,7 @@ class FDTDSolver:
                     self.set_material_region(region, material_id=mat_id)
         elif hasattr(geometry, "voxelize"):
             self._store_geometry(geometry.voxelize(self.grid))
-            self._material_id.fill(0)
+            self._material_ext.fill(0)
             self._dirty.add("ade")
         else:
             self._store_geometry(geometry)
@@ -329,15 +331,18 @@ class FDTDSolver:
         return material_id
 
     def set_material_region(self, mask, material_id: int) -> None:
-        if mask.shape != self.shape:
-            raise ValueError(f"Mask shape {mask.shape} doesn't match solver shape {self.shape}")
+        """``mask`` covers the whole grid (on a slab too: the planes next to a cut are needed on both sides)."""
+        mask = np.asarray(mask)
+        if mask.shape != self.global_shape:
+            raise ValueError(f"Mask shape {mask.shape} doesn't match solver shape {self.global_shape}")
         if material_id != 0 and material_id not in self._materials:
             raise ValueError(f"Material ID {material_id} not registered. Use register_material() first.")
-        self._material_id[mask] = material_id
+        lo, hi = self._i0 - self._has_lower, self._i1 + self._has_upper
+        self._material_ext[mask[lo:hi]] = material_id
         self._dirty.add("ade")
 
     def set_material_box(self, material_id: int, x_range, y_range, z_range) -> None:
-        mask = np.zeros(self.shape, dtype=bool)
+        mask = np.zeros(self.global_shape, dtype=bool)
         mask[x_range[0]:x_range[1], y_range[0]:y_range[1], z_range[0]:z_range[1]] = True
         self.set_material_region(mask, material_id)
 
@@ -526,7 +531,7 @@ class FDTDSolver:
         if "ade" in self._dirty:
             if self._materials and any(len(m.poles) for m in self._materials.values()):
                 poles, n_poles, rho_inf, k_inf = self._pole_table()
-                mid = np.ascontiguousarray(self._material_id, dtype=np.uint8)
+                mid = np.ascontiguousarray(self._material_ext, dtype=np.uint8)   # owned planes + live ghosts
                 _lib.check(lib.sb_set_ade(h, poles, n_poles, _lib.ptr(mid), _lib.ptr(rho_inf), _lib.ptr(k_inf),
                                           len(rho_inf), float(self.dt), float(1.0 / self.dx)))
             else:
