@@ -16,6 +16,7 @@ _PKG = Path(__file__).resolve().parent
 ROOT = _PKG.parent
 SO_PATH = Path(os.environ.get("STRATA_B200_LIB_OVERRIDE") or _PKG / "lib" / "libstrata_b200.so")   # override: kernel experiments
 SOURCES = [_PKG / "csrc" / "sb_api.cu", _PKG / "csrc" / "sb_kernels.cuh", _PKG / "csrc" / "sb_resident.cuh",
+           _PKG / "csrc" / "sb_pipeline.cuh",
            ROOT / "include" / "strata_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
@@ -74,9 +75,9 @@ class Stats(C.Structure):
                 ("pitch", C.c_int32)]
 
 
-KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_TMA, KERNEL_RESIDENT = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_TMA, KERNEL_RESIDENT, KERNEL_PIPELINE = 0, 1, 2, 3, 4, 5
 (OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH, OPT_PROFILE,
- OPT_FUSE_K3, OPT_RESIDENT_SPLIT, OPT_RESIDENT_MIN_STEPS) = range(10)
+ OPT_FUSE_K3, OPT_RESIDENT_SPLIT, OPT_RESIDENT_MIN_STEPS, OPT_LANES_K) = range(11)
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _fp = C.POINTER(C.c_float)

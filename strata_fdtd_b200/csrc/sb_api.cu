@@ -3,6 +3,7 @@
 #include "../../include/strata_b200.h"
 #include "sb_kernels.cuh"
 #include "sb_resident.cuh"
+#include "sb_pipeline.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -108,11 +109,15 @@ struct sb_solver {
     std::vector<ProfEntry> prof;
     // shared-memory-resident kernel (K5, sb_resident.cuh)
     int n_sm = 0; long long smem_optin = 0;
-    int opt_res_split = 0, opt_res_min_steps = 4;
+    int opt_res_split = 0, opt_res_min_steps = 4, opt_profile_k1_only = 0;
     std::vector<int> probe_ijk_host; DBuf<int> d_probe_ijk; DBuf<uint4> d_res_xch;
     unsigned res_epoch = 0;                // step tags of the face exchange keep growing across launches
     bool resident_used = false;
     int res_nbi = 0, res_nbj = 0;
+    // step-pipelined kernel (K6, sb_pipeline.cuh)
+    DBuf<int> d_pipe_ctr;                  // [0] ticket, [1 ..] chunk counters
+    long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 24LL << 20;   // where pipelining the steps was measured to pay
+    int opt_lanes_k = 0;                   // lanes of a warp side by side along k: 0 = best fit for nz, else 8 / 16 / 32
 };
 
 static void drop_graphs(sb_solver *h)
@@ -182,7 +187,7 @@ extern "C" int sb_destroy(sb_solver *h)
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
     h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release();
     h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
-    h->d_probe_ijk.release(); h->d_res_xch.release();
+    h->d_probe_ijk.release(); h->d_res_xch.release(); h->d_pipe_ctr.release();
     delete h;
     return 0;
 }
@@ -592,28 +597,67 @@ static PeerLink peer_link(sb_solver *h, const StepParams &P)
     return L;
 }
 
-// ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE> ------------------------------
-template <int RJ, bool GEOM, bool UNI, bool PEER>
-static void launch_march3(bool fuse, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+// ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE, W> ---------------------------
+// (strips narrower than a warp, W < 32, exist for the plain variant only: PEER / FUSE launches use W = 32)
+template <int RJ, bool GEOM, bool UNI>
+static void launch_march3(bool peer, bool fuse, int w, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
-    if (fuse) k1_step_march<RJ, GEOM, UNI, PEER, true><<<grd, blk, 0, st>>>(P);
-    else      k1_step_march<RJ, GEOM, UNI, PEER, false><<<grd, blk, 0, st>>>(P);
+    if (peer)      { if (fuse) k1_step_march<RJ, GEOM, UNI, true, true><<<grd, blk, 0, st>>>(P);
+                     else      k1_step_march<RJ, GEOM, UNI, true, false><<<grd, blk, 0, st>>>(P); }
+    else if (fuse) k1_step_march<RJ, GEOM, UNI, false, true><<<grd, blk, 0, st>>>(P);
+    else if (w == 8)  k1_step_march<RJ, GEOM, UNI, false, false, 8><<<grd, blk, 0, st>>>(P);
+    else if (w == 16) k1_step_march<RJ, GEOM, UNI, false, false, 16><<<grd, blk, 0, st>>>(P);
+    else              k1_step_march<RJ, GEOM, UNI, false, false, 32><<<grd, blk, 0, st>>>(P);
 }
-template <int RJ, bool GEOM>
-static void launch_march2(bool uni, bool peer, bool fuse, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
-{
-    if (uni) { if (peer) launch_march3<RJ, GEOM, true, true>(fuse, P, grd, blk, st);
-               else      launch_march3<RJ, GEOM, true, false>(fuse, P, grd, blk, st); }
-    else     { if (peer) launch_march3<RJ, GEOM, false, true>(fuse, P, grd, blk, st);
-               else      launch_march3<RJ, GEOM, false, false>(fuse, P, grd, blk, st); }
-}
-static void launch_march(int rj, bool peer, bool fuse, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+static void launch_march(int rj, bool peer, bool fuse, int w, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
     const bool geom = P.mask != nullptr, uni = P.icx == nullptr;
-    if (rj == 1) { if (geom) launch_march2<1, true>(uni, peer, fuse, P, grd, blk, st);
-                   else      launch_march2<1, false>(uni, peer, fuse, P, grd, blk, st); }
-    else         { if (geom) launch_march2<2, true>(uni, peer, fuse, P, grd, blk, st);
-                   else      launch_march2<2, false>(uni, peer, fuse, P, grd, blk, st); }
+    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, w, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, w, P, grd, blk, st); } }
+    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, w, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, w, P, grd, blk, st); } }
+}
+
+// launch shape of the marching kernel: rows per thread, warps along j / k, planes per chunk, tiles along k / j
+static int march_shape(sb_solver *h, bool narrow_ok, int &rj, int &wj, int &wk, int &chunk, int &gx, int &gy, int &w)
+{
+    const sb_grid_desc &d = h->d;
+    // lanes side by side along k: the width that leaves the fewest lanes hanging over the end of a row
+    w = 32;
+    if (narrow_ok && h->opt_lanes_k != 32) {
+        if (h->opt_lanes_k) w = h->opt_lanes_k;
+        else {
+            long long best = -1;
+            for (int cand : {32, 16, 8}) {
+                const long long padded = (long long)((d.nz + 4 * cand - 1) / (4 * cand)) * 4 * cand;
+                if (best < 0 || padded < best) { best = padded; w = cand; }
+            }
+        }
+    }
+    const int sub = 32 / w;                 // row groups per warp
+    rj = h->opt_rj; wk = h->opt_wk;
+    wj = h->opt_wj; int chunk_opt = h->opt_chunk_i;
+    if (rj == 0) {                          // auto: the configuration measured by autotune() for this variant
+        rj = h->tuned[0]; wj = h->tuned[1]; wk = h->tuned[2]; chunk_opt = h->tuned[3];
+    }
+    if (rj != 1 && rj != 2) return fail("rows_per_thread must be 1 or 2");
+    if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
+        wj = std::max(1, 8 / wk);
+        while (wj > 1 && (long long)((d.nz + 4 * w * wk - 1) / (4 * w * wk)) * ((d.ny + rj * wj * sub - 1) / (rj * wj * sub)) *
+                             ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
+    }
+    if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
+    gx = (d.nz + 4 * w * wk - 1) / (4 * w * wk); gy = (d.ny + rj * wj * sub - 1) / (rj * wj * sub);
+    chunk = chunk_opt;
+    if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
+        const long long want = 148LL * 8;
+        long long nchunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
+        nchunks = std::max(1LL, std::min<long long>(nchunks, (d.nx + 7) / 8));
+        chunk = (int)((d.nx + nchunks - 1) / nchunks);
+        chunk = std::max(chunk, std::min(d.nx, 8));
+        chunk = std::min(chunk, 64);
+    }
+    return 0;
 }
 
 static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
@@ -630,34 +674,14 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         h->kernels_launched++;
         return 0;
     }
-    int rj = h->opt_rj, wk = h->opt_wk;
-    int wj = h->opt_wj, chunk_opt = h->opt_chunk_i;
-    if (rj == 0) {                          // auto: the configuration measured by autotune() for this variant
-        rj = h->tuned[0]; wj = h->tuned[1]; wk = h->tuned[2]; chunk_opt = h->tuned[3];
-    }
-    if (rj != 1 && rj != 2) return fail("rows_per_thread must be 1 or 2");
-    if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
-        wj = std::max(1, 8 / wk);
-        while (wj > 1 && (long long)((d.nz + 128 * wk - 1) / (128 * wk)) * ((d.ny + rj * wj - 1) / (rj * wj)) *
-                             ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
-    }
-    if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
-    const int gx = (d.nz + 128 * wk - 1) / (128 * wk), gy = (d.ny + rj * wj - 1) / (rj * wj);
-    int chunk = chunk_opt;
-    if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
-        const long long want = 148LL * 8;
-        long long nchunks = (want + (long long)gx * gy - 1) / ((long long)gx * gy);
-        nchunks = std::max(1LL, std::min<long long>(nchunks, (d.nx + 7) / 8));
-        chunk = (int)((d.nx + nchunks - 1) / nchunks);
-        chunk = std::max(chunk, std::min(d.nx, 8));
-        chunk = std::min(chunk, 64);
-    }
+    int rj, wj, wk, chunk, gx, gy, w;
+    if (march_shape(h, !h->have_peers && !fuse, rj, wj, wk, chunk, gx, gy, w)) return 1;
     const dim3 blk(32 * wk, wj);
     if (!h->have_peers) {
         P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
         const dim3 grd(gx, gy, (d.nx + chunk - 1) / chunk);
         if (grd.z > 65535) return fail("too many i-chunks");
-        launch_march(rj, false, fuse, P, grd, blk, h->stream);
+        launch_march(rj, false, fuse, w, P, grd, blk, h->stream);
         h->kernels_launched++;
         return 0;
     }
@@ -669,13 +693,13 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         Q.peer_lo_p = Q.peer_hi_p = nullptr; Q.flag_lo = Q.flag_hi = nullptr;
         Q.i_begin = cb; Q.i_end = d.nx - cb; Q.chunk_i = chunk;
         const dim3 grd(gx, gy, (Q.i_end - Q.i_begin + chunk - 1) / chunk);
-        launch_march(rj, false, false, Q, grd, blk, h->stream);
+        launch_march(rj, false, false, 32, Q, grd, blk, h->stream);
         P.two_range = 1; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = cb;
-        launch_march(rj, true, false, P, dim3(gx, gy, 2), blk, h->stream);
+        launch_march(rj, true, false, 32, P, dim3(gx, gy, 2), blk, h->stream);
         h->kernels_launched += 2;
     } else {                                // thin slab: everything through the PEER variant
         P.two_range = 0; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-        launch_march(rj, true, false, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
+        launch_march(rj, true, false, 32, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
         h->kernels_launched++;
     }
     return 0;
@@ -899,6 +923,80 @@ static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double
     return 0;
 }
 
+// ---- K6: step-pipelined persistent launch of the marching kernel (sb_pipeline.cuh) -------------------------
+static const char *pipeline_why_not(const sb_solver *h)
+{
+    const sb_grid_desc &d = h->d;
+    if (d.has_lower || d.has_upper || h->have_peers) return "decomposed slab";
+    if (h->have_ade) return "ADE materials";
+    if (!h->plane_ops.empty()) return "Mur / radiation planes";
+    if (h->n_mics) return "microphones";
+    if (h->n_src_cells && !h->inline_ok) return "more than 8 source cells or velocity sources";
+    if (h->n_sm <= 0) return "device attributes unavailable";
+    return nullptr;
+}
+
+template <int RJ, bool GEOM, bool UNI, int W>
+static int launch_pipeline_w(sb_solver *h, PipeParams &Q, dim3 blk, long long total)
+{
+    auto kern = k6_pipeline<RJ, GEOM, UNI, W>;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)(blk.x * blk.y), 0));
+    if (per_sm < 1) return fail("pipelined kernel does not fit on an SM");
+    const long long ctas = std::min<long long>(total, (long long)per_sm * h->n_sm);
+    void *args[] = {&Q};
+    CU(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)ctas), blk, args, 0, h->stream));
+    return 0;
+}
+
+template <int RJ, bool GEOM, bool UNI>
+static int launch_pipeline_t(sb_solver *h, PipeParams &Q, dim3 blk, long long total, int w)
+{
+    if (w == 8) return launch_pipeline_w<RJ, GEOM, UNI, 8>(h, Q, blk, total);
+    if (w == 16) return launch_pipeline_w<RJ, GEOM, UNI, 16>(h, Q, blk, total);
+    return launch_pipeline_w<RJ, GEOM, UNI, 32>(h, Q, blk, total);
+}
+
+static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, float *rec_dev)
+{
+    const sb_grid_desc &d = h->d;
+    int rj, wj, wk, chunk, gx, gy, w;
+    if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, w)) return 1;
+    PipeParams Q{};
+    fill_params(h, Q.S);
+    Q.S.i_begin = 0; Q.S.i_end = d.nx; Q.S.chunk_i = chunk;
+    Q.S.n_inline = h->n_src_cells ? h->n_src_entries : 0;
+    for (int e = 0; e < Q.S.n_inline; e++) {
+        Q.S.inl_i[e] = h->inl_i[e]; Q.S.inl_j[e] = h->inl_j[e]; Q.S.inl_k[e] = h->inl_k[e];
+        Q.S.inl_src[e] = h->inl_src[e]; Q.S.inl_weight[e] = h->inl_weight[e];
+    }
+    Q.n_steps = n_steps; Q.gx = gx; Q.gy = gy; Q.nchunks = (d.nx + chunk - 1) / chunk;
+    const long long total = (long long)gx * gy * Q.nchunks * n_steps;
+    if (total >= (1LL << 31) - 65536) return fail("pipelined kernel: too many tiles in one chunk of steps");
+    if (h->d_pipe_ctr.alloc((size_t)Q.nchunks + 1)) return 1;
+    CU(cudaMemsetAsync(h->d_pipe_ctr.p, 0, ((size_t)Q.nchunks + 1) * sizeof(int), h->stream));
+    Q.ticket = h->d_pipe_ctr.p; Q.done = h->d_pipe_ctr.p + 1; Q.err_flag = h->d_err.p;
+    Q.src_vals = src_dev; Q.n_sources = h->n_sources;
+    Q.rec = rec_dev; Q.n_rec = h->n_probes; Q.n_probes = h->n_probes; Q.probe_ijk = h->d_probe_ijk.p;
+    const dim3 blk(32 * wk, wj);
+    const bool geom = Q.S.mask != nullptr, uni = Q.S.icx == nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->opt_profile) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, h->stream); }
+    int rc;
+    if (rj == 1) rc = geom ? (uni ? launch_pipeline_t<1, true, true>(h, Q, blk, total, w) : launch_pipeline_t<1, true, false>(h, Q, blk, total, w))
+                           : (uni ? launch_pipeline_t<1, false, true>(h, Q, blk, total, w) : launch_pipeline_t<1, false, false>(h, Q, blk, total, w));
+    else         rc = geom ? (uni ? launch_pipeline_t<2, true, true>(h, Q, blk, total, w) : launch_pipeline_t<2, true, false>(h, Q, blk, total, w))
+                           : (uni ? launch_pipeline_t<2, false, true>(h, Q, blk, total, w) : launch_pipeline_t<2, false, false>(h, Q, blk, total, w));
+    if (rc) return 1;
+    if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, n_steps}); }
+    h->kernels_launched++;
+    h->steps_done += n_steps;
+    if (n_steps & 1) h->cur = 1 - h->cur;
+    h->last_variant = SB_KERNEL_PIPELINE;
+    h->resident_used = true;                 // sb_synchronize looks at the error flag
+    return 0;
+}
+
 extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev, float *rec_dev)
 {
     CHECK_H(h);
@@ -916,6 +1014,14 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     if (h->opt_rj == 0 && n_steps > 0) {
         const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
         if (variant != SB_KERNEL_NAIVE && autotune(h)) return 1;
+    }
+    if (n_steps > 0 && (h->opt_kernel == SB_KERNEL_PIPELINE ||
+                        (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps && !h->opt_profile_k1_only &&
+                         (long long)h->d.nx * h->d.ny * h->d.nz >= h->opt_pipe_min_cells &&
+                         (long long)h->d.nx * h->d.ny * h->d.nz <= h->opt_pipe_max_cells))) {
+        const char *why_not = pipeline_why_not(h);
+        if (!why_not) return launch_pipeline(h, n_steps, src_dev, rec_dev);
+        if (h->opt_kernel == SB_KERNEL_PIPELINE) return fail("pipelined kernel not applicable: %s", why_not);
     }
     CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
     const bool want_graph = h->opt_graph == 1 ||
@@ -1049,7 +1155,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
 {
     if (!h) return fail("null handle");
     switch (option) {
-        case SB_OPT_KERNEL: if (value < 0 || value > 4) return fail("bad kernel variant"); h->opt_kernel = value; break;
+        case SB_OPT_KERNEL: if (value < 0 || value > 5) return fail("bad kernel variant"); h->opt_kernel = value; break;
         case SB_OPT_ROWS_PER_THREAD: if (value < 0 || value > 2) return fail("rows_per_thread must be 0 (auto), 1 or 2"); h->opt_rj = value; break;
         case SB_OPT_WARPS_J: if (value < 0 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;
@@ -1057,6 +1163,8 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
         case SB_OPT_USE_GRAPH: h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); break;
         case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
         case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value < 0 ? 0 : std::min(value, 2); break;
+        case SB_OPT_LANES_K: if (value != 0 && value != 8 && value != 16 && value != 32) return fail("lanes_k must be 0 (auto), 8, 16 or 32");
+                             h->opt_lanes_k = value; break;
         case SB_OPT_RESIDENT_SPLIT: h->opt_res_split = value ? 1 : 0; break;
         case SB_OPT_RESIDENT_MIN_STEPS: h->opt_res_min_steps = std::max(1, value); break;
         default: return fail("unknown option %d", option);
@@ -1118,6 +1226,7 @@ extern "C" int sb_synchronize(sb_solver *h)
         int err = 0;
         CU(cudaMemcpy(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
         if (err == 2) return fail("resident kernel: timed out waiting for a neighbour box's step flag");
+        if (err == 3) return fail("pipelined kernel: timed out waiting for a chunk of the previous step");
         if (err) return fail("timed out waiting for a neighbour slab's step flag (peer-to-peer halo)");
     }
     return 0;

@@ -181,29 +181,38 @@ constexpr unsigned ALL_OPEN = 0x0F0F0F0Fu;      // four cells: air, all three fa
 //   UNI  uniform grid: one scalar velocity coefficient, no inverse-cell multiplies
 //   PEER multi-GPU: neighbour flags + peer stores (launched only over the chunks that touch a cut)
 //   FUSE single-kernel step: inline point-source injection + deferred probe recording (small grids)
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE>
-__global__ void __launch_bounds__(256) k1_step_march(StepParams P)
+// The tile body is a device function so that the step-pipelined kernel (sb_pipeline.cuh) can run the same code
+// for a tile of any step; F names the input and output sets of that step.
+struct FieldSet { const float *p_in, *vx_in, *vy_in, *vz_in; float *p_out, *vx_out, *vy_out, *vz_out; };
+
+// W = lanes of a warp that lie side by side along k (32, 16 or 8): the warp covers 32/W groups of RJ rows by 4W
+// cells.  K1 is latency-bound per warp iteration, so a warp whose lanes hang over the end of the row costs as much
+// as a full one; with W chosen per grid (nz = 200: 7 strips of 32 cells instead of 2 of 128) fewer lanes idle.
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, int W = 32>
+__device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, int bx, int by, int bz)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int kl = lane & (W - 1), sub = lane / W;             // position along k inside the strip, row group inside the warp
     const int warp_k = threadIdx.x >> 5;                       // blockDim.x = 32 * WK
-    const int strip_k0 = (blockIdx.x * (blockDim.x >> 5) + warp_k) * 128;
-    const int k0 = strip_k0 + lane * 4;
-    const int j0 = (blockIdx.y * blockDim.y + threadIdx.y) * RJ;
-    int ib = P.i_begin + (int)blockIdx.z * P.chunk_i;
-    if (PEER && P.two_range) ib = blockIdx.z ? P.nx - P.chunk_i : 0;
+    const int strip_k0 = (bx * (blockDim.x >> 5) + warp_k) * (4 * W);
+    const int k0 = strip_k0 + kl * 4;
+    const int jw = (by * blockDim.y + threadIdx.y) * (32 / W) * RJ;   // first row of the warp
+    const int j0 = jw + sub * RJ;
+    int ib = P.i_begin + bz * P.chunk_i;
+    if (PEER && P.two_range) ib = bz ? P.nx - P.chunk_i : 0;
     const int ie = min(ib + P.chunk_i, P.i_end);
-    if (strip_k0 >= P.nz || j0 >= P.ny || ib >= ie) return;     // warp-uniform exit
+    if (strip_k0 >= P.nz || jw >= P.ny || ib >= ie) return;     // warp-uniform exit (rows past ny are predicated off)
     if (PEER) {
         if (P.flag_lo && ib == 0) wait_neighbour(P.flag_lo, *P.step_global, P.err_flag);
         if (P.flag_hi && ie == P.nx) wait_neighbour(P.flag_hi, *P.step_global, P.err_flag);
     }
-    if (FUSE && P.rec_prev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 32) {
+    if (FUSE && P.rec_prev && bx == 0 && by == 0 && bz == 0 && threadIdx.y == 0 && threadIdx.x < 32) {
         // probes / microphones of the previous step: its output set is this launch's (read-only) input set
-        const FieldPtrs F{{P.p_in, P.vx_in, P.vy_in, P.vz_in}};
+        const FieldPtrs FP{{F.p_in, F.vx_in, F.vy_in, F.vz_in}};
         for (int t = lane; t < P.n_probes + P.n_mics; t += 32)
-            P.rec_row[t] = t < P.n_probes ? P.p_in[P.probe_off[t]]
-                                          : gather8(F, P.mic_field, P.mic_off8, P.mic_w8, t - P.n_probes);
+            P.rec_row[t] = t < P.n_probes ? F.p_in[P.probe_off[t]]
+                                          : gather8(FP, P.mic_field, P.mic_off8, P.mic_w8, t - P.n_probes);
     }
     unsigned inl_mask = 0;                                       // inline point sources inside this thread's column
     for (int q = 0; FUSE && q < P.n_inline; q++)
@@ -214,8 +223,8 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
     // per-element validity and "z face is updated" flags
     const bool e0 = k0 < nz, e1 = k0 + 1 < nz, e2 = k0 + 2 < nz, e3 = k0 + 3 < nz;
     const bool u0 = k0 < nz - 1, u1 = k0 + 1 < nz - 1, u2 = k0 + 2 < nz - 1, u3 = k0 + 3 < nz - 1;
-    const bool edge_hi = (lane == 31) && (k0 + 4 < nz);        // needs p[k0+4] from the next strip
-    const bool edge_lo = (lane == 0) && (k0 > 0);              // needs the z face k0-1 of the previous strip
+    const bool edge_hi = (kl == W - 1) && (k0 + 4 < nz);       // needs p[k0+4] from the next strip
+    const bool edge_lo = (kl == 0) && (k0 > 0);                // needs the z face k0-1 of the previous strip
     const float4 z4 = f4(0.0f);
 
     // k tables (hoisted)
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
         const long long base = (long long)ib * P.plane + col;
 #pragma unroll
         for (int r = 0; r < RJ; r++)
-            pc[r + 1] = (row_ok[r + 1] && lane_ok) ? ld4(P.p_in + base + (long long)r * P.pitch) : z4;
+            pc[r + 1] = (row_ok[r + 1] && lane_ok) ? ld4(F.p_in + base + (long long)r * P.pitch) : z4;
         const bool have_prev = (ib > 0) || P.has_lower;
         const float cx = UNI ? P.cv_uni : (have_prev ? P.cvx[ib - 1] : 0.0f);
 #pragma unroll
@@ -252,12 +261,12 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             float4 v = z4;
             if (have_prev && row_ok[r + 1] && lane_ok) {
                 const long long cm = base - P.plane + (long long)r * P.pitch;
-                v = add4(ld4(P.vx_in + cm), mul4s(sub4(pc[r + 1], ld4(P.p_in + cm)), cx));
+                v = add4(ld4(F.vx_in + cm), mul4s(sub4(pc[r + 1], ld4(F.p_in + cm)), cx));
                 if (GEOM) v = keep4(v, *reinterpret_cast<const unsigned *>(P.mask + cm), M_XOPEN);
                 if (ib == 0) {                                   // maintain the lower ghost plane of vx
                     float4 o = v;
                     for (int s = 0; s < P.n_sponge; s++) o = mul4s(o, P.decx[s][-1]);
-                    st4(P.vx_out + cm, sel4(e0, e1, e2, e3, o, z4));
+                    st4(F.vx_out + cm, sel4(e0, e1, e2, e3, o, z4));
                 }
             }
             vxp[r] = v;
@@ -281,19 +290,19 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
         for (int r = 0; r < RJ; r++) {
             const bool ok = row_ok[r + 1] && lane_ok;
             const long long c = base + (long long)r * P.pitch;
-            pn[r] = (ok && upd_x) ? ld4(P.p_in + c + P.plane) : z4;
-            vx[r] = ok ? ld4(P.vx_in + c) : z4;
-            vz[r] = ok ? ld4(P.vz_in + c) : z4;
-            p_hi[r] = (edge_hi && row_ok[r + 1]) ? P.p_in[c + 4] : 0.0f;
-            p_lo[r] = (edge_lo && row_ok[r + 1]) ? P.p_in[c - 1] : 0.0f;
-            vz_lo[r] = (edge_lo && row_ok[r + 1]) ? P.vz_in[c - 1] : 0.0f;
+            pn[r] = (ok && upd_x) ? ld4(F.p_in + c + P.plane) : z4;
+            vx[r] = ok ? ld4(F.vx_in + c) : z4;
+            vz[r] = ok ? ld4(F.vz_in + c) : z4;
+            p_hi[r] = (edge_hi && row_ok[r + 1]) ? F.p_in[c + 4] : 0.0f;
+            p_lo[r] = (edge_lo && row_ok[r + 1]) ? F.p_in[c - 1] : 0.0f;
+            vz_lo[r] = (edge_lo && row_ok[r + 1]) ? F.vz_in[c - 1] : 0.0f;
             if (GEOM) m_lo[r] = (edge_lo && row_ok[r + 1]) ? P.mask[c - 1] : (uint8_t)0x0F;
         }
 #pragma unroll
         for (int r = -1; r < RJ; r++) {
             const bool ok = row_ok[r + 1] && lane_ok;
             const long long c = base + (long long)r * P.pitch;
-            vy[r + 1] = ok ? ld4(P.vy_in + c) : z4;
+            vy[r + 1] = ok ? ld4(F.vy_in + c) : z4;
             if (GEOM) mk[r + 1] = ok ? *reinterpret_cast<const unsigned *>(P.mask + c) : ALL_OPEN;
         }
         // warp-uniform fast path: nothing solid or rigid in this warp's cells of this plane
@@ -306,8 +315,8 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             for (int r = 0; r < RJ; r++) open = open && (m_lo[r] == 0x0F);
             masked = !__all_sync(FULL, open);
         }
-        pc[0] = (row_ok[0] && lane_ok) ? ld4(P.p_in + base - P.pitch) : z4;
-        pc[RJ + 1] = (row_ok[RJ + 1] && lane_ok) ? ld4(P.p_in + base + (long long)RJ * P.pitch) : z4;
+        pc[0] = (row_ok[0] && lane_ok) ? ld4(F.p_in + base - P.pitch) : z4;
+        pc[RJ + 1] = (row_ok[RJ + 1] && lane_ok) ? ld4(F.p_in + base + (long long)RJ * P.pitch) : z4;
 
         // undamped, rigid-masked y faces for rows -1 .. RJ-1
         float4 vyn[RJ + 1];
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             }
             // z faces: p[k+1] from the next lane (or the next strip)
             float p_next = __shfl_down_sync(FULL, p.x, 1);
-            if (lane == 31) p_next = p_hi[r];
+            if (kl == W - 1) p_next = p_hi[r];
             const float4 pk1 = make_float4(p.y, p.z, p.w, p_next);
             float4 vzn = vz[r];
             {
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
             }
             // z face k0-1: previous lane's .w, or recomputed from the previous strip's values
             float vz_prev = __shfl_up_sync(FULL, vzn.w, 1);
-            if (lane == 0) {
+            if (kl == 0) {
                 vz_prev = 0.0f;
                 if (edge_lo) {
                     vz_prev = vz_lo[r] + cvz_lo * (p.x - p_lo[r]);
@@ -388,17 +397,24 @@ __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
                             else pst.w = (float)((double)pst.w + w);
                         }
                 }
-                st4(P.p_out + c, pst);
+                st4(F.p_out + c, pst);
                 if (PEER && P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
                 if (PEER && P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
-                st4(P.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
-                st4(P.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
-                st4(P.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
+                st4(F.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
+                st4(F.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
+                st4(F.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
             }
             vxp[r] = vxn;
             pc[r + 1] = pn[r];
         }
     }
+}
+
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, int W = 32>
+__global__ void __launch_bounds__(256) k1_step_march(StepParams P)
+{
+    const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
+    k1_tile<RJ, GEOM, UNI, PEER, FUSE, W>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -22,6 +22,10 @@ VARIANTS = {
                               _lib.OPT_WARPS_J: 2, _lib.OPT_FUSE_K3: 2},
     "march_r2_graph": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_USE_GRAPH: 1},
     "march_r2_separate_k3": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_FUSE_K3: 0},
+    "march_r1_lanes8": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_LANES_K: 8, _lib.OPT_FUSE_K3: 0,
+                        _lib.OPT_CHUNK_I: 7},
+    "march_r2_lanes16": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_LANES_K: 16, _lib.OPT_FUSE_K3: 0,
+                         _lib.OPT_WARPS_J: 2},
     "march_r1_nograph_wk2": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_USE_GRAPH: 0,
                              _lib.OPT_WARPS_K: 2, _lib.OPT_WARPS_J: 2},
 }
@@ -326,3 +330,53 @@ def test_resident_refuses_what_it_cannot_do_and_auto_falls_back_to_k1():
     a.run(steps=16)
     assert a.device_stats()["kernel_variant"] == _lib.KERNEL_MARCH
     a.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K6: the marching kernel pipelined across steps in one persistent launch (csrc/sb_pipeline.cuh)
+@pytest.mark.parametrize("shape_opts", [{}, {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_CHUNK_I: 3, _lib.OPT_WARPS_J: 2, _lib.OPT_LANES_K: 16},
+                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 1, _lib.OPT_WARPS_J: 1, _lib.OPT_LANES_K: 32},
+                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 5, _lib.OPT_LANES_K: 8}])
+@pytest.mark.parametrize("name", sorted(_resident_cases()))
+def test_pipelined_kernel_matches_oracle(name, shape_opts):
+    case = _resident_cases()[name]
+    s = _with_options(build_b200_solver(case, chunk_steps=37), {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE, **shape_opts})
+    o = O.OracleSolver(case)
+    s.run(steps=case["steps"]); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"pipeline/{name}")
+    st = s.device_stats()
+    assert st["kernel_variant"] == _lib.KERNEL_PIPELINE
+    assert st["kernels_launched"] <= -(-case["steps"] // 37) + 2, "one launch per chunk"
+    s.close()
+
+
+def test_pipelined_kernel_is_the_automatic_choice_for_config_2_and_equals_the_oracle():
+    """BASELINE config 2 (200^3 + PML, here with the solid block): too large for shared memory, AUTO pipelines the steps."""
+    case = c2_case(200, steps=120, with_geometry=True)
+    s = build_b200_solver(case, chunk_steps=64)
+    o = O.OracleSolver(case)
+    s.run(steps=120); o.run_steps(120)
+    assert s.device_stats()["kernel_variant"] == _lib.KERNEL_PIPELINE
+    assert_same_as_oracle(s, o, "c2/pipeline")
+    s.close()
+
+
+@pytest.mark.parametrize("shape", [(150, 7, 9), (5, 300, 12), (3, 3, 3), (40, 40, 1), (97, 101, 103), (2, 2, 600), (300, 40, 260)])
+def test_pipelined_equals_stepwise_on_awkward_shapes(shape):
+    nx, ny, nz = shape
+    geom = np.ones(shape, dtype=bool)
+    geom[nx // 3: nx // 3 + 2, ny // 2:, : max(1, nz // 3)] = False
+    case = dict(shape=shape, resolution=1e-3, steps=90, geometry=geom,
+                pml=[dict(depth=min(3, max(1, min(shape) // 3)))] if min(shape) >= 3 else [],
+                sources=[dict(kind="point", position=(nx // 2, ny // 4, nz // 2), frequency=30e3),
+                         dict(kind="point", position=(0, 0, 0), frequency=12e3, amplitude=0.3)],
+                probes=[("a", (nx - 1, ny - 1, nz - 1)), ("b", (nx // 2, ny // 2, nz // 2)), ("c", (0, ny - 1, 0))])
+    a = _with_options(build_b200_solver(case, chunk_steps=50), {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE})
+    b = _with_options(build_b200_solver(case, chunk_steps=50), {_lib.OPT_KERNEL: _lib.KERNEL_MARCH})
+    a.run(steps=90); b.run(steps=90)
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(a.get_field(f), b.get_field(f)), f
+    for n in ("a", "b", "c"):
+        assert np.array_equal(a.get_probe_data(n)[n], b.get_probe_data(n)[n]), n
+    assert np.abs(a.get_field("p")).max() > 0
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_PIPELINE
