@@ -292,7 +292,7 @@ def run_b200_arm(a):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": label, "cells_per_gpu": cells_rank, "l2_policy": "fields (34 GB/GPU) >> L2, no flush needed"
                            if a.workload == "c5_weak" else "inputs larger than L2 for >=200^3; small grids are L2-resident by nature",
-                           "kernel": {0: "auto", 1: "naive", 2: "march", 3: "tma", 4: "resident"}[st1["kernel_variant"]],
+                           "kernel": {0: "auto", 1: "naive", 2: "march", 3: "tma", 4: "resident", 5: "pipeline"}[st1["kernel_variant"]],
                            "launch_shape": {"rows_per_thread": shape4[0], "warps_j": shape4[1], "warps_k": shape4[2],
                                             "chunk_planes": shape4[3], "source": "library autotune" if a.rows is None else "flag"},
                            "parallelism": f"slab{world}" if world > 1 else "single",
@@ -300,7 +300,8 @@ def run_b200_arm(a):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
                              "kernel": "k5_resident (per step of one chunk launch; fields stay in shared memory, so "
-                                       "'achieved' is an HBM-equivalent rate)" if st1["kernel_variant"] == 4 else "k1_step_march",
+                                       "'achieved' is an HBM-equivalent rate)" if st1["kernel_variant"] == 4 else
+                                       "k6_pipeline (k1_tile; per step of one chunk launch)" if st1["kernel_variant"] == 5 else "k1_step_march",
                              "kernel_ms_mean": mean_ms.value, "kernel_ms_min": min_ms.value, "launches_timed": n_l.value,
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_rank},
                 "e2e": {"value": cells_total * K / e2e_s / 1e9, "unit": UNIT,
