@@ -26,6 +26,7 @@ import numpy as np
 
 from . import _lib
 from .solver import _FIELDS, FDTDSolver
+from .sources import combine_corner_samples
 
 
 def slab_ranges(nx: int, world: int) -> list[tuple[int, int]]:
@@ -39,23 +40,6 @@ def slab_ranges(nx: int, world: int) -> list[tuple[int, int]]:
         out.append((lo, hi))
         lo = hi
     return out
-
-
-def combine_corner_samples(mics, gathers, corners: dict, times) -> None:
-    """Finish the microphones of a decomposed run: ``corners[(mic, gather, corner)]`` are the raw fp32 samples the
-    owning slabs recorded; each gather is summed exactly as microphones.cpp:82-116 / solver.py:1027-1034 do --
-    ``sum = 0; sum += w[c] * f[c]`` for c = 0..7 in fp32 -- and handed to the microphone's pattern."""
-    if len(times) == 0:
-        return
-    for mi, mic in enumerate(mics):
-        cols = []
-        for g, (_f, _idx8, w8) in enumerate(gathers[mi]):
-            acc = np.zeros(len(times), dtype=np.float32)
-            for c in range(8):
-                acc = acc + np.float32(w8[c]) * corners[(mi, g, c)]
-            cols.append(acc)
-        mic._data.extend(np.asarray(mic._combine(cols[0], cols[1:])).tolist())
-        mic._times.extend(np.asarray(times).tolist())
 
 
 def _drain_corner_samples(slab) -> tuple[dict, np.ndarray]:

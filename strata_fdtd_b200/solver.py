@@ -24,7 +24,7 @@ import numpy as np
 from . import _lib
 from .boundaries import plane_ops, sponge_tables
 from .grid import NonuniformGrid, UniformGrid
-from .sources import Microphone, Probe
+from .sources import Microphone, Probe, combine_corner_samples
 
 _FIELDS = ("p", "vx", "vy", "vz")
 
@@ -522,10 +522,23 @@ class FDTDSolver:
                 idx_all, w_all = np.concatenate(idx_all), np.concatenate(w_all)
                 _lib.check(lib.sb_set_gathers(h, len(fields), _lib.ptr(fields), _lib.ptr(idx_all), _lib.ptr(w_all)))
             elif mics:
-                idx8, w8 = self._native_mic_tables(mics, lib)
-                self._mic_tables = (idx8, w8)
-                self._mic_slots = [[q] for q in range(len(mics))]
-                _lib.check(lib.sb_set_mics(h, len(mics), _lib.ptr(idx8), _lib.ptr(w8)))
+                # Omnidirectional microphones are recorded as their eight raw corner samples of p -- plain probes --
+                # and summed on the host in the order of microphones.cpp:82-116 (bit-identical, see
+                # combine_corner_samples).  With nothing but probes on the device, the chunk kernels K5 / K6 apply.
+                self._mic_gathers = self.microphone_gathers(mics, lib)
+                n_cells = int(np.prod(self.shape, dtype=np.int64))
+                corner_idx = []
+                for mi, tabs in enumerate(self._mic_gathers):
+                    for c, gidx in enumerate(tabs[0][1]):
+                        if not 0 <= int(gidx) < n_cells:
+                            raise _lib.B200BackendError(f"microphone corner {8 * mi + c} out of range")
+                        corner_idx.append(int(gidx))
+                        self._corner_keys.append((mi, 0, c))
+                self._mic_tables = (np.concatenate([t[0][1] for t in self._mic_gathers]),
+                                    np.concatenate([t[0][2] for t in self._mic_gathers]))
+                flat_all = np.concatenate([flat, np.array(corner_idx, dtype=np.int64)])
+                _lib.check(lib.sb_set_probes(h, len(flat_all), _lib.ptr(flat_all)))
+                _lib.check(lib.sb_set_mics(h, 0, None, None))
             else:
                 _lib.check(lib.sb_set_mics(h, 0, None, None))
         if "ade" in self._dirty:
@@ -643,6 +656,10 @@ class FDTDSolver:
                 mic._data.extend(mic._combine(cols[0], cols[1:]).tolist())
                 mic._times.extend(times.tolist())
             self._store_corner_samples(rec, len(probes), times)
+            if self._corner_keys and not (self._has_lower or self._has_upper):     # one GPU: every corner is here
+                data = {k: np.concatenate(v) for k, v in self._corner_data.items()}
+                self._corner_data.clear(); self._corner_times.clear()
+                combine_corner_samples(mics, self._mic_gathers, data, times)
             last_idx = self._step_count + m - 1
             self._step_count += m
             self._time = t
