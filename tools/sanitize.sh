@@ -10,3 +10,10 @@ for tool in memcheck racecheck initcheck; do
 done
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k "peer_store and block_pml" > gpurun_out/sanitizer_memcheck_p2p.log 2>&1
 echo "memcheck-p2p exit=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_memcheck_p2p.log | tr '\n' ' ')"
+# the chunk kernels (shared-memory-resident K5, step-pipelined K6) and ADE across slab cuts
+SEL2='(test_resident_kernel_matches_oracle and (odd_geometry or two_sponges or nonuniform) and 0) or (test_pipelined_kernel_matches_oracle and (odd_geometry or nonuniform) and shape_opts1) or (test_ade_materials_across_slab_cuts and copy and 2)'
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 7 --target-processes all \
+      python -m pytest tests/test_parity_gpu.py tests/test_multi_gpu.py -m gpu -x -q -k "$SEL2" > gpurun_out/sanitizer_chunk_$tool.log 2>&1
+  echo "chunk-$tool exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_chunk_$tool.log | tr '\n' ' ')"
+done
