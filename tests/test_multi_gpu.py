@@ -282,6 +282,30 @@ def test_ade_materials_across_slab_cuts(name, n_slabs, halo):
     grp.close(); one.close()
 
 
+@pytest.mark.gpu
+def test_c3_full_size_ade_sphere_is_decomposition_invariant():
+    """BASELINE config 3 at full size (512^3, ADE sphere, 64 probes) is out of the oracle's reach in test time; the
+    size-independent property checked instead: two slabs (cut through the sphere, ghost-cell J kept redundantly)
+    reproduce the single-domain run bit for bit -- fields, all 64 traces."""
+    from cases import c3_case
+    case = c3_case(512, steps=0)
+    steps = 24
+    one = build_b200_solver(case)
+    one.run(steps=steps)
+    ref = {f: one.get_field(f) for f in ("p", "vx", "vy", "vz")}
+    ref_tr = {n: one.get_probe_data(n)[n] for n in one._probes}
+    one.close()
+    grp = _group_from_case(case, 2, {})
+    grp.run(steps)
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(grp.get_field(f), ref[f]), f
+    traces = grp.get_probe_data()
+    for n, tr in ref_tr.items():
+        assert np.array_equal(traces[n], tr), n
+    assert np.abs(ref["p"]).max() > 0
+    grp.close()
+
+
 def test_microphone_corner_ownership_covers_every_corner_once():
     """Host logic of the slab microphones, no device: over any split, each of the 8 corners of every gather is
     recorded by exactly one slab, and the fp32 corner sum reproduces the single-pass gather."""

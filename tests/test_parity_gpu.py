@@ -6,7 +6,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from cases import c1_case, c2_case, make_cases
+from cases import c1_case, c2_case, c3_case, make_cases
 from oracle import oracle as O
 from strata_fdtd_b200 import _lib
 from util import assert_same_as_oracle, build_b200_solver, sha
@@ -400,4 +400,18 @@ def test_omni_microphones_ride_the_chunk_kernels_as_corner_probes(name, kernel):
         assert sha(s.get_field(f)) == str(g["sha_" + f])
     want = {_lib.KERNEL_AUTO: _lib.KERNEL_RESIDENT}.get(kernel, kernel)
     assert s.device_stats()["kernel_variant"] == want
+    s.close()
+
+
+def test_c3_ade_sphere_at_128_cubed_vs_oracle():
+    """BASELINE config 3 at 1/4 scale (128^3, PML 10, ADE sphere of radius N/10 with 2 Debye + 1 Lorentz poles,
+    64 probes): every field and all 64 traces equal the oracle (= the reference's ade.cpp kernels in the documented
+    order, oracle/oracle.py) bit for bit."""
+    case = c3_case(128, steps=150)
+    assert int((np.asarray(case["material_id"]) > 0).sum()) > 8000
+    s = build_b200_solver(case, chunk_steps=64)
+    o = O.OracleSolver(case)
+    s.run(steps=150); o.run_steps(150)
+    assert_same_as_oracle(s, o, "c3/128")
+    assert len(s._probes) == 64 and np.abs(s.get_field("p")).max() > 0
     s.close()
