@@ -109,7 +109,8 @@ struct sb_solver {
     std::vector<ProfEntry> prof;
     // shared-memory-resident kernel (K5, sb_resident.cuh)
     int n_sm = 0; long long smem_optin = 0;
-    int opt_res_split = 0, opt_res_min_steps = 4, opt_profile_k1_only = 0;
+    bool coop_ok = false;                  // cooperative launches available (K5 / K6 need all their CTAs co-resident)
+    int opt_res_split = 0, opt_res_min_steps = 4;
     std::vector<int> probe_ijk_host; DBuf<int> d_probe_ijk; DBuf<uint4> d_res_xch;
     unsigned res_epoch = 0;                // step tags of the face exchange keep growing across launches
     bool resident_used = false;
@@ -172,6 +173,7 @@ extern "C" int sb_create(const sb_grid_desc *desc, int device, void *stream, sb_
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) h->n_sm = v;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess) h->smem_optin = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device) == cudaSuccess) h->coop_ok = v != 0;
     *out = h;
     return 0;
 }
@@ -851,6 +853,7 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not)
     else if (h->n_src_cells && !h->inline_ok) *why_not = "more than 8 source cells or velocity sources";
     else if (h->n_probes > K5_MAX_PROBES) *why_not = "too many probes";
     else if (h->n_sm <= 0 || h->smem_optin <= 0) *why_not = "device attributes unavailable";
+    else if (!h->coop_ok) *why_not = "cooperative launch unavailable on this device / in this process";
     if (*why_not) return 0;
     int nbi = 0, nbj = 0;
     if (!res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, h->have_mask, &nbi, &nbj)) {
@@ -888,10 +891,18 @@ struct ResidentLauncher {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K5_NT, smem));
-        if ((long long)per_sm * h->n_sm < (long long)R.nbi * R.nbj)
-            return fail("resident kernel: %d boxes cannot be co-resident", R.nbi * R.nbj);
+        if ((long long)per_sm * h->n_sm < (long long)R.nbi * R.nbj) {
+            fail("resident kernel: %d boxes cannot be co-resident", R.nbi * R.nbj);
+            return 2;
+        }
         void *args[] = {&R};
-        CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(R.nbi * R.nbj), dim3(K5_NT), args, smem, h->stream));
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3(R.nbi * R.nbj), dim3(K5_NT), args, smem, h->stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {   // e.g. SMs partitioned away (MPS / MIG)
+            cudaGetLastError();
+            fail("resident kernel: cooperative launch refused (%s)", cudaGetErrorString(e));
+            return 2;
+        }
+        CU(e);
         return 0;
     }
 };
@@ -913,7 +924,10 @@ static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->opt_profile) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, h->stream); }
     ResidentLauncher launcher{h, R, smem};
-    if (res_dispatch(R.mask != nullptr, R.icx == nullptr, R.n_sponge, launcher)) return 1;
+    if (const int rc = res_dispatch(R.mask != nullptr, R.icx == nullptr, R.n_sponge, launcher)) {
+        if (h->opt_profile) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+        return rc;                           // 2 = the device cannot hold all boxes at once: the caller falls back
+    }
     if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, n_steps}); }
     h->kernels_launched++;
     h->steps_done += n_steps;
@@ -934,6 +948,7 @@ static const char *pipeline_why_not(const sb_solver *h)
     if (h->n_mics) return "microphones";
     if (h->n_src_cells && !h->inline_ok) return "more than 8 source cells or velocity sources";
     if (h->n_sm <= 0) return "device attributes unavailable";
+    if (!h->coop_ok) return "cooperative launch unavailable on this device / in this process";
     return nullptr;
 }
 
@@ -946,7 +961,13 @@ static int launch_pipeline_w(sb_solver *h, PipeParams &Q, dim3 blk, long long to
     if (per_sm < 1) return fail("pipelined kernel does not fit on an SM");
     const long long ctas = std::min<long long>(total, (long long)per_sm * h->n_sm);
     void *args[] = {&Q};
-    CU(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)ctas), blk, args, 0, h->stream));
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)ctas), blk, args, 0, h->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        fail("pipelined kernel: cooperative launch refused (%s)", cudaGetErrorString(e));
+        return 2;
+    }
+    CU(e);
     return 0;
 }
 
@@ -988,7 +1009,7 @@ static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, flo
                            : (uni ? launch_pipeline_t<1, false, true>(h, Q, blk, total, w) : launch_pipeline_t<1, false, false>(h, Q, blk, total, w));
     else         rc = geom ? (uni ? launch_pipeline_t<2, true, true>(h, Q, blk, total, w) : launch_pipeline_t<2, true, false>(h, Q, blk, total, w))
                            : (uni ? launch_pipeline_t<2, false, true>(h, Q, blk, total, w) : launch_pipeline_t<2, false, false>(h, Q, blk, total, w));
-    if (rc) return 1;
+    if (rc) { if (h->opt_profile) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); } return rc; }
     if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, n_steps}); }
     h->kernels_launched++;
     h->steps_done += n_steps;
@@ -1009,20 +1030,26 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     if (n_steps > 0 && (h->opt_kernel == SB_KERNEL_RESIDENT ||
                         (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps))) {
         ResParams R; const char *why_not = nullptr;
-        if (resident_plan(h, R, &why_not)) return launch_resident(h, R, n_steps, src_dev, rec_dev);
-        if (h->opt_kernel == SB_KERNEL_RESIDENT) return fail("resident kernel not applicable: %s", why_not);
+        if (resident_plan(h, R, &why_not)) {
+            const int rc = launch_resident(h, R, n_steps, src_dev, rec_dev);
+            if (rc != 2 || h->opt_kernel == SB_KERNEL_RESIDENT) return rc ? 1 : 0;
+            h->coop_ok = false;              // not all boxes fit at once here: use the step-by-step path from now on
+        } else if (h->opt_kernel == SB_KERNEL_RESIDENT) return fail("resident kernel not applicable: %s", why_not);
     }
     if (h->opt_rj == 0 && n_steps > 0) {
         const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
         if (variant != SB_KERNEL_NAIVE && autotune(h)) return 1;
     }
     if (n_steps > 0 && (h->opt_kernel == SB_KERNEL_PIPELINE ||
-                        (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps && !h->opt_profile_k1_only &&
+                        (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps &&
                          (long long)h->d.nx * h->d.ny * h->d.nz >= h->opt_pipe_min_cells &&
                          (long long)h->d.nx * h->d.ny * h->d.nz <= h->opt_pipe_max_cells))) {
         const char *why_not = pipeline_why_not(h);
-        if (!why_not) return launch_pipeline(h, n_steps, src_dev, rec_dev);
-        if (h->opt_kernel == SB_KERNEL_PIPELINE) return fail("pipelined kernel not applicable: %s", why_not);
+        if (!why_not) {
+            const int rc = launch_pipeline(h, n_steps, src_dev, rec_dev);
+            if (rc != 2 || h->opt_kernel == SB_KERNEL_PIPELINE) return rc ? 1 : 0;
+            h->coop_ok = false;
+        } else if (h->opt_kernel == SB_KERNEL_PIPELINE) return fail("pipelined kernel not applicable: %s", why_not);
     }
     CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
     const bool want_graph = h->opt_graph == 1 ||
