@@ -118,8 +118,7 @@ struct sb_solver {
     // step-pipelined kernel (K6, sb_pipeline.cuh)
     DBuf<int> d_pipe_ctr;                  // [0] ticket, [1 ..] chunk counters
     long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 24LL << 20;   // where pipelining the steps was measured to pay
-    int opt_lanes_k = 32;                  // lanes of a warp side by side along k: 8 / 16 / 32, or 0 = best fit for nz
-                                           // (measured within +-5 % of each other; 32 is the proven default)
+    int opt_plane_map = 0;                 // how K1 deals the (j, k) plane to warps: 0 = auto, 1 = strips, 2 = flat
 };
 
 static void drop_graphs(sb_solver *h)
@@ -135,7 +134,7 @@ extern "C" int sb_abi_version(void) { return SB_ABI_VERSION; }
 extern "C" int sb_choose_pitch(int32_t nz, int32_t *pitch_out)
 {
     if (nz <= 0 || !pitch_out) return fail("bad nz");
-    *pitch_out = (nz + 31) / 32 * 32;          // rows start on 128-byte lines
+    *pitch_out = (nz + 7) / 8 * 8;             // rows start on 32-byte sectors; float4 access is always aligned
     return 0;
 }
 
@@ -600,57 +599,52 @@ static PeerLink peer_link(sb_solver *h, const StepParams &P)
     return L;
 }
 
-// ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE, W> ---------------------------
-// (strips narrower than a warp, W < 32, exist for the plain variant only: PEER / FUSE launches use W = 32)
+// ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE, FLAT> ------------------------
+// (the flat plane mapping exists for single-slab launches only: PEER launches always use strips)
 template <int RJ, bool GEOM, bool UNI>
-static void launch_march3(bool peer, bool fuse, int w, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+static void launch_march3(bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
     if (peer)      { if (fuse) k1_step_march<RJ, GEOM, UNI, true, true><<<grd, blk, 0, st>>>(P);
                      else      k1_step_march<RJ, GEOM, UNI, true, false><<<grd, blk, 0, st>>>(P); }
-    else if (fuse) k1_step_march<RJ, GEOM, UNI, false, true><<<grd, blk, 0, st>>>(P);
-    else if (w == 8)  k1_step_march<RJ, GEOM, UNI, false, false, 8><<<grd, blk, 0, st>>>(P);
-    else if (w == 16) k1_step_march<RJ, GEOM, UNI, false, false, 16><<<grd, blk, 0, st>>>(P);
-    else              k1_step_march<RJ, GEOM, UNI, false, false, 32><<<grd, blk, 0, st>>>(P);
+    else if (fuse) { if (flat) k1_step_march<RJ, GEOM, UNI, false, true, true><<<grd, blk, 0, st>>>(P);
+                     else      k1_step_march<RJ, GEOM, UNI, false, true, false><<<grd, blk, 0, st>>>(P); }
+    else           { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true><<<grd, blk, 0, st>>>(P);
+                     else      k1_step_march<RJ, GEOM, UNI, false, false, false><<<grd, blk, 0, st>>>(P); }
 }
-static void launch_march(int rj, bool peer, bool fuse, int w, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+static void launch_march(int rj, bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
     const bool geom = P.mask != nullptr, uni = P.icx == nullptr;
-    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, w, P, grd, blk, st); }
-                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, w, P, grd, blk, st); } }
-    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, w, P, grd, blk, st); }
-                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, w, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, w, P, grd, blk, st); } }
+    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, flat, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, flat, P, grd, blk, st); } }
+    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, flat, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, flat, P, grd, blk, st); } }
 }
 
 // launch shape of the marching kernel: rows per thread, warps along j / k, planes per chunk, tiles along k / j
-static int march_shape(sb_solver *h, bool narrow_ok, int &rj, int &wj, int &wk, int &chunk, int &gx, int &gy, int &w)
+static int march_shape(sb_solver *h, bool flat_ok, int &rj, int &wj, int &wk, int &chunk, int &gx, int &gy, bool &flat)
 {
     const sb_grid_desc &d = h->d;
-    // lanes side by side along k: the width that leaves the fewest lanes hanging over the end of a row
-    w = 32;
-    if (narrow_ok && h->opt_lanes_k != 32) {
-        if (h->opt_lanes_k) w = h->opt_lanes_k;
-        else {
-            long long best = -1;
-            for (int cand : {32, 16, 8}) {
-                const long long padded = (long long)((d.nz + 4 * cand - 1) / (4 * cand)) * 4 * cand;
-                if (best < 0 || padded < best) { best = padded; w = cand; }
-            }
-        }
-    }
-    const int sub = 32 / w;                 // row groups per warp
+    // plane mapping: strips of 128 cells per warp unless too many of their lanes would hang over the end of a row
+    const double strip_fill = (double)d.nz / ((double)((d.nz + 127) / 128) * 128.0);
+    flat = flat_ok && (h->opt_plane_map == 2 || (h->opt_plane_map == 0 && strip_fill < 0.95));
     rj = h->opt_rj; wk = h->opt_wk;
     wj = h->opt_wj; int chunk_opt = h->opt_chunk_i;
     if (rj == 0) {                          // auto: the configuration measured by autotune() for this variant
         rj = h->tuned[0]; wj = h->tuned[1]; wk = h->tuned[2]; chunk_opt = h->tuned[3];
     }
     if (rj != 1 && rj != 2) return fail("rows_per_thread must be 1 or 2");
+    const long long groups = (long long)((d.ny + rj - 1) / rj) * (d.pitch / 4);      // flat mode: float4 groups of a plane
     if (wj <= 0) {                          // auto: 8 warps per block unless the grid would be too small
         wj = std::max(1, 8 / wk);
-        while (wj > 1 && (long long)((d.nz + 4 * w * wk - 1) / (4 * w * wk)) * ((d.ny + rj * wj * sub - 1) / (rj * wj * sub)) *
-                             ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
+        auto tiles = [&](int wj_) {
+            return flat ? (groups + 32LL * wj_ * wk - 1) / (32LL * wj_ * wk)
+                        : (long long)((d.nz + 128 * wk - 1) / (128 * wk)) * ((d.ny + rj * wj_ - 1) / (rj * wj_));
+        };
+        while (wj > 1 && tiles(wj) * ((d.nx + 7) / 8) < 148LL * 6) wj >>= 1;
     }
     if (wj * wk * 32 > 256 || wj < 1 || wk < 1) return fail("warps_j*warps_k must be <= 8");
-    gx = (d.nz + 4 * w * wk - 1) / (4 * w * wk); gy = (d.ny + rj * wj * sub - 1) / (rj * wj * sub);
+    if (flat) { gx = (int)((groups + 32LL * wj * wk - 1) / (32LL * wj * wk)); gy = 1; }
+    else      { gx = (d.nz + 128 * wk - 1) / (128 * wk); gy = (d.ny + rj * wj - 1) / (rj * wj); }
     chunk = chunk_opt;
     if (chunk <= 0) {                       // enough blocks for ~8 waves of 148 SMs, chunks of 8..64 planes
         const long long want = 148LL * 8;
@@ -677,14 +671,14 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         h->kernels_launched++;
         return 0;
     }
-    int rj, wj, wk, chunk, gx, gy, w;
-    if (march_shape(h, !h->have_peers && !fuse, rj, wj, wk, chunk, gx, gy, w)) return 1;
+    int rj, wj, wk, chunk, gx, gy; bool flat;
+    if (march_shape(h, !h->have_peers, rj, wj, wk, chunk, gx, gy, flat)) return 1;
     const dim3 blk(32 * wk, wj);
     if (!h->have_peers) {
         P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
         const dim3 grd(gx, gy, (d.nx + chunk - 1) / chunk);
         if (grd.z > 65535) return fail("too many i-chunks");
-        launch_march(rj, false, fuse, w, P, grd, blk, h->stream);
+        launch_march(rj, false, fuse, flat, P, grd, blk, h->stream);
         h->kernels_launched++;
         return 0;
     }
@@ -696,13 +690,13 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         Q.peer_lo_p = Q.peer_hi_p = nullptr; Q.flag_lo = Q.flag_hi = nullptr;
         Q.i_begin = cb; Q.i_end = d.nx - cb; Q.chunk_i = chunk;
         const dim3 grd(gx, gy, (Q.i_end - Q.i_begin + chunk - 1) / chunk);
-        launch_march(rj, false, false, 32, Q, grd, blk, h->stream);
+        launch_march(rj, false, false, false, Q, grd, blk, h->stream);
         P.two_range = 1; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = cb;
-        launch_march(rj, true, false, 32, P, dim3(gx, gy, 2), blk, h->stream);
+        launch_march(rj, true, false, false, P, dim3(gx, gy, 2), blk, h->stream);
         h->kernels_launched += 2;
     } else {                                // thin slab: everything through the PEER variant
         P.two_range = 0; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-        launch_march(rj, true, false, 32, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
+        launch_march(rj, true, false, false, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
         h->kernels_launched++;
     }
     return 0;
@@ -728,14 +722,14 @@ static int autotune(sb_solver *h)
     for (int c = 0; c < (int)(sizeof cand / sizeof cand[0]); c++) {
         h->opt_rj = cand[c][0]; h->opt_wj = cand[c][1]; h->opt_wk = cand[c][2]; h->opt_chunk_i = cand[c][3];
         float t_min = 1e30f;
-        for (int rep = 0; rep < 4; rep++) {
+        for (int rep = 0; rep < 7; rep++) {                  // two warm-up launches, then the best of five
             StepParams P; fill_params(h, P);
             cudaEventRecord(e0, h->stream);
             if (launch_step_kernel(h, P, false)) { h->have_peers = save_peers; return 1; }
             cudaEventRecord(e1, h->stream);
             cudaEventSynchronize(e1);
             float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
-            if (rep) t_min = std::min(t_min, ms);
+            if (rep >= 2) t_min = std::min(t_min, ms);
         }
         if (t_min < best) { best = t_min; best_c = c; }
     }
@@ -952,10 +946,10 @@ static const char *pipeline_why_not(const sb_solver *h)
     return nullptr;
 }
 
-template <int RJ, bool GEOM, bool UNI, int W>
+template <int RJ, bool GEOM, bool UNI, bool FLAT>
 static int launch_pipeline_w(sb_solver *h, PipeParams &Q, dim3 blk, long long total)
 {
-    auto kern = k6_pipeline<RJ, GEOM, UNI, W>;
+    auto kern = k6_pipeline<RJ, GEOM, UNI, FLAT>;
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)(blk.x * blk.y), 0));
     if (per_sm < 1) return fail("pipelined kernel does not fit on an SM");
@@ -972,18 +966,23 @@ static int launch_pipeline_w(sb_solver *h, PipeParams &Q, dim3 blk, long long to
 }
 
 template <int RJ, bool GEOM, bool UNI>
-static int launch_pipeline_t(sb_solver *h, PipeParams &Q, dim3 blk, long long total, int w)
+static int launch_pipeline_t(sb_solver *h, PipeParams &Q, dim3 blk, long long total, bool flat)
 {
-    if (w == 8) return launch_pipeline_w<RJ, GEOM, UNI, 8>(h, Q, blk, total);
-    if (w == 16) return launch_pipeline_w<RJ, GEOM, UNI, 16>(h, Q, blk, total);
-    return launch_pipeline_w<RJ, GEOM, UNI, 32>(h, Q, blk, total);
+    return flat ? launch_pipeline_w<RJ, GEOM, UNI, true>(h, Q, blk, total) : launch_pipeline_w<RJ, GEOM, UNI, false>(h, Q, blk, total);
 }
 
 static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, float *rec_dev)
 {
     const sb_grid_desc &d = h->d;
-    int rj, wj, wk, chunk, gx, gy, w;
-    if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, w)) return 1;
+    // Launch shape: unless the caller fixed one, the shape that pipelines best, not the one autotune() found for
+    // step-by-step launches -- short tiles (1 row per thread, 4 warps, 64 registers: 8 CTAs per SM) of 8 planes,
+    // 16 on larger grids (measured: 200^3 50.7 us/step with 8 planes vs 53.1 with 16; 256^3 87.3 vs 83.5).
+    const int save[4] = {h->opt_rj, h->opt_wj, h->opt_wk, h->opt_chunk_i};
+    if (h->opt_rj == 0) { h->opt_rj = 1; h->opt_wj = 4; h->opt_wk = 1; if (!h->opt_chunk_i) h->opt_chunk_i = d.nx < 240 ? 8 : 16; }
+    int rj, wj, wk, chunk, gx, gy; bool w;
+    const int shape_rc = march_shape(h, true, rj, wj, wk, chunk, gx, gy, w);
+    h->opt_rj = save[0]; h->opt_wj = save[1]; h->opt_wk = save[2]; h->opt_chunk_i = save[3];
+    if (shape_rc) return 1;
     PipeParams Q{};
     fill_params(h, Q.S);
     Q.S.i_begin = 0; Q.S.i_end = d.nx; Q.S.chunk_i = chunk;
@@ -1191,8 +1190,8 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
         case SB_OPT_USE_GRAPH: h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); break;
         case SB_OPT_PROFILE: h->opt_profile = value ? 1 : 0; break;
         case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value < 0 ? 0 : std::min(value, 2); break;
-        case SB_OPT_LANES_K: if (value != 0 && value != 8 && value != 16 && value != 32) return fail("lanes_k must be 0 (auto), 8, 16 or 32");
-                             h->opt_lanes_k = value; break;
+        case SB_OPT_PLANE_MAP: if (value < 0 || value > 2) return fail("plane_map must be 0 (auto), 1 (strips) or 2 (flat)");
+                               h->opt_plane_map = value; break;
         case SB_OPT_RESIDENT_SPLIT: h->opt_res_split = value ? 1 : 0; break;
         case SB_OPT_RESIDENT_MIN_STEPS: h->opt_res_min_steps = std::max(1, value); break;
         default: return fail("unknown option %d", option);

@@ -185,24 +185,40 @@ constexpr unsigned ALL_OPEN = 0x0F0F0F0Fu;      // four cells: air, all three fa
 // for a tile of any step; F names the input and output sets of that step.
 struct FieldSet { const float *p_in, *vx_in, *vy_in, *vz_in; float *p_out, *vx_out, *vy_out, *vz_out; };
 
-// W = lanes of a warp that lie side by side along k (32, 16 or 8): the warp covers 32/W groups of RJ rows by 4W
-// cells.  K1 is latency-bound per warp iteration, so a warp whose lanes hang over the end of the row costs as much
-// as a full one; with W chosen per grid (nz = 200: 7 strips of 32 cells instead of 2 of 128) fewer lanes idle.
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, int W = 32>
+// FLAT = how the (j, k) plane is dealt to the warps.  Strip mode (false): a warp owns 128 consecutive cells of one
+// row group; rows whose length is not a multiple of 128 leave lanes idle (nz = 200: 28 of 64), and K1 is latency-bound
+// per warp iteration, so an under-filled warp costs as much as a full one.  Flat mode (true): the float4 groups of
+// the whole plane -- (row group, k) in memory order -- are dealt to the lanes consecutively, so a warp may hold the end
+// of one row group and the start of the next; the only idle lanes are the row padding.  A lane's k-neighbours are
+// still its neighbouring lanes wherever a neighbour exists (nothing crosses a row end), so the shuffles stay valid.
+// Strip mode keeps whole blocks adjacent in j (halo rows hit in L1) and is used for long rows and on slabs.
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
 __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, int bx, int by, int bz)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int kl = lane & (W - 1), sub = lane / W;             // position along k inside the strip, row group inside the warp
-    const int warp_k = threadIdx.x >> 5;                       // blockDim.x = 32 * WK
-    const int strip_k0 = (bx * (blockDim.x >> 5) + warp_k) * (4 * W);
-    const int k0 = strip_k0 + kl * 4;
-    const int jw = (by * blockDim.y + threadIdx.y) * (32 / W) * RJ;   // first row of the warp
-    const int j0 = jw + sub * RJ;
+    int k0, j0;
+    bool warp_out;                                             // the whole warp lies outside the plane
+    if (FLAT) {
+        const int P4 = P.pitch >> 2, warps_x = blockDim.x >> 5;
+        const long long g0 = ((long long)bx * (warps_x * blockDim.y) + threadIdx.y * warps_x + (threadIdx.x >> 5)) * 32;
+        const long long groups = (long long)((P.ny + RJ - 1) / RJ) * P4;
+        warp_out = g0 >= groups;
+        const long long g = g0 + lane;
+        const int q = (int)(g / P4);
+        k0 = 4 * (int)(g - (long long)q * P4);
+        j0 = q * RJ;                                           // lanes past the last row group have j0 >= ny: predicated off
+    } else {
+        const int warp_k = threadIdx.x >> 5;                   // blockDim.x = 32 * WK
+        const int strip_k0 = (bx * (blockDim.x >> 5) + warp_k) * 128;
+        k0 = strip_k0 + lane * 4;
+        j0 = (by * blockDim.y + threadIdx.y) * RJ;
+        warp_out = strip_k0 >= P.nz || j0 >= P.ny;
+    }
     int ib = P.i_begin + bz * P.chunk_i;
     if (PEER && P.two_range) ib = bz ? P.nx - P.chunk_i : 0;
     const int ie = min(ib + P.chunk_i, P.i_end);
-    if (strip_k0 >= P.nz || jw >= P.ny || ib >= ie) return;     // warp-uniform exit (rows past ny are predicated off)
+    if (warp_out || ib >= ie) return;                           // warp-uniform exit
     if (PEER) {
         if (P.flag_lo && ib == 0) wait_neighbour(P.flag_lo, *P.step_global, P.err_flag);
         if (P.flag_hi && ie == P.nx) wait_neighbour(P.flag_hi, *P.step_global, P.err_flag);
@@ -223,8 +239,8 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     // per-element validity and "z face is updated" flags
     const bool e0 = k0 < nz, e1 = k0 + 1 < nz, e2 = k0 + 2 < nz, e3 = k0 + 3 < nz;
     const bool u0 = k0 < nz - 1, u1 = k0 + 1 < nz - 1, u2 = k0 + 2 < nz - 1, u3 = k0 + 3 < nz - 1;
-    const bool edge_hi = (kl == W - 1) && (k0 + 4 < nz);       // needs p[k0+4] from the next strip
-    const bool edge_lo = (kl == 0) && (k0 > 0);                // needs the z face k0-1 of the previous strip
+    const bool edge_hi = (lane == 31) && (k0 + 4 < nz);        // needs p[k0+4] from the next warp's cells
+    const bool edge_lo = (lane == 0) && (k0 > 0);              // needs the z face k0-1 of the previous warp's cells
     const float4 z4 = f4(0.0f);
 
     // k tables (hoisted)
@@ -341,7 +357,7 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
             }
             // z faces: p[k+1] from the next lane (or the next strip)
             float p_next = __shfl_down_sync(FULL, p.x, 1);
-            if (kl == W - 1) p_next = p_hi[r];
+            if (lane == 31) p_next = p_hi[r];
             const float4 pk1 = make_float4(p.y, p.z, p.w, p_next);
             float4 vzn = vz[r];
             {
@@ -355,7 +371,7 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
             }
             // z face k0-1: previous lane's .w, or recomputed from the previous strip's values
             float vz_prev = __shfl_up_sync(FULL, vzn.w, 1);
-            if (kl == 0) {
+            if (lane == 0 || (FLAT && k0 == 0)) {                // first lane of the warp, or (flat) first cells of a row
                 vz_prev = 0.0f;
                 if (edge_lo) {
                     vz_prev = vz_lo[r] + cvz_lo * (p.x - p_lo[r]);
@@ -410,11 +426,11 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     }
 }
 
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, int W = 32>
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
 __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
 {
     const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
-    k1_tile<RJ, GEOM, UNI, PEER, FUSE, W>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+    k1_tile<RJ, GEOM, UNI, PEER, FUSE, FLAT>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ __device__ __forceinline__ int ld_acquire_gpu_s32(const int *p)
     return v;
 }
 
-template <int RJ, bool GEOM, bool UNI, int W>
+template <int RJ, bool GEOM, bool UNI, bool FLAT>
 __global__ void __launch_bounds__(256, (RJ == 1 && UNI) ? 4 : 2) k6_pipeline(const __grid_constant__ PipeParams Q)
 {
     __shared__ int s_ticket;
@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256, (RJ == 1 && UNI) ? 4 : 2) k6_pipeline(con
     const bool lead = threadIdx.x == 0 && threadIdx.y == 0;
     const int tiles_chunk = Q.gx * Q.gy;
     const long long tiles_step = (long long)tiles_chunk * Q.nchunks, total = tiles_step * Q.n_steps;
-    const int rows_tile = RJ * blockDim.y * (32 / W), cols_tile = 4 * W * (blockDim.x >> 5);   // cells of a tile along j and k
+    const int rows_tile = RJ * blockDim.y, cols_tile = 4 * blockDim.x;          // strip mode: cells of a tile along j and k
+    const int P4 = P.pitch >> 2, groups_tile = (int)(blockDim.x * blockDim.y);   // flat mode: float4 groups of a tile
     bool dead = false;
     for (;;) {
         __syncthreads();                                                         // the previous ticket has been read
@@ -78,15 +79,20 @@ __global__ void __launch_bounds__(256, (RJ == 1 && UNI) ? 4 : 2) k6_pipeline(con
         if (t & 1) F = FieldSet{P.p_out, P.vx_out, P.vy_out, P.vz_out, const_cast<float *>(P.p_in), const_cast<float *>(P.vx_in),
                                 const_cast<float *>(P.vy_in), const_cast<float *>(P.vz_in)};
         else       F = FieldSet{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
-        k1_tile<RJ, GEOM, UNI, false, false, W>(P, F, bx, by, c);
+        k1_tile<RJ, GEOM, UNI, false, false, FLAT>(P, F, bx, by, c);
         __syncthreads();                                                         // the tile's stores are visible to the block
         if (threadIdx.y == 0 && threadIdx.x < 32) {                              // sources, then probes, of the cells this tile owns
             const int i0 = c * P.chunk_i, i1 = min(i0 + P.chunk_i, P.nx);
             const int j0 = by * rows_tile, j1 = j0 + rows_tile, k0 = bx * cols_tile, k1 = k0 + cols_tile;
+            auto owns = [&](int i, int j, int k) -> bool {
+                if (i < i0 || i >= i1) return false;
+                if (FLAT) return ((long long)(j / RJ) * P4 + (k >> 2)) / groups_tile == bx;
+                return j >= j0 && j < j1 && k >= k0 && k < k1;
+            };
             if (threadIdx.x == 0)
                 for (int q = 0; q < P.n_inline; q++) {                           // float64 add, fp32 store, list order
                     const int i = P.inl_i[q], j = P.inl_j[q], k = P.inl_k[q];
-                    if (i >= i0 && i < i1 && j >= j0 && j < j1 && k >= k0 && k < k1) {
+                    if (owns(i, j, k)) {
                         float *cell = F.p_out + (long long)i * P.plane + (long long)j * P.pitch + k;
                         *cell = (float)((double)*cell + __dmul_rn(Q.src_vals[(long long)t * Q.n_sources + P.inl_src[q]], P.inl_weight[q]));
                     }
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(256, (RJ == 1 && UNI) ? 4 : 2) k6_pipeline(con
             __syncwarp();
             for (int q = threadIdx.x; q < Q.n_probes; q += 32) {
                 const int i = Q.probe_ijk[3 * q], j = Q.probe_ijk[3 * q + 1], k = Q.probe_ijk[3 * q + 2];
-                if (i >= i0 && i < i1 && j >= j0 && j < j1 && k >= k0 && k < k1)
+                if (owns(i, j, k))
                     Q.rec[(long long)t * Q.n_rec + q] = F.p_out[(long long)i * P.plane + (long long)j * P.pitch + k];
             }
             __syncwarp();

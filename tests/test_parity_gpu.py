@@ -22,10 +22,11 @@ VARIANTS = {
                               _lib.OPT_WARPS_J: 2, _lib.OPT_FUSE_K3: 2},
     "march_r2_graph": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_USE_GRAPH: 1},
     "march_r2_separate_k3": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_FUSE_K3: 0},
-    "march_r1_lanes8": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_LANES_K: 8, _lib.OPT_FUSE_K3: 0,
-                        _lib.OPT_CHUNK_I: 7},
-    "march_r2_lanes16": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_LANES_K: 16, _lib.OPT_FUSE_K3: 0,
-                         _lib.OPT_WARPS_J: 2},
+    "march_r1_flat": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_PLANE_MAP: 2, _lib.OPT_FUSE_K3: 0,
+                      _lib.OPT_CHUNK_I: 7},
+    "march_r2_flat_fused": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_PLANE_MAP: 2, _lib.OPT_FUSE_K3: 2,
+                            _lib.OPT_WARPS_J: 2},
+    "march_r2_strips": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_PLANE_MAP: 1, _lib.OPT_FUSE_K3: 0},
     "march_r1_nograph_wk2": {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_USE_GRAPH: 0,
                              _lib.OPT_WARPS_K: 2, _lib.OPT_WARPS_J: 2},
 }
@@ -334,9 +335,9 @@ def test_resident_refuses_what_it_cannot_do_and_auto_falls_back_to_k1():
 
 # ---------------------------------------------------------------------------------------------------------
 # K6: the marching kernel pipelined across steps in one persistent launch (csrc/sb_pipeline.cuh)
-@pytest.mark.parametrize("shape_opts", [{}, {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_CHUNK_I: 3, _lib.OPT_WARPS_J: 2, _lib.OPT_LANES_K: 16},
-                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 1, _lib.OPT_WARPS_J: 1, _lib.OPT_LANES_K: 32},
-                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 5, _lib.OPT_LANES_K: 8}])
+@pytest.mark.parametrize("shape_opts", [{}, {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_CHUNK_I: 3, _lib.OPT_WARPS_J: 2, _lib.OPT_PLANE_MAP: 2},
+                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 1, _lib.OPT_WARPS_J: 1, _lib.OPT_PLANE_MAP: 1},
+                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 5, _lib.OPT_PLANE_MAP: 2}])
 @pytest.mark.parametrize("name", sorted(_resident_cases()))
 def test_pipelined_kernel_matches_oracle(name, shape_opts):
     case = _resident_cases()[name]

@@ -57,7 +57,9 @@ def _pad(a, n, fill, lead=0):
 def run_emulated(emu, case, n_steps, chunk=37, nbi=0, nbj=0, n_sm=148, smem_limit=227 * 1024, split=1):
     s = build_b200_solver(case)
     nx, ny, nz = s.shape
-    pitch = (nz + 31) // 32 * 32
+    pitch = C.c_int32(0)
+    _lib.check(_lib.load().sb_choose_pitch(nz, C.byref(pitch)))           # the library's row pitch
+    pitch = pitch.value
     faces, cells, cp = s._coefficient_tables()
     cvx, cvy, cvz = _pad(faces[0], nx + 2, 0.0, 1), _pad(faces[1], ny + 4, 0.0), _pad(faces[2], pitch + 4, 0.0)
     nu = cells[0] is not None
