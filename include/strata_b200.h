@@ -79,8 +79,8 @@ enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, SB_KERNEL_T
  * plane boundaries) and the chunk has at least SB_OPT_RESIDENT_MIN_STEPS steps; results are bit-identical.      */
 /* SB_KERNEL_PIPELINE: the marching kernel's tiles of ALL steps of a chunk run from one persistent cooperative launch;
  * a tile starts as soon as the three chunks of planes it touches have finished the previous step (sb_pipeline.cuh), so
- * the tail of one step overlaps the head of the next.  SB_KERNEL_AUTO uses it for grids of up to 32 M cells that do not
- * fit the resident kernel (same applicability conditions); results are bit-identical.                              */
+ * the tail of one step overlaps the head of the next.  SB_KERNEL_AUTO uses it for grids of 6 M to 40 M cells, where it was
+ * measured to pay (same applicability conditions as the resident kernel); results are bit-identical.                              */
 enum { SB_FIELD_P = 0, SB_FIELD_VX = 1, SB_FIELD_VY = 2, SB_FIELD_VZ = 3 };
 enum { SB_OPT_KERNEL = 0, SB_OPT_ROWS_PER_THREAD = 1, SB_OPT_WARPS_J = 2, SB_OPT_WARPS_K = 3,
        SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5, SB_OPT_PROFILE = 6, SB_OPT_FUSE_K3 = 7,

@@ -117,7 +117,7 @@ struct sb_solver {
     int res_nbi = 0, res_nbj = 0;
     // step-pipelined kernel (K6, sb_pipeline.cuh)
     DBuf<int> d_pipe_ctr;                  // [0] ticket, [1 ..] chunk counters
-    long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 24LL << 20;   // where pipelining the steps was measured to pay
+    long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 40LL << 20;   // where pipelining the steps was measured to pay
     int opt_plane_map = 0;                 // how K1 deals the (j, k) plane to warps: 0 = auto, 1 = strips, 2 = flat
 };
 
@@ -1035,10 +1035,6 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
             h->coop_ok = false;              // not all boxes fit at once here: use the step-by-step path from now on
         } else if (h->opt_kernel == SB_KERNEL_RESIDENT) return fail("resident kernel not applicable: %s", why_not);
     }
-    if (h->opt_rj == 0 && n_steps > 0) {
-        const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
-        if (variant != SB_KERNEL_NAIVE && autotune(h)) return 1;
-    }
     if (n_steps > 0 && (h->opt_kernel == SB_KERNEL_PIPELINE ||
                         (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps &&
                          (long long)h->d.nx * h->d.ny * h->d.nz >= h->opt_pipe_min_cells &&
@@ -1049,6 +1045,10 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
             if (rc != 2 || h->opt_kernel == SB_KERNEL_PIPELINE) return rc ? 1 : 0;
             h->coop_ok = false;
         } else if (h->opt_kernel == SB_KERNEL_PIPELINE) return fail("pipelined kernel not applicable: %s", why_not);
+    }
+    if (h->opt_rj == 0 && n_steps > 0) {
+        const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
+        if (variant != SB_KERNEL_NAIVE && autotune(h)) return 1;
     }
     CU(cudaMemsetAsync(h->d_step_ctr.p, 0, sizeof(int), h->stream));
     const bool want_graph = h->opt_graph == 1 ||

@@ -18,10 +18,8 @@ def main():
     out = []
     sizes = [int(a) for a in sys.argv[1:]] or [100, 128, 160, 200, 256, 300, 320, 400]
     for n in sizes:
-        for label, opts in (("march_graph_strips", {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_USE_GRAPH: 1, _lib.OPT_PLANE_MAP: 1}),
-                            ("march_graph_flat", {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_USE_GRAPH: 1, _lib.OPT_PLANE_MAP: 2}),
-                            ("pipeline_strips", {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE, _lib.OPT_PLANE_MAP: 1}),
-                            ("pipeline_flat", {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE, _lib.OPT_PLANE_MAP: 2}),
+        for label, opts in (("march_graph", {_lib.OPT_KERNEL: _lib.KERNEL_MARCH, _lib.OPT_USE_GRAPH: 1}),
+                            ("pipeline", {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE}),
                             ("auto", {})):
             s = build_b200_solver(c2_case(n, steps=0))
             for k, v in opts.items():
