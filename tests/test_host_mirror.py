@@ -34,7 +34,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     pitch = ctypes.c_int32(0)
     assert lib.sb_choose_pitch(100, ctypes.byref(pitch)) == 0 and pitch.value == 104
     d = _lib.GridDesc(nx=10, ny=7, nz=100, pitch=0, global_nx=10, i_offset=0, has_lower=0, has_upper=0)
-    assert lib.sb_field_elems(ctypes.byref(d)) == 12 * 7 * 128
+    assert lib.sb_field_elems(ctypes.byref(d)) == 12 * 7 * 104
 
 
 def test_create_without_gpu_fails_loudly():
