@@ -181,7 +181,7 @@ def run_b200_arm(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     case, label = workload_case(a.workload, world)
     cells_total = int(np.prod(case["shape"], dtype=np.int64))
-    K, W = a.steps, max(3, a.warmup)
+    K, W = a.steps, max(4, a.warmup)        # >= 4 so that the warm-up runs the same (chunk) kernels as the timed region
 
     if world == 1:
         s = build_b200_solver(case, device=local_rank, chunk_steps=max(K, W))
@@ -295,8 +295,10 @@ def run_b200_arm(a):
                 "config": {"workload": label, "cells_per_gpu": cells_rank, "l2_policy": "fields (34 GB/GPU) >> L2, no flush needed"
                            if a.workload == "c5_weak" else "inputs larger than L2 for >=200^3; small grids are L2-resident by nature",
                            "kernel": {0: "auto", 1: "naive", 2: "march", 3: "tma", 4: "resident", 5: "pipeline"}[st1["kernel_variant"]],
-                           "launch_shape": {"rows_per_thread": shape4[0], "warps_j": shape4[1], "warps_k": shape4[2],
-                                            "chunk_planes": shape4[3], "source": "library autotune" if a.rows is None else "flag"},
+                           "launch_shape": ({"source": "chunk kernel: shape fixed by the library (DESIGN.md 4a / 4b)"}
+                                            if st1["kernel_variant"] in (4, 5) else
+                                            {"rows_per_thread": shape4[0], "warps_j": shape4[1], "warps_k": shape4[2],
+                                             "chunk_planes": shape4[3], "source": "library autotune" if a.rows is None else "flag"}),
                            "parallelism": f"slab{world}" if world > 1 else "single",
                            "halo": (drv.halo if drv is not None else None)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
