@@ -600,12 +600,12 @@ static PeerLink peer_link(sb_solver *h, const StepParams &P)
 }
 
 // ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE, FLAT> ------------------------
-// (the flat plane mapping exists for single-slab launches only: PEER launches always use strips)
+// (PEER launches never inject inline: a slab's step always ends with K3, which also publishes the step flag)
 template <int RJ, bool GEOM, bool UNI>
 static void launch_march3(bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
-    if (peer)      { if (fuse) k1_step_march<RJ, GEOM, UNI, true, true><<<grd, blk, 0, st>>>(P);
-                     else      k1_step_march<RJ, GEOM, UNI, true, false><<<grd, blk, 0, st>>>(P); }
+    if (peer)      { if (flat) k1_step_march<RJ, GEOM, UNI, true, false, true><<<grd, blk, 0, st>>>(P);
+                     else      k1_step_march<RJ, GEOM, UNI, true, false, false><<<grd, blk, 0, st>>>(P); }
     else if (fuse) { if (flat) k1_step_march<RJ, GEOM, UNI, false, true, true><<<grd, blk, 0, st>>>(P);
                      else      k1_step_march<RJ, GEOM, UNI, false, true, false><<<grd, blk, 0, st>>>(P); }
     else           { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true><<<grd, blk, 0, st>>>(P);
@@ -672,7 +672,7 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         return 0;
     }
     int rj, wj, wk, chunk, gx, gy; bool flat;
-    if (march_shape(h, !h->have_peers, rj, wj, wk, chunk, gx, gy, flat)) return 1;
+    if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
     const dim3 blk(32 * wk, wj);
     if (!h->have_peers) {
         P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
@@ -690,13 +690,13 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         Q.peer_lo_p = Q.peer_hi_p = nullptr; Q.flag_lo = Q.flag_hi = nullptr;
         Q.i_begin = cb; Q.i_end = d.nx - cb; Q.chunk_i = chunk;
         const dim3 grd(gx, gy, (Q.i_end - Q.i_begin + chunk - 1) / chunk);
-        launch_march(rj, false, false, false, Q, grd, blk, h->stream);
+        launch_march(rj, false, false, flat, Q, grd, blk, h->stream);
         P.two_range = 1; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = cb;
-        launch_march(rj, true, false, false, P, dim3(gx, gy, 2), blk, h->stream);
+        launch_march(rj, true, false, flat, P, dim3(gx, gy, 2), blk, h->stream);
         h->kernels_launched += 2;
     } else {                                // thin slab: everything through the PEER variant
         P.two_range = 0; P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-        launch_march(rj, true, false, false, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
+        launch_march(rj, true, false, flat, P, dim3(gx, gy, (d.nx + chunk - 1) / chunk), blk, h->stream);
         h->kernels_launched++;
     }
     return 0;

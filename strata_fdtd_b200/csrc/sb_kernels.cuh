@@ -191,7 +191,7 @@ struct FieldSet { const float *p_in, *vx_in, *vy_in, *vz_in; float *p_out, *vx_o
 // the whole plane -- (row group, k) in memory order -- are dealt to the lanes consecutively, so a warp may hold the end
 // of one row group and the start of the next; the only idle lanes are the row padding.  A lane's k-neighbours are
 // still its neighbouring lanes wherever a neighbour exists (nothing crosses a row end), so the shuffles stay valid.
-// Strip mode keeps whole blocks adjacent in j (halo rows hit in L1) and is used for long rows and on slabs.
+// Strip mode keeps whole blocks adjacent in j (halo rows hit in L1) and is used for rows that fill their strips.
 template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
 __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, int bx, int by, int bz)
 {
