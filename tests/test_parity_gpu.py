@@ -114,6 +114,19 @@ def test_c2_200cubed_vs_oracle_with_geometry():
     assert_same_as_oracle(s, o, "c2")
 
 
+def test_c2_full_config_1000_steps_vs_oracle():
+    """BASELINE config 2 as worded (200^3, PML 10, 1000 steps; SURVEY 8d parity gate): final fields and the probe
+    trace after 1000 steps equal the oracle bit for bit (the stated tolerance, 1e-5 relative, is slack)."""
+    case = c2_case(200, steps=1000)
+    s = build_b200_solver(case)
+    o = O.OracleSolver(case)
+    s.run(steps=1000); o.run_steps(1000)
+    assert_same_as_oracle(s, o, "c2/1000")
+    ref = np.abs(o.probe_array("probe")).max()
+    assert ref > 0 and np.abs(s.get_probe_data("probe")["probe"] - o.probe_array("probe")).max() <= 1e-5 * ref
+    s.close()
+
+
 def test_large_grid_march_equals_naive():
     """Size-independent property at a size the oracle cannot reach quickly: the marching kernel and the
     one-thread-per-cell kernel are two independent implementations and must agree bit-for-bit."""
