@@ -1173,6 +1173,7 @@ extern "C" int sb_reset(sb_solver *h)
     }
     for (auto *po : h->plane_ops) CU(cudaMemsetAsync(po->prev.p, 0, po->prev.n * 4, h->stream));
     CU(cudaMemsetAsync(h->d_step_global.p, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream));          // a timed-out wait is not carried into the next run
     CU(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->steps_done = 0;
     return 0;
