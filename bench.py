@@ -196,6 +196,8 @@ def run_b200_arm(a):
             slab.set_kernel_option(opt, val)
     if a.graph:
         slab.set_kernel_option(_lib.OPT_USE_GRAPH, 1)
+    if a.ade_layout is not None:
+        slab.set_kernel_option(_lib.OPT_ADE_LAYOUT, a.ade_layout)
 
     def barrier():
         if dist is not None:
@@ -333,6 +335,7 @@ def main():
     ap.add_argument("--warps-k", type=int, default=None)
     ap.add_argument("--chunk-i", type=int, default=None)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--ade-layout", type=int, default=None, help="0 auto, 1 compact list, 2 dense box (ADE workloads)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -84,7 +84,7 @@ enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, SB_KERNEL_T
 enum { SB_FIELD_P = 0, SB_FIELD_VX = 1, SB_FIELD_VY = 2, SB_FIELD_VZ = 3 };
 enum { SB_OPT_KERNEL = 0, SB_OPT_ROWS_PER_THREAD = 1, SB_OPT_WARPS_J = 2, SB_OPT_WARPS_K = 3,
        SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5, SB_OPT_PROFILE = 6, SB_OPT_FUSE_K3 = 7,
-       SB_OPT_RESIDENT_SPLIT = 8, SB_OPT_RESIDENT_MIN_STEPS = 9, SB_OPT_PLANE_MAP = 10 };
+       SB_OPT_RESIDENT_SPLIT = 8, SB_OPT_RESIDENT_MIN_STEPS = 9, SB_OPT_PLANE_MAP = 10, SB_OPT_ADE_LAYOUT = 11 };
 
 const char *sb_last_error(void);
 int sb_abi_version(void);

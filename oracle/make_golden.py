@@ -112,10 +112,14 @@ def run_case(name: str, case: dict, out_dir: Path):
 def main():
     out_dir = ROOT / "tests" / "golden"
     out_dir.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])                  # optional: regenerate just the named fixtures
     for name, case in make_cases().items():
-        run_case(name, case, out_dir)
-    run_case("c1_100cubed_1000", c1_case(1000), out_dir)
-    run_membrane_case(out_dir)
+        if not only or name in only:
+            run_case(name, case, out_dir)
+    if not only or "c1_100cubed_1000" in only:
+        run_case("c1_100cubed_1000", c1_case(1000), out_dir)
+    if not only or "membranes" in only:
+        run_membrane_case(out_dir)
 
 
 def run_membrane_case(out_dir: Path):

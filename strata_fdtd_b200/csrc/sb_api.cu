@@ -80,8 +80,10 @@ struct sb_solver {
     DBuf<double> d_src_vals; DBuf<float> d_record; DBuf<int> d_step_ctr;
     // ADE
     bool have_ade = false;
+    long long ade_material_cells = 0;
     AdeTable ade{};
-    DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat; DBuf<float> ade_J, ade_Jp;
+    DBuf<long long> ade_off; DBuf<int> ade_ijk, ade_nbr; DBuf<uint8_t> ade_mat, ade_mat_box; DBuf<float> ade_J, ade_Jp;
+    int opt_ade_layout = 0;                // 0 = auto (dense when the materials fill >= 60 % of their bounding box), 1 = compact list, 2 = dense
     // options
     int opt_kernel = SB_KERNEL_AUTO, opt_rj = 0, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
     // graph cache: key = (n_steps, starting set, source-table pointer, record pointer)
@@ -187,7 +189,7 @@ extern "C" int sb_destroy(sb_solver *h)
     for (DBuf<float> *b : {&h->cvx, &h->cvy, &h->cvz, &h->icx, &h->icy, &h->icz, &h->mic_w, &h->d_record, &h->ade_J, &h->ade_Jp}) b->release();
     h->mask.release(); h->src_off.release(); h->src_start.release(); h->src_id.release(); h->src_field.release();
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
-    h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release();
+    h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release(); h->ade_mat_box.release();
     h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
     h->d_probe_ijk.release(); h->d_res_xch.release(); h->d_pipe_ctr.release();
     delete h;
@@ -505,15 +507,54 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
     auto mplane = [&](int i) { return mat + (size_t)(i - i_lo) * pl; };
     std::vector<long long> off; std::vector<int> ijk; std::vector<uint8_t> cm;
     std::vector<long long> plane_start((size_t)(i_hi - i_lo) + 1, 0);
+    int b_lo[3] = {1 << 30, 1 << 30, 1 << 30}, b_hi[3] = {-1, -1, -1};        // bounding box of the pole-carrying cells
     for (int i = i_lo; i < i_hi; i++) {
         const uint8_t *m = mplane(i);
         long long cnt = 0;
-        for (size_t q = 0; q < pl; q++) cnt += used[m[q]];
+        for (int j = 0; j < d.ny; j++) {
+            const uint8_t *row = m + (size_t)j * d.nz;
+            int k_first = -1, k_last = -1;
+            for (int k = 0; k < d.nz; k++)
+                if (used[row[k]]) { cnt++; if (k_first < 0) k_first = k; k_last = k; }
+            if (k_first >= 0) {
+                b_lo[0] = std::min(b_lo[0], i); b_hi[0] = std::max(b_hi[0], i);
+                b_lo[1] = std::min(b_lo[1], j); b_hi[1] = std::max(b_hi[1], j);
+                b_lo[2] = std::min(b_lo[2], k_first); b_hi[2] = std::max(b_hi[2], k_last);
+            }
+        }
         plane_start[i - i_lo + 1] = plane_start[i - i_lo] + cnt;
     }
     const long long n = plane_start[i_hi - i_lo];
     if (n == 0) return 0;
     if (n >= (1LL << 31)) return fail("too many material cells");
+    // Dense layout: when the materials fill most of their bounding box, index lists and slot indirections cost more
+    // than the few empty cells of the box (a thread per box cell, neighbours found geometrically).  Single slab only.
+    const long long box_cells = (long long)(b_hi[0] - b_lo[0] + 1) * (b_hi[1] - b_lo[1] + 1) * (b_hi[2] - b_lo[2] + 1);
+    const bool slab = d.has_lower || d.has_upper;
+    if (h->opt_ade_layout == 2 && slab) return fail("the dense ADE layout is not available on decomposed slabs");
+    if (!slab && box_cells < (1LL << 31) && b_hi[0] - b_lo[0] < 65535 && b_hi[1] - b_lo[1] < 65535 &&
+        (h->opt_ade_layout == 2 || (h->opt_ade_layout == 0 && (double)n >= 0.6 * (double)box_cells))) {
+        const int bx = b_hi[0] - b_lo[0] + 1, by = b_hi[1] - b_lo[1] + 1, bz = b_hi[2] - b_lo[2] + 1;
+        std::vector<uint8_t> mb((size_t)box_cells);
+        for (int ii = 0; ii < bx; ii++)
+            for (int jj = 0; jj < by; jj++) {
+                const uint8_t *row = mplane(b_lo[0] + ii) + (size_t)(b_lo[1] + jj) * d.nz + b_lo[2];
+                uint8_t *dst = mb.data() + ((size_t)ii * by + jj) * bz;
+                for (int kk = 0; kk < bz; kk++) dst[kk] = used[row[kk]] ? row[kk] : 0;
+            }
+        if (h->ade_mat_box.upload(mb, h->stream)) return 1;
+        if (h->ade_J.alloc((size_t)box_cells * n_poles) || h->ade_Jp.alloc((size_t)box_cells * n_poles)) return 1;
+        CU(cudaMemsetAsync(h->ade_J.p, 0, (size_t)box_cells * n_poles * 4, h->stream));
+        CU(cudaMemsetAsync(h->ade_Jp.p, 0, (size_t)box_cells * n_poles * 4, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        A.n_cells = (int)box_cells; A.n_poles = n_poles;
+        A.dense = 1; A.bi0 = b_lo[0]; A.bj0 = b_lo[1]; A.bk0 = b_lo[2]; A.bx = bx; A.by = by; A.bz = bz;
+        A.mat_box = h->ade_mat_box.p;
+        A.J = h->ade_J.p; A.Jp = h->ade_Jp.p; A.inv_dx = inv_dx;
+        h->ade_material_cells = n;
+        h->have_ade = true;
+        return 0;
+    }
     off.resize((size_t)n); ijk.resize((size_t)n * 3); cm.resize((size_t)n);
     std::vector<int> nbr((size_t)n * 6, -1);
     std::vector<int> slot_prev(pl, -1), slot_cur(pl, -1), slot_next(pl, -1);
@@ -553,6 +594,7 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
     A.n_cells = (int)n; A.n_poles = n_poles;
     A.cell_off = h->ade_off.p; A.cell_ijk = h->ade_ijk.p; A.cell_mat = h->ade_mat.p; A.nbr = h->ade_nbr.p;
     A.J = h->ade_J.p; A.Jp = h->ade_Jp.p; A.inv_dx = inv_dx;
+    h->ade_material_cells = n;
     h->have_ade = true;
     return 0;
 }
@@ -783,9 +825,16 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
         // after K1: on a slab the density poles of the ghost cells read the ghost p planes, and K1's cut blocks are
         // the ones that wait for the neighbour's step flag (K2a only reads the input set, K1 never touches J)
         const int nb = (h->ade.n_cells + 255) / 256;
-        k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
         StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx;
-        k2b_fixup<<<nb, 256, 0, h->stream>>>(Q, h->ade);
+        if (h->ade.dense) {
+            const int tb = h->ade.bz >= 192 ? 256 : (h->ade.bz >= 96 ? 128 : 64);
+            const dim3 grd((h->ade.bz + tb - 1) / tb, h->ade.by, h->ade.bx);
+            k2a_density_dense<<<grd, tb, 0, h->stream>>>(h->ade, P.p_in, h->d.pitch, h->plane);
+            k2b_fixup_dense<<<grd, tb, 0, h->stream>>>(Q, h->ade);
+        } else {
+            k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
+            k2b_fixup<<<nb, 256, 0, h->stream>>>(Q, h->ade);
+        }
         h->kernels_launched += 2;
     }
     for (auto *po : h->plane_ops) {                        // Mur / radiation planes, sequential by construction
@@ -1193,6 +1242,8 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
         case SB_OPT_FUSE_K3: h->opt_fuse_k3 = value < 0 ? 0 : std::min(value, 2); break;
         case SB_OPT_PLANE_MAP: if (value < 0 || value > 2) return fail("plane_map must be 0 (auto), 1 (strips) or 2 (flat)");
                                h->opt_plane_map = value; break;
+        case SB_OPT_ADE_LAYOUT: if (value < 0 || value > 2) return fail("ade_layout must be 0 (auto), 1 (compact) or 2 (dense)");
+                                h->opt_ade_layout = value; break;
         case SB_OPT_RESIDENT_SPLIT: h->opt_res_split = value ? 1 : 0; break;
         case SB_OPT_RESIDENT_MIN_STEPS: h->opt_res_min_steps = std::max(1, value); break;
         default: return fail("unknown option %d", option);
@@ -1212,7 +1263,7 @@ extern "C" int sb_query(sb_solver *h, sb_stats *out)
     if (h->have_ade) {
         double per_cell = 0.0;
         for (int q = 0; q < h->ade.n_poles; q++) per_cell += h->ade.poles[q].is_lorentz ? 16.0 : 8.0;
-        b += per_cell * (double)h->ade.n_cells / (double)out->cells;
+        b += per_cell * (double)h->ade_material_cells / (double)out->cells;
     }
     out->algorithmic_bytes_per_cell = b;
     out->kernel_variant = h->last_variant;

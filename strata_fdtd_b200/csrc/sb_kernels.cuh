@@ -632,6 +632,10 @@ struct AdeTable {
     const int *nbr;                      // [6][n_cells]: +x,+y,+z,-x,-y,-z slot of a SAME-material neighbour or -1
     float *J, *Jp;                       // [n_poles][n_cells]
     float inv_dx;                        // uniform-grid divergence scale (solver.py:3158)
+    // dense layout (materials that fill most of their bounding box): n_cells = cells of the box, a cell's slot is its
+    // box-local index, neighbours are found geometrically -- no index lists, no dependent slot -> J loads
+    int dense, bi0, bj0, bk0, bx, by, bz;
+    const uint8_t *mat_box;              // material id per box cell, 0 where the material has no poles
     PoleDev poles[MAX_POLES];
 };
 
@@ -660,61 +664,69 @@ __global__ void k2a_density(AdeTable A, const float *p_in)
     }
 }
 
-// undamped face velocity between lower cell a and upper cell b (= a + stride) with ADE correction
-__device__ __forceinline__ float ade_face(const StepParams &P, const AdeTable &A, const float *v_in,
-                                          float cv, long long a, long long b, int slot_a, int slot_b,
-                                          int mat, uint8_t open_bit)
+// everything the auxiliary fields change at material cell (i,j,k) with slot s: its three + faces, its pressure, its
+// modulus poles; sxp .. szm = slots of the +x,+y,+z,-x,-y,-z neighbours if they carry the same material, else -1
+__device__ __forceinline__ void ade_fixup_cell(const StepParams &P, const AdeTable &A, int s, long long c, int i, int j, int k,
+                                               int mat, int sxp, int syp, int szp, int sxm, int sym, int szm)
 {
-    float v = v_in[a] + cv * (P.p_in[b] - P.p_in[a]);
-    if (slot_a >= 0 && slot_b >= 0) {
+    const int n = A.n_cells;
+    const bool upd_x = (i < P.nx - 1) || P.has_upper, upd_y = j < P.ny - 1, upd_z = k < P.nz - 1;
+    const bool sub_x = (i > 0) || P.has_lower, sub_y = j > 0, sub_z = k > 0;
+    // the six undamped face velocities around the cell, material-free part (fdtd_step.cpp:34-80 / 235-307)
+    const float pc = P.p_in[c];
+    float vxn = P.vx_in[c], vyn = P.vy_in[c], vzn = P.vz_in[c], vxm = 0.0f, vym = 0.0f, vzm = 0.0f;
+    if (upd_x) vxn = vxn + P.cvx[i] * (P.p_in[c + P.plane] - pc);
+    if (upd_y) vyn = vyn + P.cvy[j] * (P.p_in[c + P.pitch] - pc);
+    if (upd_z) vzn = vzn + P.cvz[k] * (P.p_in[c + 1] - pc);
+    if (sub_x) vxm = P.vx_in[c - P.plane] + P.cvx[i - 1] * (pc - P.p_in[c - P.plane]);
+    if (sub_y) vym = P.vy_in[c - P.pitch] + P.cvy[j - 1] * (pc - P.p_in[c - P.pitch]);
+    if (sub_z) vzm = P.vz_in[c - 1] + P.cvz[k - 1] * (pc - P.p_in[c - 1]);
+    // density-pole corrections of the faces whose two cells carry this material, pole after pole (ade.cpp:228-401:
+    // v += vcoef * (J[upper cell] - J[lower cell])); one pass over the poles serves all six faces
+    const bool cxp = upd_x && sxp >= 0, cyp = upd_y && syp >= 0, czp = upd_z && szp >= 0;
+    const bool cxm = sub_x && sxm >= 0, cym = sub_y && sym >= 0, czm = sub_z && szm >= 0;
+    if (cxp || cyp || czp || cxm || cym || czm)
+        _Pragma("unroll 1")
         for (int q = 0; q < A.n_poles; q++) {
             const PoleDev &Q = A.poles[q];
-            if (Q.target == 0 && Q.mat_id == mat) {
-                const float *J = A.J + (long long)q * A.n_cells;
-                v = v + Q.vcoef * (J[slot_b] - J[slot_a]);                  // ade.cpp:262-264
-            }
+            if (Q.target != 0 || Q.mat_id != mat) continue;
+            const float *J = A.J + (long long)q * n;
+            const float js = J[s], vc = Q.vcoef;
+            if (cxp) vxn = vxn + vc * (J[sxp] - js);
+            if (cyp) vyn = vyn + vc * (J[syp] - js);
+            if (czp) vzn = vzn + vc * (J[szp] - js);
+            if (cxm) vxm = vxm + vc * (js - J[sxm]);
+            if (cym) vym = vym + vc * (js - J[sym]);
+            if (czm) vzm = vzm + vc * (js - J[szm]);
         }
+    if (P.mask) {                                                           // rigid faces (boundaries.cpp:66-89): updated faces only
+        const uint8_t m = P.mask[c];
+        if (upd_x && !(m & M_XOPEN)) vxn = 0.0f;
+        if (upd_y && !(m & M_YOPEN)) vyn = 0.0f;
+        if (upd_z && !(m & M_ZOPEN)) vzn = 0.0f;
+        if (sub_x && !(P.mask[c - P.plane] & M_XOPEN)) vxm = 0.0f;
+        if (sub_y && !(P.mask[c - P.pitch] & M_YOPEN)) vym = 0.0f;
+        if (sub_z && !(P.mask[c - 1] & M_ZOPEN)) vzm = 0.0f;
     }
-    if (P.mask && !(P.mask[a] & open_bit)) v = 0.0f;
-    return v;
-}
-
-__global__ void k2b_fixup(StepParams P, AdeTable A)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n_cells) return;
-    const long long c = A.cell_off[s];
-    const int i = A.cell_ijk[3 * s], j = A.cell_ijk[3 * s + 1], k = A.cell_ijk[3 * s + 2];
-    if (i < 0 || i >= P.nx) return;          // ghost-plane cell of a slab: only its J is kept here (K2a), its owner does the rest
-    const int mat = A.cell_mat[s];
-    const int n = A.n_cells;
-    const int sxp = A.nbr[s], syp = A.nbr[n + s], szp = A.nbr[2 * n + s];
-    const int sxm = A.nbr[3 * n + s], sym = A.nbr[4 * n + s], szm = A.nbr[5 * n + s];
-
-    const bool upd_x = (i < P.nx - 1) || P.has_upper, upd_y = j < P.ny - 1, upd_z = k < P.nz - 1;
-    const float vxn = upd_x ? ade_face(P, A, P.vx_in, P.cvx[i], c, c + P.plane, s, sxp, mat, M_XOPEN) : P.vx_in[c];
-    const float vyn = upd_y ? ade_face(P, A, P.vy_in, P.cvy[j], c, c + P.pitch, s, syp, mat, M_YOPEN) : P.vy_in[c];
-    const float vzn = upd_z ? ade_face(P, A, P.vz_in, P.cvz[k], c, c + 1, s, szp, mat, M_ZOPEN) : P.vz_in[c];
     float ddx = vxn, ddy = vyn, ddz = vzn;
-    if (i > 0 || P.has_lower) {
-        const float vxm = ade_face(P, A, P.vx_in, P.cvx[i - 1], c - P.plane, c, sxm, s, mat, M_XOPEN);
+    if (sub_x) {
         ddx = vxn - vxm;
         if (i == 0 && sxm >= 0) {            // the redundantly kept ghost face vx[-1] carries the correction too
             float og = vxm;
+            _Pragma("unroll 1")
             for (int sp = 0; sp < P.n_sponge; sp++) og = og * P.decx[sp][-1];
             P.vx_out[c - P.plane] = og;
         }
     }
-    if (j > 0)
-        ddy = vyn - ade_face(P, A, P.vy_in, P.cvy[j - 1], c - P.pitch, c, sym, s, mat, M_YOPEN);
-    if (k > 0)
-        ddz = vzn - ade_face(P, A, P.vz_in, P.cvz[k - 1], c - 1, c, szm, s, mat, M_ZOPEN);
+    if (sub_y) ddy = vyn - vym;
+    if (sub_z) ddz = vzn - vzm;
 
     // divergence for the modulus poles: d = dx*ix; d += dy*iy; d += dz*iz   (ade.cpp:479-692)
     const float ix = P.icx ? P.icx[i] : A.inv_dx, iy = P.icy ? P.icy[j] : A.inv_dx, iz = P.icz ? P.icz[k] : A.inv_dx;
     float div = ddx * ix;
     div = div + ddy * iy;
     div = div + ddz * iz;
+    _Pragma("unroll 1")
     for (int q = 0; q < A.n_poles; q++) {
         const PoleDev &Q = A.poles[q];
         if (Q.target == 1 && Q.mat_id == mat)
@@ -726,12 +738,14 @@ __global__ void k2b_fixup(StepParams P, AdeTable A)
     float pn = P.p_in[c] + P.cp * ((ex + ey) + ez);
     const bool air = !P.mask || (P.mask[c] & M_AIR);
     if (!air) pn = 0.0f;
+    _Pragma("unroll 1")
     for (int q = 0; q < A.n_poles; q++) {
         const PoleDev &Q = A.poles[q];
         if (Q.target == 1 && Q.mat_id == mat) pn = pn + Q.pcoef * A.J[(long long)q * n + s];
     }
     if (!air) pn = 0.0f;                                                    // solver.py:2193
     float ox = vxn, oy = vyn, oz = vzn;
+    _Pragma("unroll 1")
     for (int sp = 0; sp < P.n_sponge; sp++) {
         const float dx = P.decx[sp][i], dy = P.decy[sp][j], dz = P.decz[sp][k];
         ox = ox * dx; oy = oy * dy; oz = oz * dz;
@@ -743,6 +757,51 @@ __global__ void k2b_fixup(StepParams P, AdeTable A)
     if (sxp >= 0 && upd_x) P.vx_out[c] = ox;       // only faces the ADE correction touched
     if (syp >= 0 && upd_y) P.vy_out[c] = oy;
     if (szp >= 0 && upd_z) P.vz_out[c] = oz;
+}
+
+__global__ void k2b_fixup(StepParams P, AdeTable A)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.n_cells) return;
+    const long long c = A.cell_off[s];
+    const int i = A.cell_ijk[3 * s], j = A.cell_ijk[3 * s + 1], k = A.cell_ijk[3 * s + 2];
+    if (i < 0 || i >= P.nx) return;          // ghost-plane cell of a slab: only its J is kept here (K2a), its owner does the rest
+    const int n = A.n_cells;
+    ade_fixup_cell(P, A, s, c, i, j, k, A.cell_mat[s], A.nbr[s], A.nbr[n + s], A.nbr[2 * n + s],
+                   A.nbr[3 * n + s], A.nbr[4 * n + s], A.nbr[5 * n + s]);
+}
+
+// dense layout: one thread per cell of the materials' bounding box, k fastest
+__global__ void k2a_density_dense(AdeTable A, const float *p_in, int pitch, long long plane)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y, ii = blockIdx.z;    // grid = (k blocks, by, bx)
+    if (kk >= A.bz) return;
+    const int s = (ii * A.by + jj) * A.bz + kk;
+    const int mat = A.mat_box[s];
+    if (!mat) return;
+    const float src = p_in[(long long)(A.bi0 + ii) * plane + (long long)(A.bj0 + jj) * pitch + (A.bk0 + kk)];
+    for (int q = 0; q < A.n_poles; q++) {
+        const PoleDev &Q = A.poles[q];
+        if (Q.target == 0 && Q.mat_id == mat)
+            ade_pole_update(Q, A.J + (long long)q * A.n_cells, A.Jp + (long long)q * A.n_cells, s, src);
+    }
+}
+
+__global__ void k2b_fixup_dense(StepParams P, AdeTable A)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y, ii = blockIdx.z;    // grid = (k blocks, by, bx)
+    if (kk >= A.bz) return;
+    const int s = (ii * A.by + jj) * A.bz + kk;
+    const int mat = A.mat_box[s];
+    if (!mat) return;
+    const int i = A.bi0 + ii, j = A.bj0 + jj, k = A.bk0 + kk;
+    const int sj = A.bz, si = A.by * A.bz;
+    const uint8_t *m = A.mat_box;
+    ade_fixup_cell(P, A, s, (long long)i * P.plane + (long long)j * P.pitch + k, i, j, k, mat,
+                   (ii + 1 < A.bx && m[s + si] == mat) ? s + si : -1, (jj + 1 < A.by && m[s + sj] == mat) ? s + sj : -1,
+                   (kk + 1 < A.bz && m[s + 1] == mat) ? s + 1 : -1,
+                   (ii > 0 && m[s - si] == mat) ? s - si : -1, (jj > 0 && m[s - sj] == mat) ? s - sj : -1,
+                   (kk > 0 && m[s - 1] == mat) ? s - 1 : -1);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -123,6 +123,24 @@ def make_cases() -> dict:
                    dict(id=7, rho_inf=1.1, K_inf=1.1 * 350.0 ** 2, poles=SECOND_POLES)],
         material_id=mid2,
     )
+    # --- ADE: two materials stacked so that they fill most of their bounding box (-> the dense device layout), up to
+    #     the outer faces of the grid, with an air pocket and a solid inside the first one
+    sh3 = (30, 22, 26)
+    mid3 = np.zeros(sh3, dtype=np.uint8)
+    mid3[16:23, :, :] = 3
+    mid3[23:30, :, :] = 7
+    mid3[18:20, 8:12, 8:12] = 0                                   # air pocket
+    g3 = _block_geometry(sh3, (20, 3, 14), (22, 7, 20))           # solid inside material 3
+    C["ade_dense_layers"] = dict(
+        shape=sh3, resolution=1e-3, steps=260,
+        geometry=g3,
+        pml=[dict(depth=4)],
+        sources=[dict(kind="point", position=(6, 11, 13), frequency=16e3)],
+        probes=[("m3", (19, 15, 13)), ("m7", (26, 11, 13)), ("pocket", (18, 9, 9)), ("air", (8, 6, 6)), ("face", (29, 21, 25))],
+        materials=[dict(id=3, rho_inf=1.5, K_inf=1.5 * 320.0 ** 2, poles=BENIGN_POLES),
+                   dict(id=7, rho_inf=1.1, K_inf=1.1 * 350.0 ** 2, poles=SECOND_POLES)],
+        material_id=mid3,
+    )
     # --- first-order Mur ABC on every face (edges/corners depend on the x,y,z application order)
     C["mur_all"] = dict(
         shape=(22, 26, 24), resolution=1e-3, steps=200,

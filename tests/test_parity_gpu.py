@@ -429,3 +429,19 @@ def test_c3_ade_sphere_at_128_cubed_vs_oracle():
     assert_same_as_oracle(s, o, "c3/128")
     assert len(s._probes) == 64 and np.abs(s.get_field("p")).max() > 0
     s.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("name", ["ade_sphere", "ade_two_materials_nonuniform", "ade_dense_layers"])
+def test_ade_layouts_match_oracle(name, layout):
+    """Compact list (1) and dense bounding-box layout (2) of the material cells are two data layouts of the same
+    arithmetic: both equal the oracle (= the reference's ade.cpp kernels) bit for bit on every ADE case."""
+    case = CASES[name]
+    s = _with_options(build_b200_solver(case, chunk_steps=53), {_lib.OPT_ADE_LAYOUT: layout})
+    o = O.OracleSolver(case)
+    s.run(steps=case["steps"]); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"ade/{name}/layout{layout}")
+    s.reset(); o2 = O.OracleSolver(case)                     # J fields are zeroed by reset in either layout
+    s.run(steps=40); o2.run_steps(40)
+    assert_same_as_oracle(s, o2, f"ade/{name}/layout{layout}/after reset")
+    s.close()
