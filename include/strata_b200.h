@@ -206,6 +206,17 @@ int sb_set_peers(sb_solver *h, float *const lo_p_sets[2], float *const hi_p_sets
 int sb_energy(sb_solver *h, double rho, double c, double dV, double *out);
 
 int sb_reset(sb_solver *h);                      /* zero fields, J, counters (solver.py:2781-2800) */
+/* Tuning knobs; results never depend on them (every combination is bit-identical).
+ *   SB_OPT_KERNEL            SB_KERNEL_*: which step kernel (default AUTO: resident K5 / pipelined K6 / streaming K1 by size)
+ *   SB_OPT_ROWS_PER_THREAD   K1: rows per thread, 1 or 2 (0 = autotuned together with the next three)
+ *   SB_OPT_WARPS_J / _K      K1: warps of a block along j / k;  SB_OPT_CHUNK_I: planes a tile marches over
+ *   SB_OPT_PLANE_MAP         K1: 0 auto, 1 = 128-cell strips per warp, 2 = flat (the plane's float4 groups in memory order)
+ *   SB_OPT_USE_GRAPH         step-by-step path: capture a chunk of steps into a CUDA graph (-1 auto, 0 off, 1 on)
+ *   SB_OPT_FUSE_K3           inject point sources / record probes inside K1 instead of a separate kernel (0 off, 1 small grids, 2 always)
+ *   SB_OPT_RESIDENT_SPLIT    K5: overlap the halo-free velocity updates with the face exchange (default off: measured slower)
+ *   SB_OPT_RESIDENT_MIN_STEPS  shortest sb_step_n chunk for which AUTO uses K5 / K6 (default 4)
+ *   SB_OPT_ADE_LAYOUT        material cells as 0 auto, 1 compact list, 2 dense bounding box (set before sb_set_ade)
+ *   SB_OPT_PROFILE           bracket every step-kernel launch with CUDA events (sb_profile_read)                              */
 int sb_set_option(sb_solver *h, int option, int value);
 int sb_query(sb_solver *h, sb_stats *out);
 /* With SB_OPT_PROFILE=1 every launch of the fused step kernel is bracketed by CUDA events on the
