@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/val_smoke.log 2>&1; tail -6 gpurun_out/val_smoke.log
 timeout 600 python bench.py > gpurun_out/val_bench_default.json 2> gpurun_out/val_bench_default.err; cut -c1-400 gpurun_out/val_bench_default.json
 timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/val_bench_reference.json 2>&1; cut -c1-300 gpurun_out/val_bench_reference.json
-for w in c1_100 c2_200 c3_512 c3_512_ade; do
+for w in c1_100 c2_200 c3_512 c3_512_ade c3_512_ade_slab c4_enclosure; do
   timeout 300 python bench.py --workload $w --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/val_bench_$w.json 2> gpurun_out/val_bench_$w.err; cut -c1-330 gpurun_out/val_bench_$w.json
 done
 # launch lists (kernel shares) and one full capture of the two new kernels
