@@ -391,6 +391,7 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
             if (P.n_sponge > 0) {
                 ox = mul4s(ox, dx0); oy = mul4s(oy, dy0[r]); oz = mul4(oz, dz0);
                 pnew = mul4(mul4s(mul4s(pnew, dx0), dy0[r]), dz0);
+                _Pragma("unroll 1")                              // rare (several sponge objects): keep it out of the hot code
                 for (int s = 1; s < P.n_sponge; s++) {
                     const float dxs = P.decx[s][i];
                     const float dys = row_ok[r + 1] ? P.decy[s][j0 + r] : 1.0f;
