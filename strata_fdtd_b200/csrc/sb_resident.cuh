@@ -9,7 +9,7 @@
 //   * the grid is cut into nbi x nbj boxes (full rows along k), one CTA per box, at most one CTA per
 //     SM, all co-resident (cooperative launch);
 //   * every CTA loads its box of {p,vx,vy,vz} into shared memory once, advances it n_steps times in
-//     place (velocity phase, barrier, pressure phase, barrier) and stores it back once -- HBM/L2 see
+//     place (halo receive, barrier, velocity phase, barrier, pressure phase) and stores it back once -- HBM/L2 see
 //     2 x 16 B per cell per CHUNK instead of 32 B per cell per STEP;
 //   * per step only the four p faces of a box cross CTAs.  They go through an exchange area in L2 as
 //     (value, step tag) pairs in 8-byte units, two per 16-byte volatile store -- the receiver polls the
@@ -19,8 +19,9 @@
 //     The face velocities on the low sides (vx at i0-1, vy at j0-1) are kept redundantly in the box,
 //     updated with the owner's exact operations (the same trick as the multi-GPU slabs, DESIGN.md
 //     section 5), so nothing but p travels;
-//   * the part of the velocity phase that needs no halo value runs while the neighbours' faces are in
-//     flight (R.split).
+//   * optionally (R.split, off by default: measured slower, the second pass over the items costs more than the
+//     exchange latency it hides) the part of the velocity phase that needs no halo value runs while the
+//     neighbours' faces are in flight.
 //
 // Arithmetic is the contract of sb_kernels.cuh: separately rounded fp32 operations in the reference's
 // order (fdtd_step.cpp:34-80, 109-211 / 235-439; boundaries.cpp:66-89; pml.cpp:47-149;
