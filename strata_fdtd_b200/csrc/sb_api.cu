@@ -1024,10 +1024,11 @@ static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, flo
 {
     const sb_grid_desc &d = h->d;
     // Launch shape: unless the caller fixed one, the shape that pipelines best, not the one autotune() found for
-    // step-by-step launches -- short tiles (1 row per thread, 4 warps, 64 registers: 8 CTAs per SM) of 8 planes,
-    // 16 on larger grids (measured: 200^3 50.7 us/step with 8 planes vs 53.1 with 16; 256^3 87.3 vs 83.5).
+    // step-by-step launches -- short tiles (1 row per thread, 4 warps, 64 registers: 8 CTAs per SM) of nx/16 planes
+    // (measured, us/step: 200^3 48.2 / 44.8 / 43.8 / 50.4 with 4 / 8 / 12 / 16 planes; 300^3 156.3 / 151.0 / 149.8 with
+    // 8 / 16 / 25; tools/k6_chunk_sweep.py).
     const int save[4] = {h->opt_rj, h->opt_wj, h->opt_wk, h->opt_chunk_i};
-    if (h->opt_rj == 0) { h->opt_rj = 1; h->opt_wj = 4; h->opt_wk = 1; if (!h->opt_chunk_i) h->opt_chunk_i = d.nx < 240 ? 8 : 16; }
+    if (h->opt_rj == 0) { h->opt_rj = 1; h->opt_wj = 4; h->opt_wk = 1; if (!h->opt_chunk_i) h->opt_chunk_i = std::max(8, std::min(32, d.nx / 16)); }
     int rj, wj, wk, chunk, gx, gy; bool w;
     const int shape_rc = march_shape(h, true, rj, wj, wk, chunk, gx, gy, w);
     h->opt_rj = save[0]; h->opt_wj = save[1]; h->opt_wk = save[2]; h->opt_chunk_i = save[3];
