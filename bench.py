@@ -309,7 +309,10 @@ def run_b200_arm(a):
                                        "'achieved' is an HBM-equivalent rate)" if st1["kernel_variant"] == 4 else
                                        "k6_pipeline (k1_tile; per step of one chunk launch)" if st1["kernel_variant"] == 5 else "k1_step_march",
                              "kernel_ms_mean": mean_ms.value, "kernel_ms_min": min_ms.value, "launches_timed": n_l.value,
-                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_rank},
+                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_rank,
+                             # whole-step model of sb_query: 32 (+1 with a face mask) + sum over poles of 8 (Debye) or 16
+                             # (Lorentz) bytes x the fraction of cells that carry the material
+                             "step_bytes_per_cell_model": st1["algorithmic_bytes_per_cell"]},
                 "e2e": {"value": cells_total * K / e2e_s / 1e9, "unit": UNIT,
                         "h2d_bytes_per_step": 8 * n_src, "d2h_bytes_per_step": 4 * n_rec,
                         "note": "FDTDSolver.run(): waveform table host->device and probe traces device->host every chunk; "
