@@ -631,8 +631,13 @@ class FDTDSolver:
         mics = list(self._microphones.values())
         n_rec = len(probes) + sum(len(sl) for sl in self._mic_slots) + len(self._corner_keys)
         done = 0
+        # On small grids a step takes microseconds and the per-chunk host work (waveform table, copies, trace lists)
+        # shows; nobody is watching the steps go by unless a callback / writer is attached, so use longer chunks there.
+        chunk = self._chunk_steps
+        if callback is None and writer is None and int(np.prod(self.shape, dtype=np.int64)) <= (2 << 20):
+            chunk = max(chunk, 1024)
         while done < n_steps:
-            m = min(self._chunk_steps, n_steps - done)
+            m = min(chunk, n_steps - done)
             # a chunk ends right after any step whose fields the host has to see
             for q in range(m):
                 idx = self._step_count + q
