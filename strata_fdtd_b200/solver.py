@@ -93,7 +93,7 @@ class FDTDSolver:
 
     def __init__(self, shape=None, resolution=None, grid=None, c: float = 343.0, rho: float = 1.2,
                  courant: float = 0.95, backend: str = "b200", warn_energy_drift: bool = False,
-                 energy_drift_threshold: float = 0.01, device: int | None = None, chunk_steps: int = 256,
+                 energy_drift_threshold: float = 0.01, device: int | None = None, chunk_steps: int | None = None,
                  slab: tuple[int, int] | None = None):
         if backend not in ("b200", "auto"):
             raise ValueError(f"strata_fdtd_b200 provides backend='b200' only (got {backend!r}); "
@@ -161,7 +161,8 @@ class FDTDSolver:
         self._geometry_ext = None
 
         self._device_index = device
-        self._chunk_steps = int(chunk_steps)
+        self._chunk_auto = chunk_steps is None           # the caller left the chunk length to the solver
+        self._chunk_steps = 256 if chunk_steps is None else int(chunk_steps)
         self._dev: _DeviceState | None = None
         self._dirty = {"coeffs", "geometry", "sponges", "sources", "records", "ade"}
         self._options: dict[int, int] = {}
@@ -634,7 +635,7 @@ class FDTDSolver:
         # On small grids a step takes microseconds and the per-chunk host work (waveform table, copies, trace lists)
         # shows; nobody is watching the steps go by unless a callback / writer is attached, so use longer chunks there.
         chunk = self._chunk_steps
-        if callback is None and writer is None and int(np.prod(self.shape, dtype=np.int64)) <= (2 << 20):
+        if self._chunk_auto and callback is None and writer is None and int(np.prod(self.shape, dtype=np.int64)) <= (2 << 20):
             chunk = max(chunk, 1024)
         while done < n_steps:
             m = min(chunk, n_steps - done)
