@@ -117,6 +117,8 @@ struct sb_solver {
     unsigned res_epoch = 0;                // step tags of the face exchange keep growing across launches
     bool resident_used = false;
     int res_nbi = 0, res_nbj = 0;
+    int res_tuned_key = -1, res_tuned_nbi = 0, res_tuned_nbj = 0;   // box grid measured best for the current configuration
+    DBuf<float> d_res_scratch;
     // step-pipelined kernel (K6, sb_pipeline.cuh)
     DBuf<int> d_pipe_ctr;                  // [0] ticket, [1 ..] chunk counters
     long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 40LL << 20;   // where pipelining the steps was measured to pay
@@ -125,7 +127,7 @@ struct sb_solver {
 
 static void drop_graphs(sb_solver *h)
 {
-    h->tuned_key = -1;                       // configuration changed: re-measure the launch shape as well
+    h->tuned_key = -1; h->res_tuned_key = -1;                       // configuration changed: re-measure the launch shape as well
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
 }
@@ -191,7 +193,7 @@ extern "C" int sb_destroy(sb_solver *h)
     h->src_weight.release(); h->probe_off.release(); h->mic_off.release(); h->d_src_vals.release();
     h->d_step_ctr.release(); h->ade_off.release(); h->ade_ijk.release(); h->ade_nbr.release(); h->ade_mat.release(); h->ade_mat_box.release();
     h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
-    h->d_probe_ijk.release(); h->d_res_xch.release(); h->d_pipe_ctr.release();
+    h->d_probe_ijk.release(); h->d_res_xch.release(); h->d_pipe_ctr.release(); h->d_res_scratch.release();
     delete h;
     return 0;
 }
@@ -885,7 +887,7 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
 
 // ---- K5: shared-memory-resident chunk (sb_resident.cuh) ---------------------------------------------------
 // 0 = not applicable (why_not says why), 1 = plan filled in
-static int resident_plan(sb_solver *h, ResParams &R, const char **why_not)
+static int resident_plan(sb_solver *h, ResParams &R, const char **why_not, int force_nbi = 0, int force_nbj = 0)
 {
     const sb_grid_desc &d = h->d;
     *why_not = nullptr;
@@ -898,8 +900,9 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not)
     else if (h->n_sm <= 0 || h->smem_optin <= 0) *why_not = "device attributes unavailable";
     else if (!h->coop_ok) *why_not = "cooperative launch unavailable on this device / in this process";
     if (*why_not) return 0;
-    int nbi = 0, nbj = 0;
-    if (!res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, h->have_mask, &nbi, &nbj)) {
+    int nbi = force_nbi, nbj = force_nbj;
+    if (nbi <= 0 && h->res_tuned_key >= 0) { nbi = h->res_tuned_nbi; nbj = h->res_tuned_nbj; }
+    if (nbi <= 0 && !res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, h->have_mask, &nbi, &nbj)) {
         *why_not = "grid does not fit in shared memory";
         return 0;
     }
@@ -950,7 +953,8 @@ struct ResidentLauncher {
     }
 };
 
-static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double *src_dev, float *rec_dev)
+// enqueue one resident launch of n_steps; touches no solver state except the exchange area and its step tags
+static int resident_enqueue(sb_solver *h, ResParams &R, int n_steps, const double *src_dev, float *rec_dev)
 {
     const int nb = R.nbi * R.nbj;
     R.n_steps = n_steps; R.src_vals = src_dev; R.rec = rec_dev;
@@ -964,10 +968,89 @@ static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double
     R.xch = h->d_res_xch.p; R.tag_base = h->res_epoch;
     h->res_epoch += (unsigned)n_steps;
     const size_t smem = (size_t)res_smem_bytes(R.LI, R.LJ, R.kp, R.n_probes, R.mask != nullptr);
+    ResidentLauncher launcher{h, R, smem};
+    return res_dispatch(R.mask != nullptr, R.icx == nullptr, R.n_sponge, launcher);   // 2 = not all boxes fit at once
+}
+
+// Box grids worth measuring: the heuristic choice (fewest items per thread) and the neighbours that trade an item
+// per thread for a shorter box perimeter, i.e. less face exchange -- which of the two decides depends on the grid
+// (64^3: 13 x 11 boxes 2.6 us/step, 22 x 6 boxes 3.0; 100^3: 20 x 7 and 7 x 21 equal).
+static std::vector<std::pair<int, int>> resident_candidates(const sb_solver *h)
+{
+    struct Cand { int nbi, nbj; long long iters, bytes; int perim; };
+    const sb_grid_desc &d = h->d;
+    const int kp = (d.nz + 3) / 4 * 4, K4 = kp / 4;
+    std::vector<Cand> all;
+    for (int nbi = 1; nbi <= d.nx && nbi <= h->n_sm; nbi++) {
+        const int nbj = std::min(d.ny, h->n_sm / nbi);
+        if (nbj < 1) break;
+        const int LI = (d.nx + nbi - 1) / nbi, LJ = (d.ny + nbj - 1) / nbj;
+        if ((long long)LJ * K4 > K5_NT) continue;
+        const long long bytes = res_smem_bytes(LI, LJ, kp, h->n_probes, h->have_mask);
+        if (bytes > h->smem_optin) continue;
+        const int ncol = LJ * K4, G = K5_NT / ncol;
+        const long long items = (long long)LI * ncol + ncol + (long long)LI * K4;
+        all.push_back({nbi, nbj, std::max((items + K5_NT - 1) / K5_NT, (long long)(LI + G - 1) / G), bytes, LI + LJ});
+    }
+    std::vector<std::pair<int, int>> out;
+    if (all.empty()) return out;
+    long long min_iters = all[0].iters;
+    for (auto &c : all) min_iters = std::min(min_iters, c.iters);
+    auto push = [&](const Cand &c) {
+        for (auto &o : out) if (o.first == c.nbi && o.second == c.nbj) return;
+        if (out.size() < 6) out.emplace_back(c.nbi, c.nbj);
+    };
+    std::sort(all.begin(), all.end(), [](const Cand &a, const Cand &b) { return std::tie(a.iters, a.bytes) < std::tie(b.iters, b.bytes); });
+    for (size_t q = 0; q < all.size() && q < 3; q++) push(all[q]);                 // [0] = res_choose_partition's choice
+    std::vector<Cand> near;
+    for (auto &c : all) if (c.iters <= min_iters + 1) near.push_back(c);
+    std::sort(near.begin(), near.end(), [](const Cand &a, const Cand &b) { return std::tie(a.perim, a.iters, a.bytes) < std::tie(b.perim, b.iters, b.bytes); });
+    for (size_t q = 0; q < near.size() && q < 3; q++) push(near[q]);
+    return out;
+}
+
+// Times the candidate box grids on the live state: a resident launch reads set[cur] and writes set[(cur + n) & 1], so
+// an odd number of trial steps leaves the current state untouched (records go to a scratch buffer).
+static int resident_autotune(sb_solver *h, const double *src_dev, int n_steps)
+{
+    const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->n_probes << 6);
+    if (h->res_tuned_key == key) return 0;
+    int n_trial = std::min(n_steps, 65);
+    if (!(n_trial & 1)) n_trial--;
+    if (n_trial < 33) return 0;                               // too short to tell box grids apart: keep the heuristic
+    const auto cands = resident_candidates(h);
+    if (cands.size() < 2) return 0;
+    if (h->d_res_scratch.alloc((size_t)n_trial * std::max(1, h->n_probes))) return 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f; int best_c = 0;
+    h->res_tuned_key = -1;
+    for (int c = 0; c < (int)cands.size(); c++) {
+        float t_min = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            ResParams R; const char *why_not = nullptr;
+            if (!resident_plan(h, R, &why_not, cands[c].first, cands[c].second)) break;
+            cudaEventRecord(e0, h->stream);
+            const int rc = resident_enqueue(h, R, n_trial, src_dev, h->d_res_scratch.p);
+            if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+            cudaEventRecord(e1, h->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep) t_min = std::min(t_min, ms);
+        }
+        if (t_min < best) { best = t_min; best_c = c; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CU(cudaGetLastError());
+    h->res_tuned_nbi = cands[best_c].first; h->res_tuned_nbj = cands[best_c].second; h->res_tuned_key = key;
+    return 0;
+}
+
+static int launch_resident(sb_solver *h, ResParams &R, int n_steps, const double *src_dev, float *rec_dev)
+{
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->opt_profile) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, h->stream); }
-    ResidentLauncher launcher{h, R, smem};
-    if (const int rc = res_dispatch(R.mask != nullptr, R.icx == nullptr, R.n_sponge, launcher)) {
+    if (const int rc = resident_enqueue(h, R, n_steps, src_dev, rec_dev)) {
         if (h->opt_profile) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
         return rc;                           // 2 = the device cannot hold all boxes at once: the caller falls back
     }
@@ -1080,6 +1163,11 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
                         (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps))) {
         ResParams R; const char *why_not = nullptr;
         if (resident_plan(h, R, &why_not)) {
+            if (src_dev || !h->n_src_cells) {                    // measure the candidate box grids once per configuration
+                const int trc = resident_autotune(h, src_dev, n_steps);
+                if (trc == 1) return 1;
+                if (trc == 0 && !resident_plan(h, R, &why_not)) return fail("resident kernel: %s", why_not);
+            }
             const int rc = launch_resident(h, R, n_steps, src_dev, rec_dev);
             if (rc != 2 || h->opt_kernel == SB_KERNEL_RESIDENT) return rc ? 1 : 0;
             h->coop_ok = false;              // not all boxes fit at once here: use the step-by-step path from now on
