@@ -227,3 +227,33 @@ def test_strata_fdtd_alias_resolves_names():
             "s = FDTDSolver(shape=(6,6,6), resolution=1e-3); print(s.backend, s.using_native)")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
     assert res.stdout.strip() == "b200 False", res.stderr
+
+
+def test_slab_material_storage_keeps_the_ghost_planes():
+    """Host logic of ADE on slabs, no device: a slab takes masks over the WHOLE grid and keeps the material ids of its
+    owned planes plus the live ghost plane on each cut (the device list needs them for the velocity correction across
+    the cut); a mask of the wrong shape is refused with the reference's message."""
+    import strata_fdtd_b200 as sb
+    shape = (12, 6, 5)
+    mask = np.zeros(shape, dtype=bool)
+    mask[3:9, 1:4, :] = True
+    mat = sb.PoleMaterial("m", 1.2, 1.2 * 343.0 ** 2, [sb.Pole(sb.PoleType.DEBYE, 0.1, "density", tau=1e-4)])
+    for lo, hi in ((0, 4), (4, 8), (8, 12)):
+        s = sb.FDTDSolver(shape=shape, resolution=1e-3, slab=(lo, hi))
+        s.register_material(mat, material_id=5)
+        s.set_material_region(mask, material_id=5)
+        glo, ghi = max(lo - 1, 0), min(hi + 1, shape[0])
+        assert s._material_ext.shape == (ghi - glo,) + shape[1:]
+        assert np.array_equal(s._material_ext == 5, mask[glo:ghi])
+        assert np.array_equal(s._material_id == 5, mask[lo:hi])            # the owned planes are a view of the same storage
+        with pytest.raises(ValueError, match="doesn't match solver shape"):
+            s.set_material_region(mask[lo:hi], material_id=5)
+        with pytest.raises(ValueError, match="not registered"):
+            s.set_material_region(mask, material_id=9)
+
+
+def test_chunk_length_is_the_callers_when_given():
+    import strata_fdtd_b200 as sb
+    assert sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3)._chunk_auto is True
+    s = sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3, chunk_steps=37)
+    assert s._chunk_auto is False and s._chunk_steps == 37
