@@ -1127,6 +1127,10 @@ static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, flo
     Q.n_steps = n_steps; Q.gx = gx; Q.gy = gy; Q.nchunks = (d.nx + chunk - 1) / chunk;
     const long long total = (long long)gx * gy * Q.nchunks * n_steps;
     if (total >= (1LL << 31) - 65536) return fail("pipelined kernel: too many tiles in one chunk of steps");
+    // Left to itself (AUTO) the pipeline is only used where it was measured to pay: a step must offer at least as many
+    // tiles as the GPU holds CTAs and at least four chunks of planes (long thin grids have neither: their few chunks
+    // serialise on each other); 3 = "not worthwhile here", the caller goes on to the step-by-step path.
+    if (h->opt_kernel == SB_KERNEL_AUTO && ((long long)gx * gy * Q.nchunks < (long long)h->n_sm * 8 || Q.nchunks < 4)) return 3;
     if (h->d_pipe_ctr.alloc((size_t)Q.nchunks + 1)) return 1;
     CU(cudaMemsetAsync(h->d_pipe_ctr.p, 0, ((size_t)Q.nchunks + 1) * sizeof(int), h->stream));
     Q.ticket = h->d_pipe_ctr.p; Q.done = h->d_pipe_ctr.p + 1; Q.err_flag = h->d_err.p;
@@ -1180,8 +1184,8 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
         const char *why_not = pipeline_why_not(h);
         if (!why_not) {
             const int rc = launch_pipeline(h, n_steps, src_dev, rec_dev);
-            if (rc != 2 || h->opt_kernel == SB_KERNEL_PIPELINE) return rc ? 1 : 0;
-            h->coop_ok = false;
+            if ((rc != 2 && rc != 3) || h->opt_kernel == SB_KERNEL_PIPELINE) return rc ? 1 : 0;
+            if (rc == 2) h->coop_ok = false;
         } else if (h->opt_kernel == SB_KERNEL_PIPELINE) return fail("pipelined kernel not applicable: %s", why_not);
     }
     if (h->opt_rj == 0 && n_steps > 0) {
