@@ -257,3 +257,20 @@ def test_chunk_length_is_the_callers_when_given():
     assert sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3)._chunk_auto is True
     s = sb.FDTDSolver(shape=(8, 8, 8), resolution=1e-3, chunk_steps=37)
     assert s._chunk_auto is False and s._chunk_steps == 37
+
+
+def test_no_fused_multiply_add_in_any_kernel():
+    """The arithmetic contract: every fp32 / fp64 operation is separately rounded, as in the
+    reference's -O3 build without -ffast-math.  The library is compiled --fmad=false; the SASS of all kernels (K0-K6,
+    ADE, plane ops, energy) must therefore contain no FFMA / DFMA."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", str(_lib.SO_PATH)], capture_output=True, text=True, check=True).stdout
+    kernels = re.findall(r"Function : (\S+)", sass)
+    assert len(kernels) >= 60 and any("k5_resident" in k for k in kernels) and any("k6_pipeline" in k for k in kernels)
+    fused = re.findall(r"\b(FFMA|DFMA)\b", sass)
+    assert not fused, f"{len(fused)} fused multiply-adds in the device code"
