@@ -17,3 +17,9 @@ for tool in memcheck racecheck; do
       python -m pytest tests/test_parity_gpu.py tests/test_multi_gpu.py -m gpu -x -q -k "$SEL2" > gpurun_out/sanitizer_chunk_$tool.log 2>&1
   echo "chunk-$tool exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_chunk_$tool.log | tr '\n' ' ')"
 done
+SEL3='(test_matches_oracle_and_golden and (march_r1_flat or march_r2_flat_fused) and (odd_geometry or ade_dense or nonuniform_block)) or (test_ade_layouts_match_oracle and ade_dense_layers) or (test_pipelined_kernel_matches_oracle and shape_opts3 and (odd_geometry or two_sponges))'
+for tool in memcheck racecheck; do
+  timeout 400 compute-sanitizer --tool $tool --error-exitcode 7 --target-processes all \
+      python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "$SEL3" > gpurun_out/sanitizer_flat_$tool.log 2>&1
+  echo "flat-$tool exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_flat_$tool.log | tr '\n' ' ')"
+done
