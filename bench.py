@@ -27,9 +27,8 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-for p in (str(ROOT), str(ROOT / "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
 
 METRIC = "cell_updates_per_s"
 UNIT = "Gcell-updates/s"
@@ -45,13 +44,10 @@ def measured_peak_gbs():
 
 # ----------------------------------------------------------------------------- workloads
 def workload_case(name: str, n_gpus: int) -> tuple[dict, str]:
-    from cases import c1_case, c2_case, c3_case
+    from strata_fdtd_b200.workloads import c1_case, c2_case, c3_case, c4_case, c5_case
     if name == "c5_weak":
-        nx = 256 * n_gpus
-        shape = (nx, 2048, 2048)
-        probes = [(f"p{q}", (min(nx - 1, (2 * q + 1) * nx // 16), 1024 + 64 * (q - 4), 1000)) for q in range(8)]
-        case = dict(shape=shape, resolution=1e-3, steps=0, pml=[dict(depth=10)],
-                    sources=[dict(kind="point", position=(nx // 2, 1024, 1024), frequency=1000.0)], probes=probes)
+        case = c5_case(n_gpus)
+        nx = case["shape"][0]
         return case, f"c5_weak: {nx}x2048x2048 uniform 1 mm, PML(10), 1 point source, 8 probes ({n_gpus} x 256x2048x2048 slabs)"
     if name == "c3_512":
         c = c2_case(512, steps=0)
@@ -66,11 +62,11 @@ def workload_case(name: str, n_gpus: int) -> tuple[dict, str]:
         return c2_case(200, steps=0), "c2_200: 200^3 uniform 1 mm, PML(10), 1 point source, 1 probe"
     if name == "c1_100":
         return c1_case(0), "c1_100: 100^3 uniform 1 mm, PML(10), 1 kHz pulse, 1 probe"
-    if name == "c4_enclosure":
-        from cases import c4_case
-        return (c4_case((1024, 512, 512), steps=0, materialise=False),
+    if name in ("c4_enclosure", "c4_enclosure_closed_form"):
+        enclosure = "reference" if name == "c4_enclosure" else "closed_form"
+        return (c4_case((1024, 512, 512), steps=0, materialise=False, enclosure=enclosure),
                 "c4_enclosure: 1024x512x512 nonuniform (axis 0 stretched 1.002 from the centre), ported-enclosure "
-                f"rigid masks, PML(10), 1 source, 8 probes ({n_gpus} slab(s), strong scaling)")
+                f"rigid masks ({enclosure} CSG), PML(10), 1 source, 8 probes ({n_gpus} slab(s), strong scaling)")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -114,15 +110,21 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline (reference kernels)
-def cpu_reference_sample(steps: int = 60, warmup: int = 2, shape=(512, 512, 512)):
+def cpu_reference_sample(steps: int = 60, warmup: int = 2, shape=(512, 512, 512), case: dict | None = None):
     """The reference's compiled C++/OpenMP kernels (oracle/_ref) on the host cores, same path (PML + source +
-    probe), on a bounded sub-grid of the workload.  Falls back to the oracle port if _ref is not built."""
+    probes): on ``case`` itself when given, else on a bounded sub-grid of the workload.  Falls back to the oracle
+    port if _ref is not built."""
     from oracle import oracle as O
     from oracle import ref_loader as R
-    n = shape[0]
-    case = dict(shape=shape, resolution=1e-3, steps=0, pml=[dict(depth=10)],
-                sources=[dict(kind="point", position=(n // 4, shape[1] // 2, shape[2] // 2), frequency=1000.0)],
-                probes=[("probe", (3 * n // 4, shape[1] // 2, shape[2] // 2))])
+    if case is None:
+        n = shape[0]
+        case = dict(shape=shape, resolution=1e-3, steps=0, pml=[dict(depth=10)],
+                    sources=[dict(kind="point", position=(n // 4, shape[1] // 2, shape[2] // 2), frequency=1000.0)],
+                    probes=[("probe", (3 * n // 4, shape[1] // 2, shape[2] // 2))])
+        what = "sub-grid of the workload (PML 10, point source, probe)"
+    else:
+        shape = tuple(case["shape"])
+        what = "the workload itself (whole grid, all sources and probes)"
     cores = os.cpu_count() or 1
     if R.have_ref_kernels():
         k = R.load_ref_kernels()
@@ -138,11 +140,28 @@ def cpu_reference_sample(steps: int = 60, warmup: int = 2, shape=(512, 512, 512)
     for _ in range(steps):
         drv.step()
     dt = time.perf_counter() - t0
-    cells = int(np.prod(shape))
+    cells = int(np.prod(shape, dtype=np.int64))
     return {"value": cells * steps / dt / 1e9, "unit": UNIT, "cores": int(cores), "kind": kind,
-            "sample": f"{shape[0]}x{shape[1]}x{shape[2]} sub-grid of the workload (PML 10, point source, probe), "
-                      f"{steps} steps after {warmup} warm-up, {dt:.2f} s",
+            "sample": f"{shape[0]}x{shape[1]}x{shape[2]} {what}, {steps} steps after {warmup} warm-up, {dt:.2f} s",
             "ms_per_step": dt / steps * 1e3}
+
+
+def reference_can_run(case: dict) -> tuple[bool, str]:
+    """The reference indexes cells with 32-bit ints (fdtd_types.hpp:26-42) and keeps everything in host RAM."""
+    cells = int(np.prod(case["shape"], dtype=np.int64))
+    if cells >= 2 ** 31:
+        return False, f"{cells} cells exceed the reference's int32 cell index (fdtd_types.hpp:26-42)"
+    if case.get("nonuniform") or case.get("materials") or case.get("geometry") is not None:
+        return False, "the kernel-level reference driver covers the uniform, material-free path"
+    need = cells * (4 * 4 + 1) * 1.15
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except ImportError:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    if avail < need:
+        return False, f"needs {need / 2**30:.0f} GiB of host memory, {avail / 2**30:.0f} GiB available"
+    return True, ""
 
 
 def run_reference_arm(a):
@@ -150,23 +169,104 @@ def run_reference_arm(a):
     if rank != 0:
         return
     case, label = workload_case(a.workload, a.gpus)
-    r = cpu_reference_sample(steps=max(1, a.steps), warmup=max(1, min(a.warmup, 3)))
+    ok, why_not = reference_can_run(case)
+    steps, warmup = max(1, a.steps), max(1, min(a.warmup, 3))
+    if ok:
+        r = cpu_reference_sample(steps=steps, warmup=warmup, case=case)
+        note = "reference C++/OpenMP kernels on the host cores, on the workload as worded"
+    else:
+        r = cpu_reference_sample(steps=steps, warmup=warmup)
+        note = ("reference C++/OpenMP kernels timed on a bounded 512^3 sub-grid on the host cores (rate is per cell, so "
+                f"size-comparable); not the whole workload because {why_not}")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "note": "reference C++/OpenMP kernels timed on a bounded sub-grid of the "
-                                                   "workload on the host cores; rate is per cell so it is size-comparable"},
+            "scaling": "weak" if a.workload == "c5_weak" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "note": note, "whole_workload": ok},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- N > 1: is the decomposed run right?
+def decomposition_selfcheck(dist, world: int, rank: int, local_rank: int, halo: str) -> dict:
+    """Decomposition invariance inside the bench's own process group, with the halo mode of the timed run: a small grid
+    cut into `world` slabs (solid block through the first cut, sponge, a source right next to a cut, probes on both
+    sides) must reproduce the single-GPU run of rank 0 bit for bit -- the four final fields and every trace.  The
+    reference has no multi-GPU path; this is the contract that replaces it."""
+    from strata_fdtd_b200.workloads import build_distributed_solver, build_solver
+    nx, steps = 16 * world, 64
+    g = np.ones((nx, 96, 200), dtype=bool)
+    g[12:20, 30:60, 80:140] = False
+    case = dict(shape=(nx, 96, 200), resolution=1e-3, geometry=g, pml=[dict(depth=6)],
+                sources=[dict(kind="point", position=(15, 48, 100), frequency=20e3),
+                         dict(kind="point", position=(nx - 16, 20, 40), frequency=15e3, amplitude=0.5)],
+                probes=[("below_cut", (15, 40, 60)), ("above_cut", (16, 40, 60)), ("far", (nx - 2, 20, 150)),
+                        ("low", (1, 70, 30)), ("last_cut", (nx - 17, 48, 100))])
+    d = build_distributed_solver(case, device=local_rank, chunk_steps=32, halo=halo)
+    d.run(steps=steps)
+    fields = {f: d.gather_field(f) for f in ("p", "vx", "vy", "vz")}
+    traces = d.get_probe_data()
+    verdict = [None]
+    if rank == 0:
+        one = build_solver(case, device=local_rank, distributed=False)
+        one.run(steps=steps)
+        bad = [f for f in fields if not np.array_equal(fields[f], one.get_field(f))]
+        bad += [n for n in traces if not np.array_equal(traces[n], one.get_probe_data(n)[n])]
+        alive = float(np.abs(fields["p"]).max()) > 0 and all(np.abs(t).max() > 0 for t in traces.values())
+        verdict[0] = {"invariance": "bit-exact" if not bad and alive else "MISMATCH: " + ",".join(bad or ["dead fields"]),
+                      "case": f"{nx}x96x200, {world} slabs, solid block through a cut, PML(6), 2 sources, 5 probes, "
+                              f"{steps} steps vs the single-GPU run", "halo": d.halo}
+        one.close()
+    dist.broadcast_object_list(verdict, src=0)
+    d.close()
+    return verdict[0]
+
+
+def halo_planes_equal(dist, drv) -> bool:
+    """After the timed region: every ghost plane equals the plane its owner holds, bit for bit -- the neighbour's p plane
+    on both sides of each cut and the redundantly computed ghost face vx[-1] against the lower neighbour's vx[nx-1]."""
+    import torch
+    s = drv.slab
+    dev = s._dev
+    rank, world = drv.rank, drv.world
+    torch.cuda.synchronize()
+    dist.barrier()
+    ok, live = True, False
+    with torch.cuda.stream(dev.stream):
+        for field in ("p", "vx"):
+            h = s.halo_planes(field)
+            ops, checks = [], []
+            if rank < world - 1:
+                ops.append(dist.P2POp(dist.isend, h["send_hi"].contiguous(), rank + 1))
+            if rank > 0:
+                buf = torch.empty_like(h["recv_lo"])
+                ops.append(dist.P2POp(dist.irecv, buf, rank - 1))
+                checks.append((buf, h["recv_lo"]))
+            if field == "p":
+                if rank > 0:
+                    ops.append(dist.P2POp(dist.isend, h["send_lo"].contiguous(), rank - 1))
+                if rank < world - 1:
+                    buf = torch.empty_like(h["recv_hi"])
+                    ops.append(dist.P2POp(dist.irecv, buf, rank + 1))
+                    checks.append((buf, h["recv_hi"]))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            torch.cuda.current_stream().synchronize()
+            for got, ghost in checks:
+                ok = ok and bool(torch.equal(got, ghost))
+                live = live or bool(got.abs().max() > 0)
+    # equal everywhere, and not vacuously: at least one compared plane of the job carries signal
+    t = torch.tensor([1 if ok else 0, 0 if live else 1], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t[0].item()) and not bool(t[1].item())
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_b200_arm(a):
     import torch
     from strata_fdtd_b200 import _lib
-    from util import build_b200_solver
+    from strata_fdtd_b200.workloads import build_distributed_solver, build_solver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,15 +279,15 @@ def run_b200_arm(a):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    parity_n = decomposition_selfcheck(dist, world, rank, local_rank, a.halo) if world > 1 else None
     case, label = workload_case(a.workload, world)
     cells_total = int(np.prod(case["shape"], dtype=np.int64))
     K, W = a.steps, max(4, a.warmup)        # >= 4 so that the warm-up runs the same (chunk) kernels as the timed region
 
     if world == 1:
-        s = build_b200_solver(case, device=local_rank, chunk_steps=max(K, W))
+        s = build_solver(case, device=local_rank, chunk_steps=max(K, W), distributed=False)
         slab, drv = s, None
     else:
-        from util import build_distributed_solver
         drv = build_distributed_solver(case, device=local_rank, chunk_steps=max(K, W), halo=a.halo)
         slab = drv.slab
     for opt, val in ((_lib.OPT_ROWS_PER_THREAD, a.rows), (_lib.OPT_WARPS_J, a.warps_j), (_lib.OPT_WARPS_K, a.warps_k),
@@ -256,6 +356,8 @@ def run_b200_arm(a):
         slab.end_chunk()
         t = torch.tensor([dev_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
     clocks = sampler.stop() if sampler else None
+    if parity_n is not None:
+        parity_n["halo_planes_equal"] = halo_planes_equal(dist, drv)
     st1 = slab.device_stats()
     launches = int(st1["kernels_launched"] - st0["kernels_launched"]) - (0 if world > 1 else 0)
 
@@ -320,10 +422,14 @@ def run_b200_arm(a):
                 "gpu_launches": launches, "clocks": clocks}
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if parity_n is not None:
+            line["parity_n"] = parity_n
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_n is not None and (parity_n["invariance"] != "bit-exact" or not parity_n["halo_planes_equal"]):
+        raise SystemExit(3)                  # a fast wrong answer is not a result
 
 
 def main():

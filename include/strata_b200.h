@@ -71,8 +71,8 @@ typedef struct sb_stats {
     int32_t pitch;
 } sb_stats;
 
-enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, SB_KERNEL_TMA = 3, SB_KERNEL_RESIDENT = 4,
-       SB_KERNEL_PIPELINE = 5 };
+enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, /* 3 is retired: rejected by sb_set_option */
+       SB_KERNEL_RESIDENT = 4, SB_KERNEL_PIPELINE = 5 };
 /* SB_KERNEL_RESIDENT: for grids that fit in the GPU's aggregate shared memory (about 1.3 M cells on a B200) a whole
  * sb_step_n chunk runs as ONE cooperative launch that keeps the fields on chip between steps (sb_resident.cuh).
  * SB_KERNEL_AUTO picks it when the configuration allows (single slab, point sources into p, probes only, no ADE /
@@ -156,7 +156,10 @@ int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const uint8_t *m
 /* Sources: CSR over cells.  Cell u (flat LOCAL dense index cell_idx[u] = (i*ny+j)*nz+k)
  * receives, in order e = start[u] .. start[u+1]-1,  f = f32( f64(f) + w[src_id[e]] * weight[e] )
  * (core/solver.py:2386-2433: float64 add, float32 store).  field[e] selects p/vx/vy/vz.
- * The host applies the reference's geometry test when it builds the list.                */
+ * The host applies the reference's geometry test when it builds the list.
+ * On a slab with a lower neighbour, cells of the ghost plane i = -1 (cell_idx in [-ny*nz, 0)) may be listed for
+ * field vx only: the ghost face vx[-1] is kept redundantly, so an x-normal velocity source on the neighbour's last
+ * plane has to be injected into it with the owner's operations (decomposition invariance).          */
 int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const int64_t *cell_idx,
                    const int32_t *start, const int32_t *src_id, const int32_t *field,
                    const double *weight);
@@ -205,7 +208,9 @@ int sb_set_peers(sb_solver *h, float *const lo_p_sets[2], float *const hi_p_sets
 /* 0.5*sum(p^2)/(rho c^2)*dV + 0.5*rho*sum(v^2)*dV over air cells (core/solver.py:2689-2706). */
 int sb_energy(sb_solver *h, double rho, double c, double dV, double *out);
 
-int sb_reset(sb_solver *h);                      /* zero fields, J, counters (solver.py:2781-2800) */
+/* zero fields, J, counters (solver.py:2781-2800).  With peers set, also clears this rank's step flags: every rank
+ * must be idle (synchronised + barrier) before, and barrier again after, the call.                               */
+int sb_reset(sb_solver *h);
 /* Tuning knobs; results never depend on them (every combination is bit-identical).
  *   SB_OPT_KERNEL            SB_KERNEL_*: which step kernel (default AUTO: resident K5 / pipelined K6 / streaming K1 by size)
  *   SB_OPT_ROWS_PER_THREAD   K1: rows per thread, 1 or 2 (0 = autotuned together with the next three)

@@ -12,6 +12,7 @@ from .materials import Pole, PoleMaterial, PoleType, SimpleMaterial  # noqa: F40
 from .solver import FDTDSolver  # noqa: F401
 from .sources import GaussianPulse, Microphone, Probe  # noqa: F401
 from .shim import install_into_reference  # noqa: F401
+from . import io, workloads  # noqa: F401,E402
 
 __version__ = "0.1.0"
 __all__ = ["FDTDSolver", "UniformGrid", "NonuniformGrid", "PML", "RigidBoundary", "GaussianPulse", "Probe",

@@ -42,18 +42,32 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA extension for sm_100a (cross-compiles without a GPU)."""
+    """Compile the CUDA extension for sm_100a (cross-compiles without a GPU).
+
+    Safe under torchrun, where every rank may get here at once: one process compiles (file lock), into a temporary
+    name that is moved over the library atomically, so nobody ever dlopens a half-written file."""
     if not force and not needs_build():
         return SO_PATH
+    import fcntl
     SO_PATH.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(SO_PATH), str(SOURCES[0])]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise B200BackendError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+    with open(SO_PATH.parent / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another rank built it while we waited
+                return SO_PATH
+            tmp = SO_PATH.with_name(f".{SO_PATH.name}.{os.getpid()}.tmp")
+            cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(tmp), str(SOURCES[0])]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise B200BackendError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 
@@ -75,7 +89,7 @@ class Stats(C.Structure):
                 ("pitch", C.c_int32)]
 
 
-KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_TMA, KERNEL_RESIDENT, KERNEL_PIPELINE = 0, 1, 2, 3, 4, 5
+KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_RESIDENT, KERNEL_PIPELINE = 0, 1, 2, 4, 5
 (OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH, OPT_PROFILE,
  OPT_FUSE_K3, OPT_RESIDENT_SPLIT, OPT_RESIDENT_MIN_STEPS, OPT_PLANE_MAP, OPT_ADE_LAYOUT) = range(12)
 

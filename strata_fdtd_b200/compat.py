@@ -45,6 +45,7 @@ def install_as_strata_fdtd(force_alias: bool = False):
 
     class FDTDSolver(sb.FDTDSolver):
         __doc__ = sb.FDTDSolver.__doc__
+        _coerce_backend = True
 
         def __init__(self, *args, backend="auto", **kw):
             if backend not in ("b200", "auto"):

@@ -373,7 +373,9 @@ extern "C" int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, doubl
 static inline long long dense_to_off(const sb_solver *h, long long dense)
 {
     const sb_grid_desc &d = h->d;
-    const long long k = dense % d.nz, j = (dense / d.nz) % d.ny, i = dense / ((long long)d.nz * d.ny);
+    const long long pl = (long long)d.nz * d.ny;
+    const long long i = dense >= 0 ? dense / pl : -((-dense + pl - 1) / pl);       // floor: the lower ghost plane is i = -1
+    const long long r = dense - i * pl, k = r % d.nz, j = r / d.nz;
     return i * h->plane + j * d.pitch + k;
 }
 
@@ -389,18 +391,22 @@ extern "C" int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const in
     if (!cell_idx || !start || !src_id || !field || !weight) return fail("null source table");
     const long long ncell = (long long)h->d.nx * h->d.ny * h->d.nz;
     std::vector<long long> off((size_t)n_cells);
+    const int n_ent = start[n_cells];
+    const long long ghost_lo = h->d.has_lower ? -(long long)h->d.ny * h->d.nz : 0;   // vx entries may sit on the lower ghost plane
     for (int u = 0; u < n_cells; u++) {
-        if (cell_idx[u] < 0 || cell_idx[u] >= ncell) return fail("source cell %d out of range", u);
+        if (cell_idx[u] < ghost_lo || cell_idx[u] >= ncell) return fail("source cell %d out of range", u);
+        if (cell_idx[u] < 0)
+            for (int e = start[u]; e < start[u + 1]; e++)
+                if (field[e] != 1) return fail("source cell %d: only vx entries may lie on the ghost plane", u);
         off[u] = dense_to_off(h, cell_idx[u]);
     }
-    const int n_ent = start[n_cells];
     for (int e = 0; e < n_ent; e++)
         if (src_id[e] < 0 || src_id[e] >= n_sources || field[e] < 0 || field[e] > 3) return fail("bad source entry %d", e);
     h->n_src_entries = n_ent;
     h->inline_ok = n_ent <= 8;
     for (int u = 0; u < n_cells && h->inline_ok; u++)
         for (int e = start[u]; e < start[u + 1]; e++) {
-            if (field[e] != 0) { h->inline_ok = false; break; }
+            if (field[e] != 0 || cell_idx[u] < 0) { h->inline_ok = false; break; }
             const long long dn = cell_idx[u];
             h->inl_k[e] = (int)(dn % h->d.nz); h->inl_j[e] = (int)((dn / h->d.nz) % h->d.ny);
             h->inl_i[e] = (int)(dn / ((long long)h->d.nz * h->d.ny));
@@ -705,7 +711,7 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
 {
     const sb_grid_desc &d = h->d;
     int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
-    if (variant == SB_KERNEL_TMA || h->have_peers) variant = SB_KERNEL_MARCH;   // only K1 pushes halos to peers
+    if (h->have_peers) variant = SB_KERNEL_MARCH;   // only K1 pushes halos to peers
     h->last_variant = variant;
     if (variant == SB_KERNEL_NAIVE) {
         P.i_begin = d.has_lower ? -1 : 0; P.i_end = d.nx;
@@ -794,7 +800,7 @@ static bool fused_k3(const sb_solver *h)
     // costs ~3 us): <= 4 M cells unless forced (opt_fuse_k3 == 2)
     const bool small = (long long)h->d.nx * h->d.ny * h->d.nz <= (4LL << 20);
     return h->opt_fuse_k3 && (small || h->opt_fuse_k3 == 2) && h->inline_ok && !h->have_peers && !h->have_ade &&
-           h->plane_ops.empty() && (variant == SB_KERNEL_MARCH || variant == SB_KERNEL_TMA);
+           h->plane_ops.empty() && variant == SB_KERNEL_MARCH;
 }
 
 static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev, int step, bool last)
@@ -1316,6 +1322,8 @@ extern "C" int sb_reset(sb_solver *h)
     for (auto *po : h->plane_ops) CU(cudaMemsetAsync(po->prev.p, 0, po->prev.n * 4, h->stream));
     CU(cudaMemsetAsync(h->d_step_global.p, 0, sizeof(int), h->stream));
     CU(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), h->stream));          // a timed-out wait is not carried into the next run
+    // the neighbours' "steps done" words restart with the step counter (else the first waits of the new run pass vacuously)
+    if (h->have_peers && h->my_flags) CU(cudaMemsetAsync(h->my_flags, 0, 2 * sizeof(int), h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->cur = 0; h->steps_done = 0;
     return 0;
@@ -1325,7 +1333,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
 {
     if (!h) return fail("null handle");
     switch (option) {
-        case SB_OPT_KERNEL: if (value < 0 || value > 5) return fail("bad kernel variant"); h->opt_kernel = value; break;
+        case SB_OPT_KERNEL: if (value < 0 || value > 5 || value == 3) return fail("bad kernel variant %d", value); h->opt_kernel = value; break;
         case SB_OPT_ROWS_PER_THREAD: if (value < 0 || value > 2) return fail("rows_per_thread must be 0 (auto), 1 or 2"); h->opt_rj = value; break;
         case SB_OPT_WARPS_J: if (value < 0 || value > 8) return fail("warps_j out of range"); h->opt_wj = value; break;
         case SB_OPT_WARPS_K: if (value < 1 || value > 8) return fail("warps_k out of range"); h->opt_wk = value; break;

@@ -60,6 +60,7 @@ def owner_of(i: int, ranges: list[tuple[int, int]]) -> int:
 
 class SlabSolver(FDTDSolver):
     """FDTDSolver restricted to one slab, stepped one step at a time so halos can be exchanged in between."""
+    _is_slab = True
 
     def begin_chunk(self, m: int) -> None:
         dev = self._sync_to_device()
@@ -121,14 +122,22 @@ def _chunks(n_steps: int, chunk: int):
 
 
 class DistributedFDTDSolver:
-    """One slab per process; the public surface of FDTDSolver with global coordinates.
+    """One slab per process; the public surface of FDTDSolver (core/solver.py:1442-3442) with global coordinates.
 
-    Launch with ``python -m torch.distributed.run --nproc-per-node N ...`` (one rank per GPU).  The
-    process group must exist (``torch.distributed.init_process_group``) before construction.
+    Launch with ``python -m torch.distributed.run --nproc-per-node N ...`` (one rank per GPU).  ``FDTDSolver(...)``
+    itself returns this class when it is constructed inside such a job (solver.FDTDSolver.__new__), so a script
+    written for one GPU runs unchanged on N.  Every rank makes the same calls with global arguments; results
+    (`get_probe_data`, fields, energy, microphones) are available on every rank, files are written by rank 0.
+
+    ``halo``: "p2p" = exchange fused into the step kernel over NVLink peer memory (needs the NCCL backend and
+    symmetric memory), "nccl" = one grouped send/recv pair per face and step on the step's stream (with the gloo
+    backend the planes are staged through host memory: the CPU-plumbing route the tests use on a single GPU),
+    "auto" = p2p where available.
     """
 
     def __init__(self, shape=None, resolution=None, grid=None, c=343.0, rho=1.2, courant=0.95,
-                 backend="b200", device=None, chunk_steps=64, group=None, halo="auto"):
+                 backend="b200", warn_energy_drift=False, energy_drift_threshold=0.01, device=None, chunk_steps=None,
+                 group=None, halo="auto"):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
@@ -138,13 +147,20 @@ class DistributedFDTDSolver:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         nx = int((grid.shape if grid is not None else shape)[0])
         self.ranges = slab_ranges(nx, self.world)
+        chunk_steps = 64 if chunk_steps is None else int(chunk_steps)
         self.slab = SlabSolver(shape=shape, resolution=resolution, grid=grid, c=c, rho=rho, courant=courant,
-                               backend=backend, device=device, chunk_steps=chunk_steps, slab=self.ranges[self.rank])
-        self.chunk_steps = int(chunk_steps)
+                               backend=backend, device=device, chunk_steps=chunk_steps, slab=self.ranges[self.rank],
+                               warn_energy_drift=warn_energy_drift, energy_drift_threshold=energy_drift_threshold)
+        self.chunk_steps = chunk_steps
         self._ghosts_fresh = False
+        self._staged = dist.get_backend(group) != "nccl"      # gloo cannot move device memory: stage planes on the host
         self.halo = "nccl"
         self._symm = []                          # keeps symmetric allocations / handles alive
-        if halo in ("auto", "p2p") and self.world > 1 and dist.get_backend(group) == "nccl":
+        self._energy_history: list = []
+        self._snapshots: list = []
+        self._snapshot_interval = None
+        self.last_run_stats: dict = {}
+        if halo in ("auto", "p2p") and self.world > 1 and not self._staged:
             try:
                 self._setup_p2p()
                 self.halo = "p2p"
@@ -154,6 +170,8 @@ class DistributedFDTDSolver:
                 import warnings
                 warnings.warn(f"peer-to-peer halo unavailable ({type(e).__name__}: {e}); using NCCL send/recv")
                 self.slab._p_allocator = None
+        elif halo == "p2p":
+            raise RuntimeError("halo='p2p' needs the NCCL backend and more than one rank")
 
     def _setup_p2p(self):
         """Fused halo: K1 stores its cut planes of p straight into the neighbours' ghost planes over NVLink.
@@ -201,11 +219,22 @@ class DistributedFDTDSolver:
     shape = property(lambda self: self.slab.global_shape)
     dt = property(lambda self: self.slab.dt)
     dx = property(lambda self: self.slab.dx)
+    c = property(lambda self: self.slab.c)
+    rho = property(lambda self: self.slab.rho)
     time = property(lambda self: self.slab.time)
     step_count = property(lambda self: self.slab.step_count)
     grid = property(lambda self: self.slab.grid)
+    backend = "b200"
+    using_native = False
+    using_gpu = True
+    using_b200 = True
+    has_materials = property(lambda self: self.slab.has_materials)
+    material_count = property(lambda self: self.slab.material_count)
+    _sources = property(lambda self: self.slab._sources)
+    _probes = property(lambda self: self.slab._probes)
 
     def set_geometry(self, geometry):
+        """A global bool array, an SDF object (voxelised over this slab's planes only) or ``f(i_lo, i_hi)``."""
         self.slab.set_geometry(geometry)
 
     def add_boundary(self, b):
@@ -231,8 +260,25 @@ class DistributedFDTDSolver:
     def set_material_box(self, material_id, x_range, y_range, z_range):
         self.slab.set_material_box(material_id, x_range, y_range, z_range)
 
+    def get_material_at(self, position):
+        """Material of a global cell (asked of its owner; every rank gets the answer)."""
+        i = int(position[0])
+        owner = owner_of(i, self.ranges)
+        box = [self.slab.get_material_at((i - self.slab._i0,) + tuple(position[1:])) if owner == self.rank else None]
+        self.dist.broadcast_object_list(box, src=self._peer(owner), group=self.group)
+        return box[0]
+
     def set_kernel_option(self, opt, val):
         self.slab.set_kernel_option(opt, val)
+
+    def enable_snapshots(self, interval: int, capture_velocity: bool = False) -> None:
+        if capture_velocity:
+            raise NotImplementedError("velocity snapshots are not gathered across slabs; use gather_field('vx') ...")
+        self._snapshot_interval = int(interval)
+
+    def get_snapshots(self):
+        """(time, global p) pairs -- kept on rank 0 only (the other ranks return an empty list)."""
+        return self._snapshots
 
     def _finish_microphones(self):
         """Collective: every rank receives the corner samples of all slabs and completes every microphone."""
@@ -254,60 +300,183 @@ class DistributedFDTDSolver:
         """One grouped send/recv per step: p planes both ways (and, once after uploads, vx upward)."""
         dist, s = self.dist, self.slab
         dev = s._dev
-        ops = []
-        with dev.torch.cuda.stream(dev.stream):
-            h = s.halo_planes("p")
-            if self.rank > 0:
-                ops.append(dist.P2POp(dist.isend, h["send_lo"], self._peer(self.rank - 1), self.group))
-                ops.append(dist.P2POp(dist.irecv, h["recv_lo"], self._peer(self.rank - 1), self.group))
+        torch = dev.torch
+        pairs = []                                # (send view or None, recv view or None, peer)
+        h = s.halo_planes("p")
+        if self.rank > 0:
+            pairs.append((h["send_lo"], h["recv_lo"], self.rank - 1))
+        if self.rank < self.world - 1:
+            pairs.append((h["send_hi"], h["recv_hi"], self.rank + 1))
+        if include_vx_ghost:
+            v = s.halo_planes("vx")
             if self.rank < self.world - 1:
-                ops.append(dist.P2POp(dist.isend, h["send_hi"], self._peer(self.rank + 1), self.group))
-                ops.append(dist.P2POp(dist.irecv, h["recv_hi"], self._peer(self.rank + 1), self.group))
-            if include_vx_ghost:
-                v = s.halo_planes("vx")
-                if self.rank < self.world - 1:
-                    ops.append(dist.P2POp(dist.isend, v["send_hi"], self._peer(self.rank + 1), self.group))
-                if self.rank > 0:
-                    ops.append(dist.P2POp(dist.irecv, v["recv_lo"], self._peer(self.rank - 1), self.group))
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()                      # stream-level wait on CUDA; blocking on gloo
+                pairs.append((v["send_hi"], None, self.rank + 1))
+            if self.rank > 0:
+                pairs.append((None, v["recv_lo"], self.rank - 1))
+        if not pairs:
+            return
+        with torch.cuda.stream(dev.stream):
+            ops, back = [], []
+            for send, recv, peer in pairs:
+                if send is not None:
+                    ops.append(dist.P2POp(dist.isend, send.cpu() if self._staged else send, self._peer(peer), self.group))
+                if recv is not None:
+                    buf = torch.empty(recv.shape, dtype=recv.dtype) if self._staged else recv
+                    ops.append(dist.P2POp(dist.irecv, buf, self._peer(peer), self.group))
+                    if self._staged:
+                        back.append((recv, buf))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()                          # stream-level wait on CUDA; blocking on gloo
+            for recv, buf in back:
+                recv.copy_(buf)
 
     def _peer(self, r: int) -> int:
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
-    # ---- stepping --------------------------------------------------------------------------------
-    def run(self, duration=None, steps=None, **_ignored):
-        if steps is None:
-            steps = int(np.ceil(duration / self.dt))
+    def _all_any(self, flag: bool) -> bool:
+        box = [None] * self.world
+        self.dist.all_gather_object(box, bool(flag), group=self.group)
+        return any(box)
+
+    def _prepare_ghosts(self):
+        """Collective.  After host-side edits of the fields (initial conditions) or a reset the ghost planes of p and
+        the redundantly kept ghost face vx[-1] are refreshed from their owners."""
         s = self.slab
+        stale = (not self._ghosts_fresh) or bool(s._host_dirty)
         s._sync_to_device()
-        if not self._ghosts_fresh:               # ghosts of p and vx after host-side edits / first use
-            if self.halo == "p2p":
-                _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
-                self.dist.barrier(self.group)    # nobody is still pushing into the ghosts we are about to fill
-            self._exchange(include_vx_ghost=True)
-            if self.halo == "p2p":
-                _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
-                self.dist.barrier(self.group)
-            self._ghosts_fresh = True
-        for m in _chunks(steps, self.chunk_steps):
-            s.begin_chunk(m)
-            if self.halo == "p2p":               # the kernels exchange halos themselves: enqueue the whole chunk
-                s.enqueue_steps(m)
-            else:
-                for _ in range(m):
-                    s.enqueue_step()
-                    self._exchange()
-            s.end_chunk()
-        self._finish_microphones()
+        if not self._all_any(stale):
+            return
+        if self.halo == "p2p":
+            _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
+            self.dist.barrier(self.group)    # nobody is still pushing into the ghosts we are about to fill
+        self._exchange(include_vx_ghost=True)
+        if self.halo == "p2p":
+            _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
+            self.dist.barrier(self.group)
+        self._ghosts_fresh = True
+
+    # ---- stepping --------------------------------------------------------------------------------
+    def _run_chunk(self, m: int) -> None:
+        s = self.slab
+        s.begin_chunk(m)
+        if self.halo == "p2p":               # the kernels exchange halos themselves: enqueue the whole chunk
+            s.enqueue_steps(m)
+        else:
+            for _ in range(m):
+                s.enqueue_step()
+                self._exchange()
+        s.end_chunk()
+
+    def run(self, duration=None, progress=False, track_energy=False, energy_sample_interval=1, output_file=None,
+            script_content=None, callback=None, snapshot_interval=None, steps=None, output=None):
+        """``FDTDSolver.run`` (core/solver.py:2520-2606) over all slabs.  Collective: every rank calls it with the same
+        arguments.  ``callback(step)`` runs on every rank; the result file and snapshots are produced by rank 0 from
+        the traces / planes their owners send at the end of every chunk of steps."""
+        import time as _t
+        if steps is None:
+            if duration is None:
+                raise ValueError("run() needs duration= or steps=")
+            steps = int(np.ceil(duration / self.dt))
+        output_file = output_file or output
+        s = self.slab
+        t0 = _t.time()
+        self._prepare_ghosts()
+        if track_energy and not self._energy_history:
+            self._energy_history.append((s._step_count, s._time, self.compute_energy()))
+        writer = None
+        if output_file and self.rank == 0:
+            from .io import ResultWriter
+            writer = ResultWriter(output_file, _WriterView(self), script_content)
+        elif output_file:
+            _WriterView(self).geometry                  # takes part in the collective gather of the geometry
+        bar = None
+        if progress and self.rank == 0:
+            try:
+                from tqdm import tqdm
+                bar = tqdm(total=steps, desc=f"FDTD simulation (b200 x{self.world})")
+            except ImportError:
+                bar = None
+        launches0 = s.kernel_launches()
+        done = 0
+        try:
+            while done < steps:
+                m = min(self.chunk_steps, steps - done)
+                for q in range(m):                     # a chunk ends right after any step whose fields the host has to see
+                    idx = s._step_count + q
+                    if (self._snapshot_interval and idx % self._snapshot_interval == 0) or \
+                            (track_energy and (idx + 1) % energy_sample_interval == 0) or \
+                            (output_file and snapshot_interval is not None and (done + q) % snapshot_interval == 0):
+                        m = q + 1
+                        break
+                n0 = {pr.name: len(pr.data) for pr in s._local_probes}
+                self._run_chunk(m)
+                last_idx = s._step_count - 1
+                if self._snapshot_interval and last_idx % self._snapshot_interval == 0:
+                    p = self.gather_field("p")
+                    if self.rank == 0:
+                        self._snapshots.append((float(s._chunk_times[-1]), p))
+                if track_energy and s._step_count % energy_sample_interval == 0:
+                    self._energy_history.append((s._step_count, s._time, self.compute_energy()))
+                if output_file:
+                    mine = {pr.name: np.asarray(pr.data[n0[pr.name]:], dtype=np.float32) for pr in s._local_probes}
+                    parts = [None] * self.world if self.rank == 0 else None
+                    self.dist.gather_object(mine, parts, dst=self._peer(0), group=self.group)
+                    snap = snapshot_interval is not None and (done + m - 1) % snapshot_interval == 0
+                    p = self.gather_field("p") if snap else None
+                    if writer is not None:
+                        merged = {}
+                        for part in parts:
+                            merged.update(part)
+                        names = [n for n in s._probes if n in merged]
+                        if names:
+                            writer.append_probe_block(names, np.stack([merged[n] for n in names], axis=1))
+                        if snap:
+                            writer.write_snapshot(p)
+                if bar is not None:
+                    bar.update(m)
+                if callback is not None:
+                    for q in range(m):
+                        callback(last_idx - (m - 1 - q))
+                done += m
+            self._finish_microphones()
+            if s._warn_energy_drift and len(self._energy_history) >= 2:
+                import warnings
+                rep = self.energy_report()
+                if abs(rep["energy_change_percent"]) > s._energy_drift_threshold * 100:
+                    warnings.warn(f"Energy drift detected: {rep['energy_change_percent']:.2f}% change "
+                                  f"(threshold: {s._energy_drift_threshold * 100:.1f}%). "
+                                  f"Status: {rep['conservation_status']}", UserWarning, stacklevel=2)
+        finally:
+            runtime = _t.time() - t0
+            if bar is not None:
+                bar.close()
+            cells = int(np.prod(self.shape, dtype=np.int64))
+            self.last_run_stats = {"steps": steps, "runtime_s": runtime, "n_gpus": self.world, "halo": self.halo,
+                                   "cell_updates_per_s": cells * steps / runtime if runtime > 0 else float("inf"),
+                                   "kernel_launches": s.kernel_launches() - launches0}
+            if writer is not None:
+                writer.finalize(runtime=runtime, backend="b200", num_threads=0, num_gpus=self.world)
 
     def step(self):
         self.run(steps=1)
 
+    def reset(self) -> None:
+        """Back to t = 0 on every slab (core/solver.py:2781-2800).  Collective."""
+        s = self.slab
+        if s._dev is not None:
+            _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
+        self.dist.barrier(self.group)            # no neighbour is still storing into our ghosts / flags
+        s.reset()
+        self.dist.barrier(self.group)
+        self._ghosts_fresh = False
+        self._energy_history.clear()
+        self._snapshots.clear()
+
     # ---- results ---------------------------------------------------------------------------------
     def get_probe_data(self, name=None) -> dict:
         """All probes on every rank (gathered from their owners)."""
+        if name is not None and name not in self.slab._probes:
+            raise KeyError(f"Probe '{name}' not found")
         local = {pr.name: pr.get_data() for pr in self.slab._local_probes}
         parts = [None] * self.world
         self.dist.all_gather_object(parts, local, group=self.group)
@@ -324,15 +493,85 @@ class DistributedFDTDSolver:
         self.dist.gather_object(local, parts, dst=self._peer(0), group=self.group)
         return np.concatenate(parts, axis=0) if self.rank == 0 else None
 
+    def get_field(self, name: str) -> np.ndarray:
+        """The whole field on every rank (a copy; small grids)."""
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, self.slab.get_field(name), group=self.group)
+        return np.concatenate(parts, axis=0)
+
+    def set_field(self, name: str, value) -> None:
+        """Overwrite a field from a global array (initial conditions); ghosts are refreshed by the next run()."""
+        value = np.asarray(value)
+        if value.shape != tuple(self.shape):
+            raise ValueError(f"field shape {value.shape} doesn't match solver shape {self.shape}")
+        self.slab._field_set(name, value[self.slab._i0:self.slab._i1])
+        self._ghosts_fresh = False
+
+    p = property(lambda s: s.get_field("p"), lambda s, v: s.set_field("p", v))
+    vx = property(lambda s: s.get_field("vx"), lambda s, v: s.set_field("vx", v))
+    vy = property(lambda s: s.get_field("vy"), lambda s, v: s.set_field("vy", v))
+    vz = property(lambda s: s.get_field("vz"), lambda s, v: s.set_field("vz", v))
+
     def compute_energy(self) -> float:
         import torch
         e = torch.tensor([self.slab.compute_energy()], dtype=torch.float64,
-                         device=self.slab._dev.device if self.dist.get_backend(self.group) == "nccl" else "cpu")
+                         device="cpu" if self._staged else self.slab._dev.device)
         self.dist.all_reduce(e, group=self.group)
         return float(e.item())
 
+    def get_energy_history(self):
+        return self._energy_history.copy()
+
+    def energy_report(self) -> dict:
+        return FDTDSolver.energy_report(self)
+
+    def get_sample_rate(self) -> float:
+        return 1.0 / self.dt
+
+    def get_frequency_response(self, probe_name: str, n_fft=None):
+        data = self.get_probe_data(probe_name)[probe_name]
+        if n_fft is None:
+            n_fft = int(2 ** np.ceil(np.log2(len(data))))
+        return np.fft.rfftfreq(n_fft, self.dt), np.abs(np.fft.rfft(data, n=n_fft))
+
+    def kernel_launches(self) -> int:
+        return self.slab.kernel_launches()
+
+    def device_stats(self) -> dict:
+        return self.slab.device_stats()
+
     def close(self):
         self.slab.close()
+
+
+class _WriterView:
+    """What io.ResultWriter reads from a solver, with global extents (rank 0 writes the file)."""
+
+    def __init__(self, d: DistributedFDTDSolver):
+        self._d = d
+        self._geometry = None
+
+    def __getattr__(self, name):
+        return getattr(self._d, name)
+
+    @property
+    def geometry(self):
+        """Collective: the global air mask gathered on rank 0 (all air if nobody set a geometry)."""
+        if self._geometry is None:
+            d = self._d
+            local = None if d.slab._geometry is None else np.packbits(d.slab._geometry)
+            parts = [None] * d.world if d.rank == 0 else None
+            d.dist.gather_object((local, d.slab.shape), parts, dst=d._peer(0), group=d.group)
+            if d.rank == 0:
+                planes = []
+                for bits, shp in parts:
+                    n = int(np.prod(shp, dtype=np.int64))
+                    planes.append(np.ones(shp, dtype=bool) if bits is None else
+                                  np.unpackbits(bits)[:n].reshape(shp).astype(bool))
+                self._geometry = np.concatenate(planes, axis=0)
+            else:
+                self._geometry = False
+        return self._geometry
 
 
 class LocalSlabGroup:

@@ -88,13 +88,63 @@ class _DeviceState:
             pass
 
 
+def distributed_world(auto_init: bool = True) -> int:
+    """Number of ranks this process steps a grid with: the size of the torch.distributed job it runs in, else 1.
+
+    Under ``python -m torch.distributed.run`` (RANK / WORLD_SIZE / MASTER_ADDR in the environment) the process group is
+    created on first use: NCCL, one rank per GPU, rank r on CUDA device ``STRATA_B200_DEVICES[r]`` (a comma list;
+    default LOCAL_RANK).  ``STRATA_B200_DISTRIBUTED=0`` switches the automatic route off."""
+    import os
+    if os.environ.get("STRATA_B200_DISTRIBUTED", "1") == "0":
+        return 1
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and auto_init and "RANK" in os.environ and "MASTER_ADDR" in os.environ:
+        import torch
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        devs = [int(q) for q in os.environ.get("STRATA_B200_DEVICES", "").split(",") if q.strip() != ""]
+        index = devs[local] if devs else local
+        if torch.cuda.is_available():
+            torch.cuda.set_device(index)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", index))
+        else:
+            dist.init_process_group("gloo")
+        return dist.get_world_size()
+    return 1
+
+
 class FDTDSolver:
-    """3-D acoustic pressure-velocity FDTD on a staggered grid, executed on a B200."""
+    """3-D acoustic pressure-velocity FDTD on a staggered grid, executed on a B200.
+
+    Constructed inside a multi-rank job (see ``distributed_world``) the same call returns a
+    ``multi.DistributedFDTDSolver``: the grid is cut into slabs along axis 0, one per GPU, behind the same methods
+    (``distributed=False`` keeps a solver on this rank's GPU only, ``True`` insists on the slab solver)."""
+
+    _is_slab = False            # multi.SlabSolver: one slab of a decomposed grid, never re-dispatched
+    _coerce_backend = False     # compat alias: "native" / "python" requests are served by this backend
+
+    def __new__(cls, *args, distributed: bool | None = None, **kw):
+        if not cls._is_slab and kw.get("slab") is None and distributed is not False:
+            if distributed_world() > 1:
+                from .multi import DistributedFDTDSolver
+                kw.pop("slab", None)
+                if cls._coerce_backend:
+                    kw["backend"] = "b200"
+                return DistributedFDTDSolver(*args, **kw)
+            if distributed:
+                raise RuntimeError("distributed=True needs a torch.distributed job with more than one rank "
+                                   "(python -m torch.distributed.run --nproc-per-node N ...)")
+        return super().__new__(cls)
 
     def __init__(self, shape=None, resolution=None, grid=None, c: float = 343.0, rho: float = 1.2,
                  courant: float = 0.95, backend: str = "b200", warn_energy_drift: bool = False,
                  energy_drift_threshold: float = 0.01, device: int | None = None, chunk_steps: int | None = None,
-                 slab: tuple[int, int] | None = None):
+                 slab: tuple[int, int] | None = None, distributed: bool | None = None):
         if backend not in ("b200", "auto"):
             raise ValueError(f"strata_fdtd_b200 provides backend='b200' only (got {backend!r}); "
                              "use the reference package for 'native' / 'python'")
@@ -246,6 +296,12 @@ class FDTDSolver:
                 region = ids == mat_id
                 if np.any(region):
                     self.set_material_region(region, material_id=mat_id)
+        elif hasattr(geometry, "sdf"):
+            # SDFPrimitive.voxelize (geometry/sdf.py:99-125: cell-centre points, sdf <= 0) restricted to the planes this
+            # slab holds and evaluated a few planes at a time -- never the whole-grid point array (6.4 GB at config 4)
+            self._store_geometry(lambda lo, hi: self._voxelize_planes(geometry, lo, hi))
+            self._material_ext.fill(0)
+            self._dirty.add("ade")
         elif hasattr(geometry, "voxelize"):
             self._store_geometry(geometry.voxelize(self.grid))
             self._material_ext.fill(0)
@@ -254,6 +310,23 @@ class FDTDSolver:
             self._store_geometry(geometry)
         self._rigid = True
         self._dirty |= {"geometry", "sources"}
+
+    def _voxelize_planes(self, sdf_object, i_lo: int, i_hi: int, max_points: int = 1 << 22) -> np.ndarray:
+        """``sdf_object.voxelize(grid)[i_lo:i_hi]`` without materialising the rest of the grid."""
+        g = self._grid
+        ny, nz = self.global_shape[1], self.global_shape[2]
+        Y, Z = np.meshgrid(np.asarray(g.y_coords, dtype=np.float64), np.asarray(g.z_coords, dtype=np.float64), indexing="ij")
+        yz = np.stack([Y.ravel(), Z.ravel()], axis=1)
+        xs = np.asarray(g.x_coords, dtype=np.float64)
+        out = np.empty((i_hi - i_lo, ny, nz), dtype=bool)
+        step = max(1, max_points // (ny * nz))
+        for a in range(i_lo, i_hi, step):
+            b = min(i_hi, a + step)
+            pts = np.empty(((b - a) * ny * nz, 3), dtype=np.float64)
+            pts[:, 0] = np.repeat(xs[a:b], ny * nz)
+            pts[:, 1:] = np.tile(yz, (b - a, 1))
+            out[a - i_lo:b - i_lo] = (np.asarray(sdf_object.sdf(pts)) <= 0).reshape(b - a, ny, nz)
+        return out
 
     def _to_index(self, pos, what: str):
         """metres -> int(round(pos/dx)) when any entry is a float below max(shape) (solver.py:1818-1839)."""
@@ -264,6 +337,16 @@ class FDTDSolver:
                 if not 0 <= i < n:
                     raise ValueError(f"{what} {'xyz'[a]} position {pos[a]:.4f}m (index {i}) is outside grid (0-{n-1})")
             return idx
+        if isinstance(pos, (tuple, list)) and len(pos) == 3:
+            # integer indices address the array as NumPy would (solver.py:2437 reads p[i, j, k]): negative values
+            # wrap once, anything else is an IndexError -- raised here instead of at the first recorded step
+            out = []
+            for a, (i, n) in enumerate(zip(pos, gs)):
+                i = int(i)
+                if not -n <= i < n:
+                    raise IndexError(f"{what} index {i} is out of bounds for axis {a} with size {n}")
+                out.append(i + n if i < 0 else i)
+            return tuple(out)
         return pos
 
     def add_source(self, source) -> None:
@@ -332,20 +415,34 @@ class FDTDSolver:
         return material_id
 
     def set_material_region(self, mask, material_id: int) -> None:
-        """``mask`` covers the whole grid (on a slab too: the planes next to a cut are needed on both sides)."""
-        mask = np.asarray(mask)
-        if mask.shape != self.global_shape:
-            raise ValueError(f"Mask shape {mask.shape} doesn't match solver shape {self.global_shape}")
+        """``mask``: a bool array over the whole grid or, for grids too large to materialise on every rank,
+        ``f(i_lo, i_hi) -> bool planes`` (as ``set_geometry``): a slab asks for its own planes and the live ghost
+        planes next to them, which both sides of a cut need."""
         if material_id != 0 and material_id not in self._materials:
             raise ValueError(f"Material ID {material_id} not registered. Use register_material() first.")
         lo, hi = self._i0 - self._has_lower, self._i1 + self._has_upper
-        self._material_ext[mask[lo:hi]] = material_id
+        if callable(mask):
+            part = np.asarray(mask(lo, hi), dtype=bool)
+            want = (hi - lo,) + self.global_shape[1:]
+            if part.shape != want:
+                raise ValueError(f"Mask shape {part.shape} doesn't match solver shape {want}")
+        else:
+            mask = np.asarray(mask)
+            if mask.shape != self.global_shape:
+                raise ValueError(f"Mask shape {mask.shape} doesn't match solver shape {self.global_shape}")
+            part = mask[lo:hi]
+        self._material_ext[part] = material_id
         self._dirty.add("ade")
 
     def set_material_box(self, material_id: int, x_range, y_range, z_range) -> None:
-        mask = np.zeros(self.global_shape, dtype=bool)
-        mask[x_range[0]:x_range[1], y_range[0]:y_range[1], z_range[0]:z_range[1]] = True
-        self.set_material_region(mask, material_id)
+        if material_id != 0 and material_id not in self._materials:
+            raise ValueError(f"Material ID {material_id} not registered. Use register_material() first.")
+        lo, hi = self._i0 - self._has_lower, self._i1 + self._has_upper
+        xs = slice(*x_range).indices(self.global_shape[0])       # NumPy slice semantics of the reference (solver.py:2917)
+        a, b = max(xs[0], lo) - lo, max(min(xs[1], hi) - lo, 0)
+        if b > a:
+            self._material_ext[a:b, y_range[0]:y_range[1], z_range[0]:z_range[1]] = material_id
+        self._dirty.add("ade")
 
     def get_material_at(self, position):
         mat_id = self._material_id[position]
@@ -432,10 +529,15 @@ class FDTDSolver:
                     src._check_grid_alignment(self._grid)
                     src._cached_weights = src.get_injection_weights(self._grid)
                     src._cached_mask = src._cached_weights > 0
-                m = src._cached_mask[self._i0:self._i1] & g
-                idx = np.flatnonzero(m)
                 fld = 0 if src.injection_type == "pressure" else 1 + "xyz".index(src.normal_axis)
-                cells.append(idx); wts.append(np.asarray(src._cached_weights, dtype=np.float64)[self._i0:self._i1][m])
+                # an x-normal velocity membrane on the lower neighbour's last plane: that face is kept redundantly here as
+                # the ghost vx[-1], so it receives the same injection (cells of local plane -1 have negative indices)
+                ghost = 1 if (fld == 1 and self._has_lower) else 0
+                sl = slice(self._i0 - ghost, self._i1)
+                gg = True if self._geometry is None else self._geometry_ext[self._has_lower - ghost: self._has_lower + nx]
+                m = src._cached_mask[sl] & gg
+                idx = np.flatnonzero(m) - ghost * ny * nz
+                cells.append(idx); wts.append(np.asarray(src._cached_weights, dtype=np.float64)[sl][m])
                 flds.append(np.full(idx.size, fld, dtype=np.int32)); sids.append(np.full(idx.size, sid, dtype=np.int32))
             else:
                 raise ValueError(f"unknown source_type {kind!r}")

@@ -31,17 +31,8 @@ def _stretched(n, base, ratio):
     return 0.5 * (edges[:-1] + edges[1:])
 
 
-# benign dispersive material of SURVEY.md F9 (bounded for >= 1000 steps)
-BENIGN_POLES = [
-    {"type": "debye", "target": "density", "delta_chi": 0.1, "tau": 1e-4},
-    {"type": "debye", "target": "modulus", "delta_chi": 0.1, "tau": 1e-5},
-    {"type": "lorentz", "target": "modulus", "delta_chi": 0.05, "omega_0": 2 * np.pi * 2000.0, "gamma": 2 * np.pi * 200.0},
-]
-SECOND_POLES = [
-    {"type": "lorentz", "target": "density", "delta_chi": 0.02, "omega_0": 2 * np.pi * 5000.0, "gamma": 2 * np.pi * 500.0},
-    {"type": "debye", "target": "density", "delta_chi": 0.05, "tau": 5e-5},
-    {"type": "debye", "target": "modulus", "delta_chi": 0.08, "tau": 2e-5},
-]
+from strata_fdtd_b200.workloads import (BENIGN_POLES, SECOND_POLES, c1_case, c2_case, c3_case, c4_case,  # noqa: E402,F401
+                                        enclosure_air_mask)
 
 
 def make_cases() -> dict:
@@ -220,100 +211,3 @@ def membrane_case(weights: list) -> dict:
                          frequency=m["frequency"], amplitude=m["amplitude"]))
     return dict(shape=sp["shape"], resolution=sp["resolution"], steps=sp["steps"],
                 geometry=_block_geometry(sp["shape"], lo, hi), pml=sp["pml"], sources=srcs, probes=sp["probes"])
-
-
-def enclosure_air_mask(X, Y, Z, extent):
-    """Air mask (True = air) of a ported loudspeaker enclosure filling the central 60 % of the domain.
-
-    Own closed-form construction with the proportions of the reference's CSG example
-    (examples/sdf_csg/ported_enclosure.py:34-121: 200x200x300 mm box, 18 mm walls, 130 mm driver cut-out,
-    50 mm flared port through the front wall), evaluated at cell centres X, Y, Z (metres; any sub-range of
-    planes along X) so that slabs can voxelise only what they own.  Box axis = grid axis 0, front wall at low x.
-    """
-    Lx, Ly, Lz = extent
-    cx, cy, cz = Lx / 2, Ly / 2, Lz / 2
-    hx, hy, hz = 0.3 * Lx, 0.3 * Ly, 0.3 * Lz                    # half sizes of the outer box
-    t = 0.06 * 2 * min(hx, hy, hz)                               # wall thickness (18/300 of the smallest side)
-    x = np.asarray(X)[:, None, None]; y = np.asarray(Y)[None, :, None]; z = np.asarray(Z)[None, None, :]
-    outer = (np.abs(x - cx) <= hx) & (np.abs(y - cy) <= hy) & (np.abs(z - cz) <= hz)
-    inner = (np.abs(x - cx) < hx - t) & (np.abs(y - cy) < hy - t) & (np.abs(z - cz) < hz - t)
-    solid = outer & ~inner
-    depth = x - (cx - hx)                                        # distance behind the front face
-    in_front_wall = (depth >= 0) & (depth <= t)
-    r_driver = 0.325 * 2 * hy
-    r2_d = (y - cy) ** 2 + (z - cz) ** 2
-    solid &= ~(in_front_wall & (r2_d < r_driver ** 2))
-    r_port = 0.125 * 2 * hy
-    flare = 1.5 * r_port - 0.5 * r_port * np.clip(depth / (1.6667 * t), 0.0, 1.0)   # 30 mm flare vs 18 mm wall
-    r2_p = (y - cy) ** 2 + (z - (cz + 0.6 * hz)) ** 2
-    solid &= ~(in_front_wall & (r2_p < flare ** 2))
-    return ~solid
-
-
-def c4_case(shape=(1024, 512, 512), steps: int = 1000, stretch_x: float = 1.002, materialise: bool = True) -> dict:
-    """BASELINE config 4: nonuniform grid (axis 0 stretched from the centre), ported-enclosure
-    rigid geometry, PML(10), source inside the box, 8 probes.  ``materialise=False`` returns the geometry as a
-    callable f(i_lo, i_hi) for grids too large to voxelise in one piece."""
-    from strata_fdtd_b200.grid import NonuniformGrid
-    g = NonuniformGrid.from_stretch(shape=shape, base_resolution=1e-3, stretch_x=stretch_x, center_fine=True)
-    extent = g.physical_extent()
-    X, Y, Z = g.x_coords, g.y_coords, g.z_coords
-
-    def geom(i_lo, i_hi, _chunk=16):
-        out = np.empty((i_hi - i_lo,) + tuple(shape[1:]), dtype=bool)
-        for a in range(i_lo, i_hi, _chunk):
-            b = min(a + _chunk, i_hi)
-            out[a - i_lo:b - i_lo] = enclosure_air_mask(X[a:b], Y, Z, extent)
-        return out
-
-    nx, ny, nz = shape
-    probes = [("in_centre", (nx // 2, ny // 2, nz // 2)), ("in_back", (int(0.72 * nx), ny // 2, nz // 2)),
-              ("in_corner", (int(0.3 * nx), int(0.3 * ny), int(0.3 * nz))),
-              ("driver_mouth", (int(0.19 * nx), ny // 2, nz // 2)), ("port_mouth", (int(0.19 * nx), ny // 2, int(0.68 * nz))),
-              ("front_far", (int(0.08 * nx), ny // 2, nz // 2)), ("side", (nx // 2, int(0.1 * ny), nz // 2)),
-              ("behind", (int(0.92 * nx), ny // 2, nz // 2))]
-    return dict(nonuniform=dict(x_coords=X, y_coords=Y, z_coords=Z), shape=tuple(shape), steps=steps,
-                geometry=geom(0, nx) if materialise else geom, pml=[dict(depth=10)],
-                sources=[dict(kind="point", position=(int(0.6 * nx), ny // 2, nz // 2), frequency=2000.0)],
-                probes=probes)
-
-
-def c1_case(steps: int = 1000) -> dict:
-    """BASELINE config 1 as worded: 100^3, 1 mm, PML 10, 1 kHz Gaussian pulse, 1 probe."""
-    return dict(shape=(100, 100, 100), resolution=1e-3, steps=steps, pml=[dict(depth=10)],
-                sources=[dict(kind="point", position=(25, 50, 50), frequency=1000.0)],
-                probes=[("probe", (75, 50, 50))])
-
-
-def c2_case(n: int = 200, steps: int = 1000, with_geometry: bool = False) -> dict:
-    """BASELINE config 2: N^3 uniform + PML(10), source at (N/4, N/2, N/2)."""
-    c = dict(shape=(n, n, n), resolution=1e-3, steps=steps, pml=[dict(depth=10)],
-             sources=[dict(kind="point", position=(n // 4, n // 2, n // 2), frequency=1000.0)],
-             probes=[("probe", (3 * n // 4, n // 2, n // 2))])
-    if with_geometry:
-        a, b = int(0.45 * n), int(0.55 * n)
-        c["geometry"] = _block_geometry((n, n, n), (a, a, a), (b, b, b))
-    return c
-
-
-def c3_case(n: int = 512, steps: int = 1000, slab: bool = False) -> dict:
-    """BASELINE config 3: N^3 + PML + ADE material sphere (radius N/10) + 64 probes."""
-    sh = (n, n, n)
-    mid = np.zeros(sh, dtype=np.uint8)
-    if slab:
-        mid[3 * n // 4:, :, :] = 1
-    else:
-        c = n // 2
-        r = n / 10.0
-        # cell-centre SDF < 0, evaluated plane by plane to bound temporaries
-        j, k = np.ogrid[:n, :n]
-        for i in range(max(0, int(c - r) - 1), min(n, int(c + r) + 2)):
-            mid[i][((i - c) ** 2 + (j - c) ** 2 + (k - c) ** 2) < r * r] = 1
-    s = n / 512.0
-    probes = [(f"p{a}{b}", (int(384 * s), int((32 + 64 * a) * s), int((32 + 64 * b) * s)))
-              for a in range(8) for b in range(8)]
-    return dict(shape=sh, resolution=1e-3, steps=steps, pml=[dict(depth=10)],
-                sources=[dict(kind="point", position=(int(77 * s), n // 2, n // 2), frequency=40e3)],
-                probes=probes,
-                materials=[dict(id=1, rho_inf=1.2, K_inf=1.2 * 343.0 ** 2, poles=BENIGN_POLES)],
-                material_id=mid)

@@ -47,6 +47,10 @@ def _group_from_case(case, n_slabs, opts, halo="copy"):
                                   max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
         for src in case.get("sources", []):
             kind = src.get("kind", "point")
+            if kind == "weighted":
+                from util import FixtureMembrane
+                s.add_source(FixtureMembrane(src))
+                continue
             pos = src["position"] if kind == "point" else {"axis": src["axis"], "index": src["index"]}
             s.add_source(sb.GaussianPulse(position=pos, frequency=src["frequency"], bandwidth=src.get("bandwidth"),
                                           amplitude=src.get("amplitude", 1.0), source_type=kind))
@@ -149,7 +153,7 @@ if rank == 0:
                 materials=[dict(id=1, rho_inf=1.2, K_inf=1.2 * 343.0 ** 2, poles=BENIGN_POLES)],
                 mics=[("straddles_the_cut", (0.0235, 0.0101, 0.0137)),
                       ("card", (0.0301, 0.0202, 0.0303), dict(pattern="cardioid", direction=(1.0, 0.5, 0.0)))])
-    one = build_b200_solver(case, device=0)
+    one = build_b200_solver(case, device=0, distributed=False)
     one.run(steps=100)
     for n, mic in one.microphones.items():
         assert np.array_equal(d.microphones[n].get_waveform(), mic.get_waveform()), n
@@ -176,6 +180,112 @@ def test_two_ranks_nccl_equal_single_gpu(tmp_path, halo):
                          capture_output=True, text=True, timeout=600)
     assert "TWO_RANK_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
     assert f"HALO {halo}" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["march", "naive"])
+@pytest.mark.parametrize("halo", ["copy", "p2p"])
+def test_velocity_membrane_on_the_last_plane_of_a_slab(halo, kernel):
+    """An x-normal velocity membrane injects into vx[i] on plane i = 6; with four slabs of seven planes that is the last
+    owned plane of slab 0, whose face the upper neighbour keeps redundantly as its ghost vx[-1]: the ghost must
+    receive the same injection (fp64 add on the same value) or the neighbour's first-plane divergence is wrong."""
+    from util import load_membrane_case
+    case, _ = load_membrane_case()
+    ranges = slab_ranges(case["shape"][0], 4)
+    w = case["sources"][1]["weights"]
+    assert case["sources"][1]["field"] == "vx" and w[ranges[0][1] - 1].any(), "the membrane must sit on a cut plane"
+    opts = {_lib.OPT_KERNEL: _lib.KERNEL_MARCH if kernel == "march" else _lib.KERNEL_NAIVE}
+    steps = 120
+    one = build_b200_solver(case)
+    for k, v in opts.items():
+        one.set_kernel_option(k, v)
+    grp = _group_from_case(case, 4, opts, halo=halo)
+    one.run(steps=steps); grp.run(steps)
+    for f in ("p", "vx", "vy", "vz"):
+        a, b = grp.get_field(f), one.get_field(f)
+        assert np.array_equal(a, b), f"{f} differs (first at {np.argwhere(a != b)[:1]})"
+    tr = grp.get_probe_data()
+    for pname in one._probes:
+        assert np.array_equal(tr[pname], one.get_probe_data(pname)[pname]), pname
+    assert np.abs(one.get_field("vx")).max() > 0
+    grp.close(); one.close()
+
+
+_TWO_RANK_ONE_GPU = r"""
+import os, sys, json, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from cases import make_cases
+from util import build_b200_solver
+import strata_fdtd_b200 as sb
+rank = int(os.environ["RANK"]); torch.cuda.set_device(0)
+dist.init_process_group("gloo")                       # two ranks share cuda:0; halo planes are staged through the host
+case = make_cases()["block_pml"]
+d = sb.FDTDSolver(shape=case["shape"], resolution=case["resolution"], chunk_steps=16)     # dispatches to the slab solver
+assert type(d).__name__ == "DistributedFDTDSolver" and d.halo == "nccl" and d.world == 2
+d.set_geometry(case["geometry"])
+d.add_boundary(sb.PML(depth=8))
+for s in case["sources"]:
+    d.add_source(sb.GaussianPulse(position=s["position"], frequency=s["frequency"]))
+for n, p in case["probes"]:
+    d.add_probe(n, p)
+seen = []
+out = {out!r}
+d.run(steps=50, output_file=out, callback=seen.append, track_energy=True, energy_sample_interval=10, snapshot_interval=20,
+      script_content="two ranks")
+d.run(steps=30, track_energy=True, energy_sample_interval=10)
+assert seen == list(range(50)), seen[:5]
+hist = d.get_energy_history()
+fields = {{f: d.get_field(f) for f in ("p", "vx", "vy", "vz")}}
+traces = d.get_probe_data()
+one = build_b200_solver(case, device=0, distributed=False, chunk_steps=16)
+one.run(steps=50, track_energy=True, energy_sample_interval=10)
+one.run(steps=30, track_energy=True, energy_sample_interval=10)
+for f in fields:
+    assert np.array_equal(fields[f], one.get_field(f)), f
+for n in traces:
+    assert np.array_equal(traces[n], one.get_probe_data(n)[n]), n
+h1 = one.get_energy_history()
+assert [q[0] for q in hist] == [q[0] for q in h1], (hist, h1)
+assert all(abs(a[2] - b[2]) <= 1e-9 * abs(b[2]) for a, b in zip(hist, h1))
+if rank == 0:
+    z = np.load(out, allow_pickle=False) if not sb.io.HAVE_H5PY else None
+    if z is not None:
+        attrs = json.loads(str(z["__attrs__"]))
+        assert attrs["grid@shape"] == list(case["shape"]) and attrs["simulation@num_steps"] == 50
+        assert attrs["metadata@num_gpus"] == 2
+        for n in traces:
+            assert np.array_equal(z["probes/" + n], traces[n][:50]), n
+        assert z["fields/pressure"].shape == (3,) + tuple(case["shape"])          # steps 0, 20, 40
+        assert np.array_equal(z["materials/geometry"].astype(bool), np.asarray(case["geometry"], dtype=bool))
+# reset: a second run from t = 0 reproduces the first one
+d.reset()
+d.run(steps=30)
+one.reset(); one.run(steps=30)
+assert np.array_equal(d.get_field("p"), one.get_field("p"))
+assert np.array_equal(d.get_probe_data("shadow")["shadow"], one.get_probe_data("shadow")["shadow"])
+# host-side initial conditions next to the cut reach the neighbour's ghosts
+d.reset(); one.reset()
+p0 = np.zeros(case["shape"], dtype=np.float32); p0[23, 20, 40] = 1.0; p0[24, 10, 10] = -2.0
+d.p = p0; one.p = p0
+d.run(steps=20); one.run(steps=20)
+assert np.array_equal(d.get_field("vx"), one.get_field("vx")) and np.array_equal(d.get_field("p"), one.get_field("p"))
+print("RANK_OK", rank)
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+@pytest.mark.gpu
+def test_two_processes_on_one_gpu_full_run_surface(tmp_path):
+    """The multi-process driver on a box with a single GPU (gloo, planes staged through the host): ``FDTDSolver(...)``
+    dispatches to the slab solver inside a torch.distributed job, and run() honours output_file / callback /
+    track_energy / snapshot_interval exactly as the single-GPU solver does; reset() and host-written initial
+    conditions work across the cut."""
+    script = tmp_path / "two_rank_one_gpu.py"
+    script.write_text(_TWO_RANK_ONE_GPU.format(root=str(ROOT), out=str(tmp_path / "result.h5")))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                         capture_output=True, text=True, timeout=900)
+    assert "RANK_OK 0" in res.stdout and "RANK_OK 1" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
 
 
 @pytest.mark.gpu

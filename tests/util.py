@@ -23,76 +23,9 @@ def load_membrane_case():
     return membrane_case(weights), g
 
 
-class FixtureMembrane:
-    """Duck-typed stand-in for the reference's MembraneSource (solver.py:210-370): what the solver touches."""
-    source_type = "membrane"
-
-    def __init__(self, src: dict):
-        import strata_fdtd_b200 as sb
-        m = src["spec"]
-        self.center, self.normal_axis, self.injection_type = m["center"], m["normal_axis"], m["injection_type"]
-        self.waveform = sb.GaussianPulse(position=(0, 0, 0), frequency=src["frequency"], amplitude=src["amplitude"])
-        self._weights = src["weights"]
-        self._cached_weights = None
-        self._cached_mask = None
-
-    def _check_grid_alignment(self, grid):
-        pass
-
-    def get_injection_weights(self, grid):
-        return self._weights
-
-
-def build_b200_solver(case: dict, **solver_kw):
-    import strata_fdtd_b200 as sb
-    kw = dict(c=case.get("c", 343.0), rho=case.get("rho", 1.2), courant=case.get("courant", 0.95), backend="b200")
-    kw.update(solver_kw)
-    nu = case.get("nonuniform")
-    if nu is None:
-        s = sb.FDTDSolver(shape=tuple(case["shape"]), resolution=case["resolution"], **kw)
-    else:
-        s = sb.FDTDSolver(grid=sb.NonuniformGrid(nu["x_coords"], nu["y_coords"], nu["z_coords"]), **kw)
-    if case.get("geometry") is not None:
-        g = case["geometry"]
-        s.set_geometry(g if callable(g) else np.asarray(g, dtype=bool))
-    for b in case.get("pml", []):
-        axes = tuple(b.get("axes", ("x", "y", "z")))
-        s.add_boundary(sb.PML(depth=b.get("depth", 10), axis="all" if axes == ("x", "y", "z") else axes,
-                              max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
-    for b in case.get("plane_bcs", []):
-        if b["kind"] == "mur":
-            s.add_boundary(sb.boundaries.ABCFirstOrder(axis=tuple(b.get("axes", ("x", "y", "z")))))
-        else:
-            s.add_boundary(sb.boundaries.RadiationImpedance(axis=b["axis"], side=b["side"],
-                                                            reflection_coeff=b.get("reflection_coeff"),
-                                                            pipe_radius=b.get("pipe_radius")))
-    for src in case.get("sources", []):
-        kind = src.get("kind", "point")
-        if kind == "weighted":
-            s.add_source(FixtureMembrane(src))
-            continue
-        pos = src["position"] if kind == "point" else {"axis": src["axis"], "index": src["index"]}
-        s.add_source(sb.GaussianPulse(position=pos, frequency=src["frequency"], bandwidth=src.get("bandwidth"),
-                                      amplitude=src.get("amplitude", 1.0), source_type=kind))
-    for name, pos in case.get("probes", []):
-        s.add_probe(name, position=pos)
-    for name, pos, *opt in case.get("mics", []):
-        s.add_microphone(position=pos, name=name, **(opt[0] if opt else {}))
-    for m in case.get("materials", []):
-        poles = []
-        for p in m["poles"]:
-            if p["type"] == "debye":
-                poles.append(sb.Pole(sb.PoleType.DEBYE, p["delta_chi"], p["target"], tau=p["tau"]))
-            else:
-                poles.append(sb.Pole(sb.PoleType.LORENTZ, p["delta_chi"], p["target"], omega_0=p["omega_0"],
-                                     gamma=p["gamma"]))
-        s.register_material(sb.PoleMaterial(m.get("name", f"mat{m['id']}"), m["rho_inf"], m["K_inf"], poles),
-                            material_id=m["id"])
-    if case.get("materials"):
-        mid = np.asarray(case["material_id"], dtype=np.uint8)
-        for m in case["materials"]:
-            s.set_material_region(mid == m["id"], material_id=m["id"])
-    return s
+from strata_fdtd_b200.workloads import WeightedSource as FixtureMembrane  # noqa: E402,F401
+from strata_fdtd_b200.workloads import build_distributed_solver  # noqa: E402,F401
+from strata_fdtd_b200.workloads import build_solver as build_b200_solver  # noqa: E402,F401
 
 
 def assert_same_as_oracle(s, o, what=""):
@@ -110,31 +43,3 @@ def assert_same_as_oracle(s, o, what=""):
     for name, *_ in o.mics:
         a, b = s.microphones[name].get_waveform(), o.mic_array(name)
         assert np.array_equal(a, b), f"{what}: mic {name} differs (max|d|={np.abs(a - b).max():.3e})"
-
-
-def build_distributed_solver(case: dict, **kw):
-    """DistributedFDTDSolver (one slab per rank, torch.distributed already initialised) from a case dict."""
-    import strata_fdtd_b200 as sb
-    from strata_fdtd_b200.multi import DistributedFDTDSolver
-    base = dict(c=case.get("c", 343.0), rho=case.get("rho", 1.2), courant=case.get("courant", 0.95))
-    base.update(kw)
-    nu = case.get("nonuniform")
-    if nu is None:
-        d = DistributedFDTDSolver(shape=tuple(case["shape"]), resolution=case["resolution"], **base)
-    else:
-        d = DistributedFDTDSolver(grid=sb.NonuniformGrid(nu["x_coords"], nu["y_coords"], nu["z_coords"]), **base)
-    if case.get("geometry") is not None:
-        g = case["geometry"]
-        d.set_geometry(g if callable(g) else np.asarray(g, dtype=bool))
-    for b in case.get("pml", []):
-        axes = tuple(b.get("axes", ("x", "y", "z")))
-        d.add_boundary(sb.PML(depth=b.get("depth", 10), axis="all" if axes == ("x", "y", "z") else axes,
-                              max_sigma=b.get("max_sigma"), order=b.get("order", 3)))
-    for src in case.get("sources", []):
-        kind = src.get("kind", "point")
-        pos = src["position"] if kind == "point" else {"axis": src["axis"], "index": src["index"]}
-        d.add_source(sb.GaussianPulse(position=pos, frequency=src["frequency"], bandwidth=src.get("bandwidth"),
-                                      amplitude=src.get("amplitude", 1.0), source_type=kind))
-    for name, pos in case.get("probes", []):
-        d.add_probe(name, position=pos)
-    return d
