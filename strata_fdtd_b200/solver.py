@@ -452,7 +452,7 @@ class FDTDSolver:
     def set_kernel_option(self, option: int, value: int) -> None:
         """Tuning knobs of the step kernel (``_lib.OPT_*``); results never depend on them."""
         self._options[option] = int(value)
-        if option == _lib.OPT_ADE_LAYOUT:
+        if option in (_lib.OPT_ADE_LAYOUT, _lib.OPT_KERNEL):
             self._dirty.add("ade")                   # the layout is chosen when the material tables are built
         if self._dev is not None:
             _lib.check(self._dev.lib.sb_set_option(self._dev.handle, option, int(value)))

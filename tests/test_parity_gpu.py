@@ -431,6 +431,60 @@ def test_c3_ade_sphere_at_128_cubed_vs_oracle():
     s.close()
 
 
+FUSED_SHAPES = {
+    "auto": {},
+    "r2_chunk5": {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_CHUNK_I: 5, _lib.OPT_WARPS_J: 2},
+    "r1_flat_chunk3": {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_PLANE_MAP: 2, _lib.OPT_CHUNK_I: 3},
+    "r2_strips_graph": {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_PLANE_MAP: 1, _lib.OPT_USE_GRAPH: 1},
+    "r1_flat_nograph": {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_PLANE_MAP: 2, _lib.OPT_USE_GRAPH: 0, _lib.OPT_WARPS_J: 4},
+}
+
+
+@pytest.mark.parametrize("shape", sorted(FUSED_SHAPES))
+@pytest.mark.parametrize("name", ["ade_sphere", "ade_two_materials_nonuniform", "ade_dense_layers"])
+def test_fused_ade_kernel_matches_oracle(name, shape):
+    """Layout 3: the material cells are updated inside a variant of the step kernel (K1-ADE) while the plain K1 launch
+    skips their bounding box.  Every launch shape of the plain kernel (rows per thread, strips / flat plane mapping,
+    chunk length, CUDA graph) against the oracle, including Lorentz density poles (three rotating J buffers), two
+    materials touching each other, solids inside a material and materials up to the outer faces of the grid."""
+    case = CASES[name]
+    s = _with_options(build_b200_solver(case, chunk_steps=53), {_lib.OPT_ADE_LAYOUT: 3, **FUSED_SHAPES[shape]})
+    o = O.OracleSolver(case)
+    s.run(steps=case["steps"]); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"ade/{name}/fused/{shape}")
+    assert np.abs(s.get_field("p")).max() > 0
+    s.reset(); o2 = O.OracleSolver(case)
+    s.run(steps=41); o2.run_steps(41)
+    assert_same_as_oracle(s, o2, f"ade/{name}/fused/{shape}/after reset")
+    s.close()
+
+
+def test_fused_ade_survives_a_later_geometry_change():
+    """The ADE bits share the mask bytes with the geometry: setting a geometry after the materials (and removing it
+    again) must keep them."""
+    case = dict(CASES["ade_sphere"])
+    s = _with_options(build_b200_solver(case, chunk_steps=32), {_lib.OPT_ADE_LAYOUT: 3})
+    s.run(steps=20)
+    g = np.ones(case["shape"], dtype=bool); g[18:22, 10:14, 12:20] = False          # a solid inside the sphere
+    s.set_geometry(g)
+    s.run(steps=60)
+    case2 = dict(case, geometry=g)
+    o = O.OracleSolver(case); o.run_steps(20)
+    o2 = O.OracleSolver(case2)
+    for f in ("p", "vx", "vy", "vz"):
+        getattr(o2, f)[...] = getattr(o, f)
+    for a, b in zip(o2.debye + o2.lorentz, o.debye + o.lorentz):
+        a["J"][...] = b["J"]
+        if "Jp" in a:
+            a["Jp"][...] = b["Jp"]
+    o2.time, o2.step_count = o.time, o.step_count
+    for name, _ in o2.probes:
+        o2.probe_data[name] = list(o.probe_data[name])
+    o2.run_steps(60)
+    assert_same_as_oracle(s, o2, "fused ade + late geometry")
+    s.close()
+
+
 @pytest.mark.parametrize("layout", [1, 2])
 @pytest.mark.parametrize("name", ["ade_sphere", "ade_two_materials_nonuniform", "ade_dense_layers"])
 def test_ade_layouts_match_oracle(name, layout):
