@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Golden traces of the reference's OWN example scripts, run verbatim on its native backend (TEST INFRASTRUCTURE ONLY;
+build container only).
+
+    python oracle/make_golden_scripts.py
+
+/root/reference/examples/basic_pulse.py (:27-66: metre-valued positions, 40 kHz, duration=0.001 -> 626 steps) and
+material_sphere.py are executed unchanged with ``strata_fdtd`` = the unmodified reference package (native C++ backend
+loaded through oracle/ref_loader.py).  The scripts write ``results.h5``; h5py is not installed here, so the in-memory
+tests/fake_h5py.py stands in for it -- which also records what the reference's HDF5ResultWriter produces, the schema
+our own writer is checked against.  Stored per script: dt, step count, every probe trace, SHA-256 of the final fields,
+and the tree of the result file (group / dataset names, shapes, attribute names).
+"""
+from __future__ import annotations
+
+import contextlib
+import hashlib
+import io
+import os
+import runpy
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import fake_h5py  # noqa: E402
+
+sys.modules["h5py"] = fake_h5py
+from oracle import ref_loader as R  # noqa: E402
+
+SCRIPTS = ["basic_pulse.py", "material_sphere.py"]
+
+
+def digest(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def tree(node, prefix=""):
+    out = []
+    for name, child in node.items():
+        path = f"{prefix}/{name}"
+        if isinstance(child, fake_h5py.Dataset):
+            out.append(f"D {path} {tuple(child.shape)} {child.dtype} attrs={sorted(child.attrs)}")
+        else:
+            out.append(f"G {path} attrs={sorted(child.attrs)}")
+            out += tree(child, path)
+    return out
+
+
+def main():
+    R.load_reference_package()
+    for name in SCRIPTS:
+        src = R.REF_ROOT / "examples" / name
+        with tempfile.TemporaryDirectory() as tmp:
+            cwd = os.getcwd()
+            os.chdir(tmp)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()) as out:
+                    g = runpy.run_path(str(src), run_name="__main__")
+                s = g["solver"]
+                assert s.using_native, "the reference must run its native backend"
+                from strata_fdtd.io.hdf5 import HDF5ResultReader
+                rd = HDF5ResultReader("results.h5")
+                meta = rd.get_metadata()
+                fix = {"dt": np.float64(s.dt), "steps": np.int64(s.step_count), "time": np.float64(s.time),
+                       "script_sha": np.array(hashlib.sha256(src.read_bytes()).hexdigest()),
+                       "tree": np.array("\n".join(tree(rd.file))),
+                       "stdout_head": np.array("\n".join(out.getvalue().splitlines()[:12]))}
+                for pname in rd.get_probe_names():
+                    assert np.array_equal(rd.load_probe(pname), s.get_probe_data(pname)[pname])
+                    fix["probe_" + pname] = s.get_probe_data(pname)[pname]
+                    fix["probe_pos_" + pname] = np.asarray(meta["probes"][pname]["position"])
+                for f in ("p", "vx", "vy", "vz"):
+                    fix["sha_" + f] = np.array(digest(getattr(s, f)))
+                    fix["absmax_" + f] = np.float32(np.abs(getattr(s, f)).max())
+                rd.close()
+            finally:
+                os.chdir(cwd)
+        dst = ROOT / "tests" / "golden" / f"script_{name[:-3]}.npz"
+        np.savez_compressed(dst, **fix)
+        print(f"{name}: {int(fix['steps'])} steps, probes {[k[6:] for k in fix if k.startswith('probe_') and not k.startswith('probe_pos_')]}, "
+              f"|p|max {float(fix['absmax_p']):.3e} -> {dst.name} ({dst.stat().st_size / 1024:.0f} KiB)")
+        print("  " + str(fix["tree"]).replace("\n", "\n  "))
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,38 @@ def _reference_available() -> bool:
     return spec is not None
 
 
+class Sphere:
+    """Signed-distance ball with the protocol of the reference's SDF primitives (geometry/sdf.py:302-338: ``sdf(points)``
+    = distance to the centre minus the radius; ``voxelize(grid)`` = cell centres with sdf <= 0, :99-125) -- the one
+    primitive the reference's named example scripts construct.  CSG, horns etc. stay with the reference package."""
+
+    def __init__(self, center, radius):
+        import numpy as np
+        self.center = np.array(center, dtype=np.float64)
+        self.radius = float(radius)
+        if self.radius <= 0:
+            raise ValueError(f"Sphere radius must be positive, got {self.radius}")
+
+    def sdf(self, points):
+        import numpy as np
+        points = np.asarray(points, dtype=np.float64)
+        if points.ndim != 2 or points.shape[1] != 3:
+            raise ValueError(f"points must be Nx3 array, got shape {points.shape}")
+        return np.linalg.norm(points - self.center, axis=1) - self.radius
+
+    @property
+    def bounding_box(self):
+        return self.center - self.radius, self.center + self.radius
+
+    def contains(self, points):
+        return self.sdf(points) <= 0
+
+    def voxelize(self, grid):
+        import numpy as np
+        X, Y, Z = np.meshgrid(grid.x_coords, grid.y_coords, grid.z_coords, indexing="ij")
+        return (self.sdf(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)) <= 0).reshape(grid.shape)
+
+
 def install_as_strata_fdtd(force_alias: bool = False):
     """Make ``import strata_fdtd`` work; returns the module that scripts will see."""
     if not force_alias and _reference_available():
@@ -60,6 +92,7 @@ def install_as_strata_fdtd(force_alias: bool = False):
                  PML=sb.PML, RigidBoundary=sb.RigidBoundary, ABCFirstOrder=boundaries.ABCFirstOrder,
                  RadiationImpedance=boundaries.RadiationImpedance, UniformGrid=sb.UniformGrid,
                  NonuniformGrid=sb.NonuniformGrid, Pole=sb.Pole, PoleType=sb.PoleType, SimpleMaterial=sb.SimpleMaterial,
+                 Sphere=Sphere,
                  has_native_kernels=lambda: False, has_gpu_backend=lambda: True,
                  get_native_info=lambda: {"available": False, "version": None, "has_openmp": False, "num_threads": 1},
                  __version__=sb.__version__)
@@ -69,7 +102,7 @@ def install_as_strata_fdtd(force_alias: bool = False):
     for k in ("PML", "RigidBoundary", "ABCFirstOrder", "RadiationImpedance"):
         setattr(b, k, getattr(boundaries, k))
     m = types.ModuleType("strata_fdtd.materials")
-    for k in ("Pole", "PoleType", "SimpleMaterial", "PoleMaterial"):
+    for k in ("Pole", "PoleType", "SimpleMaterial", "PoleMaterial", "WATER_20C"):
         setattr(m, k, getattr(materials, k))
     core = types.ModuleType("strata_fdtd.core")
     core.__path__ = []

@@ -42,11 +42,10 @@ class _NpzTree:
         self.attrs[f"{group}@{key}"] = value
 
     def append(self, name: str, block: np.ndarray):
-        old = self.data.get(name)
-        self.data[name] = block.copy() if old is None else np.concatenate([old, block])
+        self.data.setdefault(name, []).append(block.copy())      # joined once, at close: linear in the run length
 
     def close(self):
-        payload = dict(self.data)
+        payload = {k: (np.concatenate(v) if isinstance(v, list) else v) for k, v in self.data.items()}
         payload["__attrs__"] = np.array(json.dumps(self.attrs, default=str))
         with open(self.path, "wb") as fh:            # a file object keeps the exact name (no ".npz" appended)
             np.savez_compressed(fh, **payload)

@@ -80,8 +80,15 @@ class SimpleMaterial:
         return self._rho * self._c**2
 
     @property
+    def c_inf(self) -> float:
+        return self._c
+
+    @property
     def poles(self) -> list:
         return self._poles
+
+
+WATER_20C = SimpleMaterial(name="water_20C", _rho=998.2, _c=1482.0)       # materials/library.py:52-56 (a constant scripts import)
 
 
 @dataclass

@@ -43,4 +43,54 @@ def install_into_reference(module=None):
         g = getattr(module, gname, None)
         if g is not None and not hasattr(g, "num_cells"):
             g.num_cells = property(lambda self: int(self.shape[0]) * int(self.shape[1]) * int(self.shape[2]))
+    _repair_cli_sandbox(module)
     return module
+
+
+def _repair_cli_sandbox(module) -> None:
+    """``fdtd-compute`` restricts what a simulation script may import by replacing ``__import__`` in the process-wide
+    builtins while the script runs (cli/executor.py:57-83), so every lazy import made by *library* code in that window
+    is refused too: on Python 3.12 ``Path.parent`` imports ``ntpath`` and the CLI dies before the script starts, with any
+    backend.  The replacement applies the same allow-list to the import statements of the script itself only (its
+    globals are the namespace the CLI gets back)."""
+    try:
+        from importlib import import_module
+        executor = import_module(module.__name__ + ".cli.executor")
+    except Exception:                                # CLI extras (click / rich) not installed: nothing to repair
+        return
+    import builtins
+    import sys
+
+    allowed = {"strata_fdtd", "numpy", "np", "scipy", "math", "pathlib"}
+
+    def execute_simulation_script(script_path, script_content, verbose=False):
+        namespace = {"__name__": "__main__", "__file__": str(script_path)}
+        real_import = builtins.__import__
+
+        def guarded_import(name, globals=None, locals=None, fromlist=(), level=0):
+            if globals is namespace and level == 0 and name.split(".")[0] not in allowed:
+                raise executor.RestrictedImportError(
+                    f"Import of '{name}' is not allowed in simulation scripts. "
+                    f"Allowed modules: {', '.join(sorted(allowed))}")
+            return real_import(name, globals, locals, fromlist, level)
+
+        namespace["__builtins__"] = {**vars(builtins), "__import__": guarded_import}     # the script's private copy
+        script_dir = str(script_path.parent)
+        sys.path.insert(0, script_dir)
+        try:
+            if verbose:
+                print(f"Executing script: {script_path}")
+            exec(compile(script_content, str(script_path), "exec"), namespace)
+        finally:
+            if script_dir in sys.path:
+                sys.path.remove(script_dir)
+        return namespace
+
+    executor.execute_simulation_script = execute_simulation_script
+    compute = sys.modules.get(module.__name__ + ".cli.compute")
+    if compute is None:
+        try:
+            compute = import_module(module.__name__ + ".cli.compute")
+        except Exception:
+            return
+    compute.execute_simulation_script = execute_simulation_script
