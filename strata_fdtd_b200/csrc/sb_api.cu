@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -134,11 +135,39 @@ struct sb_solver {
     int opt_plane_map = 0;                 // how K1 deals the (j, k) plane to warps: 0 = auto, 1 = strips, 2 = flat
 };
 
+// Launch shapes measured once per (device, grid, kernel variant) are remembered for the life of the process: a second
+// solver of the same configuration (parameter sweeps, reset-and-rebuild loops) does not pay the trial launches again.
+struct TuneKey {
+    int device, nx, ny, nz, pitch, key, kind;            // kind 0 = K1 launch shape, 1 = K5 box grid
+    bool operator<(const TuneKey &o) const {
+        return std::tie(device, nx, ny, nz, pitch, key, kind) < std::tie(o.device, o.nx, o.ny, o.nz, o.pitch, o.key, o.kind);
+    }
+};
+struct TuneVal { int v[4]; float ms; };
+static std::map<TuneKey, TuneVal> g_tuned;
+static std::mutex g_tuned_mu;
+static bool tune_lookup(const sb_solver *h, int key, int kind, TuneVal &out);
+static void tune_store(const sb_solver *h, int key, int kind, const TuneVal &v);
+
 static void drop_graphs(sb_solver *h)
 {
     h->tuned_key = -1; h->res_tuned_key = -1;                       // configuration changed: re-measure the launch shape as well
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
+}
+
+static bool tune_lookup(const sb_solver *h, int key, int kind, TuneVal &out)
+{
+    std::lock_guard<std::mutex> lk(g_tuned_mu);
+    auto it = g_tuned.find(TuneKey{h->device, h->d.nx, h->d.ny, h->d.nz, h->d.pitch, key, kind});
+    if (it == g_tuned.end()) return false;
+    out = it->second;
+    return true;
+}
+static void tune_store(const sb_solver *h, int key, int kind, const TuneVal &v)
+{
+    std::lock_guard<std::mutex> lk(g_tuned_mu);
+    g_tuned[TuneKey{h->device, h->d.nx, h->d.ny, h->d.nz, h->d.pitch, key, kind}] = v;
 }
 
 extern "C" const char *sb_last_error(void) { return g_err.c_str(); }
@@ -935,6 +964,12 @@ static int autotune(sb_solver *h)
                                   {2, 8, 1, 64}, {2, 8, 1, 16}, {2, 4, 1, 16}, {2, 4, 1, 0}, {1, 0, 1, 0}};
     const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->have_peers ? 64 : 0);
     if (h->tuned_key == key) return 0;
+    TuneVal cached;
+    if (tune_lookup(h, key, 0, cached)) {
+        for (int q = 0; q < 4; q++) h->tuned[q] = cached.v[q];
+        h->tuned_ms = cached.ms; h->tuned_key = key;
+        return 0;
+    }
     const int save_rj = h->opt_rj, save_wj = h->opt_wj, save_wk = h->opt_wk, save_ch = h->opt_chunk_i;
     const bool save_peers = h->have_peers;
     const long long k0 = h->kernels_launched;
@@ -959,6 +994,7 @@ static int autotune(sb_solver *h)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (int q = 0; q < 4; q++) h->tuned[q] = cand[best_c][q];
     h->tuned_ms = best; h->tuned_key = key;
+    tune_store(h, key, 0, TuneVal{{h->tuned[0], h->tuned[1], h->tuned[2], h->tuned[3]}, best});
     h->opt_rj = save_rj; h->opt_wj = save_wj; h->opt_wk = save_wk; h->opt_chunk_i = save_ch;
     h->have_peers = save_peers; h->kernels_launched = k0;
     CU(cudaGetLastError());
@@ -1197,6 +1233,11 @@ static int resident_autotune(sb_solver *h, const double *src_dev, int n_steps)
 {
     const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->n_probes << 6);
     if (h->res_tuned_key == key) return 0;
+    TuneVal cached;
+    if (tune_lookup(h, key, 1, cached)) {
+        h->res_tuned_nbi = cached.v[0]; h->res_tuned_nbj = cached.v[1]; h->res_tuned_key = key;
+        return 0;
+    }
     int n_trial = std::min(n_steps, 65);
     if (!(n_trial & 1)) n_trial--;
     if (n_trial < 33) return 0;                               // too short to tell box grids apart: keep the heuristic
@@ -1225,6 +1266,7 @@ static int resident_autotune(sb_solver *h, const double *src_dev, int n_steps)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     CU(cudaGetLastError());
     h->res_tuned_nbi = cands[best_c].first; h->res_tuned_nbj = cands[best_c].second; h->res_tuned_key = key;
+    tune_store(h, key, 1, TuneVal{{h->res_tuned_nbi, h->res_tuned_nbj, 0, 0}, best});
     return 0;
 }
 

@@ -727,67 +727,121 @@ class FDTDSolver:
             W[:, s] = col
         return W
 
-    def _advance(self, n_steps: int, callback=None, writer=None, snapshot_interval=None) -> None:
-        dev = self._sync_to_device()
-        lib, h = dev.lib, dev.handle
+    def _io_slot(self, m: int, n_src: int, n_rec: int):
+        """Two sets of pinned host + device buffers for the waveform table and the record block of a chunk, so that the
+        host can prepare chunk n+1 and unpack chunk n-1 while the device runs chunk n."""
+        dev = self._dev
+        torch = dev.torch
+        io = getattr(self, "_io", None)
+        if io is None or io["cap"] < m or io["n_src"] != n_src or io["n_rec"] != n_rec or io["dev"] is not dev:
+            cap = max(m, io["cap"] if io and io["dev"] is dev else 0)
+            with torch.cuda.device(dev.index):
+                io = dict(cap=cap, n_src=n_src, n_rec=n_rec, dev=dev, turn=0,
+                          W_host=[torch.empty((cap, n_src), dtype=torch.float64).pin_memory() for _ in range(2)],
+                          W_dev=[torch.empty((cap, n_src), dtype=torch.float64, device=dev.device) for _ in range(2)],
+                          rec_host=[torch.empty((cap, n_rec), dtype=torch.float32).pin_memory() for _ in range(2)],
+                          rec_dev=[torch.empty((cap, n_rec), dtype=torch.float32, device=dev.device) for _ in range(2)])
+            self._io = io
+        io["turn"] ^= 1
+        return io, io["turn"]
+
+    def _launch_chunk(self, m: int) -> dict:
+        """Enqueue m steps: waveform table up, kernels, records down (all asynchronous on the solver's stream)."""
+        dev = self._dev
+        torch = dev.torch
+        n_src = max(1, len(self._sources))
+        n_rec = len(self._local_probes) + sum(len(sl) for sl in self._mic_slots) + len(self._corner_keys)
+        # the same float64 accumulation as solver.py:2072 (np.add.accumulate adds strictly left to right)
+        steps_t = np.full(m + 1, self.dt, dtype=np.float64)
+        steps_t[0] = self._time
+        acc = np.add.accumulate(steps_t)
+        times, t_end = acc[:m], float(acc[m])
+        io, k = self._io_slot(m, n_src, max(1, n_rec))
+        with torch.cuda.stream(dev.stream):
+            if self._sources:
+                io["W_host"][k][:m].numpy()[...] = self._waveform_table(times)
+                io["W_dev"][k][:m].copy_(io["W_host"][k][:m], non_blocking=True)
+            _lib.check(dev.lib.sb_step_n_async(dev.handle, m, io["W_dev"][k].data_ptr(),
+                                               io["rec_dev"][k].data_ptr() if n_rec else None))
+            if n_rec:
+                io["rec_host"][k][:m].copy_(io["rec_dev"][k][:m], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(dev.stream)
+        self._host_stale = set(_FIELDS)
+        first_idx = self._step_count
+        self._step_count += m
+        self._time = t_end
+        return dict(m=m, times=times, rec=io["rec_host"][k], n_rec=n_rec, done=done, first_idx=first_idx)
+
+    def _finish_chunk(self, tk: dict, writer=None) -> None:
+        """Wait for a launched chunk and file its samples: probes, microphones, corner samples, result writer."""
+        tk["done"].synchronize()
+        m, times = tk["m"], tk["times"]
         probes = self._local_probes
         mics = list(self._microphones.values())
-        n_rec = len(probes) + sum(len(sl) for sl in self._mic_slots) + len(self._corner_keys)
+        rec = tk["rec"][:m].numpy() if tk["n_rec"] else np.empty((m, 0), dtype=np.float32)
+        for q, pr in enumerate(probes):
+            pr.data.extend(rec[:, q].tolist())
+        for mic, slots in zip(mics, self._mic_slots):
+            cols = [np.array(rec[:, len(probes) + q]) for q in slots]
+            mic._data.extend(mic._combine(cols[0], cols[1:]).tolist())
+            mic._times.extend(times.tolist())
+        self._store_corner_samples(rec, len(probes), times)
+        if self._corner_keys and not (self._has_lower or self._has_upper):     # one GPU: every corner is here
+            data = {k: np.concatenate(v) for k, v in self._corner_data.items()}
+            self._corner_data.clear(); self._corner_times.clear()
+            combine_corner_samples(mics, self._mic_gathers, data, times)
+        if writer is not None and probes:
+            writer.append_probe_block([pr.name for pr in probes], rec[:, :len(probes)])
+
+    def _advance(self, n_steps: int, callback=None, writer=None, snapshot_interval=None) -> None:
+        dev = self._sync_to_device()
         done = 0
         # On small grids a step takes microseconds and the per-chunk host work (waveform table, copies, trace lists)
         # shows; nobody is watching the steps go by unless a callback / writer is attached, so use longer chunks there.
         chunk = self._chunk_steps
         if self._chunk_auto and callback is None and writer is None and int(np.prod(self.shape, dtype=np.int64)) <= (2 << 20):
             chunk = max(chunk, 1024)
-        while done < n_steps:
-            m = min(chunk, n_steps - done)
-            # a chunk ends right after any step whose fields the host has to see
-            for q in range(m):
-                idx = self._step_count + q
-                need = (self._snapshot_interval and idx % self._snapshot_interval == 0) or \
-                       (self._track_energy and (idx + 1) % self._energy_sample_interval == 0) or \
-                       (writer is not None and snapshot_interval is not None and (done + q) % snapshot_interval == 0)
-                if need:
-                    m = q + 1
-                    break
-            times = np.empty(m, dtype=np.float64)
-            t = self._time
-            for q in range(m):
-                times[q] = t
-                t = t + self.dt                               # same float64 accumulation as solver.py:2072
-            W = self._waveform_table(times) if self._sources else None
-            rec = np.empty((m, max(1, n_rec)), dtype=np.float32)
-            _lib.check(lib.sb_step_n(h, m, _lib.ptr(W), _lib.ptr(rec) if n_rec else None))
-            self._host_stale = set(_FIELDS)
-            for q, pr in enumerate(probes):
-                pr.data.extend(rec[:, q].tolist())
-            for mic, slots in zip(mics, self._mic_slots):
-                cols = [rec[:, len(probes) + q] for q in slots]
-                mic._data.extend(mic._combine(cols[0], cols[1:]).tolist())
-                mic._times.extend(times.tolist())
-            self._store_corner_samples(rec, len(probes), times)
-            if self._corner_keys and not (self._has_lower or self._has_upper):     # one GPU: every corner is here
-                data = {k: np.concatenate(v) for k, v in self._corner_data.items()}
-                self._corner_data.clear(); self._corner_times.clear()
-                combine_corner_samples(mics, self._mic_gathers, data, times)
-            last_idx = self._step_count + m - 1
-            self._step_count += m
-            self._time = t
-            if self._snapshot_interval and last_idx % self._snapshot_interval == 0:
-                self._snapshots.append((float(times[-1]), self.get_field("p")))
-                if self._snapshot_velocity:
-                    self._velocity_snapshots.append((float(times[-1]), *self._centred_velocities()))
-            if self._track_energy and self._step_count % self._energy_sample_interval == 0:
-                self._energy_history.append((self._step_count, self._time, self.compute_energy()))
-            if writer is not None:
-                if probes:
-                    writer.append_probe_block([pr.name for pr in probes], rec[:, :len(probes)])
-                if snapshot_interval is not None and (done + m - 1) % snapshot_interval == 0:
-                    writer.write_snapshot(self.get_field("p"))
-            if callback is not None:
+        pending = None                     # the chunk the device is working on while the host prepares the next one
+        try:
+            while done < n_steps:
+                m = min(chunk, n_steps - done)
+                # a chunk ends right after any step whose fields the host has to see
+                host_looks = False
                 for q in range(m):
-                    callback(last_idx - (m - 1 - q))
-            done += m
+                    idx = self._step_count + q
+                    need = (self._snapshot_interval and idx % self._snapshot_interval == 0) or \
+                           (self._track_energy and (idx + 1) % self._energy_sample_interval == 0) or \
+                           (writer is not None and snapshot_interval is not None and (done + q) % snapshot_interval == 0)
+                    if need:
+                        m, host_looks = q + 1, True
+                        break
+                tk = self._launch_chunk(m)
+                if pending is not None:
+                    self._finish_chunk(pending, writer)
+                    pending = None
+                if host_looks or callback is not None:
+                    # the host reads fields / reports progress at this point: complete the chunk before going on
+                    self._finish_chunk(tk, writer)
+                    last_idx, t_last = tk["first_idx"] + m - 1, float(tk["times"][-1])
+                    if self._snapshot_interval and last_idx % self._snapshot_interval == 0:
+                        self._snapshots.append((t_last, self.get_field("p")))
+                        if self._snapshot_velocity:
+                            self._velocity_snapshots.append((t_last, *self._centred_velocities()))
+                    if self._track_energy and self._step_count % self._energy_sample_interval == 0:
+                        self._energy_history.append((self._step_count, self._time, self.compute_energy()))
+                    if writer is not None and snapshot_interval is not None and (done + m - 1) % snapshot_interval == 0:
+                        writer.write_snapshot(self.get_field("p"))
+                    if callback is not None:
+                        for q in range(m):
+                            callback(last_idx - (m - 1 - q))
+                else:
+                    pending = tk
+                done += m
+        finally:
+            if pending is not None:
+                self._finish_chunk(pending, writer)
+            _lib.check(dev.lib.sb_synchronize(dev.handle))       # also surfaces a timed-out wait inside a chunk kernel
 
     def _store_corner_samples(self, rec, first_slot: int, times) -> None:
         """Slab only: keep the raw microphone corner values of a chunk until the driver combines them."""
