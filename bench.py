@@ -340,6 +340,8 @@ def run_b200_arm(a):
         barrier()
         dev_ms = e0.elapsed_time(e1)
     else:
+        if drv.halo != "p2p":
+            drv._overlap_possible()
         slab.begin_chunk(K)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -348,8 +350,7 @@ def run_b200_arm(a):
             slab.enqueue_steps(K)                # halos travel inside the step kernels (NVLink peer stores)
         else:
             for _ in range(K):
-                slab.enqueue_step()
-                drv._exchange()
+                drv._step_with_exchange()    # cut planes first, their send/recv on a second stream beside the interior
         e1.record(dev.stream)
         barrier()
         dev_ms = e0.elapsed_time(e1)
@@ -374,7 +375,7 @@ def run_b200_arm(a):
             slab.enqueue_steps(kp)
         else:
             for _ in range(kp):
-                slab.enqueue_step(); drv._exchange()
+                drv._step_with_exchange()
         slab.end_chunk()
     import ctypes as C
     mean_ms, min_ms, n_l = C.c_double(), C.c_double(), C.c_int()

@@ -187,6 +187,15 @@ int sb_step_n(sb_solver *h, int n_steps, const double *src_values_host, float *r
  * nothing is copied and the stream is not synchronised.                                  */
 int sb_step_n_async(sb_solver *h, int n_steps, const double *src_values_dev, float *record_out_dev);
 
+/* Host-driven halo exchange overlapped with the interior update: computes ONLY the planes next to this slab's cuts for
+ * the step about to run (first) and remembers that the next sb_step_n_async(h, 1, ...) has to leave them out.  The
+ * caller then sends those planes of the set being written (the one sb_current_set does NOT report) on another stream while
+ * the rest of the step runs.  *applied = 0 (and nothing is launched) where K1 is not the last writer of the cut
+ * planes -- ADE fix-ups, Mur / radiation planes, a slab thinner than 32 planes, the peer-to-peer halo -- the caller
+ * must then exchange after the whole step; sources on a cut plane are the caller's to exclude.  (SURVEY.md 8e:
+ * "compute the two face planes first, launch exchange, compute interior".)                                   */
+int sb_step_cuts_async(sb_solver *h, int *applied);
+
 /* Slab halo planes of the CURRENT set, for the exchange step of a multi-GPU run:
  * send_lo/send_hi = device addresses of owned planes 0 and nx-1 of p; recv_lo/recv_hi = the
  * ghost planes i=-1 and i=nx.  plane_elems = ny*pitch.                                   */

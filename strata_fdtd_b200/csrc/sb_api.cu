@@ -133,6 +133,7 @@ struct sb_solver {
     DBuf<int> d_pipe_ctr;                  // [0] ticket, [1 ..] chunk counters
     long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 40LL << 20;   // where pipelining the steps was measured to pay
     int opt_plane_map = 0;                 // how K1 deals the (j, k) plane to warps: 0 = auto, 1 = strips, 2 = flat
+    int cut_done = 0;                      // planes next to each cut already computed for the step about to be enqueued
 };
 
 // Launch shapes measured once per (device, grid, kernel variant) are remembered for the life of the process: a second
@@ -852,10 +853,13 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
     if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
     const dim3 blk(32 * wk, wj);
     if (!h->have_peers) {
-        P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-        const dim3 grd(gx, gy, (d.nx + chunk - 1) / chunk);
+        // planes next to a cut that sb_step_cuts_async has already computed for this step are left out
+        const int cb = h->cut_done;
+        h->cut_done = 0;
+        P.i_begin = (cb && d.has_lower) ? cb : 0; P.i_end = (cb && d.has_upper) ? d.nx - cb : d.nx; P.chunk_i = chunk;
+        const dim3 grd(gx, gy, (P.i_end - P.i_begin + chunk - 1) / chunk);
         if (grd.z > 65535) return fail("too many i-chunks");
-        launch_march(rj, false, fuse, flat, P, grd, blk, h->stream);
+        launch_march(rj, false, fuse && !cb, flat, P, grd, blk, h->stream);
         h->kernels_launched++;
         return 0;
     }
@@ -951,6 +955,37 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->kernels_launched += 2;
     h->ade_phase++;
+    return 0;
+}
+
+static int autotune(sb_solver *h);
+// Host-driven halo exchange (NCCL send/recv) overlapped with the interior: the planes next to the cuts are computed
+// first, by themselves, so that the caller can start sending them while the rest of the step runs.
+extern "C" int sb_step_cuts_async(sb_solver *h, int *applied)
+{
+    CHECK_H(h);
+    if (!applied) return fail("null argument");
+    *applied = 0;
+    const sb_grid_desc &d = h->d;
+    const int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
+    // only where K1 is the last writer of the cut planes' p: no ADE fix-ups, no plane boundaries; the caller
+    // keeps sources off the cut planes.  Anything else takes the serial exchange after the whole step.
+    if (h->have_peers || !(d.has_lower || d.has_upper) || variant != SB_KERNEL_MARCH || h->have_ade || !h->plane_ops.empty() ||
+        !h->have_coeffs || !h->set[0][0]) return 0;
+    if (h->opt_rj == 0 && autotune(h)) return 1;
+    int rj, wj, wk, chunk, gx, gy; bool flat;
+    if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
+    const int cb = std::min(8, chunk);
+    if (d.nx < 4 * cb) return 0;
+    StepParams P;
+    fill_params(h, P);
+    const dim3 blk(32 * wk, wj);
+    P.chunk_i = cb;
+    if (d.has_lower) { P.i_begin = 0; P.i_end = cb; launch_march(rj, false, false, flat, P, dim3(gx, gy, 1), blk, h->stream); h->kernels_launched++; }
+    if (d.has_upper) { P.i_begin = d.nx - cb; P.i_end = d.nx; launch_march(rj, false, false, flat, P, dim3(gx, gy, 1), blk, h->stream); h->kernels_launched++; }
+    CU(cudaGetLastError());
+    h->cut_done = cb;
+    *applied = 1;
     return 0;
 }
 

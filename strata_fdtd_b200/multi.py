@@ -105,12 +105,28 @@ class SlabSolver(FDTDSolver):
         self._step_count += m
         self._time = self._chunk_t_end
 
-    def halo_planes(self, field: str = "p") -> dict:
-        """torch views of the planes that take part in the exchange, in the CURRENT set."""
+    def halo_planes(self, field: str = "p", next_set: bool = False) -> dict:
+        """torch views of the planes that take part in the exchange, in the CURRENT set (or the one being written)."""
         dev = self._dev
-        t = dev.sets[dev.current_set()][_FIELDS.index(field)]
+        t = dev.sets[dev.current_set() ^ int(next_set)][_FIELDS.index(field)]
         nx = self.shape[0]
         return {"send_lo": t[1], "send_hi": t[nx], "recv_lo": t[0], "recv_hi": t[nx + 1]}
+
+    def enqueue_cuts(self) -> bool:
+        """First part of the next step: only the planes next to the cuts (sb_step_cuts_async).  True if launched."""
+        import ctypes as C
+        applied = C.c_int(0)
+        _lib.check(self._dev.lib.sb_step_cuts_async(self._dev.handle, C.byref(applied)))
+        return bool(applied.value)
+
+    def sources_touch_cut_planes(self) -> bool:
+        """Some source writes into the first / last owned plane next to a neighbour (those planes then change after K1)."""
+        cells = self._build_source_table()[0]
+        if len(cells) == 0:
+            return False
+        planes = np.floor_divide(cells, self.shape[1] * self.shape[2])
+        cut = ([0, -1] if self._has_lower else []) + ([self.shape[0] - 1] if self._has_upper else [])
+        return bool(np.isin(planes, cut).any())
 
 
 def _chunks(n_steps: int, chunk: int):
@@ -296,13 +312,13 @@ class DistributedFDTDSolver:
         combine_corner_samples(mics, self.slab._mic_gathers or self.slab.microphone_gathers(mics), merged, times)
 
     # ---- halo exchange ---------------------------------------------------------------------------
-    def _exchange(self, fields=("p",), include_vx_ghost=False):
+    def _exchange(self, fields=("p",), include_vx_ghost=False, next_set=False, stream=None):
         """One grouped send/recv per step: p planes both ways (and, once after uploads, vx upward)."""
         dist, s = self.dist, self.slab
         dev = s._dev
         torch = dev.torch
         pairs = []                                # (send view or None, recv view or None, peer)
-        h = s.halo_planes("p")
+        h = s.halo_planes("p", next_set=next_set)
         if self.rank > 0:
             pairs.append((h["send_lo"], h["recv_lo"], self.rank - 1))
         if self.rank < self.world - 1:
@@ -315,7 +331,7 @@ class DistributedFDTDSolver:
                 pairs.append((None, v["recv_lo"], self.rank - 1))
         if not pairs:
             return
-        with torch.cuda.stream(dev.stream):
+        with torch.cuda.stream(stream if stream is not None else dev.stream):
             ops, back = [], []
             for send, recv, peer in pairs:
                 if send is not None:
@@ -356,15 +372,47 @@ class DistributedFDTDSolver:
         self._ghosts_fresh = True
 
     # ---- stepping --------------------------------------------------------------------------------
+    def _overlap_possible(self) -> bool:
+        """Collective (cached until the set-up changes).  The send/recv of a step can run beside its interior update when
+        K1 is the last writer of the cut planes on EVERY rank: no source on a cut plane here, and the library agrees
+        (no ADE fix-ups, no Mur / radiation planes, slabs of at least 32 planes)."""
+        s = self.slab
+        key = (len(s._sources), len(s._boundaries), s.has_materials, s._options.get(_lib.OPT_KERNEL, 0))
+        if getattr(self, "_overlap_key", None) != key:
+            mine = (not self._staged) and self.world > 1 and not s.sources_touch_cut_planes() and \
+                   not s.has_materials and s.shape[0] >= 32
+            self._overlap, self._overlap_key = not self._all_any(not mine), key
+        return self._overlap
+
+    def _step_with_exchange(self) -> None:
+        """NCCL mode, one step: cut planes first, then their send/recv on a second stream while the interior runs."""
+        s = self.slab
+        dev = s._dev
+        torch = dev.torch
+        if self._overlap and s.enqueue_cuts():
+            if getattr(self, "_comm", None) is None:
+                self._comm = torch.cuda.Stream(device=dev.device)
+                self._ev_cut, self._ev_halo = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_cut.record(dev.stream)
+            self._comm.wait_event(self._ev_cut)
+            self._exchange(next_set=True, stream=self._comm)      # the cut planes of the set this step writes
+            self._ev_halo.record(self._comm)
+            s.enqueue_step()                                      # interior + sources + probes; flips the sets
+            dev.stream.wait_event(self._ev_halo)                  # the next step reads the ghosts
+        else:
+            s.enqueue_step()
+            self._exchange()
+
     def _run_chunk(self, m: int) -> None:
         s = self.slab
+        if self.halo != "p2p":
+            self._overlap_possible()             # (collective: outside the step loop)
         s.begin_chunk(m)
         if self.halo == "p2p":               # the kernels exchange halos themselves: enqueue the whole chunk
             s.enqueue_steps(m)
         else:
             for _ in range(m):
-                s.enqueue_step()
-                self._exchange()
+                self._step_with_exchange()
         s.end_chunk()
 
     def run(self, duration=None, progress=False, track_energy=False, energy_sample_interval=1, output_file=None,

@@ -167,6 +167,52 @@ dist.barrier(); dist.destroy_process_group()
 """
 
 
+_TWO_RANK_PLAIN = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from strata_fdtd_b200.workloads import build_distributed_solver, build_solver
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+g = np.ones((96, 40, 136), dtype=bool); g[40:56, 10:30, 30:90] = False          # solid block through the cut at plane 48
+case = dict(shape=(96, 40, 136), resolution=1e-3, geometry=g, pml=[dict(depth=6)],
+            sources=[dict(kind="point", position=(46, 20, 100), frequency=20e3), dict(kind="point", position=(70, 5, 20), frequency=15e3)],
+            probes=[("lo", (47, 20, 110)), ("hi", (48, 20, 110)), ("far", (90, 30, 60))])
+d = build_distributed_solver(case, chunk_steps=16, halo={halo!r})
+d.run(steps=70); d.run(steps=30)
+print("HALO", d.halo, "OVERLAP", getattr(d, "_overlap", None))
+fields = {{f: d.gather_field(f) for f in ("p", "vx", "vy", "vz")}}
+traces = d.get_probe_data()
+if rank == 0:
+    one = build_solver(case, device=0, distributed=False)
+    one.run(steps=100)
+    for f in fields:
+        assert np.array_equal(fields[f], one.get_field(f)), f
+    for n in traces:
+        assert np.array_equal(traces[n], one.get_probe_data(n)[n]) and np.abs(traces[n]).max() > 0, n
+    print("TWO_RANK_OK")
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("halo", ["nccl", "p2p"])
+def test_two_ranks_plain_case_overlapped_exchange(tmp_path, halo):
+    """Two ranks, nothing but K1 writing the cut planes: in NCCL mode the cut planes are computed first and their
+    send/recv runs on a second stream beside the interior update (north_star's wording); equal to one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "two_rank_plain.py"
+    script.write_text(_TWO_RANK_PLAIN.format(root=str(ROOT), halo=halo))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29545", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert "TWO_RANK_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert f"HALO {halo}" in res.stdout
+    if halo == "nccl":
+        assert "OVERLAP True" in res.stdout
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("halo", ["nccl", "p2p"])
 def test_two_ranks_nccl_equal_single_gpu(tmp_path, halo):
