@@ -298,6 +298,10 @@ def run_b200_arm(a):
         slab.set_kernel_option(_lib.OPT_USE_GRAPH, 1)
     if a.ade_layout is not None:
         slab.set_kernel_option(_lib.OPT_ADE_LAYOUT, a.ade_layout)
+    if a.ade_chunk is not None:
+        slab.set_kernel_option(_lib.OPT_ADE_CHUNK_I, a.ade_chunk)
+    if a.ade_warps is not None:
+        slab.set_kernel_option(_lib.OPT_ADE_WARPS, a.ade_warps)
 
     def barrier():
         if dist is not None:
@@ -445,7 +449,9 @@ def main():
     ap.add_argument("--warps-k", type=int, default=None)
     ap.add_argument("--chunk-i", type=int, default=None)
     ap.add_argument("--graph", action="store_true")
-    ap.add_argument("--ade-layout", type=int, default=None, help="0 auto, 1 compact list, 2 dense box (ADE workloads)")
+    ap.add_argument("--ade-layout", type=int, default=None, help="0 auto, 1 compact list, 2 dense box, 3 fused (ADE workloads)")
+    ap.add_argument("--ade-chunk", type=int, default=None, help="K1-ADE planes per tile")
+    ap.add_argument("--ade-warps", type=int, default=None, help="K1-ADE warps per block")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -84,7 +84,8 @@ enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, /* 3 is ret
 enum { SB_FIELD_P = 0, SB_FIELD_VX = 1, SB_FIELD_VY = 2, SB_FIELD_VZ = 3 };
 enum { SB_OPT_KERNEL = 0, SB_OPT_ROWS_PER_THREAD = 1, SB_OPT_WARPS_J = 2, SB_OPT_WARPS_K = 3,
        SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5, SB_OPT_PROFILE = 6, SB_OPT_FUSE_K3 = 7,
-       SB_OPT_RESIDENT_SPLIT = 8, SB_OPT_RESIDENT_MIN_STEPS = 9, SB_OPT_PLANE_MAP = 10, SB_OPT_ADE_LAYOUT = 11 };
+       SB_OPT_RESIDENT_SPLIT = 8, SB_OPT_RESIDENT_MIN_STEPS = 9, SB_OPT_PLANE_MAP = 10, SB_OPT_ADE_LAYOUT = 11,
+       SB_OPT_ADE_CHUNK_I = 12, SB_OPT_ADE_WARPS = 13 };
 
 const char *sb_last_error(void);
 int sb_abi_version(void);
@@ -229,7 +230,9 @@ int sb_reset(sb_solver *h);
  *   SB_OPT_FUSE_K3           inject point sources / record probes inside K1 instead of a separate kernel (0 off, 1 small grids, 2 always)
  *   SB_OPT_RESIDENT_SPLIT    K5: overlap the halo-free velocity updates with the face exchange (default off: measured slower)
  *   SB_OPT_RESIDENT_MIN_STEPS  shortest sb_step_n chunk for which AUTO uses K5 / K6 (default 4)
- *   SB_OPT_ADE_LAYOUT        material cells as 0 auto, 1 compact list, 2 dense bounding box (set before sb_set_ade)
+ *   SB_OPT_ADE_LAYOUT        material cells as 0 auto (fused on a single slab), 1 compact list, 2 dense bounding box,
+ *                            3 fused into the step kernel (K1-ADE); set before sb_set_ade
+ *   SB_OPT_ADE_CHUNK_I / SB_OPT_ADE_WARPS   K1-ADE: planes a tile marches over, warps per block (0 = default)
  *   SB_OPT_PROFILE           bracket every step-kernel launch with CUDA events (sb_profile_read)                              */
 int sb_set_option(sb_solver *h, int option, int value);
 int sb_query(sb_solver *h, sb_stats *out);

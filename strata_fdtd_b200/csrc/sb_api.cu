@@ -134,6 +134,7 @@ struct sb_solver {
     long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 40LL << 20;   // where pipelining the steps was measured to pay
     int opt_plane_map = 0;                 // how K1 deals the (j, k) plane to warps: 0 = auto, 1 = strips, 2 = flat
     int cut_done = 0;                      // planes next to each cut already computed for the step about to be enqueued
+    int opt_ade_chunk = 0, opt_ade_warps = 0;   // K1-ADE launch shape: planes per tile, warps per block (0 = default)
 };
 
 // Launch shapes measured once per (device, grid, kernel variant) are remembered for the life of the process: a second
@@ -914,7 +915,11 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     int rj, wj, wk, chunk, gx, gy; bool flat;
     if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
     if (!h->side) {
-        CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        // a higher-priority stream: the few long-running K1-ADE blocks get their SM slots ahead of the plain kernel's
+        // thousands of blocks instead of trailing behind them
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
@@ -928,14 +933,13 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     if (grd.z > 65535) return fail("too many i-chunks");
     CU(cudaEventRecord(h->ev_fork, h->stream));
     CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    launch_march(rj, false, false, flat, P, grd, blk, h->stream);
-    // the ADE variant: 1 row per thread, 8 warps; the same plane mapping, restricted to the tiles that meet the box
+    // the ADE variant first: 1 row per thread; the same plane mapping, restricted to the tiles that meet the box
     StepParams Q = P;
     Q.mask = h->mask.p + h->plane;
     Q.box_mode = 2;
     Q.i_begin = P.bi0; Q.i_end = P.bi1;
-    Q.chunk_i = std::max(4, std::min(16, (P.bi1 - P.bi0 + 7) / 8));
-    const int WJ = 8;
+    Q.chunk_i = h->opt_ade_chunk > 0 ? h->opt_ade_chunk : std::max(4, std::min(16, (P.bi1 - P.bi0 + 15) / 16));
+    const int WJ = h->opt_ade_warps > 0 ? h->opt_ade_warps : 8;
     dim3 ablk(32, WJ), agrd;
     if (flat) {
         const long long P4 = d.pitch / 4, tile = 32LL * WJ;
@@ -952,6 +956,7 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     if (uni) { if (flat) k1_step_march_ade<true, true><<<agrd, ablk, 0, h->side>>>(Q, A); else k1_step_march_ade<true, false><<<agrd, ablk, 0, h->side>>>(Q, A); }
     else     { if (flat) k1_step_march_ade<false, true><<<agrd, ablk, 0, h->side>>>(Q, A); else k1_step_march_ade<false, false><<<agrd, ablk, 0, h->side>>>(Q, A); }
     CU(cudaEventRecord(h->ev_join, h->side));
+    launch_march(rj, false, false, flat, P, grd, blk, h->stream);
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->kernels_launched += 2;
     h->ade_phase++;
@@ -1052,7 +1057,7 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
     StepParams P;
     fill_params(h, P);
     const int n_rec_all = h->n_probes + h->n_mics;
-    const bool fused = fused_k3(h);
+    const bool fused = fused_k3(h) && !h->cut_done;         // (planes computed ahead by sb_step_cuts_async: K3 runs by itself)
     if (fused) {
         P.n_inline = h->n_src_entries;
         for (int e = 0; e < h->n_src_entries; e++) {
@@ -1462,11 +1467,12 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
             if (it == h->graphs.end()) {
                 cudaGraph_t g;
                 const long long k0 = h->kernels_launched; const int cur0 = h->cur; const long long s0 = h->steps_done;
+                const long long ph0 = h->ade_phase;
                 CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                 int rc = 0;
                 for (int s = 0; s < n_steps && !rc; s++) rc = enqueue_one_step(h, src_dev, rec_dev, s, s == n_steps - 1);
                 cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
-                h->cur = cur0; h->steps_done = s0;
+                h->cur = cur0; h->steps_done = s0; h->ade_phase = ph0;
                 const long long per_launch = h->kernels_launched - k0; h->kernels_launched = k0;
                 if (rc) return 1;
                 if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
@@ -1478,6 +1484,7 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
             CU(cudaGraphLaunch(it->second.exec, h->stream));
             h->kernels_launched += it->second.launches;    // bookkeeping equivalent to n_steps enqueues
             h->steps_done += n_steps;
+            if (h->have_ade && h->ade_fused) h->ade_phase += n_steps;   // the replayed steps rotated the density-pole buffers
             if (n_steps & 1) h->cur = 1 - h->cur;
             return 0;
         }
@@ -1604,6 +1611,8 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
                                h->opt_plane_map = value; break;
         case SB_OPT_ADE_LAYOUT: if (value < 0 || value > 3) return fail("ade_layout must be 0 (auto), 1 (compact), 2 (dense) or 3 (fused)");
                                 h->opt_ade_layout = value; break;
+        case SB_OPT_ADE_CHUNK_I: if (value < 0) return fail("ade_chunk_i must be >= 0"); h->opt_ade_chunk = value; break;
+        case SB_OPT_ADE_WARPS: if (value < 0 || value > 8) return fail("ade_warps must be 0..8"); h->opt_ade_warps = value; break;
         case SB_OPT_RESIDENT_SPLIT: h->opt_res_split = value ? 1 : 0; break;
         case SB_OPT_RESIDENT_MIN_STEPS: h->opt_res_min_steps = std::max(1, value); break;
         default: return fail("unknown option %d", option);

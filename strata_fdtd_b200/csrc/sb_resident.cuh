@@ -477,42 +477,56 @@ template <typename F> static inline int res_dispatch(bool geom, bool uni, int n_
 // issues the loads of all its items at once and only then looks at the tags, so a face that has already arrived
 // costs one L2 round trip, not one per item; units whose tag is not yet the wanted step are simply read again.
 struct RecvPoll {
+    static constexpr int Q = 4;              // halo items a thread keeps the addresses of (more are looked up per step)
     int *err_flag;
     bool dead;                               // a wait timed out: stop waiting, finish the chunk, report
+    const uint4 *src0[Q];                    // the item's 32-byte source in the publisher's parity-0 slot (nullptr = no item)
+    int dst[Q];                              // where it lands in this box's shared memory
+    long long par_stride;                    // uint4 distance between the two parities of the exchange area
     static __device__ __forceinline__ uint4 ldv(const uint4 *src)
     {
         uint4 v;
         asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
         return v;
     }
+    // which items a thread receives never changes during a launch: resolve (face, row, column) -> addresses once,
+    // outside the step loop (the lookup is full of integer divisions)
+    __device__ __forceinline__ void prepare(const ResParams &R, const ResBlock &B, const ResMap &M, const ResHalo &H, int tid)
+    {
+        par_stride = res_xch_slot(R, 1, 0, 0) - res_xch_slot(R, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int idx = tid + q * K5_NT;
+            src0[q] = nullptr; dst[q] = 0;
+            if (idx < H.total) H.item(R, B, M, 0, idx, src0[q], dst[q]);
+        }
+    }
+    __device__ __forceinline__ void take(float *sm, const uint4 *src, int d, unsigned tag, uint4 a, uint4 b)
+    {
+        long long t0 = 0;
+        while (!(a.y == tag && a.w == tag && b.y == tag && b.w == tag) && !dead) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > (2LL << 30)) { atomicExch(err_flag, 2); dead = true; }   // ~1 s: never hang the GPU
+            a = ldv(src); b = ldv(src + 1);
+        }
+        st4(sm + d, make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z)));
+    }
     __device__ __forceinline__ void run(const ResParams &R, const ResBlock &B, const ResMap &M, const ResHalo &H,
                                         float *sm, int tid, int s)
     {
-        constexpr int Q = 4;
         const unsigned tag = R.tag_base + (unsigned)s;
-        for (int base = tid; base < H.total; base += Q * K5_NT) {
-            const uint4 *src[Q]; int dst[Q]; uint4 a[Q], b[Q];
+        const long long po = (s & 1) ? par_stride : 0;
+        uint4 a[Q], b[Q];
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const int idx = base + q * K5_NT;
-                src[q] = nullptr; dst[q] = 0;
-                if (idx < H.total) H.item(R, B, M, s & 1, idx, src[q], dst[q]);
-            }
+        for (int q = 0; q < Q; q++)                                    // all loads first, then the tags: one L2 round trip
+            if (src0[q]) { a[q] = ldv(src0[q] + po); b[q] = ldv(src0[q] + po + 1); }
 #pragma unroll
-            for (int q = 0; q < Q; q++)
-                if (src[q]) { a[q] = ldv(src[q]); b[q] = ldv(src[q] + 1); }
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-                if (!src[q]) continue;
-                long long t0 = 0;
-                while (!(a[q].y == tag && a[q].w == tag && b[q].y == tag && b[q].w == tag) && !dead) {
-                    if (t0 == 0) t0 = clock64();
-                    else if (clock64() - t0 > (2LL << 30)) { atomicExch(err_flag, 2); dead = true; }   // ~1 s: never hang the GPU
-                    a[q] = ldv(src[q]); b[q] = ldv(src[q] + 1);
-                }
-                st4(sm + dst[q], make_float4(__uint_as_float(a[q].x), __uint_as_float(a[q].z),
-                                             __uint_as_float(b[q].x), __uint_as_float(b[q].z)));
-            }
+        for (int q = 0; q < Q; q++)
+            if (src0[q]) take(sm, src0[q] + po, dst[q], tag, a[q], b[q]);
+        for (int idx = tid + Q * K5_NT; idx < H.total; idx += K5_NT) { // boxes with very long faces
+            const uint4 *src; int d;
+            H.item(R, B, M, s & 1, idx, src, d);
+            take(sm, src, d, tag, ldv(src), ldv(src + 1));
         }
     }
 };
@@ -539,8 +553,10 @@ __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ 
     }
     __syncthreads();
     const int n_own = spr[0];
-    RecvPoll recv{R.err_flag, false};
+    RecvPoll recv;
+    recv.err_flag = R.err_flag; recv.dead = false;
     const ResHalo H(R, B);
+    recv.prepare(R, B, M, H, tid);
 
     for (int s = 0; s < R.n_steps; s++) {
         if (s > 0) {

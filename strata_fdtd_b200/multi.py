@@ -668,10 +668,10 @@ class LocalSlabGroup:
         for s in self.slabs:
             _lib.check(s._dev.lib.sb_synchronize(s._dev.handle))
 
-    def _exchange(self, include_vx_ghost=False):
+    def _exchange(self, include_vx_ghost=False, next_set=False):
         self._sync()
         for lo, hi in zip(self.slabs[:-1], self.slabs[1:]):
-            a, b = lo.halo_planes("p"), hi.halo_planes("p")
+            a, b = lo.halo_planes("p", next_set=next_set), hi.halo_planes("p", next_set=next_set)
             b["recv_lo"].copy_(a["send_hi"])
             a["recv_hi"].copy_(b["send_lo"])
             if include_vx_ghost:
@@ -697,6 +697,19 @@ class LocalSlabGroup:
                 for _ in range(m):
                     for s in self.slabs:
                         s.enqueue_step()
+            elif self.halo == "copy_cuts":
+                # the order of the overlapped NCCL mode (cut planes first, exchange, then the rest of the step),
+                # serialised on one device: exercises sb_step_cuts_async where only one GPU is available
+                ok = not any(s.sources_touch_cut_planes() for s in self.slabs)
+                for _ in range(m):
+                    split = ok and all([s.enqueue_cuts() for s in self.slabs])
+                    if split:
+                        self._exchange(next_set=True)
+                    for s in self.slabs:
+                        s.enqueue_step()
+                    if not split:
+                        self._exchange()
+                self.cut_steps = getattr(self, "cut_steps", 0) + (m if split else 0)
             else:
                 for _ in range(m):
                     for s in self.slabs:
