@@ -188,6 +188,14 @@ int sb_step_n(sb_solver *h, int n_steps, const double *src_values_host, float *r
  * nothing is copied and the stream is not synchronised.                                  */
 int sb_step_n_async(sb_solver *h, int n_steps, const double *src_values_dev, float *record_out_dev);
 
+/* sb_step_n without the wait, for a host loop that prepares chunk n+1 and files the records of chunk n-1 while the device
+ * runs chunk n: the waveform table is copied up, the steps are enqueued and the records are copied down into
+ * record_out_host, all on the handle's stream.  `slot` (0 or 1) names one of two sets of device staging buffers;
+ * sb_step_n_wait(h, slot) returns when that chunk is complete and record_out_host is filled.  The host buffers must stay
+ * valid until then and should be page-locked (otherwise the copies are staged synchronously by the driver).       */
+int sb_step_n_submit(sb_solver *h, int slot, int n_steps, const double *src_values_host, float *record_out_host);
+int sb_step_n_wait(sb_solver *h, int slot);
+
 /* Host-driven halo exchange overlapped with the interior update: computes ONLY the planes next to this slab's cuts for
  * the step about to run (first) and remembers that the next sb_step_n_async(h, 1, ...) has to leave them out.  The
  * caller then sends those planes of the set being written (the one sb_current_set does NOT report) on another stream while

@@ -124,6 +124,8 @@ SIGNATURES = {
     "sb_mic_tables": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sb_step_n": (_i, [_vp, _i, _vp, _vp]),
     "sb_step_n_async": (_i, [_vp, _i, _vp, _vp]),
+    "sb_step_n_submit": (_i, [_vp, _i, _i, _vp, _vp]),
+    "sb_step_n_wait": (_i, [_vp, _i]),
     "sb_step_cuts_async": (_i, [_vp, C.POINTER(_i)]),
     "sb_halo_planes": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "sb_set_peers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _vp, _vp]),

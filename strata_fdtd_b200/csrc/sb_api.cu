@@ -133,6 +133,8 @@ struct sb_solver {
     DBuf<int> d_pipe_ctr;                  // [0] ticket, [1 ..] chunk counters
     long long opt_pipe_min_cells = 6LL << 20, opt_pipe_max_cells = 40LL << 20;   // where pipelining the steps was measured to pay
     int opt_plane_map = 0;                 // how K1 deals the (j, k) plane to warps: 0 = auto, 1 = strips, 2 = flat
+    // two sets of staging buffers for sb_step_n_submit / sb_step_n_wait (a chunk in flight while the host prepares the next)
+    DBuf<double> stage_src[2]; DBuf<float> stage_rec[2]; cudaEvent_t stage_done[2] = {nullptr, nullptr};
     int cut_done = 0;                      // planes next to each cut already computed for the step about to be enqueued
     int opt_ade_chunk = 0, opt_ade_warps = 0;   // K1-ADE launch shape: planes per tile, warps per block (0 = default)
 };
@@ -235,6 +237,7 @@ extern "C" int sb_destroy(sb_solver *h)
     h->d_energy.release(); h->d_step_global.release(); h->d_err.release();
     h->d_probe_ijk.release(); h->d_res_xch.release(); h->d_pipe_ctr.release(); h->d_res_scratch.release();
     for (auto &fp : h->fpole) for (auto &b : fp.b) b.release();
+    for (int q = 0; q < 2; q++) { h->stage_src[q].release(); h->stage_rec[q].release(); if (h->stage_done[q]) cudaEventDestroy(h->stage_done[q]); }
     h->ade_matpad.release();
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -895,7 +898,7 @@ static void fill_ade_fused(sb_solver *h, AdeFused &A)
     for (int q = 0; q < A.n_poles; q++) {
         A.poles[q] = h->ade.poles[q];
         sb_solver::FusedPole &fp = h->fpole[q];
-        A.bi0[q] = fp.bi0; A.bj0[q] = fp.bj0; A.bnj[q] = fp.bnj;
+        A.bi0[q] = fp.bi0; A.bj0[q] = fp.bj0; A.bni[q] = fp.bni; A.bnj[q] = fp.bnj;
         if (fp.nbuf == 0) { A.poles[q].target = 2; continue; }               // no cell carries this material: pole unused
         if (A.poles[q].target == 0) {
             if (fp.nbuf == 3) { A.Jin[q] = fp.b[ph % 3].p; A.Jpin[q] = fp.b[(ph + 2) % 3].p; A.Jout[q] = fp.b[(ph + 1) % 3].p; }
@@ -915,11 +918,7 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     int rj, wj, wk, chunk, gx, gy; bool flat;
     if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
     if (!h->side) {
-        // a higher-priority stream: the few long-running K1-ADE blocks get their SM slots ahead of the plain kernel's
-        // thousands of blocks instead of trailing behind them
-        int prio_lo = 0, prio_hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CU(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi));
+        CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
@@ -931,9 +930,13 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     P.bk0 = h->fbox[4] / 4 * 4; P.bk1 = (h->fbox[5] / 4 + 1) * 4;
     const dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
     if (grd.z > 65535) return fail("too many i-chunks");
+    // K1-ADE goes first, on the solver's own stream: its (comparatively few, long-running) blocks take their SM slots the
+    // moment the previous step ends; the plain kernel follows on a second stream -- an event wait later -- and fills
+    // the rest of the machine.  The other way round the plain kernel's thousands of small blocks hold every SM and the
+    // ADE blocks, which need a quarter of a register file each, only get in when it drains (measured: no overlap at all).
     CU(cudaEventRecord(h->ev_fork, h->stream));
     CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    // the ADE variant first: 1 row per thread; the same plane mapping, restricted to the tiles that meet the box
+    // the ADE variant: 1 row per thread; the same plane mapping, restricted to the tiles that meet the box
     StepParams Q = P;
     Q.mask = h->mask.p + h->plane;
     Q.box_mode = 2;
@@ -953,10 +956,10 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     AdeFused A;
     fill_ade_fused(h, A);
     const bool uni = Q.icx == nullptr;
-    if (uni) { if (flat) k1_step_march_ade<true, true><<<agrd, ablk, 0, h->side>>>(Q, A); else k1_step_march_ade<true, false><<<agrd, ablk, 0, h->side>>>(Q, A); }
-    else     { if (flat) k1_step_march_ade<false, true><<<agrd, ablk, 0, h->side>>>(Q, A); else k1_step_march_ade<false, false><<<agrd, ablk, 0, h->side>>>(Q, A); }
+    if (uni) { if (flat) k1_step_march_ade<true, true><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<true, false><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+    else     { if (flat) k1_step_march_ade<false, true><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<false, false><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+    launch_march(rj, false, false, flat, P, grd, blk, h->side);
     CU(cudaEventRecord(h->ev_join, h->side));
-    launch_march(rj, false, false, flat, P, grd, blk, h->stream);
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->kernels_launched += 2;
     h->ade_phase++;
@@ -1515,6 +1518,37 @@ extern "C" int sb_step_n(sb_solver *h, int n_steps, const double *src_host, floa
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     if (h->resident_used) return sb_synchronize(h);
+    return 0;
+}
+
+extern "C" int sb_step_n_submit(sb_solver *h, int slot, int n_steps, const double *src_host, float *rec_host)
+{
+    CHECK_H(h);
+    if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
+    if (n_steps <= 0) return fail("step count must be positive");
+    const int n_rec = h->n_probes + h->n_mics;
+    if (h->n_sources && h->n_src_cells && !src_host) return fail("source values required");
+    DBuf<double> &src = h->stage_src[slot];
+    DBuf<float> &rec = h->stage_rec[slot];
+    const void *old_src = src.p, *old_rec = rec.p;
+    if (src.alloc((size_t)std::max(1, n_steps * std::max(1, h->n_sources)))) return 1;
+    if (rec.alloc((size_t)std::max(1, n_steps * std::max(1, n_rec)))) return 1;
+    if (old_src != src.p || old_rec != rec.p) drop_graphs(h);          // cached graphs hold these pointers
+    if (!h->stage_done[slot]) CU(cudaEventCreateWithFlags(&h->stage_done[slot], cudaEventDisableTiming));
+    if (h->n_sources && src_host)
+        CU(cudaMemcpyAsync(src.p, src_host, (size_t)n_steps * h->n_sources * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (sb_step_n_async(h, n_steps, src.p, rec.p)) return 1;
+    if (n_rec && rec_host)
+        CU(cudaMemcpyAsync(rec_host, rec.p, (size_t)n_steps * n_rec * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->stage_done[slot], h->stream));
+    return 0;
+}
+
+extern "C" int sb_step_n_wait(sb_solver *h, int slot)
+{
+    CHECK_H(h);
+    if (slot < 0 || slot > 1 || !h->stage_done[slot]) return fail("nothing was submitted in this slot");
+    CU(cudaEventSynchronize(h->stage_done[slot]));
     return 0;
 }
 

@@ -848,10 +848,12 @@ struct AdeFused {
     const uint8_t *mat;                  // material id per cell (padded field layout, plane-0 pointer); multi only
     float inv_dx;
     PoleDev poles[MAX_POLES];
-    int bi0[MAX_POLES], bj0[MAX_POLES], bnj[MAX_POLES];
+    int bi0[MAX_POLES], bj0[MAX_POLES], bni[MAX_POLES], bnj[MAX_POLES];
     const float *Jin[MAX_POLES], *Jpin[MAX_POLES];
     float *Jout[MAX_POLES], *Jpout[MAX_POLES];       // modulus poles: the same buffers as Jin / Jpin (in place)
 };
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // byte e of w has bit 7 set -> element e takes part
 SB_HD float4 corr4(float4 v, unsigned w, float vc, float4 hi, float4 lo)
@@ -931,6 +933,20 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
     };
 
     // ---- prologue: p of plane ib, undamped (corrected, rigid-masked) vx of plane ib-1 ---------------------------
+    if (own) {                                               // the J rows of the first two planes, on their way while the fields load
+        _Pragma("unroll 1")
+        for (int q = 0; q < A.n_poles; q++) {
+            const int lj = j0 - A.bj0[q];
+            if (A.poles[q].target > 1 || lj < 0 || lj >= A.bnj[q]) continue;
+            for (int a = 0; a < 2; a++) {
+                const int li = ib + a - A.bi0[q];
+                if (li < 0 || li >= A.bni[q]) continue;
+                const long long o = ((long long)li * A.bnj[q] + lj) * P.pitch + k0;
+                prefetch_l1(A.Jin[q] + o);
+                if (A.Jpin[q]) prefetch_l1(A.Jpin[q] + o);
+            }
+        }
+    }
     float4 pc = ok ? ld4(F.p_in + (long long)ib * P.plane + col) : z4;
     float4 vxp = z4;
     if ((ib > 0 || P.has_lower) && ok) {                     // (ok is not warp-uniform: no collectives in here)
@@ -977,6 +993,20 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
         const float p_lo = (edge_lo && row0) ? F.p_in[c - 1] : 0.0f;
         const float vz_lo = (edge_lo && row0) ? F.vz_in[c - 1] : 0.0f;
         const uint8_t m_lo = (edge_lo && row0) ? P.mask[c - 1] : (uint8_t)0x0F;
+        // The J rows a plane needs are only known once its mask bytes have arrived, and every pole adds a dependent round
+        // of loads: ask for the next plane's rows now (density poles: the row that becomes the +x neighbour, i.e. plane
+        // i+2; modulus poles: plane i+1), one iteration -- far more than a DRAM round trip -- ahead of their use.
+        if (own) {
+            _Pragma("unroll 1")
+            for (int q = 0; q < A.n_poles; q++) {
+                const int ahead = A.poles[q].target == 0 ? 2 : 1;
+                const int li = i + ahead - A.bi0[q], lj = j0 - A.bj0[q];
+                if (A.poles[q].target > 1 || li < 0 || li >= A.bni[q] || lj < 0 || lj >= A.bnj[q]) continue;
+                const long long o = ((long long)li * A.bnj[q] + lj) * P.pitch + k0;
+                prefetch_l1(A.Jin[q] + o);
+                if (A.Jpin[q]) prefetch_l1(A.Jpin[q] + o);
+            }
+        }
         const bool masked = !__all_sync(FULL, (mkc & ALL_OPEN) == ALL_OPEN && (mkm & ALL_OPEN) == ALL_OPEN && (m_lo & 0x0F) == 0x0F);
         const bool ade = __any_sync(FULL, (mkc & 0x80808080u) != 0u);
 

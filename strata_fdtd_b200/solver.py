@@ -728,19 +728,17 @@ class FDTDSolver:
         return W
 
     def _io_slot(self, m: int, n_src: int, n_rec: int):
-        """Two sets of pinned host + device buffers for the waveform table and the record block of a chunk, so that the
-        host can prepare chunk n+1 and unpack chunk n-1 while the device runs chunk n."""
+        """Two page-locked host buffers for the waveform table and the record block of a chunk, so that the host can
+        prepare chunk n+1 and unpack chunk n-1 while the device runs chunk n (sb_step_n_submit / sb_step_n_wait)."""
         dev = self._dev
         torch = dev.torch
         io = getattr(self, "_io", None)
         if io is None or io["cap"] < m or io["n_src"] != n_src or io["n_rec"] != n_rec or io["dev"] is not dev:
             cap = max(m, io["cap"] if io and io["dev"] is dev else 0)
-            with torch.cuda.device(dev.index):
-                io = dict(cap=cap, n_src=n_src, n_rec=n_rec, dev=dev, turn=0,
-                          W_host=[torch.empty((cap, n_src), dtype=torch.float64).pin_memory() for _ in range(2)],
-                          W_dev=[torch.empty((cap, n_src), dtype=torch.float64, device=dev.device) for _ in range(2)],
-                          rec_host=[torch.empty((cap, n_rec), dtype=torch.float32).pin_memory() for _ in range(2)],
-                          rec_dev=[torch.empty((cap, n_rec), dtype=torch.float32, device=dev.device) for _ in range(2)])
+            keep = [torch.empty((cap, n_src), dtype=torch.float64).pin_memory() for _ in range(2)] + \
+                   [torch.empty((cap, n_rec), dtype=torch.float32).pin_memory() for _ in range(2)]
+            io = dict(cap=cap, n_src=n_src, n_rec=n_rec, dev=dev, turn=0, keep=keep,
+                      W=[t.numpy() for t in keep[:2]], rec=[t.numpy() for t in keep[2:]])
             self._io = io
         io["turn"] ^= 1
         return io, io["turn"]
@@ -748,7 +746,6 @@ class FDTDSolver:
     def _launch_chunk(self, m: int) -> dict:
         """Enqueue m steps: waveform table up, kernels, records down (all asynchronous on the solver's stream)."""
         dev = self._dev
-        torch = dev.torch
         n_src = max(1, len(self._sources))
         n_rec = len(self._local_probes) + sum(len(sl) for sl in self._mic_slots) + len(self._corner_keys)
         # the same float64 accumulation as solver.py:2072 (np.add.accumulate adds strictly left to right)
@@ -757,29 +754,23 @@ class FDTDSolver:
         acc = np.add.accumulate(steps_t)
         times, t_end = acc[:m], float(acc[m])
         io, k = self._io_slot(m, n_src, max(1, n_rec))
-        with torch.cuda.stream(dev.stream):
-            if self._sources:
-                io["W_host"][k][:m].numpy()[...] = self._waveform_table(times)
-                io["W_dev"][k][:m].copy_(io["W_host"][k][:m], non_blocking=True)
-            _lib.check(dev.lib.sb_step_n_async(dev.handle, m, io["W_dev"][k].data_ptr(),
-                                               io["rec_dev"][k].data_ptr() if n_rec else None))
-            if n_rec:
-                io["rec_host"][k][:m].copy_(io["rec_dev"][k][:m], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(dev.stream)
+        W = io["W"][k][:m]
+        if self._sources:
+            W[...] = self._waveform_table(times)
+        _lib.check(dev.lib.sb_step_n_submit(dev.handle, k, m, _lib.ptr(W), _lib.ptr(io["rec"][k]) if n_rec else None))
         self._host_stale = set(_FIELDS)
         first_idx = self._step_count
         self._step_count += m
         self._time = t_end
-        return dict(m=m, times=times, rec=io["rec_host"][k], n_rec=n_rec, done=done, first_idx=first_idx)
+        return dict(m=m, times=times, rec=io["rec"][k], n_rec=n_rec, slot=k, first_idx=first_idx)
 
     def _finish_chunk(self, tk: dict, writer=None) -> None:
         """Wait for a launched chunk and file its samples: probes, microphones, corner samples, result writer."""
-        tk["done"].synchronize()
+        _lib.check(self._dev.lib.sb_step_n_wait(self._dev.handle, tk["slot"]))
         m, times = tk["m"], tk["times"]
         probes = self._local_probes
         mics = list(self._microphones.values())
-        rec = tk["rec"][:m].numpy() if tk["n_rec"] else np.empty((m, 0), dtype=np.float32)
+        rec = tk["rec"][:m] if tk["n_rec"] else np.empty((m, 0), dtype=np.float32)
         for q, pr in enumerate(probes):
             pr.data.extend(rec[:, q].tolist())
         for mic, slots in zip(mics, self._mic_slots):
