@@ -285,7 +285,7 @@ def run_b200_arm(a):
     K, W = a.steps, max(4, a.warmup)        # >= 4 so that the warm-up runs the same (chunk) kernels as the timed region
 
     if world == 1:
-        s = build_solver(case, device=local_rank, chunk_steps=max(K, W), distributed=False)
+        s = build_solver(case, device=local_rank, distributed=False)      # the solver's own chunking, as a user gets it
         slab, drv = s, None
     else:
         drv = build_distributed_solver(case, device=local_rank, chunk_steps=max(K, W), halo=a.halo)

@@ -88,6 +88,7 @@ struct sb_solver {
     // fused layout (K1-ADE, sb_kernels.cuh): per pole, J buffers dense over its material's bounding box
     struct FusedPole { DBuf<float> b[3]; int nbuf = 0, bi0 = 0, bj0 = 0, bni = 0, bnj = 0; };
     bool ade_fused = false;
+    bool ade_concurrent = false;           // list layout whose K2a / K2b run beside K1 (K1 leaves their cells out: ADEX variants)
     FusedPole fpole[MAX_POLES];
     DBuf<uint8_t> ade_matpad; bool ade_multi = false;
     int fbox[6] = {0, 0, 0, 0, 0, 0};      // bounding box of all pole-carrying cells: i0, i1, j0, j1, k0, k1 (inclusive)
@@ -550,7 +551,7 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
 {
     CHECK_H(h);
     drop_graphs(h);
-    h->have_ade = false; h->ade_fused = false;
+    h->have_ade = false; h->ade_fused = false; h->ade_concurrent = false;
     if (n_poles == 0 || !mat) return 0;
     if (n_poles > MAX_POLES) return fail("at most %d ADE poles", MAX_POLES);
     const sb_grid_desc &d = h->d;
@@ -612,10 +613,36 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
     if (h->opt_ade_layout == 3 && slab) return fail("the fused ADE layout is not available on decomposed slabs");
     const bool march_ok = h->opt_kernel == SB_KERNEL_AUTO || h->opt_kernel == SB_KERNEL_MARCH;
     if (h->opt_ade_layout == 3 && !march_ok) return fail("the fused ADE layout needs the marching kernel");
-    if (!slab && march_ok && (h->opt_ade_layout == 0 || h->opt_ade_layout == 3)) {
+    // ADE bits in the upper nibble of the mask bytes (lower nibble: geometry, all open if there is none) and, with
+    // several materials, the ids in the field layout: what K1-ADE and the ADEX variants of K1 read
+    int n_mat = 0;
+    for (int id = 1; id < 256; id++) if (m_hi[3 * id] >= 0) n_mat++;
+    auto write_ade_bits = [&](bool want_ids) -> int {
+        if (!h->mask.p && build_mask(h, nullptr, 0)) return 1;
+        DBuf<uint8_t> md;
+        if (md.upload(mat, (size_t)(i_hi - i_lo) * pl, h->stream)) return 1;
+        h->ade_multi = want_ids && n_mat > 1;
+        if (h->ade_multi && h->ade_matpad.alloc((size_t)h->elems)) { md.release(); return 1; }
+        if (h->ade_multi) CU(cudaMemsetAsync(h->ade_matpad.p, 0, (size_t)h->elems, h->stream));
+        UsedIds U;
+        for (int id = 0; id < 256; id++) U.used[id] = used[id] ? 1 : 0;
+        dim3 blk(128), grd((d.nz + 127) / 128, d.ny, d.nx + 2);
+        k_ade_bits<<<grd, blk, 0, h->stream>>>(md.p, h->mask.p + h->plane, h->ade_multi ? h->ade_matpad.p + h->plane : nullptr, U,
+                                               d.nx, d.ny, d.nz, d.pitch, h->plane, d.has_lower, d.has_upper);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        md.release();
+        h->kernels_launched++;
+        for (int a = 0; a < 3; a++) { h->fbox[2 * a] = b_lo[a]; h->fbox[2 * a + 1] = b_hi[a]; }
+        return 0;
+    };
+    // Automatic choice on one GPU: materials that fill a sizeable part of the grid are updated inside the step kernel
+    // (fused); a sparse inclusion -- config 3's sphere is 0.4 % of the cells -- costs less as two small list kernels that
+    // run BESIDE K1 (K1-ADE's long-running, register-heavy blocks would displace more of K1 than they save).
+    const long long grid_cells = (long long)d.nx * d.ny * d.nz;
+    const bool want_fused = h->opt_ade_layout == 3 || (h->opt_ade_layout == 0 && (double)n >= 0.02 * (double)grid_cells);
+    if (!slab && march_ok && want_fused) {
         size_t total = 0, free_b = 0, total_b = 0;
-        int n_mat = 0;
-        for (int id = 1; id < 256; id++) if (m_hi[3 * id] >= 0) n_mat++;
         for (int q = 0; q < n_poles; q++) {
             const int id = poles[q].material_id;
             sb_solver::FusedPole &fp = h->fpole[q];
@@ -636,23 +663,7 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
                     CU(cudaMemsetAsync(fp.b[b].p, 0, fp.b[b].n * sizeof(float), h->stream));
                 }
             }
-            // mask bytes: lower nibble from the geometry (all open if there is none), upper nibble from the materials
-            if (!h->mask.p && build_mask(h, nullptr, 0)) return 1;
-            DBuf<uint8_t> md;
-            if (md.upload(mat, (size_t)(i_hi - i_lo) * pl, h->stream)) return 1;
-            h->ade_multi = n_mat > 1;
-            if (h->ade_multi && h->ade_matpad.alloc((size_t)h->elems)) { md.release(); return 1; }
-            if (h->ade_multi) CU(cudaMemsetAsync(h->ade_matpad.p, 0, (size_t)h->elems, h->stream));
-            UsedIds U;
-            for (int id = 0; id < 256; id++) U.used[id] = used[id] ? 1 : 0;
-            dim3 blk(128), grd((d.nz + 127) / 128, d.ny, d.nx + 2);
-            k_ade_bits<<<grd, blk, 0, h->stream>>>(md.p, h->mask.p + h->plane, h->ade_multi ? h->ade_matpad.p + h->plane : nullptr, U,
-                                                   d.nx, d.ny, d.nz, d.pitch, h->plane, d.has_lower, d.has_upper);
-            CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(h->stream));
-            md.release();
-            h->kernels_launched++;
-            for (int a = 0; a < 3; a++) { h->fbox[2 * a] = b_lo[a]; h->fbox[2 * a + 1] = b_hi[a]; }
+            if (write_ade_bits(true)) return 1;
             A.n_cells = (int)std::min<long long>(n, (1LL << 31) - 1); A.n_poles = n_poles; A.inv_dx = inv_dx;
             h->ade_material_cells = n;
             h->ade_phase = 0;
@@ -661,7 +672,10 @@ extern "C" int sb_set_ade(sb_solver *h, const sb_pole *poles, int n_poles, const
             return 0;
         }
     }
-    if (h->mask.p) {                                              // list layouts: no ADE bits in the mask bytes
+    if (!slab && march_ok) {                                      // list layouts on one GPU: K2a / K2b run beside K1
+        if (write_ade_bits(false)) return 1;
+        h->ade_concurrent = true;
+    } else if (h->mask.p) {                                       // decomposed slabs: no ADE bits in the mask bytes
         dim3 blk(128), grd((d.nz + 127) / 128, d.ny, d.nx + 2);
         k_ade_bits<<<grd, blk, 0, h->stream>>>(nullptr, h->mask.p + h->plane, nullptr, UsedIds{}, d.nx, d.ny, d.nz, d.pitch, h->plane,
                                                d.has_lower, d.has_upper);
@@ -765,6 +779,7 @@ static void fill_params(sb_solver *h, StepParams &P)
     P.n_inline = 0; P.src_row = nullptr; P.rec_prev = 0; P.n_probes = P.n_mics = 0;
     P.probe_off = P.mic_off8 = nullptr; P.mic_field = nullptr; P.mic_w8 = nullptr; P.rec_row = nullptr;
     P.box_mode = 0; P.bi0 = P.bi1 = P.bj0 = P.bj1 = P.bk0 = P.bk1 = 0; P.bx_off = P.by_off = P.bz_off = 0;
+    P.ade_mask = nullptr;
     if (h->have_peers) {
         if (d.has_lower) { P.peer_lo_p = h->peer_lo_set[out] + (long long)(h->peer_lo_nx + 1) * h->plane; P.flag_lo = h->my_flags; }
         if (d.has_upper) { P.peer_hi_p = h->peer_hi_set[out]; P.flag_hi = h->my_flags + 1; }
@@ -784,22 +799,25 @@ static PeerLink peer_link(sb_solver *h, const StepParams &P)
 // ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE, FLAT> ------------------------
 // (PEER launches never inject inline: a slab's step always ends with K3, which also publishes the step flag)
 template <int RJ, bool GEOM, bool UNI>
-static void launch_march3(bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+static void launch_march3(bool peer, bool fuse, bool flat, bool adex, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
-    if (peer)      { if (flat) k1_step_march<RJ, GEOM, UNI, true, false, true><<<grd, blk, 0, st>>>(P);
+    if (adex)      { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true, true><<<grd, blk, 0, st>>>(P);
+                     else      k1_step_march<RJ, GEOM, UNI, false, false, false, true><<<grd, blk, 0, st>>>(P); }
+    else if (peer) { if (flat) k1_step_march<RJ, GEOM, UNI, true, false, true><<<grd, blk, 0, st>>>(P);
                      else      k1_step_march<RJ, GEOM, UNI, true, false, false><<<grd, blk, 0, st>>>(P); }
     else if (fuse) { if (flat) k1_step_march<RJ, GEOM, UNI, false, true, true><<<grd, blk, 0, st>>>(P);
                      else      k1_step_march<RJ, GEOM, UNI, false, true, false><<<grd, blk, 0, st>>>(P); }
     else           { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true><<<grd, blk, 0, st>>>(P);
                      else      k1_step_march<RJ, GEOM, UNI, false, false, false><<<grd, blk, 0, st>>>(P); }
 }
-static void launch_march(int rj, bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+static void launch_march(int rj, bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st,
+                         bool adex = false)
 {
     const bool geom = P.mask != nullptr, uni = P.icx == nullptr;
-    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, flat, P, grd, blk, st); }
-                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, flat, P, grd, blk, st); } }
-    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, flat, P, grd, blk, st); }
-                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, flat, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, flat, P, grd, blk, st); } }
+    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, flat, adex, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, flat, adex, P, grd, blk, st); } }
+    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, flat, adex, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, flat, adex, P, grd, blk, st); } }
 }
 
 // launch shape of the marching kernel: rows per thread, warps along j / k, planes per chunk, tiles along k / j
@@ -997,6 +1015,53 @@ extern "C" int sb_step_cuts_async(sb_solver *h, int *applied)
     return 0;
 }
 
+// ---- K1 beside the ADE list kernels: K1 (ADEX variant) leaves the material cells' p and corrected faces out, K2a / K2b
+// compute them from the same input set on a second stream -- nothing orders the two until the join.
+static int launch_ade_lists(sb_solver *h, const StepParams &P, cudaStream_t st)
+{
+    const int nb = (h->ade.n_cells + 255) / 256;
+    StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx; Q.box_mode = 0;
+    if (h->ade.dense) {
+        const int tb = h->ade.bz >= 192 ? 256 : (h->ade.bz >= 96 ? 128 : 64);
+        const dim3 grd((h->ade.bz + tb - 1) / tb, h->ade.by, h->ade.bx);
+        k2a_density_dense<<<grd, tb, 0, st>>>(h->ade, P.p_in, h->d.pitch, h->plane);
+        k2b_fixup_dense<<<grd, tb, 0, st>>>(Q, h->ade);
+    } else {
+        k2a_density<<<nb, 256, 0, st>>>(h->ade, P.p_in);
+        k2b_fixup<<<nb, 256, 0, st>>>(Q, h->ade);
+    }
+    h->kernels_launched += 2;
+    return 0;
+}
+
+static int launch_step_lists_concurrent(sb_solver *h, StepParams &P)
+{
+    const sb_grid_desc &d = h->d;
+    h->last_variant = SB_KERNEL_MARCH;
+    int rj, wj, wk, chunk, gx, gy; bool flat;
+    if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
+    if (!h->side) {
+        CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
+    P.box_mode = 3;
+    P.bi0 = h->fbox[0]; P.bi1 = h->fbox[1] + 1; P.bj0 = h->fbox[2]; P.bj1 = h->fbox[3] + 1;
+    P.bk0 = h->fbox[4] / 4 * 4; P.bk1 = (h->fbox[5] / 4 + 1) * 4;
+    P.ade_mask = h->mask.p + h->plane;
+    const dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
+    if (grd.z > 65535) return fail("too many i-chunks");
+    CU(cudaEventRecord(h->ev_fork, h->stream));
+    CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (launch_ade_lists(h, P, h->side)) return 1;
+    CU(cudaEventRecord(h->ev_join, h->side));
+    launch_march(rj, false, false, flat, P, grd, blk, h->stream, true);
+    h->kernels_launched++;
+    CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    return 0;
+}
+
 // Launch-shape autotuning.  The best (rows per thread, warps per block, chunk length) depends on the variant
 // (uniform / tables, geometry) and on the grid; all shapes give bit-identical results, so the library simply times
 // a handful on the live buffers: K1 reads the current set and writes the other one, and without flipping `cur`
@@ -1079,26 +1144,16 @@ static int enqueue_one_step(sb_solver *h, const double *src_dev, float *rec_dev,
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, h->stream);
     }
-    const bool ade_in_k1 = h->have_ade && h->ade_fused && !h->have_peers &&
-                           (h->opt_kernel == SB_KERNEL_AUTO || h->opt_kernel == SB_KERNEL_MARCH);
-    if (ade_in_k1 ? launch_step_fused_ade(h, P) : launch_step_kernel(h, P, fused)) return 1;
+    const bool march_now = !h->have_peers && (h->opt_kernel == SB_KERNEL_AUTO || h->opt_kernel == SB_KERNEL_MARCH);
+    const bool ade_in_k1 = h->have_ade && h->ade_fused && march_now;
+    const bool ade_beside = h->have_ade && !h->ade_fused && h->ade_concurrent && march_now;
+    if (ade_in_k1 ? launch_step_fused_ade(h, P) : ade_beside ? launch_step_lists_concurrent(h, P) : launch_step_kernel(h, P, fused)) return 1;
     if (h->opt_profile) { cudaEventRecord(ev1, h->stream); h->prof.push_back({ev0, ev1, 1}); }
     if (h->have_ade && h->ade_fused && !ade_in_k1) return fail("the fused ADE layout needs the marching kernel on a single slab");
-    if (h->have_ade && !h->ade_fused) {
+    if (h->have_ade && !h->ade_fused && !ade_beside) {
         // after K1: on a slab the density poles of the ghost cells read the ghost p planes, and K1's cut blocks are
         // the ones that wait for the neighbour's step flag (K2a only reads the input set, K1 never touches J)
-        const int nb = (h->ade.n_cells + 255) / 256;
-        StepParams Q = P; Q.i_begin = 0; Q.i_end = h->d.nx;
-        if (h->ade.dense) {
-            const int tb = h->ade.bz >= 192 ? 256 : (h->ade.bz >= 96 ? 128 : 64);
-            const dim3 grd((h->ade.bz + tb - 1) / tb, h->ade.by, h->ade.bx);
-            k2a_density_dense<<<grd, tb, 0, h->stream>>>(h->ade, P.p_in, h->d.pitch, h->plane);
-            k2b_fixup_dense<<<grd, tb, 0, h->stream>>>(Q, h->ade);
-        } else {
-            k2a_density<<<nb, 256, 0, h->stream>>>(h->ade, P.p_in);
-            k2b_fixup<<<nb, 256, 0, h->stream>>>(Q, h->ade);
-        }
-        h->kernels_launched += 2;
+        if (launch_ade_lists(h, P, h->stream)) return 1;
     }
     for (auto *po : h->plane_ops) {                        // Mur / radiation planes, sequential by construction
         const int n[3] = {h->d.nx, h->d.ny, h->d.nz};
@@ -1195,9 +1250,14 @@ struct ResidentLauncher {
     template <bool GEOM, bool UNI, int NS> int run()
     {
         auto kern = k5_resident<GEOM, UNI, NS>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K5_NT, smem));
+        static thread_local const void *last_kern = nullptr; static thread_local size_t last_smem = 0; static thread_local int last_per_sm = 0;
+        static thread_local int last_dev = -1;
+        int per_sm = last_per_sm;
+        if (last_kern != (const void *)kern || last_smem != smem || last_dev != h->device) {   // (per launch these two calls cost ~20 us)
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K5_NT, smem));
+            last_kern = (const void *)kern; last_smem = smem; last_per_sm = per_sm; last_dev = h->device;
+        }
         if ((long long)per_sm * h->n_sm < (long long)R.nbi * R.nbj) {
             fail("resident kernel: %d boxes cannot be co-resident", R.nbi * R.nbj);
             return 2;

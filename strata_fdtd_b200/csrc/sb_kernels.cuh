@@ -62,8 +62,11 @@ struct StepParams {
     // A box of cells [bi0,bi1) x [bj0,bj1) x [bk0,bk1) that ANOTHER launch of the same step computes (the ADE variant
     // of the kernel, which covers the bounding box of the dispersive materials): threads of this launch still load and
     // compute there -- their neighbours' shuffles need the values -- but store nothing, and warps that lie entirely
-    // inside leave at once.  box_mode 0 = no box, 1 = this launch skips the box, 2 = this launch owns only the box.
+    // inside leave at once.  box_mode 0 = no box, 1 = this launch skips the box, 2 = this launch owns only the box,
+    // 3 (ADEX variants) = inside the box this launch leaves out, cell by cell, what the concurrently running ADE list
+    // kernels (K2a / K2b) write: p of every material cell and the + faces they correct (mask bits M_ADE, M_?SAME).
     int box_mode, bi0, bi1, bj0, bj1, bk0, bk1;
+    const uint8_t *ade_mask;             // mask bytes carrying the ADE bits (box_mode 3; == mask when GEOM)
     int bx_off, by_off, bz_off;          // block index offsets (a launch restricted to the tiles that meet the box)
 };
 
@@ -200,7 +203,7 @@ struct FieldSet { const float *p_in, *vx_in, *vy_in, *vz_in; float *p_out, *vx_o
 // of one row group and the start of the next; the only idle lanes are the row padding.  A lane's k-neighbours are
 // still its neighbouring lanes wherever a neighbour exists (nothing crosses a row end), so the shuffles stay valid.
 // Strip mode keeps whole blocks adjacent in j (halo rows hit in L1) and is used for rows that fill their strips.
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false, bool ADEX = false>
 __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, int bx, int by, int bz)
 {
     const unsigned FULL = 0xffffffffu;
@@ -259,6 +262,13 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     // per-element validity and "z face is updated" flags
     const bool e0 = k0 < nz, e1 = k0 + 1 < nz, e2 = k0 + 2 < nz, e3 = k0 + 3 < nz;
     const bool u0 = k0 < nz - 1, u1 = k0 + 1 < nz - 1, u2 = k0 + 2 < nz - 1, u3 = k0 + 3 < nz - 1;
+    // ADEX: rows of this thread inside the box of the dispersive materials (their ADE cells belong to K2a / K2b)
+    unsigned adex_rows = 0;
+    if (ADEX && P.box_mode == 3 && ib < P.bi1 && ie > P.bi0 && k0 >= P.bk0 && k0 < P.bk1) {
+#pragma unroll
+        for (int r = 0; r < RJ; r++) adex_rows |= (j0 + r >= P.bj0 && j0 + r < P.bj1) ? (1u << r) : 0u;
+    }
+    const unsigned uw = (u0 ? 0x80u : 0u) | (u1 ? 0x8000u : 0u) | (u2 ? 0x800000u : 0u) | (u3 ? 0x80000000u : 0u);
     const bool edge_hi = (lane == 31) && (k0 + 4 < nz);        // needs p[k0+4] from the next warp's cells
     const bool edge_lo = (lane == 0) && (k0 > 0);              // needs the z face k0-1 of the previous warp's cells
     const float4 z4 = f4(0.0f);
@@ -320,12 +330,14 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
         // loads (all issued before use)
         float4 pn[RJ], vx[RJ], vy[RJ + 1], vz[RJ];
         unsigned mk[RJ + 1];
+        unsigned ma[RJ];                                         // ADEX: mask word carrying the ADE bits of the row's four cells
         float p_hi[RJ], p_lo[RJ], vz_lo[RJ];
         uint8_t m_lo[RJ];
 #pragma unroll
         for (int r = 0; r < RJ; r++) {
             const bool ok = row_ok[r + 1] && lane_ok;
             const long long c = base + (long long)r * P.pitch;
+            if (ADEX) ma[r] = (ok && ((adex_rows >> r) & 1u) && i >= P.bi0 && i < P.bi1) ? *reinterpret_cast<const unsigned *>(P.ade_mask + c) : 0u;
             pn[r] = (ok && upd_x) ? ld4(F.p_in + c + P.plane) : z4;
             vx[r] = ok ? ld4(F.vx_in + c) : z4;
             vz[r] = ok ? ld4(F.vz_in + c) : z4;
@@ -434,12 +446,32 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
                             else pst.w = (float)((double)pst.w + w);
                         }
                 }
+                if (ADEX && (ma[r] & 0x80808080u)) {
+                    // some of the four cells carry a dispersive material: their p, and the + faces that K2b corrects, are
+                    // written by the list kernels running beside this launch -- store the rest element by element
+                    const unsigned a = ma[r] & 0x80808080u;
+                    const unsigned sx = upd_x ? (a & ((ma[r] & 0x10101010u) << 3)) : 0u;
+                    const unsigned sy = (j0 + r < ny - 1) ? (a & ((ma[r] & 0x20202020u) << 2)) : 0u;
+                    const unsigned sz = a & ((ma[r] & 0x40404040u) << 1) & uw;
+                    const float4 sxv = sel4(e0, e1, e2, e3, ox, z4), syv = sel4(e0, e1, e2, e3, oy, z4), szv = sel4(e0, e1, e2, e3, oz, z4);
+                    const float pe[4] = {pst.x, pst.y, pst.z, pst.w}, xe[4] = {sxv.x, sxv.y, sxv.z, sxv.w};
+                    const float ye[4] = {syv.x, syv.y, syv.z, syv.w}, ze[4] = {szv.x, szv.y, szv.z, szv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const unsigned bit = 0x80u << (8 * e);
+                        if (!(a & bit)) F.p_out[c + e] = pe[e];
+                        if (!(sx & bit)) F.vx_out[c + e] = xe[e];
+                        if (!(sy & bit)) F.vy_out[c + e] = ye[e];
+                        if (!(sz & bit)) F.vz_out[c + e] = ze[e];
+                    }
+                } else {
                 st4(F.p_out + c, pst);
                 if (PEER && P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
                 if (PEER && P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
                 st4(F.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
                 st4(F.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
                 st4(F.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
+                }
             }
             vxp[r] = vxn;
             pc[r + 1] = pn[r];
@@ -447,11 +479,11 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     }
 }
 
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false, bool ADEX = false>
 __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
 {
     const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
-    k1_tile<RJ, GEOM, UNI, PEER, FUSE, FLAT>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+    k1_tile<RJ, GEOM, UNI, PEER, FUSE, FLAT, ADEX>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
 // ------------------------------------------------------------------------------------------

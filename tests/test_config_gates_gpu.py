@@ -34,7 +34,7 @@ def _check_against_fixture(get_field, traces, g, what):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("layout", ["fused", "compact", "dense"])
+@pytest.mark.parametrize("layout", ["auto", "fused", "compact", "dense"])
 def test_c3_512_ade_sphere_1000_steps_equals_the_reference_harness(layout):
     g = np.load(GOLDEN / "c3_512_ade.npz")
     steps = int(g["steps"])
@@ -42,7 +42,7 @@ def test_c3_512_ade_sphere_1000_steps_equals_the_reference_harness(layout):
     assert int((np.asarray(case["material_id"]) != 0).sum()) == int(g["material_cells"])
     s = build_solver(case)
     assert float(s.dt) == float(g["dt"])
-    s.set_kernel_option(_lib.OPT_ADE_LAYOUT, {"fused": 0, "compact": 1, "dense": 2}[layout])
+    s.set_kernel_option(_lib.OPT_ADE_LAYOUT, {"auto": 0, "fused": 3, "compact": 1, "dense": 2}[layout])
     s.run(steps=steps)
     _check_against_fixture(s.get_field, {n: s.get_probe_data(n)[n] for n in s._probes}, g, f"c3 512^3 ({layout})")
     s.close()

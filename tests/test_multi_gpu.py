@@ -352,7 +352,7 @@ p0 = np.zeros(case["shape"], dtype=np.float32); p0[23, 20, 40] = 1.0; p0[24, 10,
 d.p = p0; one.p = p0
 d.run(steps=20); one.run(steps=20)
 assert np.array_equal(d.get_field("vx"), one.get_field("vx")) and np.array_equal(d.get_field("p"), one.get_field("p"))
-print("RANK_OK", rank)
+sys.stdout.write("RANK_OK_%d\n" % rank); sys.stdout.flush()
 dist.barrier(); dist.destroy_process_group()
 """
 
@@ -368,7 +368,7 @@ def test_two_processes_on_one_gpu_full_run_surface(tmp_path):
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
                          capture_output=True, text=True, timeout=900)
-    assert "RANK_OK 0" in res.stdout and "RANK_OK 1" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "RANK_OK_0" in res.stdout and "RANK_OK_1" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
 
 
 @pytest.mark.gpu
