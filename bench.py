@@ -390,7 +390,12 @@ def run_b200_arm(a):
     _lib.check(lib.sb_tuned(h, shape4, C.byref(tuned_ms)))
     peak, peak_src = measured_peak_gbs()
     cells_rank = int(np.prod(slab.shape, dtype=np.int64))
-    achieved = ALGO_BYTES_PER_CELL * cells_rank / (mean_ms.value * 1e-3) / 1e9
+    # algorithmic bytes of one launch of the step kernel: 32 B per cell; with dispersive materials the step kernel is
+    # two concurrent launches (K1 and K1-ADE, or K1 beside the ADE list kernels) bracketed together, and the bytes are
+    # sb_query's model: 32 + the mask byte and 8 (Debye) / 16 (Lorentz) B per pole on the cells that carry the material
+    has_ade = bool(case.get("materials"))
+    algo_bytes_per_cell = float(slab.device_stats()["algorithmic_bytes_per_cell"]) if has_ade else ALGO_BYTES_PER_CELL
+    achieved = algo_bytes_per_cell * cells_rank / (mean_ms.value * 1e-3) / 1e9
 
     if rank == 0:
         value = cells_total * K / (dev_ms * 1e-3) / 1e9
@@ -414,9 +419,11 @@ def run_b200_arm(a):
                              "traffic": traffic, "peak_source": peak_src,
                              "kernel": "k5_resident (per step of one chunk launch; fields stay in shared memory, so "
                                        "'achieved' is an HBM-equivalent rate)" if st1["kernel_variant"] == 4 else
-                                       "k6_pipeline (k1_tile; per step of one chunk launch)" if st1["kernel_variant"] == 5 else "k1_step_march",
+                                       "k6_pipeline (k1_tile; per step of one chunk launch)" if st1["kernel_variant"] == 5 else
+                                       "k1_step_march + ADE kernels of the same step (concurrent launches, timed together)" if has_ade else
+                                       "k1_step_march",
                              "kernel_ms_mean": mean_ms.value, "kernel_ms_min": min_ms.value, "launches_timed": n_l.value,
-                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_rank,
+                             "algorithmic_bytes_per_launch": algo_bytes_per_cell * cells_rank,
                              # whole-step model of sb_query: 32 (+1 with a face mask) + sum over poles of 8 (Debye) or 16
                              # (Lorentz) bytes x the fraction of cells that carry the material
                              "step_bytes_per_cell_model": st1["algorithmic_bytes_per_cell"]},

@@ -1726,6 +1726,7 @@ extern "C" int sb_query(sb_solver *h, sb_stats *out)
     if (h->have_ade) {
         double per_cell = 0.0;
         for (int q = 0; q < h->ade.n_poles; q++) per_cell += h->ade.poles[q].is_lorentz ? 16.0 : 8.0;
+        if (!h->have_mask && (h->ade_fused || h->ade_concurrent)) per_cell += 1.0;    // the mask byte carrying the ADE bits
         b += per_cell * (double)h->ade_material_cells / (double)out->cells;
     }
     out->algorithmic_bytes_per_cell = b;

@@ -903,8 +903,13 @@ SB_HD float pole_upd(const PoleDev &Q, float J, float Jp, float src)
 }
 SB_HD float4 pole_upd4(const PoleDev &Q, float4 J, float4 Jp, float4 s)
 {
-    return make_float4(pole_upd(Q, J.x, Jp.x, s.x), pole_upd(Q, J.y, Jp.y, s.y), pole_upd(Q, J.z, Jp.z, s.z), pole_upd(Q, J.w, Jp.w, s.w));
+    if (Q.is_lorentz)                                         // one (warp-uniform) branch instead of a select per element
+        return add4(add4(mul4s(J, Q.c0), mul4s(Jp, Q.c1)), mul4s(s, Q.c2));
+    return add4(mul4s(J, Q.c0), mul4s(s, Q.c1));
 }
+// corr4 / pick4 when the warp has agreed that every element of every lane takes part (the interior of a material)
+constexpr unsigned ALL_SEL = 0x80808080u;
+SB_HD float4 corr4_all(float4 v, float vc, float4 hi, float4 lo) { return add4(v, mul4s(sub4(hi, lo), vc)); }
 // which of the four cells of a mask word carry pole Q's material (bit 7 of each byte)
 __device__ __forceinline__ unsigned ade_sel(const AdeFused &A, const PoleDev &Q, unsigned mk, unsigned matw)
 {
@@ -1065,22 +1070,31 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
                 const bool lor = Q.is_lorentz != 0;
                 const float *Jin = A.Jin[q], *Jpin = A.Jpin[q];
                 const long long jb = jidx(q, i);
-                float4 Jn = z4;
-                if (selw) Jn = pick4(selw, pole_upd4(Q, ld4(Jin + jb), lor ? ld4(Jpin + jb) : z4, p), z4);
                 const unsigned xw = upd_x ? (selw & ((mkc & 0x10101010u) << 3)) : 0u;
+                const unsigned yw = updp ? (selw & ((mkc & 0x20202020u) << 2)) : 0u;
+                const unsigned mw = updm ? (selw & ((mkm & 0x20202020u) << 2)) : 0u;      // the face j0-1 -> j0 belongs to the row below
+                // inside a material every element of every lane takes part: plain float4 arithmetic, no selects
+                const bool all_sel = __all_sync(FULL, selw == ALL_SEL), all_x = __all_sync(FULL, xw == ALL_SEL);
+                const bool all_y = __all_sync(FULL, yw == ALL_SEL), all_m = __all_sync(FULL, mw == ALL_SEL);
+                float4 Jn = z4;
+                if (selw) {
+                    Jn = pole_upd4(Q, ld4(Jin + jb), lor ? ld4(Jpin + jb) : z4, p);
+                    if (!all_sel) Jn = pick4(selw, Jn, z4);
+                }
                 if (xw) {
                     const long long jx = jb + (long long)A.bnj[q] * P.pitch;
-                    vxn = corr4(vxn, xw, Q.vcoef, pole_upd4(Q, ld4(Jin + jx), lor ? ld4(Jpin + jx) : z4, pn), Jn);
+                    const float4 Jx = pole_upd4(Q, ld4(Jin + jx), lor ? ld4(Jpin + jx) : z4, pn);
+                    vxn = all_x ? corr4_all(vxn, Q.vcoef, Jx, Jn) : corr4(vxn, xw, Q.vcoef, Jx, Jn);
                 }
-                const unsigned yw = updp ? (selw & ((mkc & 0x20202020u) << 2)) : 0u;
                 if (yw) {
                     const long long jy = jb + P.pitch;
-                    vyn_c = corr4(vyn_c, yw, Q.vcoef, pole_upd4(Q, ld4(Jin + jy), lor ? ld4(Jpin + jy) : z4, pp), Jn);
+                    const float4 Jy = pole_upd4(Q, ld4(Jin + jy), lor ? ld4(Jpin + jy) : z4, pp);
+                    vyn_c = all_y ? corr4_all(vyn_c, Q.vcoef, Jy, Jn) : corr4(vyn_c, yw, Q.vcoef, Jy, Jn);
                 }
-                const unsigned mw = updm ? (selw & ((mkm & 0x20202020u) << 2)) : 0u;      // the face j0-1 -> j0 belongs to the row below
                 if (mw) {
                     const long long jm = jb - P.pitch;
-                    vyn_m = corr4(vyn_m, mw, Q.vcoef, Jn, pole_upd4(Q, ld4(Jin + jm), lor ? ld4(Jpin + jm) : z4, pm));
+                    const float4 Jm = pole_upd4(Q, ld4(Jin + jm), lor ? ld4(Jpin + jm) : z4, pm);
+                    vyn_m = all_m ? corr4_all(vyn_m, Q.vcoef, Jn, Jm) : corr4(vyn_m, mw, Q.vcoef, Jn, Jm);
                 }
                 const unsigned zw = selw & ((mkc & 0x40404040u) << 1) & uw;
                 float Jn_next = __shfl_down_sync(FULL, Jn.x, 1);
@@ -1088,7 +1102,8 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
                     Jn_next = 0.0f;
                     if (edge_hi && (zw & 0x80000000u)) Jn_next = pole_upd(Q, Jin[jb + 4], lor ? Jpin[jb + 4] : 0.0f, p_hi);
                 }
-                vzn = corr4(vzn, zw, Q.vcoef, make_float4(Jn.y, Jn.z, Jn.w, Jn_next), Jn);
+                vzn = __all_sync(FULL, zw == ALL_SEL) ? corr4_all(vzn, Q.vcoef, make_float4(Jn.y, Jn.z, Jn.w, Jn_next), Jn)
+                                                      : corr4(vzn, zw, Q.vcoef, make_float4(Jn.y, Jn.z, Jn.w, Jn_next), Jn);
                 if (edge_lo && (selw & 0x80u) && (m_lo & M_ZSAME))
                     vz_edge = vz_edge + Q.vcoef * (Jn.x - pole_upd(Q, Jin[jb - 1], lor ? Jpin[jb - 1] : 0.0f, p_lo));
                 if (selw && own) st4(A.Jout[q] + jb, Jn);
@@ -1126,9 +1141,15 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
                 const float4 J = ld4(A.Jin[q] + jb);
                 const float4 Jp = Q.is_lorentz ? ld4(A.Jpin[q] + jb) : z4;
                 const float4 Jn = pole_upd4(Q, J, Jp, div);
-                st4(A.Jout[q] + jb, pick4(selw, Jn, J));
-                if (Q.is_lorentz) st4(A.Jpout[q] + jb, pick4(selw, J, Jp));
-                pnew = corr4(pnew, selw, Q.pcoef, Jn, z4);                   // p += (-K_inf dt) J   (ade.cpp:403-473)
+                if (selw == ALL_SEL) {                                       // (per lane: no collective in this loop)
+                    st4(A.Jout[q] + jb, Jn);
+                    if (Q.is_lorentz) st4(A.Jpout[q] + jb, J);
+                    pnew = add4(pnew, mul4s(Jn, Q.pcoef));                   // p += (-K_inf dt) J   (ade.cpp:403-473)
+                } else {
+                    st4(A.Jout[q] + jb, pick4(selw, Jn, J));
+                    if (Q.is_lorentz) st4(A.Jpout[q] + jb, pick4(selw, J, Jp));
+                    pnew = corr4(pnew, selw, Q.pcoef, Jn, z4);
+                }
             }
             if (masked) pnew = keep4(pnew, mkc, M_AIR);                      // solver.py:2193
         }
