@@ -213,7 +213,8 @@ def decomposition_selfcheck(dist, world: int, rank: int, local_rank: int, halo: 
         one.run(steps=steps)
         bad = [f for f in fields if not np.array_equal(fields[f], one.get_field(f))]
         bad += [n for n in traces if not np.array_equal(traces[n], one.get_probe_data(n)[n])]
-        alive = float(np.abs(fields["p"]).max()) > 0 and all(np.abs(t).max() > 0 for t in traces.values())
+        # not vacuous: the wave has crossed the first cut (the far probes may still be silent after 64 steps)
+        alive = float(np.abs(fields["p"]).max()) > 0 and all(np.abs(traces[n]).max() > 0 for n in ("below_cut", "above_cut"))
         verdict[0] = {"invariance": "bit-exact" if not bad and alive else "MISMATCH: " + ",".join(bad or ["dead fields"]),
                       "case": f"{nx}x96x200, {world} slabs, solid block through a cut, PML(6), 2 sources, 5 probes, "
                               f"{steps} steps vs the single-GPU run", "halo": d.halo}

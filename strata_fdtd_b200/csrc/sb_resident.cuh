@@ -362,14 +362,14 @@ SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T
                 vy = add4(vy, mul4s(sub4(ld4(pp + R.kp), p), T.cvy));
                 if (GEOM) vy = keep4(vy, mk, M_YOPEN);
             }
-            if (T.u3) {                                                // fdtd_step.cpp:71-81 / 291-306, all four faces updated
-                vz = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, pp[4]), p), T.cvz4));
-                if (GEOM) vz = keep4(vz, mk, M_ZOPEN);
-            } else {                                                   // the float4 holding the last face / the row padding
-                const float4 upd = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, 0.0f), p), T.cvz4));
+            {                                                          // fdtd_step.cpp:71-81 / 291-306
+                // branch-free: the float4 that holds the last face of a row (or its padding) sits in every warp, so a
+                // branch on it made every warp run both versions; faces that are not updated keep their value
+                const float p_next = T.u3 ? pp[4] : 0.0f;
+                const float4 upd = add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, p_next), p), T.cvz4));
                 vz = sel4(T.u0, T.u1, T.u2, T.u3, upd, vz);
                 if (GEOM) {                                            // only updated faces are zeroed
-                    const unsigned m = mk | (T.u0 ? 0u : 0x08u) | (T.u1 ? 0u : 0x0800u) | (T.u2 ? 0u : 0x080000u) | 0x08000000u;
+                    const unsigned m = mk | (T.u0 ? 0u : 0x08u) | (T.u1 ? 0u : 0x0800u) | (T.u2 ? 0u : 0x080000u) | (T.u3 ? 0u : 0x08000000u);
                     vz = keep4(vz, m, M_ZOPEN);
                 }
             }

@@ -75,6 +75,26 @@ def test_reference_script_verbatim_through_the_module_runner(name, tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_script_unchanged_on_two_gpus(tmp_path):
+    """python -m torch.distributed.run --nproc-per-node 2 -m strata_fdtd_b200 basic_pulse.py: the script's plain
+    ``FDTDSolver(...)`` becomes the slab solver, rank 0 writes results.h5, and the trace is the reference's."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    path, g = _script("basic_pulse")
+    env = dict(os.environ, PYTHONPATH=str(ROOT) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29547", "-m", "strata_fdtd_b200", str(path)], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.stdout.count("Simulation complete") == 1, "only rank 0 prints"
+    z = np.load(tmp_path / "results.h5")
+    attrs = json.loads(str(z["__attrs__"]))
+    assert attrs["metadata@num_gpus"] == 2 and attrs["simulation@num_steps"] == int(g["steps"])
+    assert np.array_equal(z["probes/downstream"], g["probe_downstream"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", SCRIPTS)
 def test_reference_script_fields_traces_and_hdf5_tree(name, tmp_path, monkeypatch):
     """The same scripts in-process: final fields (SHA-256) and traces equal the reference's, and -- with an h5py

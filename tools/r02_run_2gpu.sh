@@ -11,7 +11,7 @@ for halo in p2p nccl; do
 done
 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_scale1.json 2> gpurun_out/r02_scale1.err; tail -1 gpurun_out/r02_scale1.json | cut -c1-200
 # the unchanged reference script on two GPUs through the module runner
-mkdir -p /tmp/two && cd /tmp/two && timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29563 -m strata_fdtd_b200 $GRAFT_REPO_ROOT/oracle/_ref/examples/basic_pulse.py > $GRAFT_REPO_ROOT/gpurun_out/r02_2gpu_basic_pulse.log 2>&1; cd $GRAFT_REPO_ROOT
+mkdir -p /tmp/two && cd /tmp/two && PYTHONPATH=$GRAFT_REPO_ROOT timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29563 -m strata_fdtd_b200 $GRAFT_REPO_ROOT/oracle/_ref/examples/basic_pulse.py > $GRAFT_REPO_ROOT/gpurun_out/r02_2gpu_basic_pulse.log 2>&1; cd $GRAFT_REPO_ROOT
 python - <<'PY'
 import json, numpy as np
 z = np.load("/tmp/two/results.h5"); g = np.load("tests/golden/script_basic_pulse.npz")
