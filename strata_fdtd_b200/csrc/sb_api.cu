@@ -94,7 +94,8 @@ struct sb_solver {
     int fbox[6] = {0, 0, 0, 0, 0, 0};      // bounding box of all pole-carrying cells: i0, i1, j0, j1, k0, k1 (inclusive)
     long long ade_phase = 0;               // steps since the ADE state was zeroed: selects the density-pole buffers
     bool mask_alloc_fresh = true;
-    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // K1-ADE runs beside the plain K1
+    cudaStream_t side = nullptr, side_hi = nullptr;                                  // K1 beside K1-ADE; ADE list kernels beside K1 (high priority)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // options
     int opt_kernel = SB_KERNEL_AUTO, opt_rj = 0, opt_wj = 0, opt_wk = 1, opt_chunk_i = 0, opt_graph = -1;   // 0 / -1 = auto
     // graph cache: key = (n_steps, starting set, source-table pointer, record pointer)
@@ -241,6 +242,7 @@ extern "C" int sb_destroy(sb_solver *h)
     for (int q = 0; q < 2; q++) { h->stage_src[q].release(); h->stage_rec[q].release(); if (h->stage_done[q]) cudaEventDestroy(h->stage_done[q]); }
     h->ade_matpad.release();
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->side_hi) cudaStreamDestroy(h->side_hi);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
@@ -935,8 +937,8 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     h->last_variant = SB_KERNEL_MARCH;
     int rj, wj, wk, chunk, gx, gy; bool flat;
     if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
-    if (!h->side) {
-        CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (!h->side) CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (!h->ev_fork) {
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
@@ -1040,8 +1042,14 @@ static int launch_step_lists_concurrent(sb_solver *h, StepParams &P)
     h->last_variant = SB_KERNEL_MARCH;
     int rj, wj, wk, chunk, gx, gy; bool flat;
     if (march_shape(h, true, rj, wj, wk, chunk, gx, gy, flat)) return 1;
-    if (!h->side) {
-        CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (!h->side_hi) {
+        // highest priority: the list kernels' small blocks take the slots K1's blocks free as they retire, instead of
+        // queueing behind K1's thousands of blocks and running as a tail after it
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&h->side_hi, cudaStreamNonBlocking, prio_hi));
+    }
+    if (!h->ev_fork) {
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
@@ -1053,9 +1061,9 @@ static int launch_step_lists_concurrent(sb_solver *h, StepParams &P)
     const dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
     if (grd.z > 65535) return fail("too many i-chunks");
     CU(cudaEventRecord(h->ev_fork, h->stream));
-    CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    if (launch_ade_lists(h, P, h->side)) return 1;
-    CU(cudaEventRecord(h->ev_join, h->side));
+    CU(cudaStreamWaitEvent(h->side_hi, h->ev_fork, 0));
+    if (launch_ade_lists(h, P, h->side_hi)) return 1;
+    CU(cudaEventRecord(h->ev_join, h->side_hi));
     launch_march(rj, false, false, flat, P, grd, blk, h->stream, true);
     h->kernels_launched++;
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));

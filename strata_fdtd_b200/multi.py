@@ -504,6 +504,8 @@ class DistributedFDTDSolver:
                                    "kernel_launches": s.kernel_launches() - launches0}
             if writer is not None:
                 writer.finalize(runtime=runtime, backend="b200", num_threads=0, num_gpus=self.world)
+            if output_file:
+                self.dist.barrier(self.group)        # the file exists on return, on every rank (scripts stat it right away)
 
     def step(self):
         self.run(steps=1)
