@@ -303,6 +303,8 @@ def run_b200_arm(a):
         slab.set_kernel_option(_lib.OPT_ADE_CHUNK_I, a.ade_chunk)
     if a.ade_warps is not None:
         slab.set_kernel_option(_lib.OPT_ADE_WARPS, a.ade_warps)
+    if a.ade_occ is not None:
+        slab.set_kernel_option(_lib.OPT_ADE_OCCUPANCY, a.ade_occ)
 
     def barrier():
         if dist is not None:
@@ -460,6 +462,7 @@ def main():
     ap.add_argument("--ade-layout", type=int, default=None, help="0 auto, 1 compact list, 2 dense box, 3 fused (ADE workloads)")
     ap.add_argument("--ade-chunk", type=int, default=None, help="K1-ADE planes per tile")
     ap.add_argument("--ade-warps", type=int, default=None, help="K1-ADE warps per block")
+    ap.add_argument("--ade-occ", type=int, default=None, help="K1-ADE blocks per SM aimed at (2 or 3)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -85,7 +85,7 @@ enum { SB_FIELD_P = 0, SB_FIELD_VX = 1, SB_FIELD_VY = 2, SB_FIELD_VZ = 3 };
 enum { SB_OPT_KERNEL = 0, SB_OPT_ROWS_PER_THREAD = 1, SB_OPT_WARPS_J = 2, SB_OPT_WARPS_K = 3,
        SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5, SB_OPT_PROFILE = 6, SB_OPT_FUSE_K3 = 7,
        SB_OPT_RESIDENT_SPLIT = 8, SB_OPT_RESIDENT_MIN_STEPS = 9, SB_OPT_PLANE_MAP = 10, SB_OPT_ADE_LAYOUT = 11,
-       SB_OPT_ADE_CHUNK_I = 12, SB_OPT_ADE_WARPS = 13 };
+       SB_OPT_ADE_CHUNK_I = 12, SB_OPT_ADE_WARPS = 13, SB_OPT_ADE_OCCUPANCY = 14 };
 
 const char *sb_last_error(void);
 int sb_abi_version(void);
@@ -241,6 +241,7 @@ int sb_reset(sb_solver *h);
  *   SB_OPT_ADE_LAYOUT        material cells as 0 auto (fused on a single slab), 1 compact list, 2 dense bounding box,
  *                            3 fused into the step kernel (K1-ADE); set before sb_set_ade
  *   SB_OPT_ADE_CHUNK_I / SB_OPT_ADE_WARPS   K1-ADE: planes a tile marches over, warps per block (0 = default)
+ *   SB_OPT_ADE_OCCUPANCY     K1-ADE: 256-thread blocks per SM the register allocation aims at (2 or 3)
  *   SB_OPT_PROFILE           bracket every step-kernel launch with CUDA events (sb_profile_read)                              */
 int sb_set_option(sb_solver *h, int option, int value);
 int sb_query(sb_solver *h, sb_stats *out);

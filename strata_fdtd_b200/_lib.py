@@ -92,7 +92,7 @@ class Stats(C.Structure):
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH, KERNEL_RESIDENT, KERNEL_PIPELINE = 0, 1, 2, 4, 5
 (OPT_KERNEL, OPT_ROWS_PER_THREAD, OPT_WARPS_J, OPT_WARPS_K, OPT_CHUNK_I, OPT_USE_GRAPH, OPT_PROFILE,
  OPT_FUSE_K3, OPT_RESIDENT_SPLIT, OPT_RESIDENT_MIN_STEPS, OPT_PLANE_MAP, OPT_ADE_LAYOUT, OPT_ADE_CHUNK_I,
- OPT_ADE_WARPS) = range(14)
+ OPT_ADE_WARPS, OPT_ADE_OCCUPANCY) = range(15)
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 _fp = C.POINTER(C.c_float)

@@ -139,6 +139,7 @@ struct sb_solver {
     DBuf<double> stage_src[2]; DBuf<float> stage_rec[2]; cudaEvent_t stage_done[2] = {nullptr, nullptr};
     int cut_done = 0;                      // planes next to each cut already computed for the step about to be enqueued
     int opt_ade_chunk = 0, opt_ade_warps = 0;   // K1-ADE launch shape: planes per tile, warps per block (0 = default)
+    int opt_ade_occ = 3;                        // K1-ADE register allocation: blocks of 256 threads per SM aimed at (2 or 3)
 };
 
 // Launch shapes measured once per (device, grid, kernel variant) are remembered for the life of the process: a second
@@ -976,8 +977,13 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     AdeFused A;
     fill_ade_fused(h, A);
     const bool uni = Q.icx == nullptr;
-    if (uni) { if (flat) k1_step_march_ade<true, true><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<true, false><<<agrd, ablk, 0, h->stream>>>(Q, A); }
-    else     { if (flat) k1_step_march_ade<false, true><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<false, false><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+    if (h->opt_ade_occ == 2) {
+        if (uni) { if (flat) k1_step_march_ade<true, true, 2><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<true, false, 2><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+        else     { if (flat) k1_step_march_ade<false, true, 2><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<false, false, 2><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+    } else {
+        if (uni) { if (flat) k1_step_march_ade<true, true, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<true, false, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+        else     { if (flat) k1_step_march_ade<false, true, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<false, false, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); }
+    }
     launch_march(rj, false, false, flat, P, grd, blk, h->side);
     CU(cudaEventRecord(h->ev_join, h->side));
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -1715,6 +1721,7 @@ extern "C" int sb_set_option(sb_solver *h, int option, int value)
                                 h->opt_ade_layout = value; break;
         case SB_OPT_ADE_CHUNK_I: if (value < 0) return fail("ade_chunk_i must be >= 0"); h->opt_ade_chunk = value; break;
         case SB_OPT_ADE_WARPS: if (value < 0 || value > 8) return fail("ade_warps must be 0..8"); h->opt_ade_warps = value; break;
+        case SB_OPT_ADE_OCCUPANCY: if (value != 2 && value != 3) return fail("ade_occupancy must be 2 or 3"); h->opt_ade_occ = value; break;
         case SB_OPT_RESIDENT_SPLIT: h->opt_res_split = value ? 1 : 0; break;
         case SB_OPT_RESIDENT_MIN_STEPS: h->opt_res_min_steps = std::max(1, value); break;
         default: return fail("unknown option %d", option);

@@ -1178,8 +1178,10 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
     }
 }
 
-template <bool UNI, bool FLAT>
-__global__ void __launch_bounds__(256) k1_step_march_ade(const __grid_constant__ StepParams P, const __grid_constant__ AdeFused A)
+// MINB = blocks per SM the register allocation aims at: 2 = whatever the code needs (104-122 registers), 3 = at most 80
+// (a few spilled words, half again as many warps in flight -- the kernel waits on memory most of the time)
+template <bool UNI, bool FLAT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k1_step_march_ade(const __grid_constant__ StepParams P, const __grid_constant__ AdeFused A)
 {
     const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
     k1_tile_ade<UNI, FLAT>(P, A, F, (int)blockIdx.x + P.bx_off, (int)blockIdx.y + P.by_off, (int)blockIdx.z + P.bz_off);
