@@ -802,10 +802,14 @@ static PeerLink peer_link(sb_solver *h, const StepParams &P)
 // ---- K1 dispatch over the compile-time variants <RJ, GEOM, UNI, PEER, FUSE, FLAT> ------------------------
 // (PEER launches never inject inline: a slab's step always ends with K3, which also publishes the step flag)
 template <int RJ, bool GEOM, bool UNI>
-static void launch_march3(bool peer, bool fuse, bool flat, bool adex, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
+static void launch_march3(bool peer, bool fuse, bool flat, int boxm, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st)
 {
-    if (adex)      { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true, true><<<grd, blk, 0, st>>>(P);
-                     else      k1_step_march<RJ, GEOM, UNI, false, false, false, true><<<grd, blk, 0, st>>>(P); }
+    // (the box variants exist apart so that the plain kernel carries none of their code: a run-time test of the box mode
+    //  alone cost the 64-register uniform kernel 3.5 % -- tools/k1_ab.cu, 201.1 -> 194.1 Gcell-updates/s on one box)
+    if (boxm == 3) { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true, 3><<<grd, blk, 0, st>>>(P);
+                     else      k1_step_march<RJ, GEOM, UNI, false, false, false, 3><<<grd, blk, 0, st>>>(P); }
+    else if (boxm == 1) { if (flat) k1_step_march<RJ, GEOM, UNI, false, false, true, 1><<<grd, blk, 0, st>>>(P);
+                          else      k1_step_march<RJ, GEOM, UNI, false, false, false, 1><<<grd, blk, 0, st>>>(P); }
     else if (peer) { if (flat) k1_step_march<RJ, GEOM, UNI, true, false, true><<<grd, blk, 0, st>>>(P);
                      else      k1_step_march<RJ, GEOM, UNI, true, false, false><<<grd, blk, 0, st>>>(P); }
     else if (fuse) { if (flat) k1_step_march<RJ, GEOM, UNI, false, true, true><<<grd, blk, 0, st>>>(P);
@@ -814,13 +818,13 @@ static void launch_march3(bool peer, bool fuse, bool flat, bool adex, const Step
                      else      k1_step_march<RJ, GEOM, UNI, false, false, false><<<grd, blk, 0, st>>>(P); }
 }
 static void launch_march(int rj, bool peer, bool fuse, bool flat, const StepParams &P, dim3 grd, dim3 blk, cudaStream_t st,
-                         bool adex = false)
+                         int boxm = 0)
 {
     const bool geom = P.mask != nullptr, uni = P.icx == nullptr;
-    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, flat, adex, P, grd, blk, st); }
-                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, flat, adex, P, grd, blk, st); } }
-    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, flat, adex, P, grd, blk, st); }
-                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, flat, adex, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, flat, adex, P, grd, blk, st); } }
+    if (rj == 1) { if (geom) { if (uni) launch_march3<1, true, true>(peer, fuse, flat, boxm, P, grd, blk, st); else launch_march3<1, true, false>(peer, fuse, flat, boxm, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<1, false, true>(peer, fuse, flat, boxm, P, grd, blk, st); else launch_march3<1, false, false>(peer, fuse, flat, boxm, P, grd, blk, st); } }
+    else         { if (geom) { if (uni) launch_march3<2, true, true>(peer, fuse, flat, boxm, P, grd, blk, st); else launch_march3<2, true, false>(peer, fuse, flat, boxm, P, grd, blk, st); }
+                   else      { if (uni) launch_march3<2, false, true>(peer, fuse, flat, boxm, P, grd, blk, st); else launch_march3<2, false, false>(peer, fuse, flat, boxm, P, grd, blk, st); } }
 }
 
 // launch shape of the marching kernel: rows per thread, warps along j / k, planes per chunk, tiles along k / j
@@ -984,7 +988,7 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
         if (uni) { if (flat) k1_step_march_ade<true, true, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<true, false, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); }
         else     { if (flat) k1_step_march_ade<false, true, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); else k1_step_march_ade<false, false, 3><<<agrd, ablk, 0, h->stream>>>(Q, A); }
     }
-    launch_march(rj, false, false, flat, P, grd, blk, h->side);
+    launch_march(rj, false, false, flat, P, grd, blk, h->side, 1);
     CU(cudaEventRecord(h->ev_join, h->side));
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->kernels_launched += 2;
@@ -1070,7 +1074,7 @@ static int launch_step_lists_concurrent(sb_solver *h, StepParams &P)
     CU(cudaStreamWaitEvent(h->side_hi, h->ev_fork, 0));
     if (launch_ade_lists(h, P, h->side_hi)) return 1;
     CU(cudaEventRecord(h->ev_join, h->side_hi));
-    launch_march(rj, false, false, flat, P, grd, blk, h->stream, true);
+    launch_march(rj, false, false, flat, P, grd, blk, h->stream, 3);
     h->kernels_launched++;
     CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     return 0;

@@ -22,8 +22,6 @@ namespace sb {
 
 constexpr int MAX_SPONGES = 4;
 constexpr uint8_t M_AIR = 1, M_XOPEN = 2, M_YOPEN = 4, M_ZOPEN = 8;
-// upper nibble (fused ADE path): the cell carries a material with poles; its +x / +y / +z neighbour carries the SAME one
-constexpr uint8_t M_XSAME = 0x10, M_YSAME = 0x20, M_ZSAME = 0x40, M_ADE = 0x80;
 
 struct StepParams {
     const float *p_in, *vx_in, *vy_in, *vz_in;
@@ -59,15 +57,6 @@ struct StepParams {
     const int *mic_field;
     const float *mic_w8;
     float *rec_row;                      // record slots of the previous step [n_probes + n_mics]
-    // A box of cells [bi0,bi1) x [bj0,bj1) x [bk0,bk1) that ANOTHER launch of the same step computes (the ADE variant
-    // of the kernel, which covers the bounding box of the dispersive materials): threads of this launch still load and
-    // compute there -- their neighbours' shuffles need the values -- but store nothing, and warps that lie entirely
-    // inside leave at once.  box_mode (K1: the template parameter BOXM) 0 = no box, 1 = this launch skips the box,
-    // 2 = this launch owns only the box (K1-ADE), 3 = inside the box this launch leaves out, cell by cell, what the concurrently running ADE list
-    // kernels (K2a / K2b) write: p of every material cell and the + faces they correct (mask bits M_ADE, M_?SAME).
-    int box_mode, bi0, bi1, bj0, bj1, bk0, bk1;
-    const uint8_t *ade_mask;             // mask bytes carrying the ADE bits (box_mode 3; == mask when GEOM)
-    int bx_off, by_off, bz_off;          // block index offsets (a launch restricted to the tiles that meet the box)
 };
 
 // 8-point weighted gather of one field (trilinear microphone sample): sum = 0; sum += w[c]*f[idx[c]], fp32,
@@ -203,7 +192,7 @@ struct FieldSet { const float *p_in, *vx_in, *vy_in, *vz_in; float *p_out, *vx_o
 // of one row group and the start of the next; the only idle lanes are the row padding.  A lane's k-neighbours are
 // still its neighbouring lanes wherever a neighbour exists (nothing crosses a row end), so the shuffles stay valid.
 // Strip mode keeps whole blocks adjacent in j (halo rows hit in L1) and is used for rows that fill their strips.
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false, int BOXM = 0>
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
 __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, int bx, int by, int bz)
 {
     const unsigned FULL = 0xffffffffu;
@@ -247,29 +236,9 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
             P.inl_i[q] >= ib && P.inl_i[q] < ie) inl_mask |= 1u << q;
     const bool lane_ok = k0 < P.nz;
     const int nz = P.nz, ny = P.ny;
-    // cells another launch of this step owns (box_mode 1): computed here as far as the neighbours need them, never stored
-    unsigned skip_rows = 0;
-    if (BOXM == 1 && ib >= P.bi0 && ib < P.bi1) {                // the box is aligned to this launch's chunks of planes
-        bool nothing_left = true;
-#pragma unroll
-        for (int r = 0; r < RJ; r++) {
-            const bool in = k0 >= P.bk0 && k0 < P.bk1 && j0 + r >= P.bj0 && j0 + r < P.bj1;
-            skip_rows |= in ? (1u << r) : 0u;
-            nothing_left = nothing_left && (in || !lane_ok || j0 + r >= ny);
-        }
-        if (__all_sync(FULL, nothing_left)) return;
-    }
     // per-element validity and "z face is updated" flags
     const bool e0 = k0 < nz, e1 = k0 + 1 < nz, e2 = k0 + 2 < nz, e3 = k0 + 3 < nz;
     const bool u0 = k0 < nz - 1, u1 = k0 + 1 < nz - 1, u2 = k0 + 2 < nz - 1, u3 = k0 + 3 < nz - 1;
-    // ADEX: rows of this thread inside the box of the dispersive materials (their ADE cells belong to K2a / K2b)
-    unsigned adex_rows = 0;
-    constexpr bool ADEX = BOXM == 3;
-    if (ADEX && ib < P.bi1 && ie > P.bi0 && k0 >= P.bk0 && k0 < P.bk1) {
-#pragma unroll
-        for (int r = 0; r < RJ; r++) adex_rows |= (j0 + r >= P.bj0 && j0 + r < P.bj1) ? (1u << r) : 0u;
-    }
-    const unsigned uw = (u0 ? 0x80u : 0u) | (u1 ? 0x8000u : 0u) | (u2 ? 0x800000u : 0u) | (u3 ? 0x80000000u : 0u);
     const bool edge_hi = (lane == 31) && (k0 + 4 < nz);        // needs p[k0+4] from the next warp's cells
     const bool edge_lo = (lane == 0) && (k0 > 0);              // needs the z face k0-1 of the previous warp's cells
     const float4 z4 = f4(0.0f);
@@ -331,14 +300,12 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
         // loads (all issued before use)
         float4 pn[RJ], vx[RJ], vy[RJ + 1], vz[RJ];
         unsigned mk[RJ + 1];
-        unsigned ma[RJ];                                         // ADEX: mask word carrying the ADE bits of the row's four cells
         float p_hi[RJ], p_lo[RJ], vz_lo[RJ];
         uint8_t m_lo[RJ];
 #pragma unroll
         for (int r = 0; r < RJ; r++) {
             const bool ok = row_ok[r + 1] && lane_ok;
             const long long c = base + (long long)r * P.pitch;
-            if (ADEX) ma[r] = (ok && ((adex_rows >> r) & 1u) && i >= P.bi0 && i < P.bi1) ? *reinterpret_cast<const unsigned *>(P.ade_mask + c) : 0u;
             pn[r] = (ok && upd_x) ? ld4(F.p_in + c + P.plane) : z4;
             vx[r] = ok ? ld4(F.vx_in + c) : z4;
             vz[r] = ok ? ld4(F.vz_in + c) : z4;
@@ -359,9 +326,9 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
         if (GEOM) {
             bool open = true;
 #pragma unroll
-            for (int r = -1; r < RJ; r++) open = open && ((mk[r + 1] & ALL_OPEN) == ALL_OPEN);      // upper nibble: ADE bits
+            for (int r = -1; r < RJ; r++) open = open && (mk[r + 1] == ALL_OPEN);
 #pragma unroll
-            for (int r = 0; r < RJ; r++) open = open && ((m_lo[r] & 0x0F) == 0x0F);
+            for (int r = 0; r < RJ; r++) open = open && (m_lo[r] == 0x0F);
             masked = !__all_sync(FULL, open);
         }
         pc[0] = (row_ok[0] && lane_ok) ? ld4(F.p_in + base - P.pitch) : z4;
@@ -433,7 +400,7 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
                     pnew = mul4(mul4s(mul4s(pnew, dxs), dys), dzs);
                 }
             }
-            if (row_ok[r + 1] && lane_ok && !(BOXM == 1 && ((skip_rows >> r) & 1u))) {
+            if (row_ok[r + 1] && lane_ok) {
                 const long long c = base + (long long)r * P.pitch;
                 float4 pst = sel4(e0, e1, e2, e3, pnew, z4);
                 if (FUSE && inl_mask) {                          // float64 add, fp32 store (solver.py:2421), list order
@@ -447,32 +414,12 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
                             else pst.w = (float)((double)pst.w + w);
                         }
                 }
-                if (ADEX && (ma[r] & 0x80808080u)) {
-                    // some of the four cells carry a dispersive material: their p, and the + faces that K2b corrects, are
-                    // written by the list kernels running beside this launch -- store the rest element by element
-                    const unsigned a = ma[r] & 0x80808080u;
-                    const unsigned sx = upd_x ? (a & ((ma[r] & 0x10101010u) << 3)) : 0u;
-                    const unsigned sy = (j0 + r < ny - 1) ? (a & ((ma[r] & 0x20202020u) << 2)) : 0u;
-                    const unsigned sz = a & ((ma[r] & 0x40404040u) << 1) & uw;
-                    const float4 sxv = sel4(e0, e1, e2, e3, ox, z4), syv = sel4(e0, e1, e2, e3, oy, z4), szv = sel4(e0, e1, e2, e3, oz, z4);
-                    const float pe[4] = {pst.x, pst.y, pst.z, pst.w}, xe[4] = {sxv.x, sxv.y, sxv.z, sxv.w};
-                    const float ye[4] = {syv.x, syv.y, syv.z, syv.w}, ze[4] = {szv.x, szv.y, szv.z, szv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const unsigned bit = 0x80u << (8 * e);
-                        if (!(a & bit)) F.p_out[c + e] = pe[e];
-                        if (!(sx & bit)) F.vx_out[c + e] = xe[e];
-                        if (!(sy & bit)) F.vy_out[c + e] = ye[e];
-                        if (!(sz & bit)) F.vz_out[c + e] = ze[e];
-                    }
-                } else {
                 st4(F.p_out + c, pst);
                 if (PEER && P.peer_lo_p && i == 0) st4(P.peer_lo_p + (c - base) + col, pst);           // NVLink peer store
                 if (PEER && P.peer_hi_p && i == P.nx - 1) st4(P.peer_hi_p + (c - base) + col, pst);
                 st4(F.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
                 st4(F.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
                 st4(F.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
-                }
             }
             vxp[r] = vxn;
             pc[r + 1] = pn[r];
@@ -480,11 +427,11 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     }
 }
 
-template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false, int BOXM = 0>
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false>
 __global__ void __launch_bounds__(256) k1_step_march(StepParams P)
 {
     const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
-    k1_tile<RJ, GEOM, UNI, PEER, FUSE, FLAT, BOXM>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+    k1_tile<RJ, GEOM, UNI, PEER, FUSE, FLAT>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,10 +446,9 @@ __global__ void k_build_mask(const uint8_t *geom, uint8_t *mask, int nx, int ny,
     const int i = (int)blockIdx.z - 1;                            // -1 .. nx
     if (k >= nz) return;
     const long long c = (long long)i * plane + (long long)j * pitch + k;
-    const uint8_t keep = mask[c] & 0xF0;                          // ADE bits live in the upper nibble (k_ade_bits)
-    if ((i < 0 && !has_lower) || (i >= nx && !has_upper)) { mask[c] = keep; return; }
-    auto G = [&](int ii, int jj, int kk) -> bool {                // geom == nullptr: all air
-        return !geom || geom[((long long)(ii + has_lower) * ny + jj) * nz + kk] != 0;
+    if ((i < 0 && !has_lower) || (i >= nx && !has_upper)) { mask[c] = 0; return; }
+    auto G = [&](int ii, int jj, int kk) -> bool {
+        return geom[((long long)(ii + has_lower) * ny + jj) * nz + kk] != 0;
     };
     const bool air = G(i, j, k);
     uint8_t m = air ? M_AIR : 0;
@@ -510,7 +456,7 @@ __global__ void k_build_mask(const uint8_t *geom, uint8_t *mask, int nx, int ny,
     if (!rigid || (air && (!have_xn || G(i + 1, j, k)))) m |= M_XOPEN;
     if (!rigid || (air && (j + 1 >= ny || G(i, j + 1, k)))) m |= M_YOPEN;
     if (!rigid || (air && (k + 1 >= nz || G(i, j, k + 1)))) m |= M_ZOPEN;
-    mask[c] = m | keep;
+    mask[c] = m;
 }
 
 // what K3 needs to keep the neighbours' ghosts and flags current (all nullptr on a single GPU)
@@ -857,364 +803,6 @@ __global__ void k2b_fixup_dense(StepParams P, AdeTable A)
                    (kk + 1 < A.bz && m[s + 1] == mat) ? s + 1 : -1,
                    (ii > 0 && m[s - si] == mat) ? s - si : -1, (jj > 0 && m[s - sj] == mat) ? s - sj : -1,
                    (kk > 0 && m[s - 1] == mat) ? s - 1 : -1);
-}
-
-// ------------------------------------------------------------------------------------------
-// K1-ADE: the marching kernel with the auxiliary-field recursions folded in, for the tiles that meet the bounding box of
-// the dispersive materials (the plain K1 launch of the same step skips that box, StepParams::box_mode).  A material
-// cell is computed ONCE, in the order of core/solver.py:2135-2193:
-//   density poles  J <- alpha J + beta p   (ade.cpp:25-68, 118-170)      from the input set's p
-//   velocity       v += cv dp              (fdtd_step.cpp:34-80)          then, pole after pole,
-//                  v += vcoef (J[c+] - J[c])  on faces whose two cells carry the pole's material (ade.cpp:228-401)
-//   rigid faces, divergence, modulus poles J <- f(J, div) (ade.cpp:70-112, 172-222, 479-692)
-//   pressure       p += cp div;  p += pcoef J  per modulus pole (ade.cpp:403-473);  p = 0 in solids;  sponge
-// The density fields of the +x / +-y / +-z neighbours are recomputed from their old values and the neighbours' input
-// pressure (same operations as their owners perform), so the density J arrays are double-buffered (Lorentz poles
-// rotate three buffers: J, J_prev, J_new) -- a neighbour must never see a half-updated field.  Modulus fields belong
-// to one cell only and are updated in place.  Which cells and faces take part is read from the upper nibble of the
-// mask byte (M_ADE, M_?SAME); the material id array is read only when more than one material carries poles.
-// J arrays are dense over the bounding box of the pole's material in i and j and over whole padded rows in k:
-//   index(i, j, k) = ((i - bi0) * bnj + (j - bj0)) * pitch + k.
-// ------------------------------------------------------------------------------------------
-struct AdeFused {
-    int n_poles, multi;
-    const uint8_t *mat;                  // material id per cell (padded field layout, plane-0 pointer); multi only
-    float inv_dx;
-    PoleDev poles[MAX_POLES];
-    int bi0[MAX_POLES], bj0[MAX_POLES], bni[MAX_POLES], bnj[MAX_POLES];
-    const float *Jin[MAX_POLES], *Jpin[MAX_POLES];
-    float *Jout[MAX_POLES], *Jpout[MAX_POLES];       // modulus poles: the same buffers as Jin / Jpin (in place)
-};
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// byte e of w has bit 7 set -> element e takes part
-SB_HD float4 corr4(float4 v, unsigned w, float vc, float4 hi, float4 lo)
-{
-    return make_float4((w & 0x80u) ? v.x + vc * (hi.x - lo.x) : v.x, (w & 0x8000u) ? v.y + vc * (hi.y - lo.y) : v.y,
-                       (w & 0x800000u) ? v.z + vc * (hi.z - lo.z) : v.z, (w & 0x80000000u) ? v.w + vc * (hi.w - lo.w) : v.w);
-}
-SB_HD float4 pick4(unsigned w, float4 a, float4 b)
-{
-    return make_float4((w & 0x80u) ? a.x : b.x, (w & 0x8000u) ? a.y : b.y, (w & 0x800000u) ? a.z : b.z, (w & 0x80000000u) ? a.w : b.w);
-}
-SB_HD float pole_upd(const PoleDev &Q, float J, float Jp, float src)
-{
-    return Q.is_lorentz ? Q.c0 * J + Q.c1 * Jp + Q.c2 * src : Q.c0 * J + Q.c1 * src;      // ade.cpp:158-160 / 57-59
-}
-SB_HD float4 pole_upd4(const PoleDev &Q, float4 J, float4 Jp, float4 s)
-{
-    if (Q.is_lorentz)                                         // one (warp-uniform) branch instead of a select per element
-        return add4(add4(mul4s(J, Q.c0), mul4s(Jp, Q.c1)), mul4s(s, Q.c2));
-    return add4(mul4s(J, Q.c0), mul4s(s, Q.c1));
-}
-// corr4 / pick4 when the warp has agreed that every element of every lane takes part (the interior of a material)
-constexpr unsigned ALL_SEL = 0x80808080u;
-SB_HD float4 corr4_all(float4 v, float vc, float4 hi, float4 lo) { return add4(v, mul4s(sub4(hi, lo), vc)); }
-// which of the four cells of a mask word carry pole Q's material (bit 7 of each byte)
-__device__ __forceinline__ unsigned ade_sel(const AdeFused &A, const PoleDev &Q, unsigned mk, unsigned matw)
-{
-    unsigned s = mk & 0x80808080u;
-    if (A.multi) s &= __vcmpeq4(matw, (unsigned)Q.mat_id * 0x01010101u);
-    return s;
-}
-
-template <bool UNI, bool FLAT>
-__device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused &A, const FieldSet &F, int bx, int by, int bz)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    int k0, j0;
-    bool warp_out;
-    if (FLAT) {
-        const int P4 = P.pitch >> 2, warps_x = blockDim.x >> 5;
-        const long long g0 = ((long long)bx * (warps_x * blockDim.y) + threadIdx.y * warps_x + (threadIdx.x >> 5)) * 32;
-        const long long groups = (long long)P.ny * P4;
-        warp_out = g0 >= groups;
-        const long long g = g0 + lane;
-        j0 = (int)(g / P4);
-        k0 = 4 * (int)(g - (long long)j0 * P4);
-    } else {
-        const int strip_k0 = (bx * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 128;
-        k0 = strip_k0 + lane * 4;
-        j0 = by * blockDim.y + threadIdx.y;
-        warp_out = strip_k0 >= P.nz || j0 >= P.ny;
-    }
-    const int ib = P.i_begin + bz * P.chunk_i;
-    const int ie = min(ib + P.chunk_i, P.i_end);
-    if (warp_out || ib >= ie) return;
-    const int nz = P.nz, ny = P.ny;
-    const bool lane_ok = k0 < nz;
-    const bool row0 = j0 < ny, rowm = j0 - 1 >= 0 && j0 - 1 < ny, rowp = j0 + 1 < ny;      // rows j0, j0-1, j0+1 exist
-    const bool own = lane_ok && row0 && k0 >= P.bk0 && k0 < P.bk1 && j0 >= P.bj0 && j0 < P.bj1;   // this launch stores the box only
-    if (!__any_sync(FULL, own)) return;
-    const bool e0 = k0 < nz, e1 = k0 + 1 < nz, e2 = k0 + 2 < nz, e3 = k0 + 3 < nz;
-    const bool u0 = k0 < nz - 1, u1 = k0 + 1 < nz - 1, u2 = k0 + 2 < nz - 1, u3 = k0 + 3 < nz - 1;
-    const unsigned uw = (u0 ? 0x80u : 0u) | (u1 ? 0x8000u : 0u) | (u2 ? 0x800000u : 0u) | (u3 ? 0x80000000u : 0u);
-    const bool edge_hi = (lane == 31) && (k0 + 4 < nz);
-    const bool edge_lo = (lane == 0) && (k0 > 0);
-    const bool first_in_row = lane == 0 || (FLAT && k0 == 0);
-    const float4 z4 = f4(0.0f);
-    const bool ok = row0 && lane_ok;
-
-    const float4 cvz4 = UNI ? f4(P.cv_uni) : (lane_ok ? ld4(P.cvz + k0) : z4);
-    const float4 icz4 = (!UNI && lane_ok) ? ld4(P.icz + k0) : f4(1.0f);
-    const float4 dz0 = (P.n_sponge > 0 && lane_ok) ? ld4(P.decz[0] + k0) : f4(1.0f);
-    const float cvz_lo = UNI ? P.cv_uni : (edge_lo ? P.cvz[k0 - 1] : 0.0f);
-    const bool updm = rowm && row0, updp = row0 && j0 < ny - 1;                             // the y faces j0-1 -> j0 and j0 -> j0+1 are updated
-    const float cvym = UNI ? P.cv_uni : (updm ? P.cvy[j0 - 1] : 0.0f), cvyc = UNI ? P.cv_uni : (updp ? P.cvy[j0] : 0.0f);
-    const float icy = (!UNI && row0) ? P.icy[j0] : 1.0f;
-    const float dy0 = (P.n_sponge > 0 && row0) ? P.decy[0][j0] : 1.0f;
-    const long long col = (long long)j0 * P.pitch + k0;
-    auto jidx = [&](int q, int i) -> long long {
-        return ((long long)(i - A.bi0[q]) * A.bnj[q] + (j0 - A.bj0[q])) * P.pitch + k0;
-    };
-
-    // ---- prologue: p of plane ib, undamped (corrected, rigid-masked) vx of plane ib-1 ---------------------------
-    if (own) {                                               // the J rows of the first two planes, on their way while the fields load
-        _Pragma("unroll 1")
-        for (int q = 0; q < A.n_poles; q++) {
-            const int lj = j0 - A.bj0[q];
-            if (A.poles[q].target > 1 || lj < 0 || lj >= A.bnj[q]) continue;
-            for (int a = 0; a < 2; a++) {
-                const int li = ib + a - A.bi0[q];
-                if (li < 0 || li >= A.bni[q]) continue;
-                const long long o = ((long long)li * A.bnj[q] + lj) * P.pitch + k0;
-                prefetch_l1(A.Jin[q] + o);
-                if (A.Jpin[q]) prefetch_l1(A.Jpin[q] + o);
-            }
-        }
-    }
-    float4 pc = ok ? ld4(F.p_in + (long long)ib * P.plane + col) : z4;
-    float4 vxp = z4;
-    if ((ib > 0 || P.has_lower) && ok) {                     // (ok is not warp-uniform: no collectives in here)
-        const long long cm = (long long)(ib - 1) * P.plane + col;
-        const float4 pm = ld4(F.p_in + cm);
-        const float cx = UNI ? P.cv_uni : P.cvx[ib - 1];
-        float4 v = add4(ld4(F.vx_in + cm), mul4s(sub4(pc, pm), cx));
-        const unsigned mkm = *reinterpret_cast<const unsigned *>(P.mask + cm);
-        if (mkm & 0x80808080u & ((mkm & 0x10101010u) << 3)) {
-            const unsigned matw = A.multi ? *reinterpret_cast<const unsigned *>(A.mat + cm) : 0u;
-            _Pragma("unroll 1")
-            for (int q = 0; q < A.n_poles; q++) {
-                const PoleDev &Q = A.poles[q];
-                if (Q.target != 0) continue;
-                const unsigned xw = ade_sel(A, Q, mkm, matw) & ((mkm & 0x10101010u) << 3);
-                if (!xw) continue;
-                const long long jl = jidx(q, ib - 1), jh = jl + (long long)A.bnj[q] * P.pitch;
-                const float4 Jl = pole_upd4(Q, ld4(A.Jin[q] + jl), Q.is_lorentz ? ld4(A.Jpin[q] + jl) : z4, pm);
-                const float4 Jh = pole_upd4(Q, ld4(A.Jin[q] + jh), Q.is_lorentz ? ld4(A.Jpin[q] + jh) : z4, pc);
-                v = corr4(v, xw, Q.vcoef, Jh, Jl);
-            }
-        }
-        vxp = keep4(v, mkm, M_XOPEN);
-    }
-
-    // ---- march -----------------------------------------------------------------------------------------------
-    for (int i = ib; i < ie; i++) {
-        const long long c = (long long)i * P.plane + col;
-        const bool upd_x = (i < P.nx - 1) || P.has_upper;
-        const float cx = UNI ? P.cv_uni : (upd_x ? P.cvx[i] : 0.0f);
-        const float icx = UNI ? 1.0f : P.icx[i];
-        const float dx0 = (P.n_sponge > 0) ? P.decx[0][i] : 1.0f;
-
-        const float4 pn = (ok && upd_x) ? ld4(F.p_in + c + P.plane) : z4;
-        const float4 vx = ok ? ld4(F.vx_in + c) : z4;
-        const float4 vz = ok ? ld4(F.vz_in + c) : z4;
-        const float4 vyc = ok ? ld4(F.vy_in + c) : z4;
-        const float4 vym = (rowm && lane_ok) ? ld4(F.vy_in + c - P.pitch) : z4;
-        const float4 pm = (rowm && lane_ok) ? ld4(F.p_in + c - P.pitch) : z4;
-        const float4 pp = (rowp && lane_ok) ? ld4(F.p_in + c + P.pitch) : z4;
-        const unsigned mkc = ok ? *reinterpret_cast<const unsigned *>(P.mask + c) : ALL_OPEN;
-        const unsigned mkm = (rowm && lane_ok) ? *reinterpret_cast<const unsigned *>(P.mask + c - P.pitch) : ALL_OPEN;
-        const float p_hi = (edge_hi && row0) ? F.p_in[c + 4] : 0.0f;
-        const float p_lo = (edge_lo && row0) ? F.p_in[c - 1] : 0.0f;
-        const float vz_lo = (edge_lo && row0) ? F.vz_in[c - 1] : 0.0f;
-        const uint8_t m_lo = (edge_lo && row0) ? P.mask[c - 1] : (uint8_t)0x0F;
-        // The J rows a plane needs are only known once its mask bytes have arrived, and every pole adds a dependent round
-        // of loads: ask for the next plane's rows now (density poles: the row that becomes the +x neighbour, i.e. plane
-        // i+2; modulus poles: plane i+1), one iteration -- far more than a DRAM round trip -- ahead of their use.
-        if (own) {
-            _Pragma("unroll 1")
-            for (int q = 0; q < A.n_poles; q++) {
-                const int ahead = A.poles[q].target == 0 ? 2 : 1;
-                const int li = i + ahead - A.bi0[q], lj = j0 - A.bj0[q];
-                if (A.poles[q].target > 1 || li < 0 || li >= A.bni[q] || lj < 0 || lj >= A.bnj[q]) continue;
-                const long long o = ((long long)li * A.bnj[q] + lj) * P.pitch + k0;
-                prefetch_l1(A.Jin[q] + o);
-                if (A.Jpin[q]) prefetch_l1(A.Jpin[q] + o);
-            }
-        }
-        const bool masked = !__all_sync(FULL, (mkc & ALL_OPEN) == ALL_OPEN && (mkm & ALL_OPEN) == ALL_OPEN && (m_lo & 0x0F) == 0x0F);
-        const bool ade = __any_sync(FULL, (mkc & 0x80808080u) != 0u);
-
-        // material-free velocity updates (fdtd_step.cpp:34-80 / 235-307); rigid faces come after the ADE corrections
-        const float4 p = pc;
-        float4 vyn_m = vym, vyn_c = vyc, vxn = vx, vzn = vz;
-        if (updm) vyn_m = add4(vym, mul4s(sub4(p, pm), cvym));
-        if (updp) vyn_c = add4(vyc, mul4s(sub4(pp, p), cvyc));
-        if (upd_x) vxn = add4(vx, mul4s(sub4(pn, p), cx));
-        float p_next = __shfl_down_sync(FULL, p.x, 1);
-        if (lane == 31) p_next = p_hi;
-        vzn = sel4(u0, u1, u2, u3, add4(vz, mul4(sub4(make_float4(p.y, p.z, p.w, p_next), p), cvz4)), vz);
-        float vz_edge = edge_lo ? vz_lo + cvz_lo * (p.x - p_lo) : 0.0f;        // z face k0-1 of the previous strip's cell
-
-        unsigned matw = 0u;
-        if (ade) {
-            if (A.multi && ok) matw = *reinterpret_cast<const unsigned *>(A.mat + c);
-            _Pragma("unroll 1")
-            for (int q = 0; q < A.n_poles; q++) {
-                const PoleDev &Q = A.poles[q];
-                if (Q.target != 0) continue;
-                const unsigned selw = ade_sel(A, Q, mkc, matw);
-                if (!__any_sync(FULL, selw != 0u)) continue;
-                const bool lor = Q.is_lorentz != 0;
-                const float *Jin = A.Jin[q], *Jpin = A.Jpin[q];
-                const long long jb = jidx(q, i);
-                const unsigned xw = upd_x ? (selw & ((mkc & 0x10101010u) << 3)) : 0u;
-                const unsigned yw = updp ? (selw & ((mkc & 0x20202020u) << 2)) : 0u;
-                const unsigned mw = updm ? (selw & ((mkm & 0x20202020u) << 2)) : 0u;      // the face j0-1 -> j0 belongs to the row below
-                // inside a material every element of every lane takes part: plain float4 arithmetic, no selects
-                const bool all_sel = __all_sync(FULL, selw == ALL_SEL), all_x = __all_sync(FULL, xw == ALL_SEL);
-                const bool all_y = __all_sync(FULL, yw == ALL_SEL), all_m = __all_sync(FULL, mw == ALL_SEL);
-                float4 Jn = z4;
-                if (selw) {
-                    Jn = pole_upd4(Q, ld4(Jin + jb), lor ? ld4(Jpin + jb) : z4, p);
-                    if (!all_sel) Jn = pick4(selw, Jn, z4);
-                }
-                if (xw) {
-                    const long long jx = jb + (long long)A.bnj[q] * P.pitch;
-                    const float4 Jx = pole_upd4(Q, ld4(Jin + jx), lor ? ld4(Jpin + jx) : z4, pn);
-                    vxn = all_x ? corr4_all(vxn, Q.vcoef, Jx, Jn) : corr4(vxn, xw, Q.vcoef, Jx, Jn);
-                }
-                if (yw) {
-                    const long long jy = jb + P.pitch;
-                    const float4 Jy = pole_upd4(Q, ld4(Jin + jy), lor ? ld4(Jpin + jy) : z4, pp);
-                    vyn_c = all_y ? corr4_all(vyn_c, Q.vcoef, Jy, Jn) : corr4(vyn_c, yw, Q.vcoef, Jy, Jn);
-                }
-                if (mw) {
-                    const long long jm = jb - P.pitch;
-                    const float4 Jm = pole_upd4(Q, ld4(Jin + jm), lor ? ld4(Jpin + jm) : z4, pm);
-                    vyn_m = all_m ? corr4_all(vyn_m, Q.vcoef, Jn, Jm) : corr4(vyn_m, mw, Q.vcoef, Jn, Jm);
-                }
-                const unsigned zw = selw & ((mkc & 0x40404040u) << 1) & uw;
-                float Jn_next = __shfl_down_sync(FULL, Jn.x, 1);
-                if (lane == 31) {
-                    Jn_next = 0.0f;
-                    if (edge_hi && (zw & 0x80000000u)) Jn_next = pole_upd(Q, Jin[jb + 4], lor ? Jpin[jb + 4] : 0.0f, p_hi);
-                }
-                vzn = __all_sync(FULL, zw == ALL_SEL) ? corr4_all(vzn, Q.vcoef, make_float4(Jn.y, Jn.z, Jn.w, Jn_next), Jn)
-                                                      : corr4(vzn, zw, Q.vcoef, make_float4(Jn.y, Jn.z, Jn.w, Jn_next), Jn);
-                if (edge_lo && (selw & 0x80u) && (m_lo & M_ZSAME))
-                    vz_edge = vz_edge + Q.vcoef * (Jn.x - pole_upd(Q, Jin[jb - 1], lor ? Jpin[jb - 1] : 0.0f, p_lo));
-                if (selw && own) st4(A.Jout[q] + jb, Jn);
-            }
-        }
-        // rigid faces (boundaries.cpp:66-89): updated faces only
-        if (masked) {
-            if (updm) vyn_m = keep4(vyn_m, mkm, M_YOPEN);
-            if (updp) vyn_c = keep4(vyn_c, mkc, M_YOPEN);
-            if (upd_x) vxn = keep4(vxn, mkc, M_XOPEN);
-            vzn = keep4(vzn, mkc | (u0 ? 0u : 0x08u) | (u1 ? 0u : 0x0800u) | (u2 ? 0u : 0x080000u) | (u3 ? 0u : 0x08000000u), M_ZOPEN);
-            if (edge_lo && !(m_lo & M_ZOPEN)) vz_edge = 0.0f;
-        }
-        float vz_prev = __shfl_up_sync(FULL, vzn.w, 1);
-        if (first_in_row) vz_prev = vz_edge;
-        const float4 vzm = make_float4(vz_prev, vzn.x, vzn.y, vzn.z);
-        // divergence and pressure
-        const float4 ddx = sub4(vxn, vxp), ddy = sub4(vyn_c, vyn_m), ddz = sub4(vzn, vzm);
-        float4 ex = ddx, ey = ddy, ez = ddz;
-        if (!UNI) { ex = mul4s(ddx, icx); ey = mul4s(ddy, icy); ez = mul4(ddz, icz4); }
-        float4 pnew = add4(p, mul4s(add4(add4(ex, ey), ez), P.cp));
-        if (masked) pnew = keep4(pnew, mkc, M_AIR);
-        if (ade) {
-            // modulus poles: source = divergence accumulated as d = dx*ix; d += dy*iy; d += dz*iz (ade.cpp:479-692)
-            const float ix = UNI ? A.inv_dx : icx, iy = UNI ? A.inv_dx : icy;
-            const float4 iz = UNI ? f4(A.inv_dx) : icz4;
-            const float4 div = add4(add4(mul4s(ddx, ix), mul4s(ddy, iy)), mul4(ddz, iz));
-            _Pragma("unroll 1")
-            for (int q = 0; q < A.n_poles; q++) {
-                const PoleDev &Q = A.poles[q];
-                if (Q.target != 1) continue;
-                const unsigned selw = own ? ade_sel(A, Q, mkc, matw) : 0u;
-                if (!selw) continue;
-                const long long jb = jidx(q, i);
-                const float4 J = ld4(A.Jin[q] + jb);
-                const float4 Jp = Q.is_lorentz ? ld4(A.Jpin[q] + jb) : z4;
-                const float4 Jn = pole_upd4(Q, J, Jp, div);
-                if (selw == ALL_SEL) {                                       // (per lane: no collective in this loop)
-                    st4(A.Jout[q] + jb, Jn);
-                    if (Q.is_lorentz) st4(A.Jpout[q] + jb, J);
-                    pnew = add4(pnew, mul4s(Jn, Q.pcoef));                   // p += (-K_inf dt) J   (ade.cpp:403-473)
-                } else {
-                    st4(A.Jout[q] + jb, pick4(selw, Jn, J));
-                    if (Q.is_lorentz) st4(A.Jpout[q] + jb, pick4(selw, J, Jp));
-                    pnew = corr4(pnew, selw, Q.pcoef, Jn, z4);
-                }
-            }
-            if (masked) pnew = keep4(pnew, mkc, M_AIR);                      // solver.py:2193
-        }
-        // sponge
-        float4 ox = vxn, oy = vyn_c, oz = vzn;
-        if (P.n_sponge > 0) {
-            ox = mul4s(ox, dx0); oy = mul4s(oy, dy0); oz = mul4(oz, dz0);
-            pnew = mul4(mul4s(mul4s(pnew, dx0), dy0), dz0);
-            _Pragma("unroll 1")
-            for (int s = 1; s < P.n_sponge; s++) {
-                const float dxs = P.decx[s][i];
-                const float dys = row0 ? P.decy[s][j0] : 1.0f;
-                const float4 dzs = lane_ok ? ld4(P.decz[s] + k0) : f4(1.0f);
-                ox = mul4s(ox, dxs); oy = mul4s(oy, dys); oz = mul4(oz, dzs);
-                pnew = mul4(mul4s(mul4s(pnew, dxs), dys), dzs);
-            }
-        }
-        if (own) {
-            st4(F.p_out + c, sel4(e0, e1, e2, e3, pnew, z4));
-            st4(F.vx_out + c, sel4(e0, e1, e2, e3, ox, z4));
-            st4(F.vy_out + c, sel4(e0, e1, e2, e3, oy, z4));
-            st4(F.vz_out + c, sel4(e0, e1, e2, e3, oz, z4));
-        }
-        vxp = vxn;
-        pc = pn;
-    }
-}
-
-// MINB = blocks per SM the register allocation aims at: 2 = whatever the code needs (104-122 registers), 3 = at most 80
-// (a few spilled words, half again as many warps in flight -- the kernel waits on memory most of the time)
-template <bool UNI, bool FLAT, int MINB>
-__global__ void __launch_bounds__(256, MINB) k1_step_march_ade(const __grid_constant__ StepParams P, const __grid_constant__ AdeFused A)
-{
-    const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
-    k1_tile_ade<UNI, FLAT>(P, A, F, (int)blockIdx.x + P.bx_off, (int)blockIdx.y + P.by_off, (int)blockIdx.z + P.bz_off);
-}
-
-// Upper nibble of the mask bytes from the dense material-id array (with the slab's live ghost planes, as the geometry):
-// M_ADE where the cell's material carries poles, M_?SAME where the + neighbour carries the same material; optionally
-// the ids themselves in the padded field layout.  used[m] != 0 <=> material m has poles.
-struct UsedIds { uint8_t used[256]; };
-__global__ void k_ade_bits(const uint8_t *mat, uint8_t *mask, uint8_t *mat_pad, UsedIds U, int nx, int ny, int nz, int pitch,
-                           long long plane, int has_lower, int has_upper)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    const int i = (int)blockIdx.z - 1;                            // -1 .. nx
-    if (k >= nz) return;
-    const long long c = (long long)i * plane + (long long)j * pitch + k;
-    const bool live = !((i < 0 && !has_lower) || (i >= nx && !has_upper));
-    auto M = [&](int ii, int jj, int kk) -> uint8_t { return mat[((long long)(ii + has_lower) * ny + jj) * nz + kk]; };
-    uint8_t bits = 0, id = 0;
-    if (live && mat) {                                            // mat == nullptr: clear the nibble
-        id = M(i, j, k);
-        if (U.used[id]) {
-            bits = M_ADE;
-            const bool have_xn = (i + 1 < nx) || (i + 1 == nx && has_upper);
-            if (have_xn && M(i + 1, j, k) == id) bits |= M_XSAME;
-            if (j + 1 < ny && M(i, j + 1, k) == id) bits |= M_YSAME;
-            if (k + 1 < nz && M(i, j, k + 1) == id) bits |= M_ZSAME;
-        } else id = 0;
-    }
-    mask[c] = (uint8_t)((mask[c] & 0x0F) | bits);
-    if (mat_pad) mat_pad[c] = id;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,7 +12,8 @@ int main(int argc, char **argv)
     int nx = argc > 1 ? atoi(argv[1]) : 512, ny = argc > 2 ? atoi(argv[2]) : 512, nz = argc > 3 ? atoi(argv[3]) : 512;
     int steps = argc > 4 ? atoi(argv[4]) : 20, rj = argc > 5 ? atoi(argv[5]) : 2, chunk = argc > 6 ? atoi(argv[6]) : 64;
     int var = argc > 7 ? atoi(argv[7]) : 0;      // KV>=4: 0 UNI lean, 1 tables (non-UNI), 2 UNI+PEER, 3 UNI+FUSE
-    int pitch = (nz + 31) / 32 * 32;
+    int wj = argc > 8 ? atoi(argv[8]) : 8, wk = argc > 9 ? atoi(argv[9]) : 1;
+    int pitch = (nz + 7) / 8 * 8;
     long long plane = (long long)ny * pitch, elems = (long long)(nx + 2) * plane;
     float *buf[8];
     for (int q = 0; q < 8; q++) { CK(cudaMalloc(&buf[q], elems * 4)); CK(cudaMemset(buf[q], 0, elems * 4)); }
@@ -32,8 +33,7 @@ int main(int argc, char **argv)
     int *ctr; CK(cudaMalloc(&ctr, 8)); CK(cudaMemset(ctr, 0, 8));
     P.step_global = ctr; P.err_flag = ctr + 1;
 #endif
-    int wj = 8;
-    dim3 blk(32, wj), grd((nz + 127) / 128, (ny + rj * wj - 1) / (rj * wj), (nx + chunk - 1) / chunk);
+    dim3 blk(32 * wk, wj), grd((nz + 128 * wk - 1) / (128 * wk), (ny + rj * wj - 1) / (rj * wj), (nx + chunk - 1) / chunk);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f, sum = 0;
     for (int rep = 0; rep < 5; rep++) {
