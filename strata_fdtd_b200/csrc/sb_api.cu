@@ -864,7 +864,20 @@ static int march_shape(sb_solver *h, bool flat_ok, int &rj, int &wj, int &wk, in
     return 0;
 }
 
-static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
+// the box of the dispersive materials in K1's terms: mode 1 = K1 skips it (aligned to its chunks of planes; K1-ADE owns
+// it), mode 3 = K1 leaves out, cell by cell, what the ADE list kernels write
+static void k1_set_box(const sb_solver *h, StepParams &P, int chunk, int mode)
+{
+    const sb_grid_desc &d = h->d;
+    P.box_mode = mode;
+    if (mode == 1) { P.bi0 = h->fbox[0] / chunk * chunk; P.bi1 = std::min(d.nx, (h->fbox[1] / chunk + 1) * chunk); }
+    else           { P.bi0 = h->fbox[0]; P.bi1 = h->fbox[1] + 1; }
+    P.bj0 = h->fbox[2]; P.bj1 = h->fbox[3] + 1;
+    P.bk0 = h->fbox[4] / 4 * 4; P.bk1 = (h->fbox[5] / 4 + 1) * 4;
+    P.ade_mask = h->mask.p ? h->mask.p + h->plane : nullptr;
+}
+
+static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse, int boxm = 0)
 {
     const sb_grid_desc &d = h->d;
     int variant = h->opt_kernel == SB_KERNEL_AUTO ? SB_KERNEL_MARCH : h->opt_kernel;
@@ -888,7 +901,8 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse)
         P.i_begin = (cb && d.has_lower) ? cb : 0; P.i_end = (cb && d.has_upper) ? d.nx - cb : d.nx; P.chunk_i = chunk;
         const dim3 grd(gx, gy, (P.i_end - P.i_begin + chunk - 1) / chunk);
         if (grd.z > 65535) return fail("too many i-chunks");
-        launch_march(rj, false, fuse && !cb, flat, P, grd, blk, h->stream);
+        if (boxm) k1_set_box(h, P, chunk, boxm);
+        launch_march(rj, false, fuse && !cb, flat, P, grd, blk, h->stream, boxm);
         h->kernels_launched++;
         return 0;
     }
@@ -949,10 +963,7 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
     }
     // the box, aligned to the plain launch's chunks of planes and to float4 groups
     P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-    P.box_mode = 1;
-    P.bi0 = h->fbox[0] / chunk * chunk; P.bi1 = std::min(d.nx, (h->fbox[1] / chunk + 1) * chunk);
-    P.bj0 = h->fbox[2]; P.bj1 = h->fbox[3] + 1;
-    P.bk0 = h->fbox[4] / 4 * 4; P.bk1 = (h->fbox[5] / 4 + 1) * 4;
+    k1_set_box(h, P, chunk, 1);
     const dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
     if (grd.z > 65535) return fail("too many i-chunks");
     // K1-ADE goes first, on the solver's own stream: its (comparatively few, long-running) blocks take their SM slots the
@@ -1064,10 +1075,7 @@ static int launch_step_lists_concurrent(sb_solver *h, StepParams &P)
         CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     }
     P.i_begin = 0; P.i_end = d.nx; P.chunk_i = chunk;
-    P.box_mode = 3;
-    P.bi0 = h->fbox[0]; P.bi1 = h->fbox[1] + 1; P.bj0 = h->fbox[2]; P.bj1 = h->fbox[3] + 1;
-    P.bk0 = h->fbox[4] / 4 * 4; P.bk1 = (h->fbox[5] / 4 + 1) * 4;
-    P.ade_mask = h->mask.p + h->plane;
+    k1_set_box(h, P, chunk, 3);
     const dim3 blk(32 * wk, wj), grd(gx, gy, (d.nx + chunk - 1) / chunk);
     if (grd.z > 65535) return fail("too many i-chunks");
     CU(cudaEventRecord(h->ev_fork, h->stream));
@@ -1088,7 +1096,13 @@ static int autotune(sb_solver *h)
 {
     static const int cand[][4] = {{1, 8, 1, 64}, {1, 8, 1, 16}, {1, 4, 1, 16}, {1, 2, 2, 16},
                                   {2, 8, 1, 64}, {2, 8, 1, 16}, {2, 4, 1, 16}, {2, 4, 1, 0}, {1, 0, 1, 0}};
-    const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->have_peers ? 64 : 0);
+    // with dispersive materials the step runs a box variant of K1 (the plain kernel is not what gets launched, and
+    // the variants rank the shapes differently: 2 rows per thread are best for the plain 512^3 kernel on some boxes and
+    // 12 % behind for the variant that leaves the ADE cells out), so that variant is what the trials time
+    const bool march_now = !h->have_peers && (h->opt_kernel == SB_KERNEL_AUTO || h->opt_kernel == SB_KERNEL_MARCH);
+    const int boxm = (h->have_ade && march_now) ? (h->ade_fused ? 1 : (h->ade_concurrent ? 3 : 0)) : 0;
+    const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->have_peers ? 64 : 0) |
+                    (boxm << 8) | (boxm ? ((h->fbox[1] - h->fbox[0]) & 0xFFF) << 12 : 0);
     if (h->tuned_key == key) return 0;
     TuneVal cached;
     if (tune_lookup(h, key, 0, cached)) {
@@ -1109,7 +1123,7 @@ static int autotune(sb_solver *h)
         for (int rep = 0; rep < 7; rep++) {                  // two warm-up launches, then the best of five
             StepParams P; fill_params(h, P);
             cudaEventRecord(e0, h->stream);
-            if (launch_step_kernel(h, P, false)) { h->have_peers = save_peers; return 1; }
+            if (launch_step_kernel(h, P, false, boxm)) { h->have_peers = save_peers; return 1; }
             cudaEventRecord(e1, h->stream);
             cudaEventSynchronize(e1);
             float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
