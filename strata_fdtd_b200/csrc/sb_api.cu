@@ -1120,14 +1120,14 @@ static int autotune(sb_solver *h)
     for (int c = 0; c < (int)(sizeof cand / sizeof cand[0]); c++) {
         h->opt_rj = cand[c][0]; h->opt_wj = cand[c][1]; h->opt_wk = cand[c][2]; h->opt_chunk_i = cand[c][3];
         float t_min = 1e30f;
-        for (int rep = 0; rep < 7; rep++) {                  // two warm-up launches, then the best of five
+        for (int rep = 0; rep < 4; rep++) {                  // one warm-up launch, then the best of three
             StepParams P; fill_params(h, P);
             cudaEventRecord(e0, h->stream);
             if (launch_step_kernel(h, P, false, boxm)) { h->have_peers = save_peers; return 1; }
             cudaEventRecord(e1, h->stream);
             cudaEventSynchronize(e1);
             float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
-            if (rep >= 2) t_min = std::min(t_min, ms);
+            if (rep >= 1) t_min = std::min(t_min, ms);
         }
         if (t_min < best) { best = t_min; best_c = c; }
     }
@@ -1351,7 +1351,7 @@ static std::vector<std::pair<int, int>> resident_candidates(const sb_solver *h)
     for (auto &c : all) min_iters = std::min(min_iters, c.iters);
     auto push = [&](const Cand &c) {
         for (auto &o : out) if (o.first == c.nbi && o.second == c.nbj) return;
-        if (out.size() < 6) out.emplace_back(c.nbi, c.nbj);
+        if (out.size() < 4) out.emplace_back(c.nbi, c.nbj);
     };
     std::sort(all.begin(), all.end(), [](const Cand &a, const Cand &b) { return std::tie(a.iters, a.bytes) < std::tie(b.iters, b.bytes); });
     for (size_t q = 0; q < all.size() && q < 3; q++) push(all[q]);                 // [0] = res_choose_partition's choice
@@ -1373,7 +1373,7 @@ static int resident_autotune(sb_solver *h, const double *src_dev, int n_steps)
         h->res_tuned_nbi = cached.v[0]; h->res_tuned_nbj = cached.v[1]; h->res_tuned_key = key;
         return 0;
     }
-    int n_trial = std::min(n_steps, 65);
+    int n_trial = std::min(n_steps, 33);
     if (!(n_trial & 1)) n_trial--;
     if (n_trial < 33) return 0;                               // too short to tell box grids apart: keep the heuristic
     const auto cands = resident_candidates(h);
@@ -1385,7 +1385,7 @@ static int resident_autotune(sb_solver *h, const double *src_dev, int n_steps)
     h->res_tuned_key = -1;
     for (int c = 0; c < (int)cands.size(); c++) {
         float t_min = 1e30f;
-        for (int rep = 0; rep < 3; rep++) {
+        for (int rep = 0; rep < 2; rep++) {
             ResParams R; const char *why_not = nullptr;
             if (!resident_plan(h, R, &why_not, cands[c].first, cands[c].second)) break;
             cudaEventRecord(e0, h->stream);

@@ -350,9 +350,11 @@ class DistributedFDTDSolver:
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
     def _all_any(self, flag: bool) -> bool:
-        box = [None] * self.world
-        self.dist.all_gather_object(box, bool(flag), group=self.group)
-        return any(box)
+        """Collective OR of a per-rank flag (one 4-byte all-reduce: this sits at the start of every run())."""
+        torch = self.slab._ensure_device().torch
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cpu" if self._staged else self.slab._dev.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item())
 
     def _prepare_ghosts(self):
         """Collective.  After host-side edits of the fields (initial conditions) or a reset the ghost planes of p and
