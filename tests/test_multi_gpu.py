@@ -129,7 +129,8 @@ rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 case = make_cases()["block_pml"]
 d = DistributedFDTDSolver(shape=case["shape"], resolution=case["resolution"], chunk_steps=16, halo={halo!r})
-print("HALO", d.halo)
+if rank == 0:
+    sys.stdout.write("HALO %s\n" % d.halo); sys.stdout.flush()
 d.set_geometry(case["geometry"])
 d.add_boundary(sb.PML(depth=8))
 d.add_boundary(sb.boundaries.ABCFirstOrder(axis=("y",)))      # y faces cross the cut: cut-plane cells are mirrored
@@ -215,7 +216,8 @@ case = dict(shape=(96, 40, 136), resolution=1e-3, geometry=g, pml=[dict(depth=6)
             probes=[("lo", (47, 20, 110)), ("hi", (48, 20, 110)), ("far", (90, 30, 60))])
 d = build_distributed_solver(case, chunk_steps=16, halo={halo!r})
 d.run(steps=70); d.run(steps=30)
-print("HALO", d.halo, "OVERLAP", getattr(d, "_overlap", None))
+if rank == 0:
+    sys.stdout.write("HALO %s OVERLAP %s\n" % (d.halo, getattr(d, "_overlap", None))); sys.stdout.flush()
 fields = {{f: d.gather_field(f) for f in ("p", "vx", "vy", "vz")}}
 traces = d.get_probe_data()
 if rank == 0:
