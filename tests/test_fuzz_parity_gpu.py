@@ -1,0 +1,115 @@
+"""Seeded random configurations of the hot path against the CPU oracle, bit for bit.
+
+The fixed cases of tests/cases.py pin particular features; this sweeps their combinations -- awkward extents (rows that end
+inside a float4, single-cell axes, rows longer than one 128-cell strip), random solids touching the outer faces, sponge
+layers on any subset of axes, uniform / nonuniform spacing, several sources and probes, a microphone, up to two dispersive
+materials as random boxes (density / modulus, Debye / Lorentz poles) in every ADE device layout, and every step kernel
+(streaming K1 in both plane mappings and both rows-per-thread, naive K0, shared-memory-resident K5, step-pipelined K6) --
+so that an index or predicate slip in one variant cannot hide behind the shapes the hand-written cases happen to use.
+"""
+import numpy as np
+import pytest
+
+from cases import BENIGN_POLES, SECOND_POLES
+from oracle import oracle as O
+from strata_fdtd_b200 import _lib
+from util import assert_same_as_oracle, build_b200_solver
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_case(seed: int) -> tuple[dict, dict, int]:
+    rng = np.random.default_rng(1000 + seed)
+    big_k = seed % 5 == 0
+    shape = (int(rng.integers(3, 34)), int(rng.integers(3, 30)), int(rng.integers(130, 170) if big_k else rng.integers(3, 45)))
+    if seed % 7 == 3:
+        shape = (shape[0], 1 + seed % 2, shape[2])                       # a (nearly) two-dimensional grid
+    case: dict = dict(steps=int(rng.integers(25, 60)))
+    if rng.random() < 0.3:
+        def stretched(n):
+            sizes = 1e-3 * rng.uniform(1.0, 1.3, size=n)
+            edges = np.concatenate([[0.0], np.cumsum(sizes)])
+            return 0.5 * (edges[:-1] + edges[1:])
+        case["nonuniform"] = dict(x_coords=stretched(shape[0]), y_coords=stretched(shape[1]), z_coords=stretched(shape[2]))
+    else:
+        case["shape"], case["resolution"] = shape, 1e-3
+    if rng.random() < 0.6:
+        g = np.ones(shape, dtype=bool)
+        for _ in range(int(rng.integers(1, 4))):
+            lo = [int(rng.integers(0, n)) for n in shape]
+            hi = [min(n, l + int(rng.integers(1, max(2, n // 2 + 1)))) for l, n in zip(lo, shape)]
+            g[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = False
+        if g.any():
+            case["geometry"] = g
+    air = case.get("geometry", np.ones(shape, dtype=bool))
+    pml = []
+    for _ in range(int(rng.integers(0, 3))):
+        axes = tuple(a for a, n in zip("xyz", shape) if rng.random() < 0.7 and n >= 6)
+        if axes:
+            depth = int(rng.integers(1, max(2, min(6, min(n for a, n in zip("xyz", shape) if a in axes) // 2))))
+            pml.append(dict(depth=depth, axes=axes, order=int(rng.integers(2, 4))))
+    case["pml"] = pml
+
+    def cell():
+        return tuple(int(rng.integers(0, n)) for n in shape)
+    case["sources"] = [dict(kind="point", position=cell(), frequency=float(rng.uniform(8e3, 3e4)),
+                            amplitude=float(rng.uniform(0.2, 2.0))) for _ in range(int(rng.integers(1, 4)))]
+    if not any(air[s["position"]] for s in case["sources"]):
+        free = np.argwhere(air)
+        case["sources"][0]["position"] = tuple(int(q) for q in free[len(free) // 2])
+    case["probes"] = [(f"p{q}", cell()) for q in range(int(rng.integers(1, 5)))] + [("at_source", case["sources"][0]["position"])]
+    if case.get("nonuniform") is None and all(n >= 3 for n in shape) and rng.random() < 0.4:
+        case["mics"] = [("m", tuple(float(rng.uniform(0.1, n - 1.2)) * 1e-3 for n in shape))]
+    opts: dict = {}
+    if rng.random() < 0.5:
+        mid = np.zeros(shape, dtype=np.uint8)
+        mats = []
+        for mat_id, poles in ((3, BENIGN_POLES), (7, SECOND_POLES))[: int(rng.integers(1, 3))]:
+            lo = [int(rng.integers(0, n)) for n in shape]
+            hi = [min(n, l + int(rng.integers(1, n + 1))) for l, n in zip(lo, shape)]
+            mid[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = mat_id
+            keep = [p for p in poles if rng.random() < 0.8] or poles[:1]
+            mats.append(dict(id=mat_id, rho_inf=float(rng.uniform(1.0, 1.6)), K_inf=float(rng.uniform(1.0, 1.6) * 343.0 ** 2), poles=keep))
+        mats = [m for m in mats if (mid == m["id"]).any()]
+        if mats:
+            case["materials"], case["material_id"] = mats, mid
+            opts[_lib.OPT_ADE_LAYOUT] = int(rng.integers(0, 4))
+    kernels = [_lib.KERNEL_AUTO, _lib.KERNEL_MARCH, _lib.KERNEL_MARCH, _lib.KERNEL_NAIVE]
+    if "materials" not in case and "mics" not in case:
+        kernels += [_lib.KERNEL_RESIDENT, _lib.KERNEL_PIPELINE]
+    opts[_lib.OPT_KERNEL] = kernels[int(rng.integers(0, len(kernels)))]
+    if opts[_lib.OPT_KERNEL] == _lib.KERNEL_NAIVE and opts.get(_lib.OPT_ADE_LAYOUT) == 3:
+        opts[_lib.OPT_ADE_LAYOUT] = 1                                       # the fused layout belongs to the marching kernel
+    if opts[_lib.OPT_KERNEL] in (_lib.KERNEL_MARCH, _lib.KERNEL_AUTO, _lib.KERNEL_PIPELINE) and rng.random() < 0.7:
+        opts[_lib.OPT_ROWS_PER_THREAD] = int(rng.integers(1, 3))
+        opts[_lib.OPT_PLANE_MAP] = int(rng.integers(0, 3))
+        opts[_lib.OPT_CHUNK_I] = int(rng.integers(1, 9))
+        opts[_lib.OPT_WARPS_J] = int(rng.choice([1, 2, 4, 8]))
+        opts[_lib.OPT_USE_GRAPH] = int(rng.integers(-1, 2))
+    chunk = int(rng.choice([7, 16, 64]))
+    return case, opts, chunk
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_configuration_matches_oracle(seed):
+    case, opts, chunk = _random_case(seed)
+    s = build_b200_solver(case, chunk_steps=chunk)
+    for k in (_lib.OPT_KERNEL, _lib.OPT_ADE_LAYOUT):                       # (the ADE layout is chosen when the materials are uploaded)
+        if k in opts:
+            s.set_kernel_option(k, opts[k])
+    for k, v in opts.items():
+        s.set_kernel_option(k, v)
+    o = O.OracleSolver(case)
+    steps = case["steps"]
+    try:
+        s.run(steps=steps)
+    except _lib.B200BackendError as e:
+        if "not applicable" in str(e) or "does not fit" in str(e) or "cannot be co-resident" in str(e):
+            pytest.skip(f"kernel variant refused this configuration: {e}")
+        raise
+    o.run_steps(steps)
+    what = f"seed {seed}: shape {s.shape}, opts {opts}, chunk {chunk}, " \
+           f"{'nonuniform ' if 'nonuniform' in case else ''}{'geometry ' if 'geometry' in case else ''}" \
+           f"{len(case['pml'])} sponge(s), {len(case.get('materials', []))} material(s)"
+    assert_same_as_oracle(s, o, what)
+    s.close()
