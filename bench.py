@@ -199,10 +199,10 @@ def decomposition_selfcheck(dist, world: int, rank: int, local_rank: int, halo: 
     g = np.ones((nx, 96, 200), dtype=bool)
     g[12:20, 30:60, 80:140] = False
     case = dict(shape=(nx, 96, 200), resolution=1e-3, geometry=g, pml=[dict(depth=6)],
-                sources=[dict(kind="point", position=(15, 48, 100), frequency=20e3),
+                sources=[dict(kind="point", position=(15, 20, 100), frequency=20e3),          # last plane below the first cut
                          dict(kind="point", position=(nx - 16, 20, 40), frequency=15e3, amplitude=0.5)],
-                probes=[("below_cut", (15, 40, 60)), ("above_cut", (16, 40, 60)), ("far", (nx - 2, 20, 150)),
-                        ("low", (1, 70, 30)), ("last_cut", (nx - 17, 48, 100))])
+                probes=[("below_cut", (15, 26, 104)), ("above_cut", (16, 26, 104)), ("behind_block", (18, 66, 100)),
+                        ("low", (1, 70, 30)), ("last_cut", (nx - 17, 24, 44))])
     d = build_distributed_solver(case, device=local_rank, chunk_steps=32, halo=halo)
     d.run(steps=steps)
     fields = {f: d.gather_field(f) for f in ("p", "vx", "vy", "vz")}
