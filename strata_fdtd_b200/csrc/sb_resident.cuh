@@ -420,8 +420,15 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
     const unsigned *smw = reinterpret_cast<const unsigned *>(sm);
     const int sti = (R.LJ + 2) * R.kp, svx = R.LJ * R.kp;
     const int dp = T.G * sti, dvx = T.G * svx, dvy = T.G * (R.LJ + 1) * R.kp;
-    int op = T.op, ox = T.ox, oy = T.oy, oz = T.oz;
-    for (int li = T.g; li < B.li_n; li += T.G, op += dp, ox += dvx, oy += dvy, oz += dvx) {
+    // Faces first: a thread visits its lowest plane, then its highest, then the ones in between, so that the two x faces
+    // of the box are on their way to the neighbours while the interior is still being computed -- by the time the
+    // neighbours ask for them (right after their own pressure phase) they have long arrived.  Cells are independent
+    // within this phase, so the order changes nothing in the results.
+    const int n_it = T.g < B.li_n ? (B.li_n - T.g + T.G - 1) / T.G : 0;
+    for (int it = 0; it < n_it; it++) {
+        const int m = it == 0 ? 0 : (it == 1 ? n_it - 1 : it - 1);
+        const int li = T.g + m * T.G;
+        const int op = T.op + m * dp, ox = T.ox + m * dvx, oy = T.oy + m * dvy, oz = T.oz + m * dvx;
         const float4 vx = ld4(sm + ox), vy = ld4(sm + oy), vz = ld4(sm + oz);
         float4 ddx = vx, ddy = vy;                                     // fdtd_step.cpp:109-211: zero ghost at index 0
         if (li > 0 || T.low_i) ddx = sub4(vx, ld4(sm + ox - svx));
