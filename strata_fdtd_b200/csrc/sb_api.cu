@@ -902,6 +902,19 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse, int boxm =
         const dim3 grd(gx, gy, (P.i_end - P.i_begin + chunk - 1) / chunk);
         if (grd.z > 65535) return fail("too many i-chunks");
         if (boxm) k1_set_box(h, P, chunk, boxm);
+        if (cb && P.i_end - P.i_begin > 4 * chunk) {
+            // Overlapped exchange (the cut planes are already on their way): the transport's kernels sit on another
+            // stream, two event hops behind this launch, and would find every SM taken by K1's blocks until K1 drains --
+            // measured at 8 GPUs: the exchange ran AFTER the interior, not beside it.  A short first launch gives them
+            // the slots its blocks free at its tail; the long second launch then runs beside them.
+            const int i_end = P.i_end, first = 2 * chunk;
+            P.i_end = P.i_begin + first;
+            launch_march(rj, false, false, flat, P, dim3(gx, gy, (first + chunk - 1) / chunk), blk, h->stream, boxm);
+            P.i_begin += first; P.i_end = i_end;
+            launch_march(rj, false, false, flat, P, dim3(gx, gy, (P.i_end - P.i_begin + chunk - 1) / chunk), blk, h->stream, boxm);
+            h->kernels_launched += 2;
+            return 0;
+        }
         launch_march(rj, false, fuse && !cb, flat, P, grd, blk, h->stream, boxm);
         h->kernels_launched++;
         return 0;
