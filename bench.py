@@ -279,7 +279,8 @@ def run_b200_arm(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from strata_fdtd_b200.solver import nccl_options
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=nccl_options())
     parity_n = decomposition_selfcheck(dist, world, rank, local_rank, a.halo) if world > 1 else None
     case, label = workload_case(a.workload, world)
     cells_total = int(np.prod(case["shape"], dtype=np.int64))

@@ -88,6 +88,18 @@ class _DeviceState:
             pass
 
 
+def nccl_options():
+    """Process-group options for the halo exchange: NCCL's kernels on a high-priority stream, so that the few CTAs of a
+    send/recv get SM slots beside the step kernel's thousands of blocks instead of after them (None if unavailable)."""
+    try:
+        import torch.distributed as dist
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        return opts
+    except Exception:
+        return None
+
+
 def distributed_world(auto_init: bool = True) -> int:
     """Number of ranks this process steps a grid with: the size of the torch.distributed job it runs in, else 1.
 
@@ -111,7 +123,7 @@ def distributed_world(auto_init: bool = True) -> int:
         index = devs[local] if devs else local
         if torch.cuda.is_available():
             torch.cuda.set_device(index)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", index))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", index), pg_options=nccl_options())
         else:
             dist.init_process_group("gloo")
         return dist.get_world_size()
