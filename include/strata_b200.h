@@ -177,6 +177,12 @@ int sb_set_gathers(sb_solver *h, int n, const int32_t *field, const int64_t *idx
 /* Same tables the reference derives from grid positions (microphones.cpp:16-80). */
 int sb_mic_tables(const float *grid_positions, int n_mics, int ny, int nz, int64_t *idx8, float *w8);
 
+/* Checkpoint / resume of the auxiliary fields (the reference keeps them in private full-grid arrays, core/solver.py:
+ * 3061-3083): pole index as passed to sb_set_ade, which = 0 for J, 1 for J_prev (Lorentz poles); host_dense is
+ * [nx][ny][nz], zero outside the pole's material on download; upload != 0 writes the device state instead.  Together with
+ * the four fields (sb_download_field / sb_upload_field) and the host's time / step count this is the whole solver state. */
+int sb_ade_state(sb_solver *h, int pole, int which, float *host_dense, int upload);
+
 /* ---- stepping ------------------------------------------------------------------------ */
 /* Advance n_steps.  src_values_host: [n_steps][n_sources] float64 waveform samples
  * (may be NULL if n_sources == 0).  record_out_host: [n_steps][n_probes+n_mics] fp32, written

@@ -291,6 +291,80 @@ extern "C" int sb_download_field(sb_solver *h, int field, float *host)
     return 0;
 }
 
+// Auxiliary (ADE) field of pole `pole` as a dense [nx][ny][nz] host array (zero outside the pole's material), or the
+// reverse: the checkpoint / resume counterpart of sb_download_field / sb_upload_field.  which: 0 = J, 1 = J_prev (Lorentz).
+// Works for every device layout (fused: per-material boxes with rotating buffers; compact list; dense box).
+extern "C" int sb_ade_state(sb_solver *h, int pole, int which, float *host, int upload)
+{
+    CHECK_H(h);
+    if (!host) return fail("null host pointer");
+    if (!h->have_ade) return fail("no ADE materials are set");
+    if (pole < 0 || pole >= h->ade.n_poles || which < 0 || which > 1) return fail("bad pole / field selector");
+    const sb_grid_desc &d = h->d;
+    const PoleDev &Q = h->ade.poles[pole];
+    if (which == 1 && !Q.is_lorentz) return fail("pole %d is a Debye pole: it has no J_prev", pole);
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t cells = (size_t)d.nx * d.ny * d.nz;
+    if (!upload) memset(host, 0, cells * sizeof(float));
+    const cudaMemcpyKind kind = upload ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (h->ade_fused) {
+        sb_solver::FusedPole &fp = h->fpole[pole];
+        if (fp.nbuf == 0) return 0;                                    // no cell carries this pole's material
+        const long long ph = h->ade_phase;
+        float *buf = Q.target == 0 ? (fp.nbuf == 3 ? fp.b[which == 0 ? ph % 3 : (ph + 2) % 3].p : fp.b[ph % 2].p)
+                                   : fp.b[which].p;
+        for (int ii = 0; ii < fp.bni; ii++) {                          // one strided copy per plane of the material's box
+            const int i = fp.bi0 + ii;
+            if (i < 0 || i >= d.nx) continue;
+            float *dev = buf + (size_t)ii * fp.bnj * d.pitch;
+            float *hst = host + ((size_t)i * d.ny + fp.bj0) * d.nz;
+            if (upload) CU(cudaMemcpy2DAsync(dev, (size_t)d.pitch * 4, hst, (size_t)d.nz * 4, (size_t)d.nz * 4, fp.bnj, kind, h->stream));
+            else        CU(cudaMemcpy2DAsync(hst, (size_t)d.nz * 4, dev, (size_t)d.pitch * 4, (size_t)d.nz * 4, fp.bnj, kind, h->stream));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    const AdeTable &A = h->ade;
+    float *base = (which == 0 ? A.J : A.Jp) + (size_t)pole * A.n_cells;
+    std::vector<float> tmp((size_t)A.n_cells);
+    if (!upload) CU(cudaMemcpy(tmp.data(), base, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (A.dense) {
+        std::vector<uint8_t> mb((size_t)A.n_cells);
+        CU(cudaMemcpy(mb.data(), A.mat_box, mb.size(), cudaMemcpyDeviceToHost));
+        for (int ii = 0; ii < A.bx; ii++)
+            for (int jj = 0; jj < A.by; jj++)
+                for (int kk = 0; kk < A.bz; kk++) {
+                    const size_t s = ((size_t)ii * A.by + jj) * A.bz + kk;
+                    if (mb[s] != Q.mat_id) continue;
+                    float &cell = host[((size_t)(A.bi0 + ii) * d.ny + (A.bj0 + jj)) * d.nz + (A.bk0 + kk)];
+                    if (upload) tmp[s] = cell; else cell = tmp[s];
+                }
+    } else {
+        std::vector<int> ijk((size_t)A.n_cells * 3);
+        std::vector<uint8_t> cm((size_t)A.n_cells);
+        CU(cudaMemcpy(ijk.data(), A.cell_ijk, ijk.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(cm.data(), A.cell_mat, cm.size(), cudaMemcpyDeviceToHost));
+        if (upload) CU(cudaMemcpy(tmp.data(), base, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));   // keep the ghost-plane cells
+        for (int s = 0; s < A.n_cells; s++) {
+            const int i = ijk[3 * (size_t)s], j = ijk[3 * (size_t)s + 1], k = ijk[3 * (size_t)s + 2];
+            if (i < 0 || i >= d.nx || cm[s] != Q.mat_id) continue;    // (ghost-plane cells of a slab belong to the neighbour)
+            float &cell = host[((size_t)i * d.ny + j) * d.nz + k];
+            if (upload) tmp[s] = cell; else cell = tmp[s];
+        }
+    }
+    if (upload) {
+        if (A.dense) {                                                 // cells of other materials keep their device values
+            std::vector<float> cur((size_t)A.n_cells);
+            std::vector<uint8_t> mb((size_t)A.n_cells);
+            CU(cudaMemcpy(cur.data(), base, cur.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(mb.data(), A.mat_box, mb.size(), cudaMemcpyDeviceToHost));
+            for (size_t s = 0; s < cur.size(); s++) if (mb[s] != Q.mat_id) tmp[s] = cur[s];
+        }
+        CU(cudaMemcpy(base, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
 // table of n entries padded to `padded` with `fill`, optionally with one leading ghost entry
 static int upload_table(DBuf<float> &buf, const float *src, int n, int padded, float fill, cudaStream_t s)
 {
@@ -902,19 +976,6 @@ static int launch_step_kernel(sb_solver *h, StepParams &P, bool fuse, int boxm =
         const dim3 grd(gx, gy, (P.i_end - P.i_begin + chunk - 1) / chunk);
         if (grd.z > 65535) return fail("too many i-chunks");
         if (boxm) k1_set_box(h, P, chunk, boxm);
-        if (cb && P.i_end - P.i_begin > 4 * chunk) {
-            // Overlapped exchange (the cut planes are already on their way): the transport's kernels sit on another
-            // stream, two event hops behind this launch, and would find every SM taken by K1's blocks until K1 drains --
-            // measured at 8 GPUs: the exchange ran AFTER the interior, not beside it.  A short first launch gives them
-            // the slots its blocks free at its tail; the long second launch then runs beside them.
-            const int i_end = P.i_end, first = 2 * chunk;
-            P.i_end = P.i_begin + first;
-            launch_march(rj, false, false, flat, P, dim3(gx, gy, (first + chunk - 1) / chunk), blk, h->stream, boxm);
-            P.i_begin += first; P.i_end = i_end;
-            launch_march(rj, false, false, flat, P, dim3(gx, gy, (P.i_end - P.i_begin + chunk - 1) / chunk), blk, h->stream, boxm);
-            h->kernels_launched += 2;
-            return 0;
-        }
         launch_march(rj, false, fuse && !cb, flat, P, grd, blk, h->stream, boxm);
         h->kernels_launched++;
         return 0;

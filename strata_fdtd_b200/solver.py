@@ -1005,6 +1005,45 @@ class FDTDSolver:
         for b in self._boundaries:
             b.reset()
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def get_state(self) -> dict:
+        """Everything a run needs to continue elsewhere: the four fields, time, step count and -- with dispersive
+        materials -- the auxiliary fields J (and J_prev of Lorentz poles) as dense arrays in pole-table order
+        (Debye poles of all materials first, then Lorentz; the reference keeps them private, solver.py:3061-3083)."""
+        st = {"time": float(self._time), "step_count": int(self._step_count)}
+        for f in _FIELDS:
+            st[f] = self.get_field(f)
+        if self._materials and any(len(m.poles) for m in self._materials.values()):
+            dev = self._sync_to_device()
+            poles, n_poles, _r, _k = self._pole_table()
+            ade = []
+            for q in range(n_poles):
+                ent = {"material_id": int(poles[q].material_id), "is_lorentz": bool(poles[q].is_lorentz),
+                       "target": "density" if poles[q].target == 0 else "modulus"}
+                for which, key in ((0, "J"), (1, "J_prev")):
+                    if which == 1 and not poles[q].is_lorentz:
+                        continue
+                    a = np.zeros(self.shape, dtype=np.float32)
+                    _lib.check(dev.lib.sb_ade_state(dev.handle, q, which, _lib.ptr(a), 0))
+                    ent[key] = a
+                ade.append(ent)
+            st["ade"] = ade
+        return st
+
+    def set_state(self, state: dict) -> None:
+        """Inverse of ``get_state`` on a solver with the same set-up (grid, materials in the same order)."""
+        for f in _FIELDS:
+            self._field_set(f, np.asarray(state[f], dtype=np.float32))
+        self._time, self._step_count = float(state["time"]), int(state["step_count"])
+        dev = self._sync_to_device()
+        for q, ent in enumerate(state.get("ade", [])):
+            for which, key in ((0, "J"), (1, "J_prev")):
+                if key in ent:
+                    a = np.ascontiguousarray(ent[key], dtype=np.float32)
+                    if a.shape != self.shape:
+                        raise ValueError(f"auxiliary field shape {a.shape} doesn't match solver shape {self.shape}")
+                    _lib.check(dev.lib.sb_ade_state(dev.handle, q, which, _lib.ptr(a), 1))
+
     def kernel_launches(self) -> int:
         if self._dev is None:
             return 0

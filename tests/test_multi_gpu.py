@@ -189,8 +189,6 @@ def test_cut_planes_first_then_exchange_then_interior(name, n_slabs):
                     probes=[("a", (39, 12, 30)), ("b", (40, 12, 30)), ("c", (40 * n_slabs - 3, 5, 5))])
     steps = 70
     one = build_b200_solver(case)
-    # 4-plane chunks: the rest of the step after the cut planes is long enough to be launched in two parts (the short
-    # first launch that lets the transport's kernels onto the SMs in the overlapped NCCL mode)
     grp = _group_from_case(case, n_slabs, {_lib.OPT_CHUNK_I: 4} if name == "block_pml" else {}, halo="copy_cuts")
     one.run(steps=steps); grp.run(steps)
     for f in ("p", "vx", "vy", "vz"):
