@@ -23,3 +23,13 @@ for tool in memcheck racecheck; do
       python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "$SEL3" > gpurun_out/sanitizer_flat_$tool.log 2>&1
   echo "flat-$tool exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_flat_$tool.log | tr '\n' ' ')"
 done
+# round 2: the fused ADE kernel (K1-ADE), K1's box variants beside the ADE list kernels, the cut-first schedule, the
+# checkpoint path, K5 after its changes, and a slice of the random configurations
+SEL4='(test_fused_ade_kernel_matches_oracle and (auto or r1_flat_chunk3 or r2_strips_graph)) or (test_ade_layouts_match_oracle and (ade_two or ade_dense)) or test_fused_ade_survives or (test_checkpoint_and_resume and ade_dense) or (test_resident_kernel_matches_oracle and (odd_geometry or nonuniform) and 0) or (test_random_configuration_matches_oracle and (0] or 1] or 3] or 7]))'
+for tool in memcheck initcheck racecheck; do
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 7 --target-processes all \
+      python -m pytest tests/test_parity_gpu.py tests/test_fuzz_parity_gpu.py -m gpu -x -q -k "$SEL4" > gpurun_out/sanitizer_r02_$tool.log 2>&1
+  echo "r02-$tool exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_r02_$tool.log | tr '\n' ' ')"
+done
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k "cut_planes_first or velocity_membrane" > gpurun_out/sanitizer_r02_memcheck_multi.log 2>&1
+echo "r02-memcheck-multi exit=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_r02_memcheck_multi.log | tr '\n' ' ')"
