@@ -708,14 +708,14 @@ __device__ __forceinline__ void ade_pole_update(const PoleDev &q, float *J, floa
 // K2a: density poles, source = p of the previous step (solver.py:2138-2139)
 __global__ void k2a_density(AdeTable A, const float *p_in)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n_cells) return;
-    const int mat = A.cell_mat[s];
-    const float src = p_in[A.cell_off[s]];
-    for (int q = 0; q < A.n_poles; q++) {
-        const PoleDev &Q = A.poles[q];
-        if (Q.target == 0 && Q.mat_id == mat)
-            ade_pole_update(Q, A.J + (long long)q * A.n_cells, A.Jp + (long long)q * A.n_cells, s, src);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n_cells; s += gridDim.x * blockDim.x) {
+        const int mat = A.cell_mat[s];
+        const float src = p_in[A.cell_off[s]];
+        for (int q = 0; q < A.n_poles; q++) {
+            const PoleDev &Q = A.poles[q];
+            if (Q.target == 0 && Q.mat_id == mat)
+                ade_pole_update(Q, A.J + (long long)q * A.n_cells, A.Jp + (long long)q * A.n_cells, s, src);
+        }
     }
 }
 
@@ -816,14 +816,14 @@ __device__ __forceinline__ void ade_fixup_cell(const StepParams &P, const AdeTab
 
 __global__ void k2b_fixup(StepParams P, AdeTable A)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.n_cells) return;
-    const long long c = A.cell_off[s];
-    const int i = A.cell_ijk[3 * s], j = A.cell_ijk[3 * s + 1], k = A.cell_ijk[3 * s + 2];
-    if (i < 0 || i >= P.nx) return;          // ghost-plane cell of a slab: only its J is kept here (K2a), its owner does the rest
     const int n = A.n_cells;
-    ade_fixup_cell(P, A, s, c, i, j, k, A.cell_mat[s], A.nbr[s], A.nbr[n + s], A.nbr[2 * n + s],
-                   A.nbr[3 * n + s], A.nbr[4 * n + s], A.nbr[5 * n + s]);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const long long c = A.cell_off[s];
+        const int i = A.cell_ijk[3 * s], j = A.cell_ijk[3 * s + 1], k = A.cell_ijk[3 * s + 2];
+        if (i < 0 || i >= P.nx) continue;    // ghost-plane cell of a slab: only its J is kept here (K2a), its owner does the rest
+        ade_fixup_cell(P, A, s, c, i, j, k, A.cell_mat[s], A.nbr[s], A.nbr[n + s], A.nbr[2 * n + s],
+                       A.nbr[3 * n + s], A.nbr[4 * n + s], A.nbr[5 * n + s]);
+    }
 }
 
 // dense layout: one thread per cell of the materials' bounding box, k fastest
