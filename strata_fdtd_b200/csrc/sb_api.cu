@@ -1060,7 +1060,7 @@ static int launch_step_fused_ade(sb_solver *h, StepParams &P)
         Q.bx_off = (int)((long long)P.bj0 * P4 / tile);
         agrd.x = (unsigned)(((long long)P.bj1 * P4 + tile - 1) / tile - Q.bx_off); agrd.y = 1;
     } else {
-        Q.bx_off = P.bk0 / 128; agrd.x = (unsigned)((P.bk1 + 127) / 128 - Q.bx_off);
+        Q.bx_off = 0; agrd.x = (unsigned)((P.bk1 - P.bk0 + 127) / 128);          // strips are counted from the box's first cell
         Q.by_off = P.bj0 / WJ;  agrd.y = (unsigned)((P.bj1 + WJ - 1) / WJ - Q.by_off);
     }
     agrd.z = (unsigned)((Q.i_end - Q.i_begin + Q.chunk_i - 1) / Q.chunk_i);

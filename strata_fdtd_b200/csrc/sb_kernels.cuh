@@ -935,10 +935,12 @@ __device__ __forceinline__ void k1_tile_ade(const StepParams &P, const AdeFused 
         j0 = (int)(g / P4);
         k0 = 4 * (int)(g - (long long)j0 * P4);
     } else {
-        const int strip_k0 = (bx * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 128;
+        // strips start at the box, not at multiples of 128: a material 100 cells wide that straddles a multiple of 128
+        // (config 3's sphere, centred at k = 256) is then one strip per row instead of two
+        const int strip_k0 = P.bk0 + (bx * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 128;
         k0 = strip_k0 + lane * 4;
         j0 = by * blockDim.y + threadIdx.y;
-        warp_out = strip_k0 >= P.nz || j0 >= P.ny;
+        warp_out = strip_k0 >= P.bk1 || strip_k0 >= P.nz || j0 >= P.ny;
     }
     const int ib = P.i_begin + bz * P.chunk_i;
     const int ie = min(ib + P.chunk_i, P.i_end);
