@@ -33,7 +33,12 @@ import fake_h5py  # noqa: E402
 sys.modules["h5py"] = fake_h5py
 from oracle import ref_loader as R  # noqa: E402
 
-SCRIPTS = ["basic_pulse.py", "material_sphere.py"]
+SCRIPTS = ["basic_pulse.py", "material_sphere.py", "multiple_probes.py", "waveguide.py", "organ_pipes.py",
+           "pzt_transducer.py", "frequency_sweep.py"]
+# examples/nonuniform_grid.py does not run upstream: add_probe (core/solver.py:1863-1884) converts metres with the
+# MINIMUM spacing, so its "edge" probe lands outside the 80-cell grid and the script dies with a ValueError before any
+# step (SURVEY-style finding F15).  The fixture keeps the error so that backend="b200" is held to the same behaviour.
+FAILING = ["nonuniform_grid.py"]
 
 
 def digest(a) -> str:
@@ -54,7 +59,10 @@ def tree(node, prefix=""):
 
 def main():
     R.load_reference_package()
+    only = sys.argv[1:]
     for name in SCRIPTS:
+        if only and name[:-3] not in only:
+            continue
         src = R.REF_ROOT / "examples" / name
         with tempfile.TemporaryDirectory() as tmp:
             cwd = os.getcwd()
@@ -88,5 +96,29 @@ def main():
         print("  " + str(fix["tree"]).replace("\n", "\n  "))
 
 
+def failures():
+    import json
+    out = {}
+    for name in FAILING:
+        src = R.REF_ROOT / "examples" / name
+        with tempfile.TemporaryDirectory() as tmp:
+            cwd = os.getcwd()
+            os.chdir(tmp)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    runpy.run_path(str(src), run_name="__main__")
+                raise SystemExit(f"{name} was expected to fail on the reference")
+            except Exception as e:                               # noqa: BLE001 -- whatever the reference raises is the fixture
+                out[name[:-3]] = {"type": type(e).__name__, "message": str(e),
+                                  "script_sha": hashlib.sha256(src.read_bytes()).hexdigest()}
+            finally:
+                os.chdir(cwd)
+    dst = ROOT / "tests" / "golden" / "script_failures.json"
+    dst.write_text(json.dumps(out, indent=1) + "\n")
+    print(f"{dst.name}: {out}")
+
+
 if __name__ == "__main__":
     main()
+    if not sys.argv[1:] or "failures" in sys.argv[1:]:
+        failures()

@@ -28,10 +28,33 @@ def _reference_available() -> bool:
     return spec is not None
 
 
-class Sphere:
-    """Signed-distance ball with the protocol of the reference's SDF primitives (geometry/sdf.py:302-338: ``sdf(points)``
-    = distance to the centre minus the radius; ``voxelize(grid)`` = cell centres with sdf <= 0, :99-125) -- the one
-    primitive the reference's named example scripts construct.  CSG, horns etc. stay with the reference package."""
+class _Solid:
+    """Protocol of the reference's SDF primitives (geometry/sdf.py:49-125): ``sdf(points)`` on an (N, 3) array of metres,
+    negative inside; ``contains``; ``voxelize(grid)`` = cell centres with sdf <= 0.  Only the handful of shapes the
+    reference's example scripts name live here; horns, transforms, smooth CSG etc. stay with the reference package."""
+
+    def sdf(self, points):
+        raise NotImplementedError
+
+    @staticmethod
+    def _points(points):
+        import numpy as np
+        points = np.asarray(points, dtype=np.float64)
+        if points.ndim != 2 or points.shape[1] != 3:
+            raise ValueError(f"points must be Nx3 array, got shape {points.shape}")
+        return points
+
+    def contains(self, points):
+        return self.sdf(points) <= 0
+
+    def voxelize(self, grid):
+        import numpy as np
+        X, Y, Z = np.meshgrid(grid.x_coords, grid.y_coords, grid.z_coords, indexing="ij")
+        return (self.sdf(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)) <= 0).reshape(grid.shape)
+
+
+class Sphere(_Solid):
+    """Ball: distance to the centre minus the radius (geometry/sdf.py:302-338)."""
 
     def __init__(self, center, radius):
         import numpy as np
@@ -42,22 +65,83 @@ class Sphere:
 
     def sdf(self, points):
         import numpy as np
-        points = np.asarray(points, dtype=np.float64)
-        if points.ndim != 2 or points.shape[1] != 3:
-            raise ValueError(f"points must be Nx3 array, got shape {points.shape}")
-        return np.linalg.norm(points - self.center, axis=1) - self.radius
+        return np.linalg.norm(self._points(points) - self.center, axis=1) - self.radius
 
     @property
     def bounding_box(self):
         return self.center - self.radius, self.center + self.radius
 
-    def contains(self, points):
-        return self.sdf(points) <= 0
 
-    def voxelize(self, grid):
+class Box(_Solid):
+    """Axis-aligned box from (center, size) or (min_corner, max_corner) (geometry/sdf.py:232-300): outside, the length of
+    the positive part of |x - c| - size/2; inside, its largest (negative) component."""
+
+    def __init__(self, center=None, size=None, min_corner=None, max_corner=None):
         import numpy as np
-        X, Y, Z = np.meshgrid(grid.x_coords, grid.y_coords, grid.z_coords, indexing="ij")
-        return (self.sdf(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)) <= 0).reshape(grid.shape)
+        if center is not None and size is not None:
+            self.center, self.size = np.array(center, dtype=np.float64), np.array(size, dtype=np.float64)
+        elif min_corner is not None and max_corner is not None:
+            lo, hi = np.array(min_corner, dtype=np.float64), np.array(max_corner, dtype=np.float64)
+            self.center, self.size = (lo + hi) / 2, hi - lo
+        else:
+            raise ValueError("Must provide either (center, size) or (min_corner, max_corner)")
+        if np.any(self.size <= 0):
+            raise ValueError(f"Box size must be positive, got {self.size}")
+
+    def sdf(self, points):
+        import numpy as np
+        q = np.abs(self._points(points) - self.center) - self.size / 2
+        return np.linalg.norm(np.maximum(q, 0), axis=1) + np.minimum(np.max(q, axis=1), 0)
+
+    @property
+    def bounding_box(self):
+        return self.center - self.size / 2, self.center + self.size / 2
+
+
+class Union(_Solid):
+    """min over the children (geometry/sdf.py:549-610)."""
+
+    def __init__(self, *children):
+        self.children = children
+
+    def sdf(self, points):
+        import numpy as np
+        out = self.children[0].sdf(points)
+        for c in self.children[1:]:
+            out = np.minimum(out, c.sdf(points))
+        return out
+
+
+class Intersection(_Solid):
+    """max over the children (geometry/sdf.py:612-683)."""
+
+    def __init__(self, *children):
+        self.children = children
+
+    def sdf(self, points):
+        import numpy as np
+        out = self.children[0].sdf(points)
+        for c in self.children[1:]:
+            out = np.maximum(out, c.sdf(points))
+        return out
+
+
+class Difference(_Solid):
+    """base minus the others: max(base, -s1, -s2, ...) (geometry/sdf.py:685-735)."""
+
+    def __init__(self, base, *subtracted):
+        self.base, self.subtracted = base, subtracted
+
+    def sdf(self, points):
+        import numpy as np
+        out = self.base.sdf(points)
+        for c in self.subtracted:
+            out = np.maximum(out, -c.sdf(points))
+        return out
+
+    @property
+    def bounding_box(self):
+        return self.base.bounding_box
 
 
 def install_as_strata_fdtd(force_alias: bool = False):
@@ -92,7 +176,7 @@ def install_as_strata_fdtd(force_alias: bool = False):
                  PML=sb.PML, RigidBoundary=sb.RigidBoundary, ABCFirstOrder=boundaries.ABCFirstOrder,
                  RadiationImpedance=boundaries.RadiationImpedance, UniformGrid=sb.UniformGrid,
                  NonuniformGrid=sb.NonuniformGrid, Pole=sb.Pole, PoleType=sb.PoleType, SimpleMaterial=sb.SimpleMaterial,
-                 Sphere=Sphere,
+                 Sphere=Sphere, Box=Box, Union=Union, Intersection=Intersection, Difference=Difference,
                  has_native_kernels=lambda: False, has_gpu_backend=lambda: True,
                  get_native_info=lambda: {"available": False, "version": None, "has_openmp": False, "num_threads": 1},
                  __version__=sb.__version__)

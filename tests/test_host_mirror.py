@@ -179,6 +179,36 @@ def test_grids_match_reference_live():
 
 
 @pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
+def test_script_solids_match_reference_live():
+    """The few SDF shapes the reference's example scripts import (compat.py) against geometry/sdf.py: same distances,
+    same voxels -- on a uniform and on a stretched grid."""
+    ref = R.load_reference_package()
+    from strata_fdtd_b200 import compat as C
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-0.02, 0.12, size=(4000, 3))
+
+    def build(m):
+        a = m.Box(center=(0.05, 0.04, 0.06), size=(0.04, 0.03, 0.05))
+        b = m.Box(min_corner=(0.03, 0.03, 0.03), max_corner=(0.06, 0.09, 0.05))
+        c = m.Sphere(center=(0.05, 0.05, 0.05), radius=0.022)
+        return [a, b, c, m.Union(a, c), m.Intersection(a, b, c), m.Difference(a, c), m.Difference(m.Union(a, b), c, b)]
+    grids = [(sb.UniformGrid((30, 28, 34), 3e-3), ref.UniformGrid((30, 28, 34), 3e-3)),
+             (sb.NonuniformGrid.from_stretch((30, 28, 34), 2e-3, stretch_x=1.05), ref.NonuniformGrid.from_stretch((30, 28, 34), 2e-3, stretch_x=1.05))]
+    for ours, theirs in zip(build(C), build(ref)):
+        assert np.array_equal(ours.sdf(pts), theirs.sdf(pts)), type(theirs).__name__
+        assert np.array_equal(ours.contains(pts), theirs.contains(pts))
+        for g_ours, g_theirs in grids:
+            v = theirs.voxelize(g_theirs)
+            assert v.any() and np.array_equal(ours.voxelize(g_ours), v), type(theirs).__name__
+        if hasattr(ours, "bounding_box"):
+            assert all(np.array_equal(x, y) for x, y in zip(ours.bounding_box, theirs.bounding_box))
+    with pytest.raises(ValueError, match="Box size must be positive"):
+        C.Box(center=(0, 0, 0), size=(1, 0, 1))
+    with pytest.raises(ValueError, match="Must provide either"):
+        C.Box(center=(0, 0, 0))
+
+
+@pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
 def test_shim_registers_backend_with_reference():
     ref = R.load_reference_package()
     sb.install_into_reference(ref)
@@ -221,7 +251,7 @@ def test_result_writer_schema_without_device(tmp_path):
 def test_strata_fdtd_alias_resolves_names():
     import subprocess, sys
     code = ("from strata_fdtd_b200.compat import install_as_strata_fdtd; install_as_strata_fdtd(force_alias=True); "
-            "from strata_fdtd import FDTDSolver, PML, GaussianPulse, NonuniformGrid; "
+            "from strata_fdtd import FDTDSolver, PML, GaussianPulse, NonuniformGrid, Box, Difference, Sphere; "
             "from strata_fdtd.materials import Pole, PoleType, SimpleMaterial; "
             "from strata_fdtd.boundaries import RadiationImpedance; "
             "s = FDTDSolver(shape=(6,6,6), resolution=1e-3); print(s.backend, s.using_native)")

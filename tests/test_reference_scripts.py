@@ -1,11 +1,15 @@
 """The reference's own example scripts and CLI on backend="b200" (BASELINE north_star: "example scripts and fdtd-compute
 work unchanged"), and the HDF5 result schema.
 
-* GPU: /root/reference/examples/basic_pulse.py and material_sphere.py, byte-identical copies of which travel in
+* GPU: /root/reference/examples/{basic_pulse, material_sphere, multiple_probes, waveguide, organ_pipes, pzt_transducer,
+  frequency_sweep}.py (ADE sphere, rigid geometry, a 16-element phased array, a user-defined chirp source class, 3127
+  steps for the pipes), byte-identical copies of which travel in
   oracle/_ref/examples/ (put there by __graft_entry__.build(); never committed), run through
   ``python -m strata_fdtd_b200 <script>``; their probe traces and final fields must equal, bit for bit, what the
   UNMODIFIED reference produced with its native backend in the build container (tests/golden/script_*.npz, written
-  by oracle/make_golden_scripts.py) -- metre-valued positions, ``duration=`` and all.
+  by oracle/make_golden_scripts.py) -- metre-valued positions, ``duration=`` and all.  examples/nonuniform_grid.py
+  fails upstream (a probe position outside the grid); it must fail the same way here.  sealed_subwoofer.py needs the
+  reference's enclosure builder (geometry toolkit, out of scope) and is not run.
 * CPU: our ResultWriter, given an h5py (tests/fake_h5py.py -- the real one is installed nowhere here), produces the
   tree the reference's HDF5ResultWriter produced for the same script, and the reference's HDF5ResultReader
   (io/hdf5.py:236-375) reads it back; ``fdtd-compute --dry-run`` gets past print_simulation_info.
@@ -26,7 +30,7 @@ from util import sha
 ROOT = Path(__file__).resolve().parents[1]
 GOLDEN = ROOT / "tests" / "golden"
 REF_EXAMPLES = ROOT / "oracle" / "_ref" / "examples"
-SCRIPTS = ["basic_pulse", "material_sphere"]
+SCRIPTS = ["basic_pulse", "material_sphere", "multiple_probes", "waveguide", "organ_pipes", "pzt_transducer", "frequency_sweep"]
 
 
 def _tree(node, prefix=""):
@@ -72,6 +76,22 @@ def test_reference_script_verbatim_through_the_module_runner(name, tmp_path):
             pname = key[6:]
             assert np.array_equal(z["probes/" + pname], g[key]), f"{name}: probe {pname} differs from the reference"
             assert attrs[f"probes/{pname}@position"] == [int(q) for q in g["probe_pos_" + pname]]
+
+
+@pytest.mark.gpu
+def test_reference_script_that_fails_upstream_fails_the_same_way(tmp_path):
+    """examples/nonuniform_grid.py: the reference raises ValueError from add_probe (core/solver.py:1863-1884 converts
+    metres with the minimum spacing); same exception, same message, before any step."""
+    want = json.loads((GOLDEN / "script_failures.json").read_text())["nonuniform_grid"]
+    path = REF_EXAMPLES / "nonuniform_grid.py"
+    if not path.exists():
+        pytest.skip(f"{path} not present")
+    assert hashlib.sha256(path.read_bytes()).hexdigest() == want["script_sha"]
+    env = dict(os.environ, PYTHONPATH=str(ROOT) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    res = subprocess.run([sys.executable, "-m", "strata_fdtd_b200", str(path)], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode != 0
+    assert res.stderr.strip().splitlines()[-1] == f"{want['type']}: {want['message']}", res.stderr[-2000:]
 
 
 @pytest.mark.gpu
