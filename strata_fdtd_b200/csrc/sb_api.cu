@@ -1504,12 +1504,26 @@ static const char *pipeline_why_not(const sb_solver *h)
     const sb_grid_desc &d = h->d;
     if (d.has_lower || d.has_upper || h->have_peers) return "decomposed slab";
     if (h->have_ade) return "ADE materials";
-    if (!h->plane_ops.empty()) return "Mur / radiation planes";
+    if ((int)h->plane_ops.size() > K6_MAX_OPS) return "more than 8 Mur / radiation planes";
     if (h->n_mics) return "microphones";
     if (h->n_src_cells && !h->inline_ok) return "more than 8 source cells or velocity sources";
     if (h->n_sm <= 0) return "device attributes unavailable";
     if (!h->coop_ok) return "cooperative launch unavailable on this device / in this process";
     return nullptr;
+}
+
+// A Mur / radiation plane is updated inside the tile that owns its cells (sb_pipeline.cuh): the face cell and its
+// interior neighbour must fall into the same tile.  On the low side that takes a tile two cells thick, on the high side
+// an extent n with (n - 1) % thickness != 0.
+static bool pipe_tile_holds_planes(const sb_solver *h, int chunk, int rows_tile, int cols_tile)
+{
+    const int n[3] = {h->d.nx, h->d.ny, h->d.nz}, thick[3] = {chunk, rows_tile, cols_tile};
+    for (auto *po : h->plane_ops) {
+        const int a = po->op.axis, t = std::min(thick[a], n[a]);
+        if (n[a] < 2 || t < 2) return false;
+        if (po->op.side == 1 && (n[a] - 1) % t == 0) return false;
+    }
+    return true;
 }
 
 template <int RJ, bool GEOM, bool UNI, bool FLAT>
@@ -1547,7 +1561,29 @@ static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, flo
     const int save[4] = {h->opt_rj, h->opt_wj, h->opt_wk, h->opt_chunk_i};
     if (h->opt_rj == 0) { h->opt_rj = 1; h->opt_wj = 4; h->opt_wk = 1; if (!h->opt_chunk_i) h->opt_chunk_i = std::max(8, std::min(32, d.nx / 16)); }
     int rj, wj, wk, chunk, gx, gy; bool w;
-    const int shape_rc = march_shape(h, true, rj, wj, wk, chunk, gx, gy, w);
+    const bool ops = !h->plane_ops.empty();                 // plane updates live in strip-mode tiles
+    int shape_rc = march_shape(h, !ops, rj, wj, wk, chunk, gx, gy, w);
+    if (!shape_rc && ops && !pipe_tile_holds_planes(h, chunk, rj * wj, 128 * wk)) {
+        // another tile shape that keeps every (face, neighbour) pair together -- only where the caller left the shape open
+        bool found = false;
+        if (save[0] == 0) {
+            static const int shapes[][2] = {{4, 1}, {3, 1}, {5, 1}, {2, 1}, {4, 2}, {3, 2}, {2, 2}, {2, 3}, {1, 3}};
+            for (auto &sh : shapes) {
+                for (int c = h->opt_chunk_i; c <= std::min(d.nx, h->opt_chunk_i + 3) && !found; c++)
+                    if (pipe_tile_holds_planes(h, c, sh[0], 128 * sh[1])) {
+                        h->opt_wj = sh[0]; h->opt_wk = sh[1]; h->opt_chunk_i = c;
+                        found = true;
+                    }
+                if (found) break;
+            }
+        }
+        if (found) shape_rc = march_shape(h, false, rj, wj, wk, chunk, gx, gy, w);
+        else {
+            h->opt_rj = save[0]; h->opt_wj = save[1]; h->opt_wk = save[2]; h->opt_chunk_i = save[3];
+            if (h->opt_kernel == SB_KERNEL_AUTO) return 3;
+            return fail("pipelined kernel not applicable: no tile shape keeps every Mur / radiation face next to its interior neighbour");
+        }
+    }
     h->opt_rj = save[0]; h->opt_wj = save[1]; h->opt_wk = save[2]; h->opt_chunk_i = save[3];
     if (shape_rc) return 1;
     PipeParams Q{};
@@ -1564,12 +1600,17 @@ static int launch_pipeline(sb_solver *h, int n_steps, const double *src_dev, flo
     // Left to itself (AUTO) the pipeline is only used where it was measured to pay: a step must offer at least as many
     // tiles as the GPU holds CTAs and at least four chunks of planes (long thin grids have neither: their few chunks
     // serialise on each other); 3 = "not worthwhile here", the caller goes on to the step-by-step path.
-    if (h->opt_kernel == SB_KERNEL_AUTO && ((long long)gx * gy * Q.nchunks < (long long)h->n_sm * 8 || Q.nchunks < 4)) return 3;
+    // With Mur / radiation planes the alternative is one more launch per plane and step, and the pipeline wins from the
+    // smallest grids on (us/step with six planes, step-by-step vs pipelined: 64^3 35.1 / 21.7, 100^3 33.0 / 24.2,
+    // 160^3 48.8 / 39.7, 200^3 74.9 / 56.1, 256^3 119.3 / 95.4, 300^3 192.4 / 174.7; tools/plane_ops_timing.py).
+    if (h->opt_kernel == SB_KERNEL_AUTO && (((long long)gx * gy * Q.nchunks < (long long)h->n_sm * 8 && !ops) || Q.nchunks < 4)) return 3;
     if (h->d_pipe_ctr.alloc((size_t)Q.nchunks + 1)) return 1;
     CU(cudaMemsetAsync(h->d_pipe_ctr.p, 0, ((size_t)Q.nchunks + 1) * sizeof(int), h->stream));
     Q.ticket = h->d_pipe_ctr.p; Q.done = h->d_pipe_ctr.p + 1; Q.err_flag = h->d_err.p;
     Q.src_vals = src_dev; Q.n_sources = h->n_sources;
     Q.rec = rec_dev; Q.n_rec = h->n_probes; Q.n_probes = h->n_probes; Q.probe_ijk = h->d_probe_ijk.p;
+    Q.n_ops = (int)h->plane_ops.size();
+    for (int o = 0; o < Q.n_ops; o++) Q.ops[o] = h->plane_ops[o]->op;
     const dim3 blk(32 * wk, wj);
     const bool geom = Q.S.mask != nullptr, uni = Q.S.icx == nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1613,7 +1654,7 @@ extern "C" int sb_step_n_async(sb_solver *h, int n_steps, const double *src_dev,
     }
     if (n_steps > 0 && (h->opt_kernel == SB_KERNEL_PIPELINE ||
                         (h->opt_kernel == SB_KERNEL_AUTO && n_steps >= h->opt_res_min_steps &&
-                         (long long)h->d.nx * h->d.ny * h->d.nz >= h->opt_pipe_min_cells &&
+                         ((long long)h->d.nx * h->d.ny * h->d.nz >= h->opt_pipe_min_cells || !h->plane_ops.empty()) &&
                          (long long)h->d.nx * h->d.ny * h->d.nz <= h->opt_pipe_max_cells))) {
         const char *why_not = pipeline_why_not(h);
         if (!why_not) {

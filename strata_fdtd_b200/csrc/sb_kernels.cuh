@@ -553,6 +553,16 @@ struct PlaneOp {
     float *prev;                 // previous interior-neighbour plane, n_a * n_b floats
 };
 
+// the new face value from the previous interior neighbour, the face cell `pb` and its interior neighbour `pi` after the
+// pressure update (boundaries/_boundaries.py:476-513 Mur, :700-760 radiation impedance; float64 intermediates)
+__device__ __forceinline__ float plane_op_value(const PlaneOp &op, float prev, float pb, float pi)
+{
+    const double abc = __dadd_rn((double)prev, __dmul_rn(op.mur, (double)(pi - pb)));
+    if (op.kind == 0) return (float)abc;
+    const double rigid = op.weak_r ? (double)(op.r32 * pi) : __dmul_rn(op.R, (double)pi);
+    return (float)__dadd_rn(rigid, __dmul_rn(op.one_minus_R, abc));
+}
+
 __global__ void k4_plane_op(PlaneOp op, float *p, int nx, int ny, int nz, int pitch, long long plane, PeerLink L)
 {
     const int n[3] = {nx, ny, nz};
@@ -567,14 +577,7 @@ __global__ void k4_plane_op(PlaneOp op, float *p, int nx, int ny, int nz, int pi
     const long long ii = (long long)c[0] * plane + (long long)c[1] * pitch + c[2];
     const long long t = (long long)a * n[b_ax] + b;
     const float pb = p[ib], pi = p[ii];
-    const double abc = __dadd_rn((double)op.prev[t], __dmul_rn(op.mur, (double)(pi - pb)));
-    float out;
-    if (op.kind == 0) {
-        out = (float)abc;
-    } else {
-        const double rigid = op.weak_r ? (double)(op.r32 * pi) : __dmul_rn(op.R, (double)pi);
-        out = (float)__dadd_rn(rigid, __dmul_rn(op.one_minus_R, abc));
-    }
+    const float out = plane_op_value(op, op.prev[t], pb, pi);
     p[ib] = out;
     mirror_injection(L, 0, ib, out);          // a y / z face cell on a cut plane: keep the neighbour's ghost current
     op.prev[t] = pi;

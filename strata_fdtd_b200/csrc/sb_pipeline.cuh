@@ -12,14 +12,20 @@
 //   * tickets are handed out in increasing order and a tile only ever waits for smaller tickets, which are
 //     held by co-resident CTAs (cooperative launch): no deadlock, no grid-wide barrier, and the tail of step t
 //     overlaps the head of step t+1;
-//   * point sources and probes are served by the tile that owns their cell, right after its stores (the values
-//     are final there: sponge applied, solver.py:2386-2439 order), so no separate kernel runs per step.
+//   * Mur / radiation planes, point sources and probes are served by the tile that owns their cells, right after its
+//     stores (the values are final there: sponge applied, solver.py:2386-2439 order), so no separate kernel runs per
+//     step.  A plane update reads and writes a face cell, its interior neighbour and one `prev` entry: the host only
+//     picks tile shapes that keep each such pair inside one tile, so running the list of planes in order inside every
+//     tile (a block barrier between two planes: they meet on the edges of the grid) is the sequential order of
+//     boundaries/_boundaries.py.
 //
 // Results are bit-identical to the step-by-step path: same tile code, same operations per cell.
 #pragma once
 #include "sb_kernels.cuh"
 
 namespace sb {
+
+constexpr int K6_MAX_OPS = 8;
 
 struct PipeParams {
     StepParams S;                          // tables, extents, tile shape (chunk_i); S.*_in = set holding the state on entry
@@ -33,6 +39,8 @@ struct PipeParams {
     float *rec;                            // [n_steps][n_rec]
     int n_rec, n_probes;
     const int *probe_ijk;                  // 3 ints per probe
+    int n_ops;                             // Mur / radiation planes, list order (strip mapping only)
+    PlaneOp ops[K6_MAX_OPS];
 };
 
 __device__ __forceinline__ int ld_acquire_gpu_s32(const int *p)
@@ -40,6 +48,33 @@ __device__ __forceinline__ int ld_acquire_gpu_s32(const int *p)
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// the plane updates of the cells a strip-mode tile owns: i0 <= i < i1, j0 <= j < j1, k0 <= k < k1 (already clipped)
+__device__ __noinline__ void k6_plane_ops(const PipeParams &Q, float *p, int i0, int i1, int j0, int j1, int k0, int k1)
+{
+    const StepParams &P = Q.S;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    const int n[3] = {P.nx, P.ny, P.nz}, lo[3] = {i0, j0, k0}, hi[3] = {i1, j1, k1};
+    for (int o = 0; o < Q.n_ops; o++) {
+        const PlaneOp &op = Q.ops[o];
+        const int ax = op.axis, a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
+        const int face = op.side ? n[ax] - 1 : 0, inner = op.side ? n[ax] - 2 : 1;
+        if (face >= lo[ax] && face < hi[ax]) {                                   // (uniform over the block)
+            const int eb = hi[b_ax] - lo[b_ax], cells = (hi[a_ax] - lo[a_ax]) * eb;
+            const long long stride[3] = {P.plane, (long long)P.pitch, 1};
+            for (int idx = tid; idx < cells; idx += nt) {
+                const int a = lo[a_ax] + idx / eb, b = lo[b_ax] + idx % eb;
+                const long long base = (long long)a * stride[a_ax] + (long long)b * stride[b_ax];
+                const long long ib = base + face * stride[ax], ii = base + inner * stride[ax];
+                float *prev = op.prev + (long long)a * n[b_ax] + b;
+                const float pi = __ldcg(p + ii);
+                __stcg(p + ib, plane_op_value(op, __ldcg(prev), __ldcg(p + ib), pi));
+                __stcg(prev, pi);
+            }
+            __syncthreads();                                                     // the next plane may meet this one on an edge
+        }
+    }
 }
 
 template <int RJ, bool GEOM, bool UNI, bool FLAT>
@@ -81,6 +116,10 @@ __global__ void __launch_bounds__(256, (RJ == 1 && UNI) ? 4 : 2) k6_pipeline(con
         else       F = FieldSet{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
         k1_tile<RJ, GEOM, UNI, false, false, FLAT>(P, F, bx, by, c);
         __syncthreads();                                                         // the tile's stores are visible to the block
+        if (!FLAT && Q.n_ops) {
+            const int i0 = c * P.chunk_i, j0 = by * rows_tile, k0 = bx * cols_tile;
+            k6_plane_ops(Q, F.p_out, i0, min(i0 + P.chunk_i, P.nx), j0, min(j0 + rows_tile, P.ny), k0, min(k0 + cols_tile, P.nz));
+        }
         if (threadIdx.y == 0 && threadIdx.x < 32) {                              // sources, then probes, of the cells this tile owns
             const int i0 = c * P.chunk_i, i1 = min(i0 + P.chunk_i, P.nx);
             const int j0 = by * rows_tile, j1 = j0 + rows_tile, k0 = bx * cols_tile, k1 = k0 + cols_tile;

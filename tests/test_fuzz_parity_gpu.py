@@ -87,6 +87,20 @@ def _random_case(seed: int) -> tuple[dict, dict, int]:
         opts[_lib.OPT_WARPS_J] = int(rng.choice([1, 2, 4, 8]))
         opts[_lib.OPT_USE_GRAPH] = int(rng.integers(-1, 2))
     chunk = int(rng.choice([7, 16, 64]))
+    # Mur / radiation planes (a stream of their own, so that the configurations above stay what they were): any subset of
+    # faces in any order after the sponges -- edges and corners depend on that order; K5 does not take them
+    rng2 = np.random.default_rng(7000 + seed)
+    if rng2.random() < 0.4 and min(shape) >= 3 and opts[_lib.OPT_KERNEL] != _lib.KERNEL_RESIDENT:
+        bcs = []
+        for _ in range(int(rng2.integers(1, 4))):
+            if rng2.random() < 0.5:
+                axes = tuple(a for a in "xyz" if rng2.random() < 0.6) or ("y",)
+                bcs.append(dict(kind="mur", axes=axes))
+            else:
+                bcs.append(dict(kind="radiation", axis="xyz"[int(rng2.integers(0, 3))], side=("low", "high")[int(rng2.integers(0, 2))],
+                                **(dict(reflection_coeff=float(rng2.uniform(0.1, 0.9))) if rng2.random() < 0.5
+                                   else dict(pipe_radius=float(rng2.uniform(0.004, 0.02))))))
+        case["plane_bcs"] = bcs
     return case, opts, chunk
 
 
@@ -110,7 +124,7 @@ def test_random_configuration_matches_oracle(seed):
     o.run_steps(steps)
     what = f"seed {seed}: shape {s.shape}, opts {opts}, chunk {chunk}, " \
            f"{'nonuniform ' if 'nonuniform' in case else ''}{'geometry ' if 'geometry' in case else ''}" \
-           f"{len(case['pml'])} sponge(s), {len(case.get('materials', []))} material(s)"
+           f"{len(case['pml'])} sponge(s), {len(case.get('materials', []))} material(s), planes {case.get('plane_bcs', [])}"
     assert_same_as_oracle(s, o, what)
     s.close()
 

@@ -364,6 +364,64 @@ def test_pipelined_kernel_matches_oracle(name, shape_opts):
     s.close()
 
 
+@pytest.mark.parametrize("shape_opts", [{}, {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_CHUNK_I: 4, _lib.OPT_WARPS_J: 2},
+                                        {_lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 5, _lib.OPT_WARPS_J: 3, _lib.OPT_PLANE_MAP: 2}])
+@pytest.mark.parametrize("name", ["mur_all", "pml_radiation_mur"])
+def test_pipelined_kernel_applies_mur_and_radiation_planes(name, shape_opts):
+    """Mur / radiation planes inside K6: every tile updates the face cells it owns, plane by plane in list order (edges and
+    corners depend on it), before its sources and probes -- one launch per chunk of steps, no K4 launches."""
+    case = CASES[name]
+    s = _with_options(build_b200_solver(case, chunk_steps=37), {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE, **shape_opts})
+    o = O.OracleSolver(case)
+    s.run(steps=case["steps"]); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"pipeline-planes/{name}")
+    st = s.device_stats()
+    assert st["kernel_variant"] == _lib.KERNEL_PIPELINE
+    assert st["kernels_launched"] <= -(-case["steps"] // 37) + 2, "one launch per chunk"
+    s.close()
+
+
+@pytest.mark.parametrize("shape", [(25, 21, 129), (17, 9, 129), (9, 5, 30), (33, 13, 3)])
+def test_pipelined_kernel_picks_tiles_that_keep_plane_pairs_together(shape):
+    """Extents where the default tiles would separate a high face from its interior neighbour ((n - 1) % tile == 0 along
+    i, j or k): the launcher picks another tile shape; results equal the step-by-step path (K1 + K4)."""
+    nx, ny, nz = shape
+    case = dict(shape=shape, resolution=1e-3, steps=80, pml=[],
+                plane_bcs=[dict(kind="mur", axes=("z", "x")), dict(kind="radiation", axis="y", side="high", reflection_coeff=0.4),
+                           dict(kind="mur", axes=("y",))],
+                sources=[dict(kind="point", position=(nx // 2, ny // 2, nz // 2), frequency=30e3),
+                         dict(kind="point", position=(nx - 1, ny - 1, nz - 1), frequency=14e3, amplitude=0.4)],
+                probes=[("corner", (nx - 1, ny - 1, nz - 1)), ("origin", (0, 0, 0)), ("edge", (nx - 1, 0, nz - 2)), ("mid", (nx // 2, ny // 2, nz // 3))])
+    a = _with_options(build_b200_solver(case, chunk_steps=40), {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE})
+    b = _with_options(build_b200_solver(case, chunk_steps=40), {_lib.OPT_KERNEL: _lib.KERNEL_MARCH})
+    o = O.OracleSolver(case)
+    a.run(steps=80); b.run(steps=80); o.run_steps(80)
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_PIPELINE
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(a.get_field(f), b.get_field(f)), f
+    assert_same_as_oracle(a, o, f"pipeline-planes/{shape}")
+    a.close(); b.close()
+
+
+def test_pipelined_kernel_refuses_a_fixed_tile_shape_that_separates_a_plane_pair():
+    case = dict(shape=(25, 21, 20), resolution=1e-3, steps=8, pml=[], plane_bcs=[dict(kind="mur", axes=("x",))],
+                sources=[dict(kind="point", position=(12, 10, 10), frequency=30e3)], probes=[("a", (0, 0, 0))])
+    s = _with_options(build_b200_solver(case), {_lib.OPT_KERNEL: _lib.KERNEL_PIPELINE, _lib.OPT_ROWS_PER_THREAD: 1, _lib.OPT_CHUNK_I: 8})
+    with pytest.raises(_lib.B200BackendError, match="no tile shape keeps every Mur / radiation face"):
+        s.run(steps=8)
+    s.close()
+    # ... and where no shape at all does (9 rows and 257 columns: 8 % rows and 256 % columns are 0 for every shape of at
+    # most 8 warps), the automatic choice quietly stays with the step-by-step path
+    case = dict(case, shape=(17, 9, 257), plane_bcs=[dict(kind="mur", axes=("x", "y", "z"))],
+                sources=[dict(kind="point", position=(8, 4, 128), frequency=30e3)], steps=24)
+    a = build_b200_solver(case)
+    o = O.OracleSolver(case)
+    a.run(steps=24); o.run_steps(24)
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_MARCH
+    assert_same_as_oracle(a, o, "planes/no-pipeline-shape")
+    a.close()
+
+
 def test_pipelined_kernel_is_the_automatic_choice_for_config_2_and_equals_the_oracle():
     """BASELINE config 2 (200^3 + PML, here with the solid block): too large for shared memory, AUTO pipelines the steps."""
     case = c2_case(200, steps=120, with_geometry=True)
