@@ -74,7 +74,7 @@ struct sb_solver {
     DBuf<long long> src_off; DBuf<int> src_start, src_id, src_field; DBuf<double> src_weight;
     // host copy of small source tables: enables the single-kernel step (injection inside K1)
     int n_src_entries = 0; bool inline_ok = false;
-    int inl_i[8], inl_j[8], inl_k[8], inl_src[8]; double inl_weight[8];
+    int inl_i[SB_MAX_INLINE], inl_j[SB_MAX_INLINE], inl_k[SB_MAX_INLINE], inl_src[SB_MAX_INLINE]; double inl_weight[SB_MAX_INLINE];
     int opt_fuse_k3 = 1;
     int tuned[4] = {1, 0, 1, 0}, tuned_key = -1; float tuned_ms = 0.f;
     int n_probes = 0, n_mics = 0;
@@ -543,7 +543,7 @@ extern "C" int sb_set_sources(sb_solver *h, int n_sources, int n_cells, const in
     for (int e = 0; e < n_ent; e++)
         if (src_id[e] < 0 || src_id[e] >= n_sources || field[e] < 0 || field[e] > 3) return fail("bad source entry %d", e);
     h->n_src_entries = n_ent;
-    h->inline_ok = n_ent <= 8;
+    h->inline_ok = n_ent <= SB_MAX_INLINE;
     for (int u = 0; u < n_cells && h->inline_ok; u++)
         for (int e = start[u]; e < start[u + 1]; e++) {
             if (field[e] != 0 || cell_idx[u] < 0) { h->inline_ok = false; break; }
@@ -1318,7 +1318,7 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not, int f
     else if (h->have_ade) *why_not = "ADE materials";
     else if (!h->plane_ops.empty()) *why_not = "Mur / radiation planes";
     else if (h->n_mics) *why_not = "microphones";
-    else if (h->n_src_cells && !h->inline_ok) *why_not = "more than 8 source cells or velocity sources";
+    else if (h->n_src_cells && !h->inline_ok) *why_not = "more than 32 source cells or velocity sources";
     else if (h->n_probes > K5_MAX_PROBES) *why_not = "too many probes";
     else if (h->n_sm <= 0 || h->smem_optin <= 0) *why_not = "device attributes unavailable";
     else if (!h->coop_ok) *why_not = "cooperative launch unavailable on this device / in this process";
@@ -1506,7 +1506,7 @@ static const char *pipeline_why_not(const sb_solver *h)
     if (h->have_ade) return "ADE materials";
     if ((int)h->plane_ops.size() > K6_MAX_OPS) return "more than 8 Mur / radiation planes";
     if (h->n_mics) return "microphones";
-    if (h->n_src_cells && !h->inline_ok) return "more than 8 source cells or velocity sources";
+    if (h->n_src_cells && !h->inline_ok) return "more than 32 source cells or velocity sources";
     if (h->n_sm <= 0) return "device attributes unavailable";
     if (!h->coop_ok) return "cooperative launch unavailable on this device / in this process";
     return nullptr;

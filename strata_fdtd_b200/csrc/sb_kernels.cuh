@@ -25,6 +25,10 @@ constexpr uint8_t M_AIR = 1, M_XOPEN = 2, M_YOPEN = 4, M_ZOPEN = 8;
 // upper nibble (fused ADE path): the cell carries a material with poles; its +x / +y / +z neighbour carries the SAME one
 constexpr uint8_t M_XSAME = 0x10, M_YSAME = 0x20, M_ZSAME = 0x40, M_ADE = 0x80;
 
+// point-source entries (cell, source, weight) a step / chunk kernel applies itself instead of leaving them to K3: a
+// phased array of a few dozen elements still fits (one bit each in a thread's 32-bit ownership mask)
+constexpr int SB_MAX_INLINE = 32;
+
 struct StepParams {
     const float *p_in, *vx_in, *vy_in, *vz_in;
     float *p_out, *vx_out, *vy_out, *vz_out;
@@ -50,8 +54,8 @@ struct StepParams {
     // right before it stores p, and the probes / microphones of the PREVIOUS step are recorded from the input set
     // by the first warp of block 0 (they are final there); a tail launch records the last step of a chunk.
     int n_inline;                        // 0 = off
-    int inl_i[8], inl_j[8], inl_k[8], inl_src[8];
-    double inl_weight[8];
+    int inl_i[SB_MAX_INLINE], inl_j[SB_MAX_INLINE], inl_k[SB_MAX_INLINE], inl_src[SB_MAX_INLINE];
+    double inl_weight[SB_MAX_INLINE];
     const double *src_row;               // this step's waveform samples [n_sources]
     int rec_prev;                        // 1 = record the previous step's slots in this launch
     int n_probes, n_mics;
@@ -203,6 +207,16 @@ struct FieldSet { const float *p_in, *vx_in, *vy_in, *vz_in; float *p_out, *vx_o
 // of one row group and the start of the next; the only idle lanes are the row padding.  A lane's k-neighbours are
 // still its neighbouring lanes wherever a neighbour exists (nothing crosses a row end), so the shuffles stay valid.
 // Strip mode keeps whole blocks adjacent in j (halo rows hit in L1) and is used for rows that fill their strips.
+// One more such steering (see k1_min_blocks below): the variant with solids AND spacing tables, one row per thread --
+// config 4 -- keeps the run-time form of the box test, which is never true there (box_mode is 0 whenever BOXM is 0).  With
+// it ptxas emits the schedule that runs at 199.1 Gcell-updates/s instead of 187.9 (tools/k1_ab.cu, variant 4).
+#if defined(SB_K1_RTBOX_ALL)
+#define SB_K1_RTBOX(RJ, GEOM, UNI) true
+#elif defined(SB_K1_RTBOX_NONE)
+#define SB_K1_RTBOX(RJ, GEOM, UNI) false
+#else
+#define SB_K1_RTBOX(RJ, GEOM, UNI) ((RJ) == 1 && (GEOM) && !(UNI))
+#endif
 template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false, int BOXM = 0>
 __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, int bx, int by, int bz)
 {
@@ -249,7 +263,8 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     const int nz = P.nz, ny = P.ny;
     // cells another launch of this step owns (box_mode 1): computed here as far as the neighbours need them, never stored
     unsigned skip_rows = 0;
-    if (BOXM == 1 && ib >= P.bi0 && ib < P.bi1) {                // the box is aligned to this launch's chunks of planes
+    constexpr bool RTBOX = BOXM == 0 && !PEER && !FUSE && !FLAT && SB_K1_RTBOX(RJ, GEOM, UNI);
+    if ((BOXM == 1 || (RTBOX && P.box_mode == 1)) && ib >= P.bi0 && ib < P.bi1) {   // the box is aligned to this launch's chunks of planes
         bool nothing_left = true;
 #pragma unroll
         for (int r = 0; r < RJ; r++) {
@@ -433,7 +448,7 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
                     pnew = mul4(mul4s(mul4s(pnew, dxs), dys), dzs);
                 }
             }
-            if (row_ok[r + 1] && lane_ok && !(BOXM == 1 && ((skip_rows >> r) & 1u))) {
+            if (row_ok[r + 1] && lane_ok && !((BOXM == 1 || RTBOX) && ((skip_rows >> r) & 1u))) {
                 const long long c = base + (long long)r * P.pitch;
                 float4 pst = sel4(e0, e1, e2, e3, pnew, z4);
                 if (FUSE && inl_mask) {                          // float64 add, fp32 store (solver.py:2421), list order
@@ -480,8 +495,29 @@ __device__ __forceinline__ void k1_tile(const StepParams &P, const FieldSet &F, 
     }
 }
 
+// Register target per variant.  The kernel is bound by memory latency x bytes in flight, and how ptxas orders the ~20 loads
+// of a plane changes with the register budget it aims at -- by up to 6 % either way, differently for every variant, with
+// identical instruction counts.  The table below is measured, variant by variant, with tools/k1_ab.cu on B200 (CUDA 12.9;
+// 1024x512x512 and 256x2048x2048, Gcell-updates/s, unspecified / 2 / 3 blocks per SM):
+//   plain uniform              203.0 / 205.9 / 202.3      uniform + solids          188.6 / 198.4 / 164.3
+//   spacing tables             200.9 / 194.2 / 205.1      tables + solids (config 4) 187.9 / 166.8 / 187.9  (199.1 with RTBOX)
+//   uniform + peer stores      199.3 / 206.2 / 203.9      2 rows, peer stores        186.9 / 200.6 / 182.3
+// 0 = leave it to the compiler (every variant not listed, among them the box modes with solids: 188.9 / 152.8 / 161.1).
+template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT, int BOXM>
+constexpr int k1_min_blocks()
+{
+#ifdef SB_K1_MINB
+    return SB_K1_MINB;                                           // experiments (tools/k1_ab.cu)
+#else
+    if (BOXM == 3 && RJ == 1 && !GEOM && UNI && !PEER && !FUSE && !FLAT) return 2;   // config 3's sphere: 202.4 / 204.7 / 202.6
+    if (FLAT || BOXM != 0 || FUSE) return 0;
+    if (RJ == 1) return (GEOM && !UNI) ? 0 : (!GEOM && !UNI) ? (PEER ? 0 : 3) : ((GEOM && PEER) ? 0 : 2);
+    return (PEER && UNI && !GEOM) ? 2 : 0;
+#endif
+}
+
 template <int RJ, bool GEOM, bool UNI, bool PEER, bool FUSE, bool FLAT = false, int BOXM = 0>
-__global__ void __launch_bounds__(256) k1_step_march(StepParams P)
+__global__ void __launch_bounds__(256, k1_min_blocks<RJ, GEOM, UNI, PEER, FUSE, FLAT, BOXM>()) k1_step_march(StepParams P)
 {
     const FieldSet F{P.p_in, P.vx_in, P.vy_in, P.vz_in, P.p_out, P.vx_out, P.vy_out, P.vz_out};
     k1_tile<RJ, GEOM, UNI, PEER, FUSE, FLAT, BOXM>(P, F, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);

@@ -65,8 +65,8 @@ struct ResParams {
     long long plane;
     int nbi, nbj, LI, LJ, kp;              // box grid, largest box extents, shared-memory row pitch (floats, multiple of 4)
     int n_inline;                          // point sources (p field), list order
-    int inl_i[8], inl_j[8], inl_k[8], inl_src[8];
-    double inl_weight[8];
+    int inl_i[SB_MAX_INLINE], inl_j[SB_MAX_INLINE], inl_k[SB_MAX_INLINE], inl_src[SB_MAX_INLINE];
+    double inl_weight[SB_MAX_INLINE];
     const double *src_vals;                // [n_steps][n_sources]
     int n_sources;
     int n_probes, n_rec;

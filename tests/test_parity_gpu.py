@@ -346,6 +346,51 @@ def test_resident_refuses_what_it_cannot_do_and_auto_falls_back_to_k1():
     a.close()
 
 
+def _array_case(n_src):
+    """A line array of point sources (pzt_transducer.py has 16), two of them in the same cell, several in one float4."""
+    shape = (30, 26, 44)
+    src = [dict(kind="point", position=(4 + (q % 3), 3 + (q * 5) % 20, 6 + (2 * q) % 34), frequency=20e3 + 900.0 * q,
+                amplitude=0.5 + 0.05 * q) for q in range(n_src)]
+    src[1]["position"] = src[0]["position"]
+    src[2]["position"] = (src[0]["position"][0], src[0]["position"][1], src[0]["position"][2] + 1)
+    return dict(shape=shape, resolution=1e-3, steps=96, pml=[dict(depth=3)], geometry=_np_block(shape), sources=src,
+                probes=[("a", (20, 13, 22)), ("at_src", src[0]["position"]), ("far", (29, 25, 43))])
+
+
+def _np_block(shape):
+    g = np.ones(shape, dtype=bool)
+    g[14:17, 8:20, 10:30] = False
+    return g
+
+
+@pytest.mark.parametrize("kernel", [_lib.KERNEL_RESIDENT, _lib.KERNEL_PIPELINE, _lib.KERNEL_MARCH])
+def test_chunk_kernels_take_a_phased_array_of_point_sources(kernel):
+    """Up to 32 point-source entries are applied by the step / chunk kernels themselves (K5, K6, K1 with K3 fused in)."""
+    case = _array_case(24)
+    s = _with_options(build_b200_solver(case, chunk_steps=32), {_lib.OPT_KERNEL: kernel})
+    o = O.OracleSolver(case)
+    s.run(steps=96); o.run_steps(96)
+    assert s.device_stats()["kernel_variant"] == kernel
+    assert_same_as_oracle(s, o, f"array/{kernel}")
+    if kernel != _lib.KERNEL_MARCH:
+        assert s.device_stats()["kernels_launched"] <= 5, "one launch per chunk"
+    s.close()
+
+
+def test_more_sources_than_the_chunk_kernels_hold_run_step_by_step():
+    case = _array_case(40)
+    s = _with_options(build_b200_solver(case, chunk_steps=32), {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT})
+    with pytest.raises(_lib.B200BackendError, match="more than 32 source cells"):
+        s.run(steps=8)
+    s.close()
+    a = build_b200_solver(case, chunk_steps=32)
+    o = O.OracleSolver(case)
+    a.run(steps=96); o.run_steps(96)
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_MARCH
+    assert_same_as_oracle(a, o, "array/40")
+    a.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # K6: the marching kernel pipelined across steps in one persistent launch (csrc/sb_pipeline.cuh)
 @pytest.mark.parametrize("shape_opts", [{}, {_lib.OPT_ROWS_PER_THREAD: 2, _lib.OPT_CHUNK_I: 3, _lib.OPT_WARPS_J: 2, _lib.OPT_PLANE_MAP: 2},

@@ -75,7 +75,7 @@ def run_emulated(emu, case, n_steps, chunk=37, nbi=0, nbj=0, n_sm=148, smem_limi
         mask = np.zeros((nx + 2, ny, pitch), dtype=np.uint8)
         mask[1:nx + 1, :, :nz] = _mask_bytes(s._geometry, s._rigid)
     cell_idx, start, sids, flds, wts = s._build_source_table()
-    assert len(sids) <= 8 and not np.any(flds), "emulated cases use point sources into p"
+    assert len(sids) <= 32 and not np.any(flds), "emulated cases use point sources into p"
     ijks, w = [], []
     for u, c in enumerate(cell_idx):
         for e in range(start[u], start[u + 1]):
