@@ -77,8 +77,13 @@ __device__ __noinline__ void k6_plane_ops(const PipeParams &Q, float *p, int i0,
     }
 }
 
+#ifdef SB_K6_MINB_FIXED                    // experiments
+#define SB_K6_MINB(RJ, UNI) SB_K6_MINB_FIXED
+#else
+#define SB_K6_MINB(RJ, UNI) (((RJ) == 1 && (UNI)) ? 4 : 2)
+#endif
 template <int RJ, bool GEOM, bool UNI, bool FLAT>
-__global__ void __launch_bounds__(256, (RJ == 1 && UNI) ? 4 : 2) k6_pipeline(const __grid_constant__ PipeParams Q)
+__global__ void __launch_bounds__(256, SB_K6_MINB(RJ, UNI)) k6_pipeline(const __grid_constant__ PipeParams Q)
 {
     __shared__ int s_ticket;
     const StepParams &P = Q.S;
