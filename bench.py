@@ -416,7 +416,9 @@ def run_b200_arm(a):
                            "launch_shape": ({"source": "chunk kernel: shape fixed by the library (DESIGN.md 4a / 4b)"}
                                             if st1["kernel_variant"] in (4, 5) else
                                             {"rows_per_thread": shape4[0], "warps_j": shape4[1], "warps_k": shape4[2],
-                                             "chunk_planes": shape4[3], "source": "library autotune" if a.rows is None else "flag"}),
+                                             "chunk_planes": shape4[3], "source": "library autotune"} if a.rows is None else
+                                            {"rows_per_thread": a.rows, "warps_j": a.warps_j, "warps_k": a.warps_k,
+                                             "chunk_planes": a.chunk_i, "source": "flag"}),
                            "parallelism": f"slab{world}" if world > 1 else "single",
                            "halo": (drv.halo if drv is not None else None)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -509,7 +509,8 @@ constexpr int k1_min_blocks()
 #ifdef SB_K1_MINB
     return SB_K1_MINB;                                           // experiments (tools/k1_ab.cu)
 #else
-    if (BOXM == 3 && RJ == 1 && !GEOM && UNI && !PEER && !FUSE && !FLAT) return 2;   // config 3's sphere: 202.4 / 204.7 / 202.6
+    if (BOXM != 0 && RJ == 1 && !GEOM && UNI && !PEER && !FUSE && !FLAT) return 2;   // config 3: beside the list kernels (BOXM 3)
+                                                                                       // 202.4 / 204.7 / 202.6, beside K1-ADE (BOXM 1) 197.9 / 205.2 / 204.1
     if (FLAT || BOXM != 0 || FUSE) return 0;
     if (RJ == 1) return (GEOM && !UNI) ? 0 : (!GEOM && !UNI) ? (PEER ? 0 : 3) : ((GEOM && PEER) ? 0 : 2);
     return (PEER && UNI && !GEOM) ? 2 : 0;

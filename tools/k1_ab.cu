@@ -11,7 +11,7 @@ int main(int argc, char **argv)
 {
     int nx = argc > 1 ? atoi(argv[1]) : 512, ny = argc > 2 ? atoi(argv[2]) : 512, nz = argc > 3 ? atoi(argv[3]) : 512;
     int steps = argc > 4 ? atoi(argv[4]) : 20, rj = argc > 5 ? atoi(argv[5]) : 2, chunk = argc > 6 ? atoi(argv[6]) : 64;
-    int var = argc > 7 ? atoi(argv[7]) : 0;      // KV>=4: 0 UNI lean, 1 tables (non-UNI), 2 UNI+PEER, 3 UNI+FUSE, 4 tables + solids (config 4), 5 UNI + solids, 6 / 7 = 5 with the ADE box left to the list kernels (BOXM 3) / skipped (BOXM 1), 8 = config 3's sphere: no solids, BOXM 3
+    int var = argc > 7 ? atoi(argv[7]) : 0;      // KV>=4: 0 UNI lean, 1 tables (non-UNI), 2 UNI+PEER, 3 UNI+FUSE, 4 tables + solids (config 4), 5 UNI + solids, 6 / 7 = 5 with the ADE box left to the list kernels (BOXM 3) / skipped (BOXM 1), 8 = config 3's sphere: no solids, BOXM 3, 9 = config 3's slab: no solids, BOXM 1 (the last quarter of the planes skipped)
     int wj = argc > 8 ? atoi(argv[8]) : 8, wk = argc > 9 ? atoi(argv[9]) : 1;
     int pitch = (nz + 7) / 8 * 8;
     long long plane = (long long)ny * pitch, elems = (long long)(nx + 2) * plane;
@@ -36,11 +36,12 @@ int main(int argc, char **argv)
         P.mask = d + plane;
     }
     if (var == 8) { uint8_t *d; CK(cudaMalloc(&d, elems)); CK(cudaMemset(d, 0x0F, elems)); P.ade_mask = d + plane; }
-    if (var >= 6 && var <= 8) {                  // config 3's sphere: the middle fifth of every axis
-        P.box_mode = var == 7 ? 1 : 3;
+    if (var >= 6 && var <= 9) {                  // config 3's sphere: the middle fifth of every axis
+        P.box_mode = (var == 7 || var == 9) ? 1 : 3;
         P.bi0 = (2 * nx / 5) / chunk * chunk; P.bi1 = (3 * nx / 5 / chunk + 1) * chunk; P.bj0 = 2 * ny / 5; P.bj1 = 3 * ny / 5;
         P.bk0 = (2 * nz / 5) / 4 * 4; P.bk1 = (3 * nz / 5) / 4 * 4;
-        if (var != 8) P.ade_mask = P.mask;
+        if (var < 8) P.ade_mask = P.mask;
+        if (var == 9) { P.bi0 = 3 * nx / 4 / chunk * chunk; P.bi1 = nx; P.bj0 = 0; P.bj1 = ny; P.bk0 = 0; P.bk1 = (nz + 3) / 4 * 4; }   // config 3's slab
     }
 #endif
 #if KV >= 2
@@ -67,6 +68,7 @@ int main(int argc, char **argv)
                 else if (var == 6) k1_step_march<1, true, true, false, false, false, 3><<<grd, blk>>>(P);
                 else if (var == 7) k1_step_march<1, true, true, false, false, false, 1><<<grd, blk>>>(P);
                 else if (var == 8) k1_step_march<1, false, true, false, false, false, 3><<<grd, blk>>>(P);
+                else if (var == 9) k1_step_march<1, false, true, false, false, false, 1><<<grd, blk>>>(P);
                 else k1_step_march<1, false, true, false, true><<<grd, blk>>>(P);
             } else {
                 if (var == 0) k1_step_march<2, false, true, false, false><<<grd, blk>>>(P);
@@ -77,6 +79,7 @@ int main(int argc, char **argv)
                 else if (var == 6) k1_step_march<2, true, true, false, false, false, 3><<<grd, blk>>>(P);
                 else if (var == 7) k1_step_march<2, true, true, false, false, false, 1><<<grd, blk>>>(P);
                 else if (var == 8) k1_step_march<2, false, true, false, false, false, 3><<<grd, blk>>>(P);
+                else if (var == 9) k1_step_march<2, false, true, false, false, false, 1><<<grd, blk>>>(P);
                 else k1_step_march<2, false, true, false, true><<<grd, blk>>>(P);
             }
 #else
