@@ -337,8 +337,14 @@ def run_b200_arm(a):
         times = np.cumsum(np.full(K, float(s.dt))) + s.time
         src.copy_(torch.from_numpy(np.ascontiguousarray(s._waveform_table(times)[:, :max(1, n_src)])).reshape(-1))
         torch.cuda.synchronize()
+        # The e2e passes above kept the board at its power limit for a while (a step kernel at ~100 % of the HBM bandwidth
+        # draws ~1 kW on real data); let the limiter's average recover so that this region starts like a fresh job, then
+        # warm up.  The untimed pass of K steps is only needed where the library captures a K-step CUDA graph or runs a
+        # chunk kernel (<= 32 M cells); on large grids W steps are the warm-up.
+        time.sleep(2.0)
         _lib.check(lib.sb_step_n_async(h, W, src.data_ptr(), rec.data_ptr()))
-        _lib.check(lib.sb_step_n_async(h, K, src.data_ptr(), rec.data_ptr()))   # untimed: instantiates the K-step graph
+        if cells_total <= (32 << 20):
+            _lib.check(lib.sb_step_n_async(h, K, src.data_ptr(), rec.data_ptr()))   # untimed: instantiates the K-step graph
         barrier()
         st0 = slab.device_stats()                # launches are counted over the timed region only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
