@@ -11,3 +11,10 @@ for tool in memcheck initcheck racecheck; do
 done
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k "cut_planes_first or velocity_membrane" > gpurun_out/sanitizer_r02_memcheck_multi.log 2>&1
 echo "r02-memcheck-multi exit=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_r02_memcheck_multi.log | tr '\n' ' ')"
+# later in round 2: Mur / radiation planes inside K6's tiles, 24 point sources inside K5 / K6 / K1, decomposition fuzz
+SEL5='test_pipelined_kernel_applies_mur or (test_pipelined_kernel_picks_tiles and (shape0 or shape2)) or test_chunk_kernels_take_a_phased_array or (test_random_configuration_is_decomposition_invariant and (102] or 107] or 119]))'
+for tool in memcheck racecheck; do
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 7 --target-processes all \
+      python -m pytest tests/test_parity_gpu.py tests/test_fuzz_parity_gpu.py -m gpu -x -q -k "$SEL5" > gpurun_out/sanitizer_r02b_$tool.log 2>&1
+  echo "r02b-$tool exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_r02b_$tool.log | tr '\n' ' ')"
+done
