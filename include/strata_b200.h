@@ -76,12 +76,12 @@ enum { SB_KERNEL_AUTO = 0, SB_KERNEL_NAIVE = 1, SB_KERNEL_MARCH = 2, /* 3 is ret
 /* SB_KERNEL_RESIDENT: for grids that fit in the GPU's aggregate shared memory (about 1.3 M cells on a B200) a whole
  * sb_step_n chunk runs as ONE cooperative launch that keeps the fields on chip between steps (sb_resident.cuh).
  * SB_KERNEL_AUTO picks it when the configuration allows (single slab, at most 32 point-source entries into p, probes
- * only, no ADE / plane boundaries) and the chunk has at least SB_OPT_RESIDENT_MIN_STEPS steps; results are bit-identical. */
+ * only, no ADE, at most 8 plane boundaries) and the chunk has at least SB_OPT_RESIDENT_MIN_STEPS steps; bit-identical. */
 /* SB_KERNEL_PIPELINE: the marching kernel's tiles of ALL steps of a chunk run from one persistent cooperative launch;
  * a tile starts as soon as the three chunks of planes it touches have finished the previous step (sb_pipeline.cuh), so
  * the tail of one step overlaps the head of the next.  SB_KERNEL_AUTO uses it for grids of 6 M to 40 M cells, where it was
- * measured to pay (same applicability conditions as the resident kernel, except that it also applies up to 8 plane
- * boundaries -- sb_add_plane_op -- inside its tiles, and is then used from the smallest grids on); bit-identical results. */
+ * measured to pay (same applicability conditions as the resident kernel; with plane boundaries -- sb_add_plane_op, applied
+ * inside its tiles -- it is used for every grid that does not fit the resident kernel); bit-identical results.            */
 enum { SB_FIELD_P = 0, SB_FIELD_VX = 1, SB_FIELD_VY = 2, SB_FIELD_VZ = 3 };
 enum { SB_OPT_KERNEL = 0, SB_OPT_ROWS_PER_THREAD = 1, SB_OPT_WARPS_J = 2, SB_OPT_WARPS_K = 3,
        SB_OPT_CHUNK_I = 4, SB_OPT_USE_GRAPH = 5, SB_OPT_PROFILE = 6, SB_OPT_FUSE_K3 = 7,

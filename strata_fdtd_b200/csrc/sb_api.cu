@@ -1316,17 +1316,23 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not, int f
     *why_not = nullptr;
     if (d.has_lower || d.has_upper || h->have_peers) *why_not = "decomposed slab";
     else if (h->have_ade) *why_not = "ADE materials";
-    else if (!h->plane_ops.empty()) *why_not = "Mur / radiation planes";
+    else if ((int)h->plane_ops.size() > SB_MAX_PLANE_OPS) *why_not = "more than 8 Mur / radiation planes";
     else if (h->n_mics) *why_not = "microphones";
     else if (h->n_src_cells && !h->inline_ok) *why_not = "more than 32 source cells or velocity sources";
     else if (h->n_probes > K5_MAX_PROBES) *why_not = "too many probes";
     else if (h->n_sm <= 0 || h->smem_optin <= 0) *why_not = "device attributes unavailable";
     else if (!h->coop_ok) *why_not = "cooperative launch unavailable on this device / in this process";
     if (*why_not) return 0;
+    // a Mur / radiation face and its interior neighbour must lie in one box: two planes / rows per box on such an axis
+    int min_li = 1, min_lj = 1;
+    for (auto *po : h->plane_ops) { if (po->op.axis == 0) min_li = 2; if (po->op.axis == 1) min_lj = 2; }
     int nbi = force_nbi, nbj = force_nbj;
     if (nbi <= 0 && h->res_tuned_key >= 0) { nbi = h->res_tuned_nbi; nbj = h->res_tuned_nbj; }
-    if (nbi <= 0 && !res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, h->have_mask, &nbi, &nbj)) {
-        *why_not = "grid does not fit in shared memory";
+    if (nbi > 0 && (d.nx / nbi < min_li || d.ny / nbj < min_lj)) nbi = 0;          // (a grid tuned before the planes were added)
+    if (nbi <= 0 && !res_choose_partition(d.nx, d.ny, d.nz, h->n_sm, h->smem_optin, h->n_probes, h->have_mask, &nbi, &nbj,
+                                          min_li, min_lj)) {
+        *why_not = h->plane_ops.empty() ? "grid does not fit in shared memory"
+                                        : "grid does not fit in shared memory in boxes that hold the Mur / radiation face pairs";
         return 0;
     }
     StepParams P;
@@ -1349,6 +1355,8 @@ static int resident_plan(sb_solver *h, ResParams &R, const char **why_not, int f
     R.n_sources = h->n_sources;
     R.n_probes = h->n_probes; R.n_rec = h->n_probes; R.probe_ijk = h->d_probe_ijk.p;
     R.err_flag = h->d_err.p; R.split = h->opt_res_split;
+    R.n_ops = (int)h->plane_ops.size();
+    for (int o = 0; o < R.n_ops; o++) R.ops[o] = h->plane_ops[o]->op;
     return 1;
 }
 
@@ -1356,7 +1364,7 @@ struct ResidentLauncher {
     sb_solver *h; ResParams &R; size_t smem;
     template <bool GEOM, bool UNI, int NS> int run()
     {
-        auto kern = k5_resident<GEOM, UNI, NS>;
+        auto kern = R.n_ops ? k5_resident<GEOM, UNI, NS, true> : k5_resident<GEOM, UNI, NS, false>;
         static thread_local const void *last_kern = nullptr; static thread_local size_t last_smem = 0; static thread_local int last_per_sm = 0;
         static thread_local int last_dev = -1;
         int per_sm = last_per_sm;
@@ -1443,6 +1451,7 @@ static int resident_autotune(sb_solver *h, const double *src_dev, int n_steps)
 {
     const int key = (h->have_mask ? 1 : 0) | (h->nonuniform ? 2 : 0) | ((int)h->sponges.size() << 2) | (h->n_probes << 6);
     if (h->res_tuned_key == key) return 0;
+    if (!h->plane_ops.empty()) return 0;                      // trial steps would advance the planes' `prev` state
     TuneVal cached;
     if (tune_lookup(h, key, 1, cached)) {
         h->res_tuned_nbi = cached.v[0]; h->res_tuned_nbj = cached.v[1]; h->res_tuned_key = key;
@@ -1504,7 +1513,7 @@ static const char *pipeline_why_not(const sb_solver *h)
     const sb_grid_desc &d = h->d;
     if (d.has_lower || d.has_upper || h->have_peers) return "decomposed slab";
     if (h->have_ade) return "ADE materials";
-    if ((int)h->plane_ops.size() > K6_MAX_OPS) return "more than 8 Mur / radiation planes";
+    if ((int)h->plane_ops.size() > SB_MAX_PLANE_OPS) return "more than 8 Mur / radiation planes";
     if (h->n_mics) return "microphones";
     if (h->n_src_cells && !h->inline_ok) return "more than 32 source cells or velocity sources";
     if (h->n_sm <= 0) return "device attributes unavailable";

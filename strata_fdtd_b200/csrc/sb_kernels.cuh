@@ -581,6 +581,8 @@ __device__ __forceinline__ void signal_step_done(const PeerLink &L)
 // Mur coefficient and (1-R) are float64, R*p_i is fp32 when R is a Python float ("weak" scalar) and
 // float64 when it is a NumPy float64; the sum is rounded to fp32 once on store.
 // ------------------------------------------------------------------------------------------
+constexpr int SB_MAX_PLANE_OPS = 8;          // planes the chunk kernels (K5, K6) apply themselves
+
 struct PlaneOp {
     int axis, side;              // axis 0/1/2, side 0 = low face, 1 = high face
     int kind;                    // 0 = Mur, 1 = radiation impedance

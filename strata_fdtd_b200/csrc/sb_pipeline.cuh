@@ -25,7 +25,7 @@
 
 namespace sb {
 
-constexpr int K6_MAX_OPS = 8;
+constexpr int K6_MAX_OPS = SB_MAX_PLANE_OPS;
 
 struct PipeParams {
     StepParams S;                          // tables, extents, tile shape (chunk_i); S.*_in = set holding the state on entry

@@ -77,6 +77,8 @@ struct ResParams {
     unsigned tag_base;                     // p after step s of this launch travels with tag tag_base + s + 1 (never 0)
     int *err_flag;
     int split;                             // 1 = overlap the halo-free part of the velocity phase with the exchange
+    int n_ops;                             // Mur / radiation planes, list order; with any, the faces are published and the
+    PlaneOp ops[SB_MAX_PLANE_OPS];         // sources added in a pass of their own after the planes (res_after_planes)
 };
 
 // shared-memory layout, float offsets; p carries a one-cell halo on all four sides, vx / vy a low-side ghost;
@@ -111,14 +113,19 @@ static inline long long res_smem_bytes(int LI, int LJ, int kp, int n_probes, boo
 
 // Box grid for a given SM count and shared-memory limit: fewest items per thread, then least shared memory.
 // Returns false when the grid does not fit on chip.
+// min_li / min_lj: smallest box extent allowed along i / j (2 where a Mur / radiation plane lies on that axis: a face cell
+// and its interior neighbour must share a box).
 static inline bool res_choose_partition(int nx, int ny, int nz, int n_sm, long long smem_limit, int n_probes, bool geom,
-                                        int *nbi_out, int *nbj_out)
+                                        int *nbi_out, int *nbj_out, int min_li = 1, int min_lj = 1)
 {
     const int kp = (nz + 3) / 4 * 4, K4 = kp / 4;
     long long best_cost = -1;
     for (int nbi = 1; nbi <= nx && nbi <= n_sm; nbi++) {
-        const int nbj = ny < n_sm / nbi ? ny : n_sm / nbi;
+        int nbj = ny < n_sm / nbi ? ny : n_sm / nbi;
         if (nbj < 1) break;
+        if (nx / nbi < min_li) break;
+        if (ny / nbj < min_lj) nbj = ny / min_lj;
+        if (nbj < 1) continue;
         const int LI = (nx + nbi - 1) / nbi, LJ = (ny + nbj - 1) / nbj;
         if ((long long)LJ * K4 > K5_NT) continue;                     // one thread per (row, float4) column at least
         if ((long long)(LI + 2) * (LJ + 2) * kp * 2 >= (1LL << 30)) continue;
@@ -409,7 +416,8 @@ SB_HD void res_phase_v(const ResParams &R, const ResBlock &B, const ResThread &T
 }
 
 // ---- pressure phase: p += cp * div v, solids, sponge, point sources; publishes the box faces ----------
-template <bool GEOM, bool UNI, int NS>
+// OPS: Mur / radiation planes are registered -- sources and face publishing are left to res_after_planes
+template <bool GEOM, bool UNI, int NS, bool OPS = false>
 SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T, float *sm, int s)
 {
     if (!T.active) return;
@@ -445,7 +453,7 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
                     pn = mul4(mul4s(mul4s(pn, SB_LDG(R.decx[q] + B.i0 + li)), SB_LDG(R.decy[q] + T.gj)), ld4(R.decz[q] + T.k0));
         }
         // (row padding is not masked here: no valid cell ever reads a padded element, and res_store writes zeros there)
-        if (T.inl_mask) {                                              // float64 add, fp32 store (solver.py:2421), list order
+        if (!OPS && T.inl_mask) {                                      // float64 add, fp32 store (solver.py:2421), list order
             for (int q = 0; q < R.n_inline; q++)
                 if (((T.inl_mask >> q) & 1u) && R.inl_i[q] == B.i0 + li) {
                     const double w = SB_DMUL(R.src_vals[(long long)s * R.n_sources + R.inl_src[q]], R.inl_weight[q]);
@@ -458,7 +466,7 @@ SB_HD void res_phase_p(const ResParams &R, const ResBlock &B, const ResThread &T
         }
         st4(sm + op, pn);
         const bool f_lo = li == 0 && T.low_i, f_hi = li == B.li_n - 1 && T.up_i;
-        if (f_lo || f_hi || T.pub_j) {                                 // a face some neighbour needs
+        if (!OPS && (f_lo || f_hi || T.pub_j)) {                       // a face some neighbour needs
             if (f_lo) res_publish(xo + T.lj * K2, pn, tag);
             if (f_hi) res_publish(xo + R.xch_face + T.lj * K2, pn, tag);
             if (T.pub_jlo) res_publish(xo + 2 * R.xch_face + li * K2, pn, tag);
@@ -480,6 +488,60 @@ template <typename F> static inline int res_dispatch(bool geom, bool uni, int n_
 }
 
 #if defined(__CUDACC__) && !defined(SB_RESIDENT_NO_KERNEL)
+// ---- Mur / radiation planes, then point sources, then the faces (core/solver.py:2572-2584 order) ----------------------
+// Runs after the pressure phase when plane updates are registered.  A plane update reads and writes a face cell and its
+// interior neighbour, both inside one box (the host only picks box grids that keep them together) and in shared memory;
+// planes on different axes meet on the edges of the grid, so the list is walked in order with a block barrier after every
+// plane that touched this box -- the sequential order of boundaries/_boundaries.py:476-513, 700-760.  `prev` stays in global
+// memory: every entry is read and written by one thread of one box, step after step.
+__device__ __noinline__ void res_after_planes(const ResParams &R, const ResBlock &B, const ResMap &M, float *sm, int tid, int s)
+{
+    const int n[3] = {R.nx, R.ny, R.nz}, lo[3] = {B.i0, B.j0, 0}, ext[3] = {B.li_n, B.lj_n, R.nz};
+    const int stride[3] = {(R.LJ + 2) * R.kp, R.kp, 1};                  // of p in shared memory along i, j, k
+    const int base = M.p(0, 0);
+    __syncthreads();                                                   // p of this step complete in the box
+    for (int o = 0; o < R.n_ops; o++) {
+        const PlaneOp &op = R.ops[o];
+        const int ax = op.axis, a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
+        const int face = op.side ? n[ax] - 1 : 0, inner = op.side ? n[ax] - 2 : 1;
+        if (face < lo[ax] || face >= lo[ax] + ext[ax]) continue;       // (uniform over the block)
+        const int eb = ext[b_ax], cells = ext[a_ax] * eb;
+        for (int idx = tid; idx < cells; idx += K5_NT) {
+            const int la = idx / eb, lb = idx - la * eb;
+            const int off = base + la * stride[a_ax] + lb * stride[b_ax];
+            const int ob = off + (face - lo[ax]) * stride[ax], oi = off + (inner - lo[ax]) * stride[ax];
+            float *prev = op.prev + (long long)(lo[a_ax] + la) * n[b_ax] + (lo[b_ax] + lb);
+            const float pi = sm[oi];
+            sm[ob] = plane_op_value(op, *prev, sm[ob], pi);
+            *prev = pi;
+        }
+        __syncthreads();
+    }
+    if (tid == 0)                                                      // float64 add, fp32 store (solver.py:2421), list order
+        for (int q = 0; q < R.n_inline; q++) {
+            const int li = R.inl_i[q] - B.i0, lj = R.inl_j[q] - B.j0;
+            if (li < 0 || li >= B.li_n || lj < 0 || lj >= B.lj_n) continue;
+            float *cell = sm + M.p(li, lj) + R.inl_k[q];
+            *cell = (float)((double)*cell + __dmul_rn(R.src_vals[(long long)s * R.n_sources + R.inl_src[q]], R.inl_weight[q]));
+        }
+    __syncthreads();
+    // the faces the neighbouring boxes need, as res_phase_p publishes them when there are no planes
+    const int K4 = R.kp >> 2, K2 = R.kp >> 1;
+    const unsigned tag = R.tag_base + (unsigned)s + 1u;
+    uint4 *xo = R.xch + res_xch_slot(R, (s + 1) & 1, B.bi * R.nbj + B.bj, 0);
+    const int ni = B.lj_n * K4, nj = B.li_n * K4;
+    const int n0 = B.i0 > 0 ? ni : 0, n1 = B.i0 + B.li_n < R.nx ? ni : 0, n2 = B.j0 > 0 ? nj : 0, n3 = B.j0 + B.lj_n < R.ny ? nj : 0;
+    for (int idx = tid; idx < n0 + n1 + n2 + n3; idx += K5_NT) {
+        int f = 0, q = idx;
+        if (q >= n0) { q -= n0; f = 1;
+            if (q >= n1) { q -= n1; f = 2;
+                if (q >= n2) { q -= n2; f = 3; } } }
+        const int row = q / K4, k0 = 4 * (q - row * K4);
+        const int li = f == 0 ? 0 : f == 1 ? B.li_n - 1 : row, lj = f < 2 ? row : (f == 2 ? 0 : B.lj_n - 1);
+        res_publish(xo + (long long)f * R.xch_face + row * K2 + (k0 >> 1), ld4(sm + M.p(li, lj) + k0), tag);
+    }
+}
+
 // Receiver: the (value, tag) units of p after step s-1 that the neighbours published -> halo of the box.  A thread
 // issues the loads of all its items at once and only then looks at the tags, so a face that has already arrived
 // costs one L2 round trip, not one per item; units whose tag is not yet the wanted step are simply read again.
@@ -538,7 +600,7 @@ struct RecvPoll {
     }
 };
 
-template <bool GEOM, bool UNI, int NS>
+template <bool GEOM, bool UNI, int NS, bool OPS>
 __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ ResParams R)
 {
     extern __shared__ float4 k5_smem4[];
@@ -579,7 +641,8 @@ __global__ void __launch_bounds__(K5_NT, 1) k5_resident(const __grid_constant__ 
                 R.rec[(long long)(s - 1) * R.n_rec + spr[1 + 2 * q]] = sm[spr[2 + 2 * q]];
         res_phase_v<GEOM, UNI, NS>(R, B, T, sm, s, (s > 0 && R.split) ? 1 : 2);
         __syncthreads();
-        res_phase_p<GEOM, UNI, NS>(R, B, T, sm, s);                    // publishes the box faces as it goes
+        res_phase_p<GEOM, UNI, NS, OPS>(R, B, T, sm, s);               // publishes the box faces as it goes
+        if (OPS) res_after_planes(R, B, M, sm, tid, s);                // ... unless plane updates have to come first
     }
     __syncthreads();
     if (R.n_steps > 0)

@@ -330,6 +330,52 @@ def test_resident_equals_march_on_awkward_shapes(shape):
     assert a.device_stats()["kernel_variant"] == _lib.KERNEL_RESIDENT
 
 
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("name", ["mur_all", "pml_radiation_mur"])
+def test_resident_kernel_applies_mur_and_radiation_planes(name, split):
+    """Mur / radiation planes inside K5: after the pressure phase every box updates the face cells it holds in shared memory,
+    plane by plane in list order, then adds its sources and only then publishes its faces to the neighbouring boxes."""
+    case = CASES[name]
+    s = _with_options(build_b200_solver(case, chunk_steps=37), {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT, _lib.OPT_RESIDENT_SPLIT: split})
+    o = O.OracleSolver(case)
+    s.run(steps=case["steps"]); o.run_steps(case["steps"])
+    assert_same_as_oracle(s, o, f"resident-planes/{name}/split{split}")
+    st = s.device_stats()
+    assert st["kernel_variant"] == _lib.KERNEL_RESIDENT
+    assert st["kernels_launched"] <= -(-case["steps"] // 37) + 2, "one launch per chunk"
+    s.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (100, 100, 100), (33, 13, 3), (5, 7, 130), (148, 3, 9)])
+def test_small_grids_with_planes_run_resident_by_default_and_match_the_stepwise_path(shape):
+    """AUTO: with planes a grid that fits in shared memory runs K5 (box grids of >= 2 planes / rows where a face pair needs
+    them); sources sit on faces, edges and next to them, two of them in one cell; equals K1 + K4 step by step and the oracle."""
+    nx, ny, nz = shape
+    geom = np.ones(shape, dtype=bool)
+    geom[nx // 3: nx // 3 + 2, ny // 2:, : max(1, nz // 3)] = False
+    case = dict(shape=shape, resolution=1e-3, steps=70, geometry=geom, pml=[dict(depth=2, axes=("z",))] if nz >= 6 else [],
+                plane_bcs=[dict(kind="mur", axes=("y", "x")), dict(kind="radiation", axis="z", side="low", reflection_coeff=0.3),
+                           dict(kind="radiation", axis="x", side="high", pipe_radius=0.01), dict(kind="mur", axes=("z",))],
+                sources=[dict(kind="point", position=(0, 0, 0), frequency=25e3), dict(kind="point", position=(nx - 1, ny - 2, nz - 1), frequency=18e3),
+                         dict(kind="point", position=(nx // 2, ny // 2, nz // 2), frequency=30e3),
+                         dict(kind="point", position=(nx // 2, ny // 2, nz // 2), frequency=11e3, amplitude=0.5), dict(kind="point", position=(1, 1, 1), frequency=21e3)],
+                probes=[("corner", (nx - 1, ny - 1, nz - 1)), ("origin", (0, 0, 0)), ("edge", (nx - 1, 0, nz - 2)), ("mid", (nx // 2, ny // 2, nz // 3))])
+    a = build_b200_solver(case, chunk_steps=35)
+    b = _with_options(build_b200_solver(case, chunk_steps=35), {_lib.OPT_KERNEL: _lib.KERNEL_MARCH})
+    a.run(steps=70); b.run(steps=70)
+    assert a.device_stats()["kernel_variant"] == _lib.KERNEL_RESIDENT
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(a.get_field(f), b.get_field(f)), f
+    for n in ("corner", "origin", "edge", "mid"):
+        assert np.array_equal(a.get_probe_data(n)[n], b.get_probe_data(n)[n]), n
+    if nx * ny * nz <= 300_000:
+        o = O.OracleSolver(case)
+        o.run_steps(70)
+        assert_same_as_oracle(a, o, f"resident-planes/{shape}")
+    assert np.abs(a.get_field("p")).max() > 0
+    a.close(); b.close()
+
+
 def test_resident_refuses_what_it_cannot_do_and_auto_falls_back_to_k1():
     case = CASES["directional_mics"]                          # velocity gathers that cross boxes stay on the K1 path
     s = _with_options(build_b200_solver(case), {_lib.OPT_KERNEL: _lib.KERNEL_RESIDENT})
@@ -457,7 +503,7 @@ def test_pipelined_kernel_refuses_a_fixed_tile_shape_that_separates_a_plane_pair
     s.close()
     # ... and where no shape at all does (9 rows and 257 columns: 8 % rows and 256 % columns are 0 for every shape of at
     # most 8 warps), the automatic choice quietly stays with the step-by-step path
-    case = dict(case, shape=(17, 9, 257), plane_bcs=[dict(kind="mur", axes=("x", "y", "z"))],
+    case = dict(case, shape=(900, 9, 257), plane_bcs=[dict(kind="mur", axes=("x", "y", "z"))],     # (too large for K5)
                 sources=[dict(kind="point", position=(8, 4, 128), frequency=30e3)], steps=24)
     a = build_b200_solver(case)
     o = O.OracleSolver(case)
