@@ -174,6 +174,8 @@ class DistributedFDTDSolver:
         self._symm = []                          # keeps symmetric allocations / handles alive
         self._energy_history: list = []
         self._snapshots: list = []
+        self._velocity_snapshots: list = []
+        self._snapshot_velocity = False
         self._snapshot_interval = None
         self.last_run_stats: dict = {}
         if halo in ("auto", "p2p") and self.world > 1 and not self._staged:
@@ -288,9 +290,12 @@ class DistributedFDTDSolver:
         self.slab.set_kernel_option(opt, val)
 
     def enable_snapshots(self, interval: int, capture_velocity: bool = False) -> None:
-        if capture_velocity:
-            raise NotImplementedError("velocity snapshots are not gathered across slabs; use gather_field('vx') ...")
         self._snapshot_interval = int(interval)
+        self._snapshot_velocity = bool(capture_velocity)
+
+    def get_velocity_snapshots(self):
+        """(time, vx, vy, vz) at the cell centres of the whole grid -- kept on rank 0 only, like the pressure snapshots."""
+        return self._velocity_snapshots
 
     def get_snapshots(self):
         """(time, global p) pairs -- kept on rank 0 only (the other ranks return an empty list)."""
@@ -463,8 +468,12 @@ class DistributedFDTDSolver:
                 last_idx = s._step_count - 1
                 if self._snapshot_interval and last_idx % self._snapshot_interval == 0:
                     p = self.gather_field("p")
+                    v = [self.gather_field(f) for f in ("vx", "vy", "vz")] if self._snapshot_velocity else None
                     if self.rank == 0:
                         self._snapshots.append((float(s._chunk_times[-1]), p))
+                        if v is not None:
+                            from .solver import centre_velocities
+                            self._velocity_snapshots.append((float(s._chunk_times[-1]), *centre_velocities(*v)))
                 if track_energy and s._step_count % energy_sample_interval == 0:
                     self._energy_history.append((s._step_count, s._time, self.compute_energy()))
                 if output_file:
@@ -523,6 +532,7 @@ class DistributedFDTDSolver:
         self._ghosts_fresh = False
         self._energy_history.clear()
         self._snapshots.clear()
+        self._velocity_snapshots.clear()
 
     # ---- results ---------------------------------------------------------------------------------
     def get_probe_data(self, name=None) -> dict:

@@ -130,6 +130,20 @@ def distributed_world(auto_init: bool = True) -> int:
     return 1
 
 
+def centre_velocities(vx, vy, vz):
+    """Face velocities averaged to the cell centres, as the reference's velocity snapshots hold them: 0.5 * (v[c - 1] + v[c])
+    along the field's own axis, with a zero face below the first cell."""
+    out = []
+    for axis, v in enumerate((vx, vy, vz)):
+        c = np.zeros_like(v)
+        lo = [slice(None)] * 3; hi = [slice(None)] * 3; first = [slice(None)] * 3
+        lo[axis] = slice(0, -1); hi[axis] = slice(1, None); first[axis] = 0
+        c[tuple(hi)] = 0.5 * (v[tuple(lo)] + v[tuple(hi)])
+        c[tuple(first)] = 0.5 * v[tuple(first)]
+        out.append(c)
+    return out
+
+
 class FDTDSolver:
     """3-D acoustic pressure-velocity FDTD on a staggered grid, executed on a B200.
 
@@ -938,16 +952,7 @@ class FDTDSolver:
         return self._velocity_snapshots
 
     def _centred_velocities(self):
-        out = []
-        for axis, name in enumerate(("vx", "vy", "vz")):
-            v = self.get_field(name)
-            c = np.zeros_like(v)
-            lo = [slice(None)] * 3; hi = [slice(None)] * 3; first = [slice(None)] * 3
-            lo[axis] = slice(0, -1); hi[axis] = slice(1, None); first[axis] = 0
-            c[tuple(hi)] = 0.5 * (v[tuple(lo)] + v[tuple(hi)])
-            c[tuple(first)] = 0.5 * v[tuple(first)]
-            out.append(c)
-        return out
+        return centre_velocities(*(self.get_field(name) for name in ("vx", "vy", "vz")))
 
     def compute_energy(self) -> float:
         """(1/2) sum(p^2/(rho c^2) + rho |v|^2) dV over air cells (solver.py:2689-2706), reduced on the device."""

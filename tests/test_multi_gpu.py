@@ -315,6 +315,7 @@ for n, p in case["probes"]:
     d.add_probe(n, p)
 seen = []
 out = {out!r}
+d.enable_snapshots(25, capture_velocity=True)
 d.run(steps=50, output_file=out, callback=seen.append, track_energy=True, energy_sample_interval=10, snapshot_interval=20,
       script_content="two ranks")
 d.run(steps=30, track_energy=True, energy_sample_interval=10)
@@ -323,12 +324,21 @@ hist = d.get_energy_history()
 fields = {{f: d.get_field(f) for f in ("p", "vx", "vy", "vz")}}
 traces = d.get_probe_data()
 one = build_b200_solver(case, device=0, distributed=False, chunk_steps=16)
+one.enable_snapshots(25, capture_velocity=True)
 one.run(steps=50, track_energy=True, energy_sample_interval=10)
 one.run(steps=30, track_energy=True, energy_sample_interval=10)
 for f in fields:
     assert np.array_equal(fields[f], one.get_field(f)), f
 for n in traces:
     assert np.array_equal(traces[n], one.get_probe_data(n)[n]), n
+if rank == 0:                                         # pressure and cell-centred velocity snapshots of the whole grid
+    sp, sv, op_, ov = d.get_snapshots(), d.get_velocity_snapshots(), one.get_snapshots(), one.get_velocity_snapshots()
+    assert len(sp) == len(op_) >= 3 and len(sv) == len(ov) == len(sp)
+    for a, b in zip(sp, op_):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    for a, b in zip(sv, ov):
+        assert a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
+    assert np.abs(sv[-1][1]).max() > 0
 h1 = one.get_energy_history()
 assert [q[0] for q in hist] == [q[0] for q in h1], (hist, h1)
 assert all(abs(a[2] - b[2]) <= 1e-9 * abs(b[2]) for a, b in zip(hist, h1))
