@@ -145,6 +145,10 @@ int sb_add_sponge(sb_solver *h, const float *decay_x, const float *decay_y, cons
  * axis 0/1/2, side 0 = low face, 1 = high face.  The previous-plane state lives in the library.       */
 int sb_clear_plane_ops(sb_solver *h);
 int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, double mur, double R, int weak_r);
+/* Checkpoint / resume of that state (the reference's ``_p_prev_*`` arrays, boundaries/_boundaries.py:447-473): plane `op`
+ * in the order added; host holds the face's two in-plane extents, row-major ([ny][nz], [nx][nz] or [nx][ny] floats);
+ * *elems_out (optional) receives their product; upload != 0 writes the device state instead of reading it.            */
+int sb_plane_op_state(sb_solver *h, int op, float *host, int64_t *elems_out, int upload);
 
 /* ADE materials.  material_id_host: uint8 [nx][ny][nz], on a slab PLUS its live ghost planes as for
  * sb_set_geometry ([nx + has_lower + has_upper] planes, lower ghost first): the auxiliary density fields of the
@@ -181,7 +185,8 @@ int sb_mic_tables(const float *grid_positions, int n_mics, int ny, int nz, int64
 /* Checkpoint / resume of the auxiliary fields (the reference keeps them in private full-grid arrays, core/solver.py:
  * 3061-3083): pole index as passed to sb_set_ade, which = 0 for J, 1 for J_prev (Lorentz poles); host_dense is
  * [nx][ny][nz], zero outside the pole's material on download; upload != 0 writes the device state instead.  Together with
- * the four fields (sb_download_field / sb_upload_field) and the host's time / step count this is the whole solver state. */
+ * the four fields (sb_download_field / sb_upload_field), sb_plane_op_state and the host's time / step count this is the
+ * whole solver state.                                                                                                   */
 int sb_ade_state(sb_solver *h, int pole, int which, float *host_dense, int upload);
 
 /* ---- stepping ------------------------------------------------------------------------ */

@@ -123,6 +123,7 @@ SIGNATURES = {
     "sb_set_gathers": (_i, [_vp, _i, _vp, _vp, _vp]),
     "sb_mic_tables": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "sb_ade_state": (_i, [_vp, _i, _i, _vp, _i]),
+    "sb_plane_op_state": (_i, [_vp, _i, _vp, _vp, _i]),
     "sb_step_n": (_i, [_vp, _i, _vp, _vp]),
     "sb_step_n_async": (_i, [_vp, _i, _vp, _vp]),
     "sb_step_n_submit": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -490,6 +490,19 @@ extern "C" int sb_clear_plane_ops(sb_solver *h)
     return 0;
 }
 
+extern "C" int sb_plane_op_state(sb_solver *h, int op, float *host, int64_t *elems_out, int upload)
+{
+    CHECK_H(h);
+    if (op < 0 || op >= (int)h->plane_ops.size()) return fail("no plane update %d", op);
+    PlaneOpHost *po = h->plane_ops[op];
+    if (elems_out) *elems_out = (int64_t)po->prev.n;
+    if (!host) return elems_out ? 0 : fail("null host pointer");
+    CU(cudaStreamSynchronize(h->stream));
+    if (upload) CU(cudaMemcpy(po->prev.p, host, po->prev.n * sizeof(float), cudaMemcpyHostToDevice));
+    else        CU(cudaMemcpy(host, po->prev.p, po->prev.n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int sb_add_plane_op(sb_solver *h, int axis, int side, int kind, double mur, double R, int weak_r)
 {
     CHECK_H(h);

@@ -1014,7 +1014,8 @@ class FDTDSolver:
     def get_state(self) -> dict:
         """Everything a run needs to continue elsewhere: the four fields, time, step count and -- with dispersive
         materials -- the auxiliary fields J (and J_prev of Lorentz poles) as dense arrays in pole-table order
-        (Debye poles of all materials first, then Lorentz; the reference keeps them private, solver.py:3061-3083)."""
+        (Debye poles of all materials first, then Lorentz; the reference keeps them private, solver.py:3061-3083), and
+        the previous-plane arrays of Mur / radiation boundaries in the order their faces were registered."""
         st = {"time": float(self._time), "step_count": int(self._step_count)}
         for f in _FIELDS:
             st[f] = self.get_field(f)
@@ -1033,6 +1034,18 @@ class FDTDSolver:
                     ent[key] = a
                 ade.append(ent)
             st["ade"] = ade
+        if any(plane_ops(b, self) is not None for b in self._boundaries):
+            dev = self._sync_to_device()
+            planes, q = [], 0
+            while True:                                             # the previous-plane state of every Mur / radiation face
+                n = C.c_int64(0)
+                if dev.lib.sb_plane_op_state(dev.handle, q, None, C.byref(n), 0) != 0:
+                    break
+                a = np.zeros(n.value, dtype=np.float32)
+                _lib.check(dev.lib.sb_plane_op_state(dev.handle, q, _lib.ptr(a), None, 0))
+                planes.append(a)
+                q += 1
+            st["planes"] = planes
         return st
 
     def set_state(self, state: dict) -> None:
@@ -1048,6 +1061,13 @@ class FDTDSolver:
                     if a.shape != self.shape:
                         raise ValueError(f"auxiliary field shape {a.shape} doesn't match solver shape {self.shape}")
                     _lib.check(dev.lib.sb_ade_state(dev.handle, q, which, _lib.ptr(a), 1))
+        for q, a in enumerate(state.get("planes", [])):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            n = C.c_int64(0)
+            _lib.check(dev.lib.sb_plane_op_state(dev.handle, q, None, C.byref(n), 0))
+            if a.size != n.value:
+                raise ValueError(f"plane state {q} has {a.size} entries, the solver's face has {n.value}")
+            _lib.check(dev.lib.sb_plane_op_state(dev.handle, q, _lib.ptr(a), None, 1))
 
     def kernel_launches(self) -> int:
         if self._dev is None:

@@ -650,6 +650,26 @@ def test_ade_layouts_match_oracle(name, layout):
     s.close()
 
 
+@pytest.mark.parametrize("kernel", [_lib.KERNEL_AUTO, _lib.KERNEL_MARCH, _lib.KERNEL_PIPELINE])
+@pytest.mark.parametrize("name", ["mur_all", "pml_radiation_mur"])
+def test_checkpoint_and_resume_with_plane_boundaries(name, kernel):
+    """The previous-plane arrays of Mur / radiation faces are part of the state: get_state() after 90 steps -> set_state()
+    on a fresh solver running another kernel -> the continued run equals the uninterrupted one and the oracle."""
+    case = CASES[name]
+    a = _with_options(build_b200_solver(case, chunk_steps=41), {_lib.OPT_KERNEL: kernel})
+    a.run(steps=90)
+    st = a.get_state()
+    assert len(st["planes"]) >= 4 and all(np.abs(q).max() > 0 for q in st["planes"])
+    b = _with_options(build_b200_solver(case, chunk_steps=29), {_lib.OPT_KERNEL: _lib.KERNEL_MARCH if kernel != _lib.KERNEL_MARCH else _lib.KERNEL_AUTO})
+    b.set_state(st)
+    o = O.OracleSolver(case)
+    a.run(steps=70); b.run(steps=70); o.run_steps(160)
+    for f in ("p", "vx", "vy", "vz"):
+        assert np.array_equal(a.get_field(f), b.get_field(f)), f
+        assert np.array_equal(b.get_field(f), getattr(o, f)), f
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("layout", [1, 2, 3])
 @pytest.mark.parametrize("name", ["ade_two_materials_nonuniform", "ade_dense_layers"])
 def test_checkpoint_and_resume_with_auxiliary_fields(name, layout):
