@@ -521,6 +521,29 @@ class DistributedFDTDSolver:
     def step(self):
         self.run(steps=1)
 
+    def get_state(self) -> dict:
+        """This rank's shard of the solver state (FDTDSolver.get_state of its slab plus the slab's place in the grid): every
+        rank saves its own, e.g. ``np.savez(f"ckpt_{rank}.npz", ...)``.  No communication."""
+        st = self.slab.get_state()
+        st["world"], st["rank"], st["i_range"] = self.world, self.rank, (int(self.slab._i0), int(self.slab._i1))
+        return st
+
+    def set_state(self, state: dict) -> None:
+        """Collective.  Restores a shard written by ``get_state`` under the same decomposition; the ghost planes are
+        refreshed from their owners before the next step.  Dispersive materials are refused here: their auxiliary fields
+        on the ghost planes belong to the neighbour's shard, which this call does not see."""
+        if tuple(state.get("i_range", ())) != (int(self.slab._i0), int(self.slab._i1)) or state.get("world") != self.world:
+            raise ValueError(f"state of planes {state.get('i_range')} in a job of {state.get('world')} ranks does not fit this "
+                             f"rank's planes {(int(self.slab._i0), int(self.slab._i1))} in a job of {self.world}")
+        if state.get("ade"):
+            raise NotImplementedError("resuming dispersive materials on a decomposed grid (use a single-GPU checkpoint)")
+        if self.slab._dev is not None:
+            _lib.check(self.slab._dev.lib.sb_synchronize(self.slab._dev.handle))
+        self.dist.barrier(self.group)            # no neighbour is still storing into our ghosts
+        self.slab.set_state(state)
+        self._ghosts_fresh = False
+        self.dist.barrier(self.group)
+
     def reset(self) -> None:
         """Back to t = 0 on every slab (core/solver.py:2781-2800).  Collective."""
         s = self.slab

@@ -364,6 +364,20 @@ p0 = np.zeros(case["shape"], dtype=np.float32); p0[23, 20, 40] = 1.0; p0[24, 10,
 d.p = p0; one.p = p0
 d.run(steps=20); one.run(steps=20)
 assert np.array_equal(d.get_field("vx"), one.get_field("vx")) and np.array_equal(d.get_field("p"), one.get_field("p"))
+# checkpoint: every rank keeps its own shard; a fresh job resumed from the shards continues like the uninterrupted one
+st = d.get_state()
+assert st["world"] == 2 and st["i_range"] == (d.slab._i0, d.slab._i1) and st["p"].shape[0] == d.slab._i1 - d.slab._i0
+d2 = sb.FDTDSolver(shape=case["shape"], resolution=case["resolution"], chunk_steps=9)
+d2.set_geometry(case["geometry"]); d2.add_boundary(sb.PML(depth=8))
+for s in case["sources"]:
+    d2.add_source(sb.GaussianPulse(position=s["position"], frequency=s["frequency"]))
+for n, p in case["probes"]:
+    d2.add_probe(n, p)
+d2.set_state(st)
+d.run(steps=25); d2.run(steps=25); one.run(steps=25)
+for f in ("p", "vx", "vy", "vz"):
+    assert np.array_equal(d2.get_field(f), d.get_field(f)) and np.array_equal(d2.get_field(f), one.get_field(f)), f
+assert d2.slab.step_count == d.slab.step_count
 sys.stdout.write("RANK_OK_%d\n" % rank); sys.stdout.flush()
 dist.barrier(); dist.destroy_process_group()
 """
