@@ -56,11 +56,16 @@ __device__ __noinline__ void k6_plane_ops(const PipeParams &Q, float *p, int i0,
     const StepParams &P = Q.S;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
     const int n[3] = {P.nx, P.ny, P.nz}, lo[3] = {i0, j0, k0}, hi[3] = {i1, j1, k1};
+    int last_ax = -1;
     for (int o = 0; o < Q.n_ops; o++) {
         const PlaneOp &op = Q.ops[o];
         const int ax = op.axis, a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
         const int face = op.side ? n[ax] - 1 : 0, inner = op.side ? n[ax] - 2 : 1;
         if (face >= lo[ax] && face < hi[ax]) {                                   // (uniform over the block)
+            // planes on another axis may meet the previous ones on an edge; on the same axis a thread meets the same
+            // (a, b) column again and its own program order is enough
+            if (last_ax >= 0 && last_ax != ax) __syncthreads();
+            last_ax = ax;
             const int eb = hi[b_ax] - lo[b_ax], cells = (hi[a_ax] - lo[a_ax]) * eb;
             const long long stride[3] = {P.plane, (long long)P.pitch, 1};
             for (int idx = tid; idx < cells; idx += nt) {
@@ -72,9 +77,9 @@ __device__ __noinline__ void k6_plane_ops(const PipeParams &Q, float *p, int i0,
                 __stcg(p + ib, plane_op_value(op, __ldcg(prev), __ldcg(p + ib), pi));
                 __stcg(prev, pi);
             }
-            __syncthreads();                                                     // the next plane may meet this one on an edge
         }
     }
+    if (last_ax >= 0) __syncthreads();                                           // sources and probes come next
 }
 
 #ifdef SB_K6_MINB_FIXED                    // experiments

@@ -491,8 +491,8 @@ template <typename F> static inline int res_dispatch(bool geom, bool uni, int n_
 // ---- Mur / radiation planes, then point sources, then the faces (core/solver.py:2572-2584 order) ----------------------
 // Runs after the pressure phase when plane updates are registered.  A plane update reads and writes a face cell and its
 // interior neighbour, both inside one box (the host only picks box grids that keep them together) and in shared memory;
-// planes on different axes meet on the edges of the grid, so the list is walked in order with a block barrier after every
-// plane that touched this box -- the sequential order of boundaries/_boundaries.py:476-513, 700-760.  `prev` stays in global
+// planes on different axes meet on the edges of the grid, so the list is walked in order with a block barrier wherever the
+// axis changes -- the sequential order of boundaries/_boundaries.py:476-513, 700-760.  `prev` stays in global
 // memory: every entry is read and written by one thread of one box, step after step.
 __device__ __noinline__ void res_after_planes(const ResParams &R, const ResBlock &B, const ResMap &M, float *sm, int tid, int s)
 {
@@ -500,11 +500,16 @@ __device__ __noinline__ void res_after_planes(const ResParams &R, const ResBlock
     const int stride[3] = {(R.LJ + 2) * R.kp, R.kp, 1};                  // of p in shared memory along i, j, k
     const int base = M.p(0, 0);
     __syncthreads();                                                   // p of this step complete in the box
+    int last_ax = -1;
     for (int o = 0; o < R.n_ops; o++) {
         const PlaneOp &op = R.ops[o];
         const int ax = op.axis, a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
         const int face = op.side ? n[ax] - 1 : 0, inner = op.side ? n[ax] - 2 : 1;
         if (face < lo[ax] || face >= lo[ax] + ext[ax]) continue;       // (uniform over the block)
+        // consecutive planes on one axis need no barrier: a thread meets the same (a, b) column in each of them, so the two
+        // sides (disjoint cells) and repeated updates of one face are ordered by the thread's own program order
+        if (last_ax >= 0 && last_ax != ax) __syncthreads();
+        last_ax = ax;
         const int eb = ext[b_ax], cells = ext[a_ax] * eb;
         for (int idx = tid; idx < cells; idx += K5_NT) {
             const int la = idx / eb, lb = idx - la * eb;
@@ -515,8 +520,8 @@ __device__ __noinline__ void res_after_planes(const ResParams &R, const ResBlock
             sm[ob] = plane_op_value(op, *prev, sm[ob], pi);
             *prev = pi;
         }
-        __syncthreads();
     }
+    if (last_ax >= 0 && R.n_inline) __syncthreads();
     if (tid == 0)                                                      // float64 add, fp32 store (solver.py:2421), list order
         for (int q = 0; q < R.n_inline; q++) {
             const int li = R.inl_i[q] - B.i0, lj = R.inl_j[q] - B.j0;
