@@ -15,6 +15,7 @@ timeout 300 python bench.py --workload c1_100 --steps 4000 --warmup 5 --no-cpu-b
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/val_launches_default.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/val_launches_ade_slab.csv python bench.py --workload c3_512_ade_slab --steps 8 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/val_launches_ade_sphere.csv python bench.py --workload c3_512_ade --steps 8 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+if [ -n "${SKIP_NCU_FULL:-}" ]; then ls -la gpurun_out | grep val_ | awk '{print $5, $9}'; exit 0; fi
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k1_step_march_ade -s 20 -c 1 -o gpurun_out/val_prof_k1ade_slab python bench.py --workload c3_512_ade_slab --steps 8 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k1_step_march -s 45 -c 1 -o gpurun_out/val_prof_k1_default python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 250 ncu --set full --clock-control none --import-source on -k regex:k5_resident -s 8 -c 1 -o gpurun_out/val_prof_k5_c1 python bench.py --workload c1_100 --steps 256 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
