@@ -26,6 +26,8 @@ for name, csv, rep, workload in jobs:
     b = str(OUT / rep) if rep and (OUT / rep).exists() else "-"
     if a == "-" and b == "-":
         continue
+    if rep and b == "-" and (PROF / f"{tag}_{name}_summary.json").exists():
+        continue                             # a pass without the full ncu capture must not drop the one already kept
     subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), f"{tag}_{name}", a, b, workload], check=False,
                    stdout=subprocess.DEVNULL)
 print(sorted(p.name for p in PROF.glob(f"{tag}_*")))
