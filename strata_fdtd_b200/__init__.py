@@ -10,11 +10,12 @@ from .boundaries import PML, RigidBoundary  # noqa: F401
 from .grid import NonuniformGrid, UniformGrid  # noqa: F401
 from .materials import Pole, PoleMaterial, PoleType, SimpleMaterial  # noqa: F401
 from .solver import FDTDSolver  # noqa: F401
-from .sources import GaussianPulse, Microphone, Probe  # noqa: F401
+from .sources import POLAR_PATTERNS, GaussianPulse, Microphone, Probe  # noqa: F401
+from .membranes import CircularMembraneSource, MembraneSource, RectangularMembraneSource  # noqa: F401
 from .shim import install_into_reference  # noqa: F401
 from . import io, workloads  # noqa: F401,E402
 
 __version__ = "0.1.0"
 __all__ = ["FDTDSolver", "UniformGrid", "NonuniformGrid", "PML", "RigidBoundary", "GaussianPulse", "Probe",
-           "Microphone", "Pole", "PoleType", "SimpleMaterial", "PoleMaterial", "B200BackendError", "build",
-           "install_into_reference"]
+           "Microphone", "POLAR_PATTERNS", "MembraneSource", "CircularMembraneSource", "RectangularMembraneSource",
+           "Pole", "PoleType", "SimpleMaterial", "PoleMaterial", "B200BackendError", "build", "install_into_reference"]

@@ -157,7 +157,7 @@ def install_as_strata_fdtd(force_alias: bool = False):
             for k in [k for k in sys.modules if k == "strata_fdtd" or k.startswith("strata_fdtd.")]:
                 del sys.modules[k]
     import strata_fdtd_b200 as sb
-    from . import boundaries, materials
+    from . import boundaries, materials, sources
 
     class FDTDSolver(sb.FDTDSolver):
         __doc__ = sb.FDTDSolver.__doc__
@@ -177,6 +177,8 @@ def install_as_strata_fdtd(force_alias: bool = False):
                  RadiationImpedance=boundaries.RadiationImpedance, UniformGrid=sb.UniformGrid,
                  NonuniformGrid=sb.NonuniformGrid, Pole=sb.Pole, PoleType=sb.PoleType, SimpleMaterial=sb.SimpleMaterial,
                  Sphere=Sphere, Box=Box, Union=Union, Intersection=Intersection, Difference=Difference,
+                 POLAR_PATTERNS=sources.POLAR_PATTERNS, MembraneSource=sb.MembraneSource,
+                 CircularMembraneSource=sb.CircularMembraneSource, RectangularMembraneSource=sb.RectangularMembraneSource,
                  has_native_kernels=lambda: False, has_gpu_backend=lambda: True,
                  get_native_info=lambda: {"available": False, "version": None, "has_openmp": False, "num_threads": 1},
                  __version__=sb.__version__)
@@ -191,15 +193,24 @@ def install_as_strata_fdtd(force_alias: bool = False):
     core = types.ModuleType("strata_fdtd.core")
     core.__path__ = []
     solver_mod = types.ModuleType("strata_fdtd.core.solver")
-    for k in ("FDTDSolver", "GaussianPulse", "Probe", "Microphone"):
+    for k in ("FDTDSolver", "GaussianPulse", "Probe", "Microphone", "POLAR_PATTERNS", "MembraneSource", "CircularMembraneSource",
+              "RectangularMembraneSource", "has_native_kernels", "has_gpu_backend", "get_native_info"):
         setattr(solver_mod, k, names[k])
     grid_mod = types.ModuleType("strata_fdtd.core.grid")
     grid_mod.UniformGrid, grid_mod.NonuniformGrid = sb.UniformGrid, sb.NonuniformGrid
     core.solver, core.grid = solver_mod, grid_mod
-    root.boundaries, root.materials, root.core = b, m, core
+    geo = types.ModuleType("strata_fdtd.geometry")               # the few shapes above; the toolkit itself stays upstream
+    geo.__path__ = []
+    for k in ("Sphere", "Box", "Union", "Intersection", "Difference"):
+        setattr(geo, k, names[k])
+    prim = types.ModuleType("strata_fdtd.geometry.primitives")
+    prim.SPEED_OF_SOUND = 343.0                                  # geometry/primitives.py:19
+    geo.primitives = prim
+    root.boundaries, root.materials, root.core, root.geometry = b, m, core, geo
     sys.modules.update({"strata_fdtd": root, "strata_fdtd.boundaries": b, "strata_fdtd.materials": m,
                         "strata_fdtd.core": core, "strata_fdtd.core.solver": solver_mod,
-                        "strata_fdtd.core.grid": grid_mod})
+                        "strata_fdtd.core.grid": grid_mod, "strata_fdtd.geometry": geo,
+                        "strata_fdtd.geometry.primitives": prim})
     return root
 
 

@@ -162,10 +162,60 @@ class Microphone:
         Z = self._solver_rho * self._solver_c
         return (1 - k) * pressure + k * Z * v_dot_d               # fp32 term + float64 term
 
+    def record(self, pressure_field, time: float, vx=None, vy=None, vz=None) -> None:
+        """One sample taken on the host from whole-field arrays (the reference's per-step Python path, solver.py:1004-1058).
+        ``run()`` never calls this -- it gathers on the device -- but scripts and the reference's own tests do."""
+        if self._grid_position is None:
+            raise RuntimeError("Microphone not initialized. Add to solver first.")
+
+        def sample(field, g, clamp):
+            idx, wts = trilinear_tables(g, field.shape, clamp=clamp)
+            flat, acc = field.reshape(-1), 0.0
+            for q, w in zip(idx, wts):
+                acc += w * flat[q]
+            return acc
+        pressure = sample(np.asarray(pressure_field), self._grid_position, False)
+        if self.is_directional():
+            if vx is None or vy is None or vz is None:
+                raise ValueError("Velocity fields (vx, vy, vz) are required for directional microphones")
+            vel = []
+            for axis, f in enumerate((vx, vy, vz)):               # staggered positions, clamped (solver.py:1073-1097)
+                f = np.asarray(f)
+                g = list(self._grid_position)
+                g[axis] -= 0.5
+                vel.append(sample(f, [max(0.0, min(q, n - 1.001)) for q, n in zip(g, f.shape)], True))
+            pressure = self._combine(np.array([pressure]), [np.array([q]) for q in vel])[0]
+        self._data.append(pressure)
+        self._times.append(time)
+
     def get_waveform(self, weighting=None) -> np.ndarray:
         if weighting not in ("Z", None):
             raise NotImplementedError("frequency weighting is post-processing; use strata_fdtd.analysis on the raw waveform")
         return np.array(self._data, dtype=np.float32)
+
+    def to_wav(self, filepath: str, sample_rate: int = 44100, normalize: bool = True, bit_depth: int = 16) -> None:
+        """Mono WAV of the recording, linearly resampled from 1/dt to ``sample_rate`` when they differ by more than 1 Hz,
+        optionally scaled to 0.95 of full scale (solver.py:1337-1418)."""
+        import wave
+        if len(self._data) == 0:
+            raise RuntimeError("No data recorded. Run simulation first.")
+        if bit_depth not in (16, 32):
+            raise ValueError("bit_depth must be 16 or 32")
+        w = self.get_waveform()
+        if self._solver_dt is not None and abs(1.0 / self._solver_dt - sample_rate) > 1.0:
+            n_out = int(len(w) * sample_rate / (1.0 / self._solver_dt))
+            if n_out != len(w):
+                w = np.interp(np.linspace(0, len(w) - 1, n_out), np.arange(len(w)), w).astype(np.float32)
+        if normalize:
+            peak = np.max(np.abs(w))
+            if peak > 0:
+                w = w / peak * 0.95
+        ints = (w * (32767 if bit_depth == 16 else 2147483647)).astype(np.int16 if bit_depth == 16 else np.int32)
+        with wave.open(filepath, "wb") as f:
+            f.setnchannels(1)
+            f.setsampwidth(bit_depth // 8)
+            f.setframerate(sample_rate)
+            f.writeframes(ints.tobytes())
 
     def get_time_axis(self) -> np.ndarray:
         return np.array(self._times, dtype=np.float64)
@@ -181,6 +231,11 @@ class Microphone:
 
     def __len__(self) -> int:
         return len(self._data)
+
+    def __repr__(self) -> str:
+        who = f"'{self.name}'" if self.name else "unnamed"
+        aim = f", direction={self.direction}" if self.is_directional() else ""
+        return f"Microphone({who}, position={self.position}, pattern='{self._pattern_name}'{aim}, samples={len(self._data)})"
 
 
 def combine_corner_samples(mics, gathers, corners: dict, times) -> None:

@@ -209,6 +209,55 @@ def test_script_solids_match_reference_live():
 
 
 @pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
+def test_membrane_sources_match_reference_live():
+    """Circular / rectangular membrane mirrors (membranes.py) against core/solver.py:210-755: masks, weights (bit for bit),
+    coordinate helpers, cached Bessel zeros, the off-grid warning and the validation messages."""
+    import warnings
+    ref = R.load_reference_package()
+    from strata_fdtd.core.solver import CircularMembraneSource as RC, RectangularMembraneSource as RR
+    wave = sb.GaussianPulse(position=(0, 0, 0), frequency=200.0)
+    grids = [(sb.UniformGrid((24, 30, 20), 2e-3), ref.UniformGrid((24, 30, 20), 2e-3)),
+             (sb.NonuniformGrid.from_stretch((26, 22, 30), 2e-3, stretch_x=1.04, stretch_z=1.03),
+              ref.NonuniformGrid.from_stretch((26, 22, 30), 2e-3, stretch_x=1.04, stretch_z=1.03))]
+    for g_ours, g_ref in grids:
+        ext = g_ours.physical_extent()
+        c = (0.47 * ext[0], 0.52 * ext[1], 0.41 * ext[2])
+        for axis in "xyz":
+            for mode in ((0, 1), (1, 1), (2, 2), (3, 2), (0, 3)):
+                kw = dict(center=c, normal_axis=axis, waveform=wave, mode=mode, radius=0.35 * min(ext), injection_type="velocity")
+                a, b = sb.CircularMembraneSource(**kw), RC(**kw)
+                assert a._alpha == b._alpha and a._BESSEL_ZEROS == b._BESSEL_ZEROS and a.source_type == b.source_type
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    assert np.array_equal(a.get_injection_mask(g_ours), b.get_injection_mask(g_ref))
+                    wa, wb = a.get_injection_weights(g_ours), b.get_injection_weights(g_ref)
+                assert wa.dtype == wb.dtype and np.array_equal(wa, wb) and wb.max() == 1.0, (axis, mode)
+                for x, y in zip(a._grid_to_membrane_coords(g_ours), b._grid_to_membrane_coords(g_ref)):
+                    assert np.array_equal(x, y)
+            for mode in ((1, 1), (2, 1), (3, 4)):
+                kw = dict(center=c, normal_axis=axis, waveform=wave, mode=mode, size=(0.5 * min(ext), 0.3 * min(ext)))
+                a, b = sb.RectangularMembraneSource(**kw), RR(**kw)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    assert np.array_equal(a.get_injection_mask(g_ours), b.get_injection_mask(g_ref))
+                    assert np.array_equal(a.get_injection_weights(g_ours), b.get_injection_weights(g_ref)), (axis, mode)
+                for x, y in zip(a._grid_to_rectangular_coords(g_ours), b._grid_to_rectangular_coords(g_ref)):
+                    assert np.array_equal(x, y)
+    pts_r, pts_t = np.linspace(0, 0.03, 50), np.linspace(-3, 3, 50)
+    kw = dict(center=(0.01, 0.01, 0.01), normal_axis="z", waveform=wave, mode=(1, 2), radius=0.02)
+    assert np.array_equal(sb.CircularMembraneSource(**kw).mode_shape(pts_r, pts_t), RC(**kw).mode_shape(pts_r, pts_t))
+    off = dict(center=(0.0201, 0.02, -0.0005), normal_axis="z", waveform=wave, radius=0.01)         # 0.75 cells below the first plane
+    for cls in (sb.CircularMembraneSource, RC):
+        with pytest.warns(UserWarning, match=r"is 0\.00\d+m \(0\.\d cells\) off-grid in z-direction"):
+            cls(**off).get_injection_weights(grids[0][0])
+    for bad, msg in ((dict(mode=(-1, 1)), "Azimuthal mode m must be non-negative"), (dict(mode=(0, 0)), "Radial mode n must be positive")):
+        with pytest.raises(ValueError, match=msg):
+            sb.CircularMembraneSource(center=c, normal_axis="x", waveform=wave, radius=0.01, **bad)
+    with pytest.raises(ValueError, match="Mode index n must be >= 1"):
+        sb.RectangularMembraneSource(center=c, normal_axis="x", waveform=wave, size=(0.01, 0.01), mode=(1, 0))
+
+
+@pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
 def test_shim_registers_backend_with_reference():
     ref = R.load_reference_package()
     sb.install_into_reference(ref)
