@@ -12,10 +12,11 @@ from .materials import Pole, PoleMaterial, PoleType, SimpleMaterial  # noqa: F40
 from .solver import FDTDSolver  # noqa: F401
 from .sources import POLAR_PATTERNS, GaussianPulse, Microphone, Probe  # noqa: F401
 from .membranes import CircularMembraneSource, MembraneSource, RectangularMembraneSource  # noqa: F401
+from .waveforms import AudioFileWaveform  # noqa: F401
 from .shim import install_into_reference  # noqa: F401
 from . import io, workloads  # noqa: F401,E402
 
 __version__ = "0.1.0"
 __all__ = ["FDTDSolver", "UniformGrid", "NonuniformGrid", "PML", "RigidBoundary", "GaussianPulse", "Probe",
-           "Microphone", "POLAR_PATTERNS", "MembraneSource", "CircularMembraneSource", "RectangularMembraneSource",
+           "Microphone", "POLAR_PATTERNS", "AudioFileWaveform", "MembraneSource", "CircularMembraneSource", "RectangularMembraneSource",
            "Pole", "PoleType", "SimpleMaterial", "PoleMaterial", "B200BackendError", "build", "install_into_reference"]

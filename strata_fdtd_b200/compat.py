@@ -177,7 +177,7 @@ def install_as_strata_fdtd(force_alias: bool = False):
                  RadiationImpedance=boundaries.RadiationImpedance, UniformGrid=sb.UniformGrid,
                  NonuniformGrid=sb.NonuniformGrid, Pole=sb.Pole, PoleType=sb.PoleType, SimpleMaterial=sb.SimpleMaterial,
                  Sphere=Sphere, Box=Box, Union=Union, Intersection=Intersection, Difference=Difference,
-                 POLAR_PATTERNS=sources.POLAR_PATTERNS, MembraneSource=sb.MembraneSource,
+                 POLAR_PATTERNS=sources.POLAR_PATTERNS, AudioFileWaveform=sb.AudioFileWaveform, MembraneSource=sb.MembraneSource,
                  CircularMembraneSource=sb.CircularMembraneSource, RectangularMembraneSource=sb.RectangularMembraneSource,
                  has_native_kernels=lambda: False, has_gpu_backend=lambda: True,
                  get_native_info=lambda: {"available": False, "version": None, "has_openmp": False, "num_threads": 1},

@@ -258,6 +258,31 @@ def test_membrane_sources_match_reference_live():
 
 
 @pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
+def test_audio_file_waveform_matches_reference_live(tmp_path):
+    """waveforms.AudioFileWaveform against core/waveforms.py:33-231 on a stereo 16-bit file: samples, resampling to 1/dt,
+    channel selection, trimming, looping and the zero tail -- identical arrays."""
+    from scipy.io import wavfile
+    R.load_reference_package()
+    from strata_fdtd.core.waveforms import AudioFileWaveform as RefWave
+    rate = 22050
+    tt = np.arange(int(0.05 * rate)) / rate
+    stereo = np.stack([np.sin(2 * np.pi * 440 * tt), 0.5 * np.sin(2 * np.pi * 1000 * tt + 0.3)], axis=1)
+    path = tmp_path / "tone.wav"
+    wavfile.write(path, rate, (stereo * 32767).astype(np.int16))
+    dt = 1.6e-6
+    t = np.arange(0, 40000) * dt
+    for kw in (dict(), dict(channel=1, amplitude=0.25), dict(start_time=0.01, duration=0.02, loop=True), dict(channel=0, start_time=0.03)):
+        a, b = sb.AudioFileWaveform(path, **kw), RefWave(path, **kw)
+        assert a.native_sample_rate == b.native_sample_rate and a.num_samples == b.num_samples and a.duration_seconds == b.duration_seconds
+        wa, wb = a.waveform(t, dt), b.waveform(t, dt)
+        assert wa.dtype == wb.dtype and np.array_equal(wa, wb) and np.abs(wb).max() > 0, kw
+    with pytest.raises(ValueError, match="Channel 2 requested but file only has 2 channels"):
+        sb.AudioFileWaveform(path, channel=2)
+    with pytest.raises(FileNotFoundError, match="Audio file not found"):
+        sb.AudioFileWaveform(tmp_path / "missing.wav")
+
+
+@pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
 def test_shim_registers_backend_with_reference():
     ref = R.load_reference_package()
     sb.install_into_reference(ref)

@@ -1,9 +1,9 @@
 """The reference's OWN solver and grid test files, unmodified, against backend="b200".
 
 /root/reference/tests/test_fdtd.py, test_grid.py, test_microphone.py, test_microphone_directional.py, test_membrane_source.py,
-test_circular_membrane.py and test_rectangular_membrane.py (229 tests -- 213 pass, 11 skip themselves for want of the reference's C++ kernels, 5 are listed below: wave speed, symmetry, rigid walls, PML absorption, energy
+test_circular_membrane.py, test_rectangular_membrane.py and test_waveforms.py (253 tests -- 237 pass, 11 skip themselves for want of the reference's C++ kernels, 5 are listed below: wave speed, symmetry, rigid walls, PML absorption, energy
 conservation in a closed pipe over 2000 steps, probes, Gaussian pulses, radiation impedance, nonuniform grids, trilinear and
-directional microphones, WAV export, Bessel / sinusoidal membrane modes and their injection, ...) travel to
+directional microphones, WAV export, Bessel / sinusoidal membrane modes and their injection, audio-file waveforms, ...) travel to
 the GPU box as byte-identical copies in oracle/_ref/tests/ (put there by __graft_entry__.build(); oracle/_ref is git-ignored,
 reference files never enter this repository).  They are collected with tests/ref_alias_plugin.py, which makes
 ``import strata_fdtd`` resolve to this package (compat.install_as_strata_fdtd) -- the situation of a user who switches a
@@ -22,7 +22,7 @@ ROOT = Path(__file__).resolve().parents[1]
 REF_TESTS = ROOT / "oracle" / "_ref" / "tests"
 
 FILES = ["test_grid.py", "test_fdtd.py", "test_microphone.py", "test_microphone_directional.py", "test_membrane_source.py",
-         "test_circular_membrane.py", "test_rectangular_membrane.py"]
+         "test_circular_membrane.py", "test_rectangular_membrane.py", "test_waveforms.py"]
 
 # test id -> why it cannot pass on any backend but the reference's own
 EXPECTED_DIFFERENCES = {
@@ -58,6 +58,18 @@ def test_reference_solver_and_grid_tests_pass_on_b200(tmp_path):
     passed = {t for t, o in outcome.items() if o == "passed"}
     unexpected = failed - set(EXPECTED_DIFFERENCES)
     assert not unexpected, f"reference tests failing on b200: {sorted(unexpected)}\n" + res.stdout[-6000:]
-    assert len(passed) >= 213, f"only {len(passed)} of the reference's tests passed: {res.stdout[-2000:]}"
+    assert len(passed) >= 237, f"only {len(passed)} of the reference's tests passed: {res.stdout[-2000:]}"
     fixed = set(EXPECTED_DIFFERENCES) & passed
     assert not fixed, f"listed as expected differences but passing: {sorted(fixed)}"
+
+
+def test_reference_waveform_tests_pass_on_the_mirror():
+    """The one of those files that needs no device (test_waveforms.py: loading, trimming, resampling, looping of audio-file
+    sources) also runs in the CPU suite, from the reference tree or its copy."""
+    src = next((d for d in (REF_TESTS, Path("/root/reference/tests")) if (d / "test_waveforms.py").exists()), None)
+    if src is None:
+        pytest.skip("the reference's tests are not on this box")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(ROOT / "tests"), str(ROOT), os.environ.get("PYTHONPATH", "")]))
+    res = subprocess.run([sys.executable, "-m", "pytest", str(src / "test_waveforms.py"), "-p", "ref_alias_plugin", "-q", "--no-header",
+                          "-p", "no:cacheprovider", "--rootdir", str(ROOT / "tests")], cwd=ROOT / "tests", env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "24 passed" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
