@@ -954,6 +954,24 @@ class FDTDSolver:
     def _centred_velocities(self):
         return centre_velocities(*(self.get_field(name) for name in ("vx", "vy", "vz")))
 
+    def _compute_divergence(self) -> np.ndarray:
+        """Velocity divergence of the current state, evaluated on the host from the downloaded fields -- a diagnostic with the
+        arithmetic of the reference's helper of the same name (core/solver.py:3214-3270: backward differences with a zero
+        face below index 0; 1/dx, or the per-cell inverse spacings on a nonuniform grid).  The step kernels do not use it."""
+        v = [self.get_field(f) for f in ("vx", "vy", "vz")]
+        parts = []
+        for axis in range(3):
+            d = v[axis].copy()
+            hi = [slice(None)] * 3; lo = [slice(None)] * 3
+            hi[axis], lo[axis] = slice(1, None), slice(0, -1)
+            d[tuple(hi)] -= v[axis][tuple(lo)]
+            parts.append(d)
+        if getattr(self._grid, "is_uniform", self._spacing_arrays is None):
+            return ((parts[0] + parts[1]) + parts[2]) / self.dx
+        sa = self._spacing_arrays
+        inv = [np.asarray(sa[f"inv_d{a}_cell"], dtype=np.float32) for a in "xyz"]
+        return (parts[0] * inv[0][:, None, None] + parts[1] * inv[1][None, :, None]) + parts[2] * inv[2][None, None, :]
+
     def compute_energy(self) -> float:
         """(1/2) sum(p^2/(rho c^2) + rho |v|^2) dV over air cells (solver.py:2689-2706), reduced on the device."""
         dev = self._sync_to_device()
