@@ -199,6 +199,15 @@ def install_as_strata_fdtd(force_alias: bool = False):
     grid_mod = types.ModuleType("strata_fdtd.core.grid")
     grid_mod.UniformGrid, grid_mod.NonuniformGrid = sb.UniformGrid, sb.NonuniformGrid
     core.solver, core.grid = solver_mod, grid_mod
+    from . import io as sbio
+    io_mod = types.ModuleType("strata_fdtd.io")                  # the result-file reader / writer interface (io/hdf5.py)
+    io_mod.__path__ = []
+    hdf5_mod = types.ModuleType("strata_fdtd.io.hdf5")
+    for mod in (io_mod, hdf5_mod):
+        mod.HDF5ResultWriter, mod.HDF5ResultReader = sbio.HDF5ResultWriter, sbio.HDF5ResultReader
+    io_mod.hdf5 = hdf5_mod
+    root.io = io_mod
+    sys.modules.update({"strata_fdtd.io": io_mod, "strata_fdtd.io.hdf5": hdf5_mod})
     geo = types.ModuleType("strata_fdtd.geometry")               # the few shapes above; the toolkit itself stays upstream
     geo.__path__ = []
     for k in ("Sphere", "Box", "Union", "Intersection", "Difference"):

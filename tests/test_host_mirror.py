@@ -320,6 +320,16 @@ def test_result_writer_schema_without_device(tmp_path):
         attrs = json.loads(str(z["__attrs__"]))
         assert attrs["metadata@backend"] == "b200" and attrs["simulation@num_steps"] == 7
         assert attrs["grid@shape"] == [4, 5, 6] and attrs["sources/source_0@frequency"] == 1e3
+    # the reference reader's interface (io/hdf5.py:243-375) over whichever container was written
+    with sbio.HDF5ResultReader(out) as rd:
+        meta = rd.get_metadata()
+        assert meta["metadata"]["backend"] == "b200" and meta["simulation"]["num_steps"] == 7 and list(meta["grid"]["shape"]) == [4, 5, 6]
+        assert meta["sources"][0]["frequency"] == 1e3 and list(meta["probes"]["b"]["position"]) == [2, 2, 2]
+        assert rd.get_probe_names() == ["a", "b"] and np.array_equal(rd.load_probe("b"), blk[:, 1])
+        assert rd.get_num_snapshots() == 1 and np.array_equal(rd.load_timestep(0), np.full((4, 5, 6), 2.0, np.float32))
+        assert rd.load_geometry().dtype == bool and rd.load_geometry().all()
+        with pytest.raises(KeyError, match="Probe 'zz' not found. Available: \\['a', 'b'\\]"):
+            rd.load_probe("zz")
 
 
 def test_strata_fdtd_alias_resolves_names():
