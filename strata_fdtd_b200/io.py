@@ -269,7 +269,7 @@ class HDF5ResultReader:
         pre = group + "/"
         names = [k[len(pre):] for k in self._npz.files if k.startswith(pre)] + \
                 [k[len(pre):].split("@")[0] for k in self._attrs if k.startswith(pre)]
-        return list(dict.fromkeys(n.split("/")[0] for n in names))
+        return sorted(set(n.split("/")[0] for n in names))        # (h5py lists group members in alphabetical order)
 
     def _has(self, path: str) -> bool:
         return path in self.file if self.file is not None else path in self._npz.files
