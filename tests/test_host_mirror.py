@@ -283,6 +283,34 @@ def test_audio_file_waveform_matches_reference_live(tmp_path):
 
 
 @pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
+def test_microphone_host_sampling_matches_reference_live(tmp_path):
+    """Microphone.record (the per-step Python path of core/solver.py:1004-1173) on random fields: omnidirectional, every named
+    polar pattern and a callable pattern give the reference's samples exactly; to_wav writes the same bytes."""
+    import types
+    ref = R.load_reference_package()
+    rng = np.random.default_rng(5)
+    shape = (12, 10, 14)
+    fields = [rng.standard_normal(shape).astype(np.float32) for _ in range(4)]
+    host = types.SimpleNamespace(dx=2e-3, dt=3.1e-6, rho=1.2, c=343.0, shape=shape)
+    for pattern in list(sb.POLAR_PATTERNS) + [lambda th: 0.3 + 0.7 * np.cos(th) ** 2]:
+        kw = dict(position=(0.0113, 0.0087, 0.0141), name="m", pattern=pattern, direction=(0.3, -0.5, 0.8))
+        a, b = sb.Microphone(**kw), ref.Microphone(**kw)
+        a._initialize(host); b._initialize(host)
+        for q in range(120):                                      # (to_wav at 48 kHz keeps 17 of them)
+            scaled = [f * np.float32(np.sin(0.21 * q)) for f in fields]
+            a.record(scaled[0], q * host.dt, *scaled[1:]); b.record(scaled[0], q * host.dt, *scaled[1:])
+        assert np.array_equal(a.get_waveform(), b.get_waveform()) and np.array_equal(a.get_time_axis(), b.get_time_axis()), pattern
+        assert repr(a) == repr(b) and len(a) == len(b) == 120
+        for bits in (16, 32):
+            a.to_wav(str(tmp_path / "a.wav"), sample_rate=48000, bit_depth=bits); b.to_wav(str(tmp_path / "b.wav"), sample_rate=48000, bit_depth=bits)
+            assert (tmp_path / "a.wav").read_bytes() == (tmp_path / "b.wav").read_bytes()
+    with pytest.raises(ValueError, match="Velocity fields \\(vx, vy, vz\\) are required"):
+        m = sb.Microphone(position=(0.01, 0.01, 0.01), pattern="cardioid"); m._initialize(host); m.record(fields[0], 0.0)
+    with pytest.raises(RuntimeError, match="Microphone not initialized"):
+        sb.Microphone(position=(0.01, 0.01, 0.01)).record(fields[0], 0.0)
+
+
+@pytest.mark.skipif(not R.have_reference_package(), reason="reference sources not on this box")
 def test_shim_registers_backend_with_reference():
     ref = R.load_reference_package()
     sb.install_into_reference(ref)
